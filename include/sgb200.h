@@ -1,0 +1,151 @@
+/*
+ * sgb200.h -- C ABI of the B200-native CFG-DDPM sampling kernels (libsgb200.so).
+ *
+ * The reference (gibbona1/SpectrogramGenAI) has no FFI layer: its hot path is Python calling
+ * torch.nn modules.  Each entry point below therefore cites the torch
+ * call site(s) in /root/reference/src/diff_modules.py that it replaces.  INTEGRATION.md shows
+ * the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch owns all memory);
+ *     kernels never allocate, free or synchronise;
+ *   - activations are channels-last: [rows, H, W, C] ("NHWC"), rows = batch rows
+ *     (2n when the conditional and unconditional passes are batched);
+ *   - `act` tensors are SG_F32 (fp32-accurate SIMT engine) or SG_BF16 (tcgen05 engine);
+ *   - every function returns 0 on success, non-zero on error; sg_last_error() returns a
+ *     thread-local human-readable reason.  No exceptions, no CPU fallback: a non-sm_100
+ *     device is an error (SG_ERR_ARCH).
+ *   - `stream` is a cudaStream_t passed as void*; all launches are capturable in a CUDA graph.
+ */
+#ifndef SGB200_H
+#define SGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 1
+
+typedef enum { SG_F32 = 0, SG_BF16 = 1 } sg_dtype;
+typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
+
+enum {
+  SG_OK = 0,
+  SG_ERR_ARG = 1,    /* bad shape / null pointer / unsupported combination */
+  SG_ERR_ARCH = 2,   /* device is not sm_100 (B200)                        */
+  SG_ERR_LAUNCH = 3, /* CUDA launch or driver error                        */
+};
+
+typedef void* sg_stream_t;
+
+int sg_abi_version(void);
+const char* sg_last_error(void);
+/* 0 iff `device` is a compute-capability 10.x device with the sm_100a image loadable. */
+int sg_device_check(int device);
+
+/* ---- K5: sinusoidal timestep encoding + label embedding + the six emb_layer projections ----
+ * replaces UNet.pos_encoding (:168-173), label_emb add (:214-215) and emb_layer of Down/Up
+ * (:105-108,:112 / :126-129,:135).
+ *   t        int64 [rows] timesteps, or NULL to use *step (device int32) for every row
+ *   y        int64 [rows] class ids; a negative id means "unconditional row" (y=None, :427)
+ *   inv_freq fp32 [128]    1/10000^(2k/256), built by the caller exactly as :169 does
+ *   label    fp32 [num_classes, 256] (may be NULL iff every y < 0)
+ *   w_emb    fp32 [emb_total, 256], b_emb fp32 [emb_total]: emb_layer.1 of down1..3, up1..3 concatenated
+ *   temb     fp32 [rows, 256] out (encoding + label row);  emb fp32 [rows, emb_total] out
+ */
+int sg_time_embed(const int64_t* t, const int32_t* step, const int64_t* y, const float* inv_freq,
+                  const float* label, int num_classes, const float* w_emb, const float* b_emb,
+                  int emb_total, int rows, float* temb, float* emb, sg_stream_t stream);
+
+/* ---- inc.double_conv.0: 3x3 conv, c_in in {1..4}, NCHW fp32 input -> raw fp32 NHWC [rows,S,S,64] ----
+ * replaces nn.Conv2d(c_in, 64, 3, padding=1, bias=False) (:82 via :144).  Row r reads sample
+ * r % n_src of x (the cond/uncond halves share x).  Also emits GroupNorm partial sums:
+ * partials fp32 [rows, P, 2] (sum, sum of squares), P = sg_conv_in_partials(S).
+ */
+int sg_conv_in_partials(int S);
+int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w /*[64,c_in,3,3]*/, int rows,
+               float* raw, float* partials, sg_stream_t stream);
+
+/* ---- K1: implicit-GEMM 3x3 (taps=9, pad 1) or 1x1 (taps=1; Linear) over NHWC activations ----
+ * replaces nn.Conv2d(.,.,3,padding=1,bias=False) (:82,:85) and the Linear layers of
+ * SelfAttention (in_proj/out_proj inside nn.MultiheadAttention :56,:69; ff_self :60,:62).
+ * out[m, co] = sum_{tap, ci} a[pixel(m) + tap offset, ci] * w[tap, co, ci]; epilogue, in order:
+ * + bias[co]; GELU(erf) if gelu; + residual[m, co].  M = rows*H*W.
+ * SG_ENGINE_SIMT: fp32 CUDA-core kernel (act = SG_F32).  SG_ENGINE_TC: tcgen05/TMEM kernel fed
+ * by TMA (act = SG_BF16, fp32 accumulate).  Requires Cin % 64 == 0 (TC) / % 16 (SIMT), Cout % 64 == 0.
+ */
+typedef struct {
+  const void* a;         /* act  [rows, H, W, Cin]                              */
+  const void* w;         /* act  [taps, Cout, Cin]  (packed by the caller)      */
+  const float* bias;     /* fp32 [Cout] or NULL                                 */
+  const float* residual; /* fp32 [M, Cout] or NULL                              */
+  float* out_f32;        /* fp32 [M, Cout] or NULL                              */
+  void* out_act;         /* act  [M, Cout] or NULL                              */
+  float* partials;       /* fp32 [rows, P, 2] GroupNorm partial sums or NULL    */
+  int32_t rows, H, W, Cin, Cout, taps, gelu;
+  int32_t engine;        /* sg_engine                                           */
+} sg_igemm_args;
+int sg_igemm_partials(int engine, int H, int W, int Cout); /* P for the given geometry */
+int sg_igemm(const sg_igemm_args* args, sg_stream_t stream);
+
+/* ---- K2: GroupNorm(1, C) finalize + affine (+GELU | +residual,GELU | +time-embedding) ----
+ * replaces nn.GroupNorm(1,C) + nn.GELU (:83-84,:86), F.gelu(x + double_conv(x)) (:91) and
+ * the broadcast "x + emb" of Down/Up (:113,:136).  mode: 0 = affine only, 1 = GELU(affine),
+ * 2 = GELU(residual + affine) (residual fp32 [rows,HW,C] required).  emb (fp32, row stride
+ * emb_stride, already offset to this layer's slice) is added last when non-NULL.
+ */
+int sg_gn_apply(const float* raw, const float* partials, int P, const float* gamma, const float* beta,
+                int rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride,
+                float* out_f32, void* out_act, int act_dtype, sg_stream_t stream);
+
+/* ---- K3a: MaxPool2d(2) (:100).  in fp32 [rows,H,W,C] -> fp32 and/or act [rows,H/2,W/2,C] ---- */
+int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, void* out_act, int act_dtype,
+                sg_stream_t stream);
+
+/* ---- K3b: Upsample(x2, bilinear, align_corners=True) + cat([skip, x], dim=1) (:120,:132-133) ----
+ * x fp32 [rows,h,w,Cx], skip fp32 [rows,2h,2w,Cs] -> [rows,2h,2w,Cs+Cx] (skip channels first).
+ */
+int sg_upsample_cat(const float* x, const float* skip, int rows, int h, int w, int Cx, int Cs, float* out_f32,
+                    void* out_act, int act_dtype, sg_stream_t stream);
+
+/* ---- LayerNorm over C (:57 self.ln, :59 ff_self.0).  in fp32 [M,C] -> act [M,C]; C in {64,128,256} ---- */
+int sg_layernorm(const float* in, const float* gamma, const float* beta, int M, int C, void* out_act,
+                 int act_dtype, sg_stream_t stream);
+
+/* ---- K4: multi-head self-attention core, never materialising the L x L matrix ----
+ * replaces the scaled-dot-product inside nn.MultiheadAttention (:56,:69): per row and head,
+ * softmax(q k^T / sqrt(d)) v.  qkv act [rows*L, 3C] = in_proj output (q | k | v, head h at
+ * columns [h*d,(h+1)*d) of each third); out act [rows*L, C].  d = C/heads in {16,32,64}.
+ */
+int sg_attention(const void* qkv, void* out, int rows, int L, int C, int heads, int engine, sg_stream_t stream);
+
+/* ---- outc: 1x1 conv 64 -> c_out with bias, NHWC fp32 in, NCHW fp32 out (:166,:195) ---- */
+int sg_conv_out(const float* in, const float* w /*[c_out,64]*/, const float* b, int rows, int HW, int c_out,
+                float* eps, sg_stream_t stream);
+
+/* ---- K6: CFG lerp + posterior update, one kernel (:426-439) ----
+ * x fp32 [n, E] in/out (E = c*S*S).  eps fp32: rows [0,n) conditional, rows [n,2n) unconditional
+ * (eps_uncond_offset_rows = n), or cfg_scale <= 0 for the single-forward branch (:426).
+ * coef fp32 [T,3] = (1/sqrt(alpha), (1-alpha)/sqrt(1-alpha_hat), sqrt(beta)) built by the caller
+ * with the reference's own expressions.  i = *step (device int32) is the current timestep.
+ * Noise z: `noise` != NULL -> injected fp32 [T-1, n, E], z = noise[T - i] (index 0 is x_T);
+ * else Philox4x32-10(seed; sample_base + sample, i, element) + Box-Muller.  z = 0 at i == 1 (:434-435).
+ * Arithmetic uses un-fused fp32 multiplies/adds in the reference's evaluation order, so for equal
+ * eps inputs and injected noise the update is bit-identical to the CPU reference.
+ */
+int sg_cfg_update(float* x, const float* eps, int n, int E, float cfg_scale, const float* coef, int T,
+                  const int32_t* step, const float* noise, uint64_t seed, int64_t sample_base, sg_stream_t stream);
+/* *step -= 1 (one thread); the last node of a captured sampling step. */
+int sg_step_advance(int32_t* step, sg_stream_t stream);
+/* x_T from the same Philox stream (throughput mode): x[sample, e] = N(0,1)(seed; sample_base+sample, T, e). */
+int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base, int step_tag, sg_stream_t stream);
+
+/* ---- K8: (clamp(x,-1,1)+1)/2*255 -> truncating uint8 cast (:440-441) ---- */
+int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGB200_H */
