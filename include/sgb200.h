@@ -10,11 +10,13 @@
  *   - every pointer is a DEVICE pointer owned by the caller (PyTorch owns all memory);
  *     kernels never allocate, free or synchronise;
  *   - activations are channels-last: [rows, H, W, C] ("NHWC"), rows = batch rows
- *     (2n when the conditional and unconditional passes are batched);
- *   - `act` tensors are SG_F32 (fp32-accurate SIMT engine) or SG_BF16 (tcgen05 engine);
+ *     (2n when the conditional and unconditional passes are batched).  H and W are powers
+ *     of two;
+ *   - "act" tensors are SG_F32 (fp32-accurate SIMT engine) or SG_BF16 / SG_F16 (tcgen05
+ *     engine: 16-bit operands, fp32 accumulation in TMEM);
  *   - every function returns 0 on success, non-zero on error; sg_last_error() returns a
  *     thread-local human-readable reason.  No exceptions, no CPU fallback: a non-sm_100
- *     device is an error (SG_ERR_ARCH).
+ *     device is an error (SG_ERR_ARCH);
  *   - `stream` is a cudaStream_t passed as void*; all launches are capturable in a CUDA graph.
  */
 #ifndef SGB200_H
@@ -26,9 +28,9 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 1
+#define SG_ABI_VERSION 2
 
-typedef enum { SG_F32 = 0, SG_BF16 = 1 } sg_dtype;
+typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
 
 enum {
@@ -44,18 +46,22 @@ int sg_abi_version(void);
 const char* sg_last_error(void);
 /* 0 iff `device` is a compute-capability 10.x device with the sm_100a image loadable. */
 int sg_device_check(int device);
+/* Make `device` current for this library's CUDA runtime on the calling thread (one rank = one GPU). */
+int sg_set_device(int device);
 
 /* ---- K5: sinusoidal timestep encoding + label embedding + the six emb_layer projections ----
  * replaces UNet.pos_encoding (:168-173), label_emb add (:214-215) and emb_layer of Down/Up
  * (:105-108,:112 / :126-129,:135).
- *   t        int64 [rows] timesteps, or NULL to use *step (device int32) for every row
- *   y        int64 [rows] class ids; a negative id means "unconditional row" (y=None, :427)
+ *   t        fp32 [rows] timesteps (the reference promotes long -> fp32 in the multiply at :171),
+ *            or NULL to use (float)*step (device int32) for every row
+ *   y        int64 [rows] class ids; a negative id means "unconditional row" (y=None, :427);
+ *            NULL = all rows unconditional
  *   inv_freq fp32 [128]    1/10000^(2k/256), built by the caller exactly as :169 does
  *   label    fp32 [num_classes, 256] (may be NULL iff every y < 0)
  *   w_emb    fp32 [emb_total, 256], b_emb fp32 [emb_total]: emb_layer.1 of down1..3, up1..3 concatenated
  *   temb     fp32 [rows, 256] out (encoding + label row);  emb fp32 [rows, emb_total] out
  */
-int sg_time_embed(const int64_t* t, const int32_t* step, const int64_t* y, const float* inv_freq,
+int sg_time_embed(const float* t, const int32_t* step, const int64_t* y, const float* inv_freq,
                   const float* label, int num_classes, const float* w_emb, const float* b_emb,
                   int emb_total, int rows, float* temb, float* emb, sg_stream_t stream);
 
@@ -73,8 +79,9 @@ int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w /*[64,
  * SelfAttention (in_proj/out_proj inside nn.MultiheadAttention :56,:69; ff_self :60,:62).
  * out[m, co] = sum_{tap, ci} a[pixel(m) + tap offset, ci] * w[tap, co, ci]; epilogue, in order:
  * + bias[co]; GELU(erf) if gelu; + residual[m, co].  M = rows*H*W.
- * SG_ENGINE_SIMT: fp32 CUDA-core kernel (act = SG_F32).  SG_ENGINE_TC: tcgen05/TMEM kernel fed
- * by TMA (act = SG_BF16, fp32 accumulate).  Requires Cin % 64 == 0 (TC) / % 16 (SIMT), Cout % 64 == 0.
+ * SG_ENGINE_SIMT: fp32 CUDA-core kernel (act_dtype = SG_F32).  SG_ENGINE_TC: tcgen05/TMEM kernel
+ * fed by TMA (act_dtype = SG_BF16 or SG_F16, fp32 accumulate).
+ * Requires Cin % 64 == 0 (TC) / % 16 (SIMT), Cout % 64 == 0.
  */
 typedef struct {
   const void* a;         /* act  [rows, H, W, Cin]                              */
@@ -86,6 +93,7 @@ typedef struct {
   float* partials;       /* fp32 [rows, P, 2] GroupNorm partial sums or NULL    */
   int32_t rows, H, W, Cin, Cout, taps, gelu;
   int32_t engine;        /* sg_engine                                           */
+  int32_t act_dtype;     /* sg_dtype of a, w and out_act                        */
 } sg_igemm_args;
 int sg_igemm_partials(int engine, int H, int W, int Cout); /* P for the given geometry */
 int sg_igemm(const sg_igemm_args* args, sg_stream_t stream);
@@ -111,23 +119,26 @@ int sg_upsample_cat(const float* x, const float* skip, int rows, int h, int w, i
                     void* out_act, int act_dtype, sg_stream_t stream);
 
 /* ---- LayerNorm over C (:57 self.ln, :59 ff_self.0).  in fp32 [M,C] -> act [M,C]; C in {64,128,256} ---- */
-int sg_layernorm(const float* in, const float* gamma, const float* beta, int M, int C, void* out_act,
+int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t M, int C, void* out_act,
                  int act_dtype, sg_stream_t stream);
 
 /* ---- K4: multi-head self-attention core, never materialising the L x L matrix ----
  * replaces the scaled-dot-product inside nn.MultiheadAttention (:56,:69): per row and head,
  * softmax(q k^T / sqrt(d)) v.  qkv act [rows*L, 3C] = in_proj output (q | k | v, head h at
- * columns [h*d,(h+1)*d) of each third); out act [rows*L, C].  d = C/heads in {16,32,64}.
+ * columns [h*d,(h+1)*d) of each third); out [rows*L, C].  d = C/heads in {16,32,64}.
+ * SG_ENGINE_SIMT: qkv is fp32, out has dtype act_dtype (fp32 or 16-bit).  SG_ENGINE_TC: qkv and out are
+ * both act_dtype (SG_BF16 / SG_F16).
  */
-int sg_attention(const void* qkv, void* out, int rows, int L, int C, int heads, int engine, sg_stream_t stream);
+int sg_attention(const void* qkv, void* out, int rows, int L, int C, int heads, int engine, int act_dtype,
+                 sg_stream_t stream);
 
 /* ---- outc: 1x1 conv 64 -> c_out with bias, NHWC fp32 in, NCHW fp32 out (:166,:195) ---- */
 int sg_conv_out(const float* in, const float* w /*[c_out,64]*/, const float* b, int rows, int HW, int c_out,
                 float* eps, sg_stream_t stream);
 
 /* ---- K6: CFG lerp + posterior update, one kernel (:426-439) ----
- * x fp32 [n, E] in/out (E = c*S*S).  eps fp32: rows [0,n) conditional, rows [n,2n) unconditional
- * (eps_uncond_offset_rows = n), or cfg_scale <= 0 for the single-forward branch (:426).
+ * x fp32 [n, E] in/out (E = c*S*S).  eps fp32 [2n, E]: rows [0,n) conditional, rows [n,2n)
+ * unconditional; with cfg_scale <= 0 only rows [0,n) are read (the single-forward branch, :426).
  * coef fp32 [T,3] = (1/sqrt(alpha), (1-alpha)/sqrt(1-alpha_hat), sqrt(beta)) built by the caller
  * with the reference's own expressions.  i = *step (device int32) is the current timestep.
  * Noise z: `noise` != NULL -> injected fp32 [T-1, n, E], z = noise[T - i] (index 0 is x_T);
@@ -139,7 +150,7 @@ int sg_cfg_update(float* x, const float* eps, int n, int E, float cfg_scale, con
                   const int32_t* step, const float* noise, uint64_t seed, int64_t sample_base, sg_stream_t stream);
 /* *step -= 1 (one thread); the last node of a captured sampling step. */
 int sg_step_advance(int32_t* step, sg_stream_t stream);
-/* x_T from the same Philox stream (throughput mode): x[sample, e] = N(0,1)(seed; sample_base+sample, T, e). */
+/* x_T from the same Philox stream (throughput mode): x[sample, e] = N(0,1)(seed; sample_base+sample, step_tag, e). */
 int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base, int step_tag, sg_stream_t stream);
 
 /* ---- K8: (clamp(x,-1,1)+1)/2*255 -> truncating uint8 cast (:440-441) ---- */

@@ -1,0 +1,94 @@
+"""Builds libsgb200.so (the C-ABI CUDA library) in-tree for sm_100a with nvcc.
+
+    python -m spectrogramgenai_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with the
+repo snapshot; there is no JIT, no torch cpp_extension cache and no other backend.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+INCLUDE = os.path.join(os.path.dirname(PKG), "include")
+LIB_DIR = os.path.join(PKG, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libsgb200.so")
+OBJ_DIR = os.path.join(os.path.dirname(PKG), "build", "obj")
+
+SOURCES = [
+    "abi.cu",
+    "elementwise.cu",
+    "norm.cu",
+    "embed.cu",
+    "conv_simt.cu",
+    "attention_simt.cu",
+    "igemm_tc.cu",
+    "attention_tc.cu",
+]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "-I", INCLUDE,
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    return "nvcc"
+
+
+def _deps_mtime() -> float:
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "sgb200.h")]
+    return max(os.path.getmtime(f) for f in files)
+
+
+def needs_build() -> bool:
+    return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _deps_mtime()
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    header_mtime = max(
+        os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(".cuh")
+    )
+    header_mtime = max(header_mtime, os.path.getmtime(os.path.join(INCLUDE, "sgb200.h")))
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        srcp = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(srcp), header_mtime):
+            return obj
+        cmd = [nvcc, *NVCC_FLAGS, "-c", srcp, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    tmp = LIB_PATH + ".tmp"
+    r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

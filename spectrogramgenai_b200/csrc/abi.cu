@@ -1,0 +1,59 @@
+// C-ABI plumbing of libsgb200.so: version, thread-local error string, device check.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return SG_ERR_LAUNCH;
+  }
+  return SG_OK;
+}
+
+}  // namespace sg
+
+extern "C" {
+
+int sg_abi_version(void) { return SG_ABI_VERSION; }
+
+const char* sg_last_error(void) { return sg::g_err; }
+
+int sg_device_check(int device) {
+  cudaDeviceProp p;
+  cudaError_t e = cudaGetDeviceProperties(&p, device);
+  if (e != cudaSuccess) {
+    sg::set_error("cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+    return SG_ERR_LAUNCH;
+  }
+  if (p.major != 10) {
+    sg::set_error("device %d is sm_%d%d; libsgb200 ships only an sm_100a image (B200) and has no fallback", device,
+                  p.major, p.minor);
+    return SG_ERR_ARCH;
+  }
+  return SG_OK;
+}
+
+int sg_set_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    sg::set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    return SG_ERR_LAUNCH;
+  }
+  return SG_OK;
+}
+
+}  // extern "C"

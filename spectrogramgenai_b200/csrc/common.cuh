@@ -1,0 +1,166 @@
+// Shared helpers for the sgb200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sgb200.h"
+
+namespace sg {
+
+// ---- error plumbing (thread-local last-error string, returned through the C ABI) -------------
+void set_error(const char* fmt, ...);
+int launch_status(const char* what);  // cudaGetLastError -> SG_OK / SG_ERR_LAUNCH
+
+#define SG_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      ::sg::set_error(__VA_ARGS__);  \
+      return SG_ERR_ARG;             \
+    }                                \
+  } while (0)
+
+static inline cudaStream_t as_stream(sg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- activation-type load/store ---------------------------------------------------------------
+template <typename T>
+struct ActIO;
+
+template <>
+struct ActIO<float> {
+  static __device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+  }
+  static __device__ __forceinline__ void store2(float* p, float a, float b) {
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
+  }
+};
+
+template <>
+struct ActIO<__nv_bfloat16> {
+  static __device__ __forceinline__ void store4(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&lo);
+    v.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = v;
+  }
+  static __device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+  }
+};
+
+template <>
+struct ActIO<__half> {
+  static __device__ __forceinline__ void store4(__half* p, float a, float b, float c, float d) {
+    __half2 lo = __floats2half2_rn(a, b);
+    __half2 hi = __floats2half2_rn(c, d);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&lo);
+    v.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = v;
+  }
+  static __device__ __forceinline__ void store2(__half* p, float a, float b) {
+    *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b);
+  }
+};
+
+// pack two fp32 into one 32-bit word of 16-bit values (lo = a), runtime format
+__device__ __forceinline__ uint32_t pack16(float a, float b, int dtype) {
+  if (dtype == SG_BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t w, int dtype) {
+  if (dtype == SG_BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
+  return __half22float2(*reinterpret_cast<__half2*>(&w));
+}
+// store 4 consecutive values to an fp32 and/or 16-bit destination at element offset `off`
+__device__ __forceinline__ void store4_dual(float* o32, void* o16, int dtype, int64_t off, float a, float b, float c,
+                                            float d) {
+  if (o32) *reinterpret_cast<float4*>(o32 + off) = make_float4(a, b, c, d);
+  if (o16) {
+    uint2 v;
+    v.x = pack16(a, b, dtype);
+    v.y = pack16(c, d, dtype);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o16) + off) = v;
+  }
+}
+
+// exact (erf) GELU, as torch.nn.GELU() default
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Per-tile GroupNorm partial sums.
+// `rowstat` is shared memory [BM][2] holding (sum, sumsq) of each tile row over this tile's
+// columns.  Rows of the tile are M-consecutive pixels; a tile holds BM/HW whole samples when
+// HW < BM, else it lies inside one sample.  Writes partials[sample][p][2] deterministically.
+//   P       partials per sample,  p_base  = partial slot of this tile for a sample it covers
+template <int BM>
+__device__ __forceinline__ void write_tile_partials(const float (*rowstat)[2], int tid, int m0, int M, int HW,
+                                                    float* partials, int P, int tile_n, int n_tiles) {
+  const int group = HW < BM ? HW : BM;  // rows per sample inside this tile
+  const int groups = BM / group;
+  if (tid < groups) {
+    const int r0 = tid * group;
+    if (m0 + r0 < M) {
+      float s = 0.f, q = 0.f;
+      for (int r = 0; r < group; ++r) {
+        s += rowstat[r0 + r][0];
+        q += rowstat[r0 + r][1];
+      }
+      const int sample = (m0 + r0) / HW;
+      const int tile_in_sample = HW < BM ? 0 : ((m0 % HW) / BM);
+      const int p = tile_in_sample * n_tiles + tile_n;
+      partials[((int64_t)sample * P + p) * 2 + 0] = s;
+      partials[((int64_t)sample * P + p) * 2 + 1] = q;
+    }
+  }
+}
+
+// ---- Philox4x32-10 + Box-Muller ------------------------------------------------------------------
+struct Philox4 {
+  uint32_t v[4];
+};
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 o;
+  o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+// four N(0,1) draws for elements [4*q, 4*q+4) of (sample, step)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t sample, uint32_t step, uint32_t q) {
+  Philox4 r = philox4x32_10(q, step, (uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = ((float)r.v[0] + 0.5f) * k, u1 = ((float)r.v[1] + 0.5f) * k;
+  const float u2 = ((float)r.v[2] + 0.5f) * k, u3 = ((float)r.v[3] + 0.5f) * k;
+  const float r0 = sqrtf(-2.0f * logf(fmaxf(u0, 1e-30f))), r1 = sqrtf(-2.0f * logf(fmaxf(u2, 1e-30f)));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+}  // namespace sg

@@ -1,0 +1,217 @@
+// Memory-bound kernels of the sampling path: CFG lerp + posterior update (K6), uint8 tail (K8),
+// Philox x_T, step counter, MaxPool2d(2) (K3a) and bilinear-upsample + skip-concat (K3b).
+// All are HBM-roofline kernels: 128-bit coalesced accesses, no shared memory, one pass.
+#include "common.cuh"
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------------
+// K6  (/root/reference/src/diff_modules.py:426-439)
+//   eps = lerp(eps_u, eps_c, s)            ATen evaluates |s| >= 0.5 as eps_c - (eps_c - eps_u) * (1 - s)
+//   x   = c1 * (x - c2 * eps) + c3 * z     every product / sum rounded separately (torch runs them as
+//                                          separate elementwise ops), hence the __f*_rn intrinsics
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lerp_aten(float u, float c, float w) {
+  const float d = __fsub_rn(c, u);
+  return (fabsf(w) < 0.5f) ? __fadd_rn(u, __fmul_rn(w, d)) : __fsub_rn(c, __fmul_rn(d, __fsub_rn(1.0f, w)));
+}
+__device__ __forceinline__ float posterior(float x, float e, float c1, float c2, float c3, float z) {
+  return __fadd_rn(__fmul_rn(c1, __fsub_rn(x, __fmul_rn(c2, e))), __fmul_rn(c3, z));
+}
+
+__global__ void __launch_bounds__(256) cfg_update_kernel(float* __restrict__ x, const float* __restrict__ eps, int n,
+                                                         int E4, float cfg, const float* __restrict__ coef, int T,
+                                                         const int32_t* __restrict__ step,
+                                                         const float* __restrict__ noise, uint64_t seed,
+                                                         int64_t sample_base) {
+  const int64_t total = (int64_t)n * E4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int i = *step;
+  const float c1 = coef[i * 3 + 0], c2 = coef[i * 3 + 1], c3 = coef[i * 3 + 2];
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* e4 = reinterpret_cast<const float4*>(eps);
+  float4 xv = x4[idx];
+  float4 ec = __ldcs(e4 + idx);
+  float4 e = ec;
+  if (cfg > 0.0f) {
+    const float4 eu = __ldcs(e4 + total + idx);
+    e.x = lerp_aten(eu.x, ec.x, cfg);
+    e.y = lerp_aten(eu.y, ec.y, cfg);
+    e.z = lerp_aten(eu.z, ec.z, cfg);
+    e.w = lerp_aten(eu.w, ec.w, cfg);
+  }
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i > 1) {
+    if (noise != nullptr) {
+      z = __ldcs(reinterpret_cast<const float4*>(noise) + (int64_t)(T - i) * total + idx);
+    } else {
+      const int64_t sample = idx / E4;
+      z = philox_normal4(seed, (uint64_t)(sample_base + sample), (uint32_t)i, (uint32_t)(idx - sample * E4));
+    }
+  }
+  xv.x = posterior(xv.x, e.x, c1, c2, c3, z.x);
+  xv.y = posterior(xv.y, e.y, c1, c2, c3, z.y);
+  xv.z = posterior(xv.z, e.z, c1, c2, c3, z.z);
+  xv.w = posterior(xv.w, e.w, c1, c2, c3, z.w);
+  reinterpret_cast<float4*>(x)[idx] = xv;
+}
+
+__global__ void step_advance_kernel(int32_t* step) { *step -= 1; }
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ x, int n, int E4, uint64_t seed,
+                                                            int64_t sample_base, int step_tag) {
+  const int64_t total = (int64_t)n * E4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t sample = idx / E4;
+  reinterpret_cast<float4*>(x)[idx] =
+      philox_normal4(seed, (uint64_t)(sample_base + sample), (uint32_t)step_tag, (uint32_t)(idx - sample * E4));
+}
+
+// K8 (:440-441): clamp(-1,1) -> +1 -> /2 -> *255 -> truncating cast
+__device__ __forceinline__ uint32_t quant_u8(float v) {
+  v = fminf(fmaxf(v, -1.0f), 1.0f);
+  v = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
+  return (uint32_t)(int)v;  // v in [0,255]; NaN -> 0 like the CPU cast of clamp(NaN)... (NaN never occurs in parity runs)
+}
+__global__ void __launch_bounds__(256) to_uint8_kernel(const float* __restrict__ x, int64_t count4,
+                                                       uint32_t* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[idx];
+  out[idx] = quant_u8(v.x) | (quant_u8(v.y) << 8) | (quant_u8(v.z) << 16) | (quant_u8(v.w) << 24);
+}
+__global__ void to_uint8_tail_kernel(const float* __restrict__ x, int64_t begin, int64_t count, uint8_t* out) {
+  const int64_t idx = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < count) out[idx] = (uint8_t)quant_u8(x[idx]);
+}
+
+// K3a  MaxPool2d(2)  (:100).  NHWC, one thread = 4 channels of one output pixel.
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ in, int64_t total4, int Ho, int Wo,
+                                                       int C4, float* __restrict__ o32, void* __restrict__ o16,
+                                                       int dtype) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int c4 = (int)(idx % C4);
+  int64_t p = idx / C4;
+  const int wo = (int)(p % Wo);
+  p /= Wo;
+  const int ho = (int)(p % Ho);
+  const int64_t r = p / Ho;
+  const int W = Wo * 2;
+  const float4* src = reinterpret_cast<const float4*>(in) + ((r * (Ho * 2) + ho * 2) * W + wo * 2) * C4 + c4;
+  const float4 a = __ldg(src), b = __ldg(src + C4), c = __ldg(src + (int64_t)W * C4),
+               d = __ldg(src + (int64_t)W * C4 + C4);
+  const float m0 = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
+  const float m1 = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+  const float m2 = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
+  const float m3 = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+  store4_dual(o32, o16, dtype, idx * 4, m0, m1, m2, m3);
+}
+
+// K3b  Upsample(x2, bilinear, align_corners=True) + cat([skip, x], dim=1)   (:120, :132-133)
+// One thread = 4 channels of one output pixel of the concatenated tensor.
+__global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restrict__ x, const float* __restrict__ skip,
+                                                           int64_t total4, int h, int w, int Cx4, int Cs4,
+                                                           float sh, float sw, float* __restrict__ o32,
+                                                           void* __restrict__ o16, int dtype) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int Ct4 = Cx4 + Cs4;
+  const int c4 = (int)(idx % Ct4);
+  int64_t p = idx / Ct4;
+  const int H = 2 * h, W = 2 * w;
+  const int wo = (int)(p % W);
+  p /= W;
+  const int ho = (int)(p % H);
+  const int64_t r = p / H;
+  float4 v;
+  if (c4 < Cs4) {
+    v = __ldg(reinterpret_cast<const float4*>(skip) + ((r * H + ho) * W + wo) * Cs4 + c4);
+  } else {
+    const int cx = c4 - Cs4;
+    // align_corners=True: src = dst * (in-1)/(out-1)
+    const float fy = sh * (float)ho, fx = sw * (float)wo;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    const float4* base = reinterpret_cast<const float4*>(x) + r * h * w * Cx4 + cx;
+    const float4 a = __ldg(base + ((int64_t)y0 * w + x0) * Cx4), b = __ldg(base + ((int64_t)y0 * w + x1) * Cx4);
+    const float4 c = __ldg(base + ((int64_t)y1 * w + x0) * Cx4), d = __ldg(base + ((int64_t)y1 * w + x1) * Cx4);
+    v.x = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
+    v.y = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
+    v.z = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
+    v.w = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
+  }
+  store4_dual(o32, o16, dtype, idx * 4, v.x, v.y, v.z, v.w);
+}
+
+static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+int sg_cfg_update(float* x, const float* eps, int n, int E, float cfg_scale, const float* coef, int T,
+                  const int32_t* step, const float* noise, uint64_t seed, int64_t sample_base, sg_stream_t stream) {
+  SG_REQUIRE(x && eps && coef && step, "sg_cfg_update: null pointer");
+  SG_REQUIRE(n > 0 && E > 0 && E % 4 == 0 && T > 1, "sg_cfg_update: bad shape n=%d E=%d T=%d", n, E, T);
+  const int64_t total = (int64_t)n * (E / 4);
+  cfg_update_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(x, eps, n, E / 4, cfg_scale, coef, T, step, noise,
+                                                                     seed, sample_base);
+  return launch_status("sg_cfg_update");
+}
+
+int sg_step_advance(int32_t* step, sg_stream_t stream) {
+  SG_REQUIRE(step, "sg_step_advance: null pointer");
+  step_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(step);
+  return launch_status("sg_step_advance");
+}
+
+int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base, int step_tag, sg_stream_t stream) {
+  SG_REQUIRE(x && n > 0 && E > 0 && E % 4 == 0, "sg_philox_normal: bad arguments");
+  const int64_t total = (int64_t)n * (E / 4);
+  philox_normal_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(x, n, E / 4, seed, sample_base, step_tag);
+  return launch_status("sg_philox_normal");
+}
+
+int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream) {
+  SG_REQUIRE(x && out && count >= 0, "sg_to_uint8: bad arguments");
+  if (count == 0) return SG_OK;
+  const int64_t c4 = count / 4;
+  if (c4 > 0)
+    to_uint8_kernel<<<cdiv(c4, 256), 256, 0, as_stream(stream)>>>(x, c4, reinterpret_cast<uint32_t*>(out));
+  if (count % 4) to_uint8_tail_kernel<<<1, 32, 0, as_stream(stream)>>>(x, c4 * 4, count, out);
+  return launch_status("sg_to_uint8");
+}
+
+int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, void* out_act, int act_dtype,
+                sg_stream_t stream) {
+  SG_REQUIRE(in && (out_f32 || out_act), "sg_maxpool2: null pointer");
+  SG_REQUIRE(rows > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "sg_maxpool2: bad shape");
+  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_maxpool2: out_act needs a 16-bit dtype");
+  const int64_t total4 = (int64_t)rows * (H / 2) * (W / 2) * (C / 4);
+  maxpool2_kernel<<<cdiv(total4, 256), 256, 0, as_stream(stream)>>>(in, total4, H / 2, W / 2, C / 4, out_f32, out_act,
+                                                                    act_dtype);
+  return launch_status("sg_maxpool2");
+}
+
+int sg_upsample_cat(const float* x, const float* skip, int rows, int h, int w, int Cx, int Cs, float* out_f32,
+                    void* out_act, int act_dtype, sg_stream_t stream) {
+  SG_REQUIRE(x && skip && (out_f32 || out_act), "sg_upsample_cat: null pointer");
+  SG_REQUIRE(rows > 0 && h >= 1 && w >= 1 && Cx % 4 == 0 && Cs % 4 == 0, "sg_upsample_cat: bad shape");
+  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_upsample_cat: out_act needs a 16-bit dtype");
+  const int64_t total4 = (int64_t)rows * (2 * h) * (2 * w) * ((Cx + Cs) / 4);
+  // torch: scale = (in - 1) / (out - 1) in fp32 (area_pixel_compute_scale, align_corners=True)
+  const float sh = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
+  const float sw = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
+  upsample_cat_kernel<<<cdiv(total4, 256), 256, 0, as_stream(stream)>>>(x, skip, total4, h, w, Cx / 4, Cs / 4, sh, sw,
+                                                                        out_f32, out_act, act_dtype);
+  return launch_status("sg_upsample_cat");
+}
+
+}  // extern "C"

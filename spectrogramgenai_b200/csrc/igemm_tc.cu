@@ -1,0 +1,329 @@
+// K1 (tensor-core engine): implicit-GEMM 3x3 convolution / linear layer on tcgen05 + TMEM, fed by TMA.
+//
+//   out[m, co] = sum_{tap, ci} act[pixel(m) + tap, ci] * w[tap, co, ci]         M = rows*H*W, N = Cout, K = taps*Cin
+//
+// * A operand: the NHWC activation tensor is described by ONE rank-4 tensor map {C, W, H, rows}.  For k-block
+//   (tap, 64-channel slice) the producer issues a single TMA box load {64, bw, bh, bn} at
+//   (c0, w0+dx, h0+dy, n0); the conv's zero padding is TMA's out-of-bounds zero fill, so there is no im2col
+//   buffer, no halo logic and no predication anywhere.  The box lands as 128 rows x 128 B (SWIZZLE_128B),
+//   which is exactly the canonical K-major UMMA operand tile.
+// * B operand: weights pre-packed [tap][Cout][Cin] (16-bit), rank-2 map, box {64, BN}.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block into a TMEM accumulator;
+//   tcgen05.commit releases the smem stage back to the producer and finally signals the epilogue.
+// * Epilogue warps read TMEM (tcgen05.ld 32x32b: one accumulator row per thread), apply bias / GELU /
+//   residual, write fp32 and/or 16-bit outputs, and emit deterministic GroupNorm(1,C) partial sums.
+// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+// Two CTAs are resident per SM (<= 101 KB smem, <= 128 TMEM columns each), so one CTA's epilogue overlaps
+// the other's main loop.
+#include "tc_common.cuh"
+
+namespace sg {
+namespace tc {
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr);
+    if (e == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    else set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+              const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return SG_ERR_LAUNCH;
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gs[i] = strides[i];
+  }
+  const CUtensorMapDataType dt = dtype == SG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return SG_ERR_ARG;
+  }
+  return SG_OK;
+}
+
+constexpr int BM = 128;        // UMMA M (one TMEM lane per output row)
+constexpr int BK = 64;         // one 128-byte swizzle span of 16-bit channels per k-block
+constexpr int A_BYTES = BM * BK * 2;
+
+struct IgemmGeom {
+  int64_t M;
+  int H, W, HW;
+  int Cout, taps, cblocks;  // cblocks = Cin / 64
+  int n_tiles;              // Cout / BN
+  int tiles_per_sample;     // HW / 128 when HW >= 128, else 0
+  int samples_per_tile;     // 128 / HW when HW < 128, else 0
+  uint32_t tx_bytes;        // bytes one k-block's two TMA boxes deliver
+  uint32_t idesc;
+};
+struct IgemmEpi {
+  const float* bias;
+  const float* residual;
+  float* out_f32;
+  void* out_act;
+  float* partials;
+  int gelu, P, act_dtype;
+};
+
+template <int BN, int STAGES>
+constexpr int igemm_smem_bytes() {
+  return 1024 /*alignment slack*/ + STAGES * (A_BYTES + BN * BK * 2) + 256 /*barriers*/ + BM * 2 * 4 /*rowstat*/;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                       const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
+                                                       const IgemmEpi ep) {
+  constexpr int B_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + STAGES * (A_BYTES + B_BYTES) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x % g.n_tiles;
+  const int mt = blockIdx.x / g.n_tiles;
+  const int n0 = tile_n * BN;
+  const int64_t m0 = (int64_t)mt * BM;
+  const int nk = g.taps * g.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int cn, ch, cw;
+      if (g.taps == 1) {
+        cn = 0; ch = 0; cw = (int)m0;  // linear layer: the map is {Cin, M, 1, 1}
+      } else if (g.tiles_per_sample > 0) {
+        cn = mt / g.tiles_per_sample;
+        const int p0 = (mt % g.tiles_per_sample) * BM;
+        ch = p0 / g.W;
+        cw = p0 % g.W;
+      } else {
+        cn = mt * g.samples_per_tile; ch = 0; cw = 0;
+      }
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int tap = kb / g.cblocks, c0 = (kb % g.cblocks) * BK;
+        int dy = 0, dx = 0;
+        if (g.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        mbar_arrive_expect_tx(&full[s], g.tx_bytes);
+        tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, cw + dx, ch + dy, cn);
+        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], c0, tap * g.Cout + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = make_desc_k128(smem_u32(sA + s * A_BYTES));
+        const uint64_t bdesc = make_desc_k128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
+          umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, g.idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int64_t m = m0 + r;
+    const bool valid = m < g.M;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float s_sum = 0.f, s_sq = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      const int64_t off = m * g.Cout + nb;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (ep.bias) x += __ldg(ep.bias + nb + j);
+        if (ep.gelu) x = gelu_erf(x);
+        f[j] = x;
+      }
+      if (valid) {
+        if (ep.residual) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(ep.residual + off) + j4);
+            f[j4 * 4 + 0] += rr.x; f[j4 * 4 + 1] += rr.y; f[j4 * 4 + 2] += rr.z; f[j4 * 4 + 3] += rr.w;
+          }
+        }
+        if (ep.out_f32) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            reinterpret_cast<float4*>(ep.out_f32 + off)[j4] =
+                make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+        }
+        if (ep.out_act) {
+          uint16_t* dst = reinterpret_cast<uint16_t*>(ep.out_act) + off;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4 w;
+            w.x = pack16(f[j8 * 8 + 0], f[j8 * 8 + 1], ep.act_dtype);
+            w.y = pack16(f[j8 * 8 + 2], f[j8 * 8 + 3], ep.act_dtype);
+            w.z = pack16(f[j8 * 8 + 4], f[j8 * 8 + 5], ep.act_dtype);
+            w.w = pack16(f[j8 * 8 + 6], f[j8 * 8 + 7], ep.act_dtype);
+            reinterpret_cast<uint4*>(dst)[j8] = w;
+          }
+        }
+        if (ep.partials) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            s_sum += f[j];
+            s_sq += f[j] * f[j];
+          }
+        }
+      }
+    }
+    if (ep.partials) {
+      rowstat[r][0] = s_sum;
+      rowstat[r][1] = s_sq;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      write_tile_partials<BM>(rowstat, (int)threadIdx.x - 64, m0, g.M, g.HW, ep.partials, ep.P, tile_n, g.n_tiles);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const IgemmEpi& ep, int grid,
+                  cudaStream_t stream) {
+  constexpr int smem = igemm_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("sg_igemm(tc): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
+      return SG_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  igemm_tc_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(tmA, tmB, g, ep);
+  return launch_status("sg_igemm(tc)");
+}
+
+}  // namespace tc
+
+int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
+  using namespace tc;
+  SG_REQUIRE(a->act_dtype == SG_BF16 || a->act_dtype == SG_F16, "sg_igemm(tc): act_dtype must be SG_BF16 or SG_F16");
+  SG_REQUIRE(a->Cin % 64 == 0, "sg_igemm(tc): Cin=%d %% 64 != 0", a->Cin);
+  SG_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
+             "sg_igemm(tc): operands must be 16-byte aligned");
+  const int BN = (a->Cout % 128 == 0) ? 128 : 64;
+  const int HW = a->H * a->W;
+  IgemmGeom g;
+  g.M = (int64_t)a->rows * HW;
+  g.H = a->H; g.W = a->W; g.HW = HW;
+  g.Cout = a->Cout; g.taps = a->taps; g.cblocks = a->Cin / 64;
+  g.n_tiles = a->Cout / BN;
+  g.tiles_per_sample = HW >= 128 ? HW / 128 : 0;
+  g.samples_per_tile = HW >= 128 ? 0 : 128 / HW;
+  g.idesc = make_idesc(a->act_dtype, 128, BN, 0, 0);
+  SG_REQUIRE(g.M < (1ll << 31), "sg_igemm(tc): M too large");
+
+  CUtensorMap tmA, tmB;
+  uint32_t box_rows;
+  const uint64_t cb = (uint64_t)a->Cin * 2;
+  if (a->taps == 1) {
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)g.M, 1, 1};
+    const uint64_t strides[3] = {cb, cb * g.M, cb * g.M};
+    const uint32_t box[4] = {64, (uint32_t)(g.M < 128 ? g.M : 128), 1, 1};
+    box_rows = box[1];
+    int rc = make_tmap(&tmA, a->act_dtype, 4, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
+    const uint32_t bw = a->W < 128 ? a->W : 128;
+    const uint32_t bh = (uint32_t)a->H < 128 / bw ? a->H : 128 / bw;
+    uint32_t bn = 128 / (bw * bh);
+    if (bn > (uint32_t)a->rows) bn = a->rows;
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->rows};
+    const uint64_t strides[3] = {cb, cb * a->W, cb * a->W * a->H};
+    const uint32_t box[4] = {64, bw, bh, bn};
+    box_rows = bw * bh * bn;
+    int rc = make_tmap(&tmA, a->act_dtype, 4, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->Cin, (uint64_t)a->taps * a->Cout};
+    const uint64_t strides[1] = {cb};
+    const uint32_t box[2] = {64, (uint32_t)BN};
+    int rc = make_tmap(&tmB, a->act_dtype, 2, a->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  g.tx_bytes = box_rows * 128u + (uint32_t)BN * 128u;
+
+  IgemmEpi ep;
+  ep.bias = a->bias; ep.residual = a->residual; ep.out_f32 = a->out_f32; ep.out_act = a->out_act;
+  ep.partials = a->partials; ep.gelu = a->gelu; ep.act_dtype = a->act_dtype;
+  ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
+  const int64_t grid = (int64_t)cdiv(g.M, BM) * g.n_tiles;
+  SG_REQUIRE(grid < (1ll << 31), "sg_igemm(tc): grid too large");
+  if (BN == 128) return launch<128, 3>(tmA, tmB, g, ep, (int)grid, stream);
+  return launch<64, 4>(tmA, tmB, g, ep, (int)grid, stream);
+}
+
+}  // namespace sg

@@ -1,0 +1,178 @@
+// K2: GroupNorm(1, C) finalize + apply (+GELU / +residual / +time-embedding), and LayerNorm over C.
+// Both are single-pass, HBM-bound kernels (1 read + 1..2 writes of the activation, 128-bit accesses).
+#include "common.cuh"
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(num_groups=1) over (C, H, W) of each row (/root/reference/src/diff_modules.py:83,:86;
+// torch eps 1e-5, biased variance).  The conv kernels leave per-tile (sum, sum-of-squares) partials;
+// each block re-reduces its row's P partials in fp64 (deterministic, P <= a few thousand floats from L2),
+// then streams its slice of the row.
+// grid = (chunks, rows); one thread handles 4 consecutive channels of one pixel per iteration.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ raw, const float* __restrict__ partials,
+                                                       int P, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int64_t per_row4, int C4,
+                                                       int mode, const float* __restrict__ residual,
+                                                       const float* __restrict__ emb, int emb_stride,
+                                                       float* __restrict__ o32, void* __restrict__ o16, int dtype) {
+  __shared__ double red[2][8];
+  __shared__ float stat[2];
+  const int row = blockIdx.y;
+  {
+    double s = 0.0, q = 0.0;
+    const float2* pp = reinterpret_cast<const float2*>(partials) + (int64_t)row * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      const float2 v = pp[i];
+      s += (double)v.x;
+      q += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = s;
+      red[1][threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double ts = 0.0, tq = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+        ts += red[0][i];
+        tq += red[1][i];
+      }
+      const double cnt = (double)per_row4 * 4.0;
+      const double mean = ts / cnt;
+      double var = tq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stat[0] = (float)mean;
+      stat[1] = (float)(1.0 / sqrt(var + 1e-5));
+    }
+    __syncthreads();
+  }
+  const float mean = stat[0], rstd = stat[1];
+  const int64_t base4 = (int64_t)row * per_row4;
+  const float4* r4 = reinterpret_cast<const float4*>(raw) + base4;
+  const float4* res4 = residual ? reinterpret_cast<const float4*>(residual) + base4 : nullptr;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  const float4* e4 = emb ? reinterpret_cast<const float4*>(emb + (int64_t)row * emb_stride) : nullptr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_row4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const float4 v = __ldcs(r4 + i);
+    const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4);
+    float y0 = (v.x - mean) * rstd * g.x + b.x;
+    float y1 = (v.y - mean) * rstd * g.y + b.y;
+    float y2 = (v.z - mean) * rstd * g.z + b.z;
+    float y3 = (v.w - mean) * rstd * g.w + b.w;
+    if (mode == 2) {
+      const float4 r = __ldg(res4 + i);
+      y0 += r.x; y1 += r.y; y2 += r.z; y3 += r.w;
+    }
+    if (mode >= 1) {
+      y0 = gelu_erf(y0); y1 = gelu_erf(y1); y2 = gelu_erf(y2); y3 = gelu_erf(y3);
+    }
+    if (e4) {
+      const float4 e = __ldg(e4 + c4);
+      y0 += e.x; y1 += e.y; y2 += e.z; y3 += e.w;
+    }
+    store4_dual(o32, o16, dtype, (base4 + i) * 4, y0, y1, y2, y3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over C (:57, :59; eps 1e-5).  One warp per token; the token's C values live in registers
+// (C/32 per lane), two-pass mean / variance like torch.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int64_t M,
+                                                        float* __restrict__ o32, void* __restrict__ o16, int dtype) {
+  constexpr int V = C / 32;  // 2, 4 or 8 values per lane, contiguous
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= M) return;
+  float v[V];
+  const float* src = in + tok * C + lane * V;
+  if constexpr (V == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(src);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < V / 4; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(src + 4 * j);
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) s += v[j];
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const float d = v[j] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+  float y[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) y[j] = (v[j] - mean) * rstd * __ldg(gamma + lane * V + j) + __ldg(beta + lane * V + j);
+  const int64_t off = tok * C + lane * V;
+  if constexpr (V == 2) {
+    if (o32) *reinterpret_cast<float2*>(o32 + off) = make_float2(y[0], y[1]);
+    if (o16) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(o16) + off) = pack16(y[0], y[1], dtype);
+  } else {
+#pragma unroll
+    for (int j = 0; j < V / 4; ++j) store4_dual(o32, o16, dtype, off + 4 * j, y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+  }
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+int sg_gn_apply(const float* raw, const float* partials, int P, const float* gamma, const float* beta, int rows,
+                int HW, int C, int mode, const float* residual, const float* emb, int emb_stride, float* out_f32,
+                void* out_act, int act_dtype, sg_stream_t stream) {
+  SG_REQUIRE(raw && partials && gamma && beta && (out_f32 || out_act), "sg_gn_apply: null pointer");
+  SG_REQUIRE(rows > 0 && HW > 0 && C % 4 == 0 && P > 0, "sg_gn_apply: bad shape rows=%d HW=%d C=%d P=%d", rows, HW, C, P);
+  SG_REQUIRE(mode >= 0 && mode <= 2, "sg_gn_apply: mode %d", mode);
+  SG_REQUIRE(mode != 2 || residual, "sg_gn_apply: mode 2 needs a residual");
+  SG_REQUIRE(!emb || emb_stride % 4 == 0, "sg_gn_apply: emb stride must be a multiple of 4");
+  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_gn_apply: out_act needs a 16-bit dtype");
+  const int64_t per_row4 = (int64_t)HW * (C / 4);
+  // enough blocks to fill 148 SMs x 8 resident blocks, at most one float4 per thread per pass
+  int chunks = cdiv(per_row4, 256 * 4);
+  const int want = cdiv(148 * 8, rows);
+  if (chunks > want) chunks = want > 1 ? want : 1;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, rows);
+  gn_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(raw, partials, P, gamma, beta, per_row4, C / 4, mode, residual,
+                                                       emb, emb_stride, out_f32, out_act, act_dtype);
+  return launch_status("sg_gn_apply");
+}
+
+int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t M, int C, void* out_act, int act_dtype,
+                 sg_stream_t stream) {
+  SG_REQUIRE(in && gamma && beta && out_act, "sg_layernorm: null pointer");
+  SG_REQUIRE(M > 0, "sg_layernorm: M=%lld", (long long)M);
+  float* o32 = act_dtype == SG_F32 ? reinterpret_cast<float*>(out_act) : nullptr;
+  void* o16 = act_dtype == SG_F32 ? nullptr : out_act;
+  const int blocks = cdiv(M, 8);
+  cudaStream_t s = as_stream(stream);
+  switch (C) {
+    case 64: layernorm_kernel<64><<<blocks, 256, 0, s>>>(in, gamma, beta, M, o32, o16, act_dtype); break;
+    case 128: layernorm_kernel<128><<<blocks, 256, 0, s>>>(in, gamma, beta, M, o32, o16, act_dtype); break;
+    case 256: layernorm_kernel<256><<<blocks, 256, 0, s>>>(in, gamma, beta, M, o32, o16, act_dtype); break;
+    default: SG_REQUIRE(false, "sg_layernorm: C=%d not in {64,128,256}", C);
+  }
+  return launch_status("sg_layernorm");
+}
+
+}  // extern "C"

@@ -1,0 +1,323 @@
+"""Drop-in Python surface of the reference's class-conditional DDPM sampling path, executed by libsgb200.
+
+Mirrors /root/reference/src/diff_modules.py:
+  * UNet_conditional(c_in, c_out, time_dim, num_classes, remove_deep_conv).forward(x, t, y)   (:204-217)
+    -- same constructor, same 183-key state_dict (names and shapes), same call signature;
+  * Diffusion(noise_steps, beta_start, beta_end, img_size, num_classes, c_in, c_out, device, **kwargs)
+    with .beta/.alpha/.alpha_hat/.model/.img_size/.device/.c_in/.num_classes, .prepare_noise_schedule(),
+    .sample(use_ema, labels, cfg_scale=3) -> uint8 [n, c_in, S, S]  (:411-442) and .load(dir, ...) (:509-510);
+    the upstream positional form sample(model, n, labels, cfg_scale) is accepted as an alias;
+  * EMA.reset_parameters (:48-49) -- the load side of EMA; the reference never builds `ema_model`
+    (:393 is commented out, so sample(use_ema=True) raises AttributeError there); here load() fills it
+    from `ema_ckpt.pt` when that file exists.
+
+The modules hold parameters only.  All arithmetic runs in hand-written sm_100a kernels behind the C ABI
+(include/sgb200.h); there is no torch-op or CPU fallback, and a non-B200 device is an error.
+"""
+from __future__ import annotations
+
+import copy
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _cabi, ops
+from .engine import MODES, TIME_DIM, PackedWeights, UNetPlan
+
+__all__ = ["UNet_conditional", "Diffusion", "EMA", "state_dict_schema"]
+
+
+# ----------------------------------------------------------------------------------------------------
+# state_dict schema (names/shapes of the reference's nn.Module tree)
+# ----------------------------------------------------------------------------------------------------
+def _dc(p, cin, cout, cmid=None):
+    cmid = cmid or cout
+    return [(f"{p}.double_conv.0.weight", (cmid, cin, 3, 3)), (f"{p}.double_conv.1.weight", (cmid,)),
+            (f"{p}.double_conv.1.bias", (cmid,)), (f"{p}.double_conv.3.weight", (cout, cmid, 3, 3)),
+            (f"{p}.double_conv.4.weight", (cout,)), (f"{p}.double_conv.4.bias", (cout,))]
+
+
+def _emb(p, cout):
+    return [(f"{p}.emb_layer.1.weight", (cout, TIME_DIM)), (f"{p}.emb_layer.1.bias", (cout,))]
+
+
+def _sa(p, c):
+    return [(f"{p}.mha.in_proj_weight", (3 * c, c)), (f"{p}.mha.in_proj_bias", (3 * c,)),
+            (f"{p}.mha.out_proj.weight", (c, c)), (f"{p}.mha.out_proj.bias", (c,)),
+            (f"{p}.ln.weight", (c,)), (f"{p}.ln.bias", (c,)),
+            (f"{p}.ff_self.0.weight", (c,)), (f"{p}.ff_self.0.bias", (c,)),
+            (f"{p}.ff_self.1.weight", (c, c)), (f"{p}.ff_self.1.bias", (c,)),
+            (f"{p}.ff_self.3.weight", (c, c)), (f"{p}.ff_self.3.bias", (c,))]
+
+
+def state_dict_schema(c_in=1, c_out=1, num_classes=None, remove_deep_conv=False):
+    """Ordered (key, shape) list, identical to the reference model's state_dict."""
+    s = _dc("inc", c_in, 64)
+    for name, cin, cout, sa_c in (("down1", 64, 128, 128), ("down2", 128, 256, 256), ("down3", 256, 256, 256)):
+        s += _dc(f"{name}.maxpool_conv.1", cin, cin) + _dc(f"{name}.maxpool_conv.2", cin, cout) + _emb(name, cout)
+        s += _sa(f"sa{name[-1]}", sa_c)
+    if remove_deep_conv:
+        s += _dc("bot1", 256, 256) + _dc("bot3", 256, 256)
+    else:
+        s += _dc("bot1", 256, 512) + _dc("bot2", 512, 512) + _dc("bot3", 512, 256)
+    for i, (name, cin, cout) in enumerate((("up1", 512, 128), ("up2", 256, 64), ("up3", 128, 64))):
+        s += _dc(f"{name}.conv.0", cin, cin) + _dc(f"{name}.conv.1", cin, cout, cin // 2) + _emb(name, cout)
+        s += _sa(f"sa{4 + i}", cout)
+    s += [("outc.weight", (c_out, 64, 1, 1)), ("outc.bias", (c_out,))]
+    if num_classes is not None:
+        s += [("label_emb.weight", (num_classes, TIME_DIM))]
+    return s
+
+
+class _Params(nn.Module):
+    """A bare container node; the tree of these reproduces the reference's parameter names."""
+
+
+def _init_param(name, shape):
+    """torch's default initialisers for the corresponding reference layers."""
+    t = torch.empty(shape)
+    leaf = name.rsplit(".", 1)[-1]
+    is_norm = any(s in name for s in (".double_conv.1.", ".double_conv.4.", ".ln.", ".ff_self.0."))
+    if name == "label_emb.weight":
+        return nn.init.normal_(t)
+    if is_norm:
+        return nn.init.ones_(t) if leaf == "weight" else nn.init.zeros_(t)
+    if name.endswith("in_proj_weight"):
+        return nn.init.xavier_uniform_(t)
+    if name.endswith("in_proj_bias") or name.endswith("out_proj.bias"):
+        return nn.init.zeros_(t)
+    if leaf == "weight":
+        return nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+    return t  # Linear / outc biases: filled by the caller from the weight's fan-in
+
+
+class UNet_conditional(nn.Module):
+    """ε-prediction UNet with timestep and class conditioning (reference :139-217), B200-only."""
+
+    def __init__(self, c_in=1, c_out=1, time_dim=256, num_classes=None, remove_deep_conv=False,
+                 compute_dtype="fp32", **kwargs):
+        super().__init__()
+        if time_dim != TIME_DIM:
+            # the reference hard-wires emb_dim=256 in Down/Up (:97,:117), so any other time_dim fails there too
+            raise ValueError("time_dim must be 256 (Down/Up hard-wire emb_dim=256 in the reference)")
+        if kwargs:
+            raise TypeError(f"unexpected arguments {sorted(kwargs)}")
+        self.c_in, self.c_out = c_in, c_out
+        self.time_dim = time_dim
+        self.num_classes = num_classes
+        self.remove_deep_conv = remove_deep_conv
+        self.compute_dtype = compute_dtype
+        fan = {}
+        for key, shape in state_dict_schema(c_in, c_out, num_classes, remove_deep_conv):
+            *path, leaf = key.split(".")
+            node = self
+            for part in path:
+                if part not in node._modules:
+                    node.add_module(part, _Params())
+                node = node._modules[part]
+            t = _init_param(key, shape)
+            if leaf == "weight" and len(shape) >= 2:
+                fan[".".join(path)] = int(torch.tensor(shape[1:]).prod())
+            elif leaf == "bias" and ".".join(path) in fan and not any(
+                    s in key for s in (".double_conv.", ".ln.", ".ff_self.0.", "out_proj")):
+                bound = 1.0 / math.sqrt(fan[".".join(path)])
+                nn.init.uniform_(t, -bound, bound)
+            node.register_parameter(leaf, nn.Parameter(t))
+        self._packed = None
+        self._packed_key = None
+        self._plans = {}
+
+    # ------------------------------------------------------------------ engine plumbing
+    def set_compute_dtype(self, mode: str):
+        """'fp32' (CUDA-core engine, <=1e-4 of the reference) or 'bf16' / 'f16' (tcgen05 engine)."""
+        if mode not in MODES:
+            raise ValueError(f"compute dtype must be one of {sorted(MODES)}")
+        self.compute_dtype = mode
+        return self
+
+    def _weights_key(self):
+        ps = list(self.parameters())
+        return (self.compute_dtype, str(ps[0].device), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+
+    def packed_weights(self) -> PackedWeights:
+        """Kernel-layout weights; rebuilt whenever a parameter was modified (load_state_dict, .to(), ...)."""
+        key = self._weights_key()
+        if self._packed is None or key != self._packed_key:
+            dev = next(self.parameters()).device
+            _cabi.require_b200(dev)
+            self._packed = PackedWeights(self.state_dict(), dev, self.compute_dtype)
+            self._packed_key = key
+            self._plans = {}
+        return self._packed
+
+    def plan(self, *, n_src, rows, S, use_step=False, debug=False) -> UNetPlan:
+        w = self.packed_weights()
+        key = (n_src, rows, S, use_step, debug)
+        if key not in self._plans:
+            self._plans[key] = UNetPlan(w, n_src=n_src, rows=rows, S=S, use_step=use_step, debug=debug)
+        return self._plans[key]
+
+    def release_plans(self):
+        self._plans = {}
+
+    # ------------------------------------------------------------------ reference API
+    @torch.no_grad()
+    def forward(self, x, t, y=None):
+        """x [n, c_in, S, S]; t [n] (long or float); y [n] int64 class ids or None.  Returns ε [n, c_out, S, S] fp32."""
+        if x.dim() != 4 or x.shape[1] != self.c_in or x.shape[2] != x.shape[3]:
+            raise ValueError(f"x must be [n, {self.c_in}, S, S], got {tuple(x.shape)}")
+        if y is not None and self.num_classes is None:
+            raise AttributeError("'UNet_conditional' object has no attribute 'label_emb'")  # as the reference would
+        n, S = x.shape[0], x.shape[2]
+        plan = self.plan(n_src=n, rows=n, S=S)
+        plan.x_in.copy_(x.to(torch.float32))
+        plan.t.copy_(t.reshape(-1).to(torch.float32))
+        if y is None:
+            plan.y.fill_(-1)
+        else:
+            plan.y.copy_(y.reshape(-1).to(torch.int64))
+        plan.run()
+        return plan.eps.clone()
+
+
+class EMA:
+    """Load side of the reference's EMA helper (:24-49)."""
+
+    def __init__(self, beta=0.995):
+        self.beta = beta
+        self.step = 0
+
+    def reset_parameters(self, ema_model, model):
+        ema_model.load_state_dict(model.state_dict())
+
+
+class Diffusion:
+    """Linear-β DDPM with classifier-free-guidance ancestral sampling (reference :370-442)."""
+
+    def __init__(self, noise_steps=1000, beta_start=1e-4, beta_end=0.02, img_size=256, num_classes=10, c_in=1,
+                 c_out=1, device="cuda", **kwargs):
+        self.noise_steps = noise_steps
+        self.beta_start = beta_start
+        self.beta_end = beta_end
+        self.device = torch.device(device)
+        _cabi.require_b200(self.device)
+        # (:387-389) evaluated on the host exactly like the CPU reference, then moved
+        beta = self.prepare_noise_schedule()
+        alpha = 1.0 - beta
+        alpha_hat = torch.cumprod(alpha, dim=0)
+        self.beta, self.alpha, self.alpha_hat = beta.to(self.device), alpha.to(self.device), alpha_hat.to(self.device)
+        # posterior coefficients with the reference's own expressions (:436-439)
+        self._coef = torch.stack([1 / torch.sqrt(alpha), (1 - alpha) / (torch.sqrt(1 - alpha_hat)), torch.sqrt(beta)],
+                                 dim=1).contiguous().to(self.device)
+        self.img_size = img_size
+        self.model = UNet_conditional(c_in, c_out, num_classes=num_classes, **kwargs).to(self.device)
+        self.ema_model = None  # filled by load() when an EMA checkpoint exists
+        self.c_in = c_in
+        self.num_classes = num_classes
+        self.gpu_launches = 0  # kernels launched by the last sample() call
+
+    def prepare_noise_schedule(self):
+        return torch.linspace(self.beta_start, self.beta_end, self.noise_steps)
+
+    # ------------------------------------------------------------------ checkpoints (:509-510)
+    def load(self, model_cpkt_path, model_ckpt="ckpt.pt", ema_model_ckpt="ema_ckpt.pt"):
+        self.model.load_state_dict(torch.load(os.path.join(model_cpkt_path, model_ckpt), weights_only=True))
+        ema_path = os.path.join(model_cpkt_path, ema_model_ckpt)
+        if os.path.exists(ema_path):
+            self.ema_model = copy.deepcopy(self.model).eval().requires_grad_(False)
+            self.ema_model.load_state_dict(torch.load(ema_path, weights_only=True))
+
+    # ------------------------------------------------------------------ sampling (:411-442)
+    @torch.no_grad()
+    def sample(self, use_ema, labels, cfg_scale=3, *legacy, noise=None, seed=0, sample_base=0, micro_batch=512,
+               return_float=False, use_graph=True, max_steps=None):
+        """Reference form: sample(use_ema, labels, cfg_scale=3) -> uint8 [n, c_in, S, S].
+        Upstream alias: sample(model, n, labels, cfg_scale=3).
+
+        Extra keyword-only controls (ours):
+          noise        fp32 [T-1, n, c, S, S] injected Gaussians: noise[0] = x_T, noise[k] = z at i = T-k
+                       (the order the reference consumes its generator).  Default: Philox4x32-10 keyed by
+                       (seed, sample_base + sample index, timestep) -- independent of batch split / GPU count.
+          micro_batch  samples per captured loop (n is processed in chunks of this size)
+          return_float return the fp32 state before the uint8 quantisation
+          max_steps    run only the first k loop iterations (benchmarking a bounded number of timesteps)
+        """
+        if isinstance(use_ema, nn.Module):  # upstream (model, n, labels, cfg_scale)
+            model, n_expected = use_ema, labels
+            labels = cfg_scale
+            cfg_scale = legacy[0] if legacy else 3
+            if len(labels) != n_expected:
+                raise ValueError("n does not match len(labels)")
+        else:
+            if legacy:
+                raise TypeError("too many positional arguments")
+            if use_ema and self.ema_model is None:
+                raise AttributeError("'Diffusion' object has no attribute 'ema_model' (no EMA checkpoint loaded)")
+            model = self.ema_model if use_ema else self.model
+        labels = torch.as_tensor(labels).reshape(-1).to(device=self.device, dtype=torch.int64)
+        n = len(labels)
+        S, c, T = self.img_size, self.c_in, self.noise_steps
+        if n > 0 and self.num_classes is not None and (int(labels.min()) < 0 or int(labels.max()) >= self.num_classes):
+            raise IndexError("index out of range in self")  # nn.Embedding's error in the reference
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=torch.float32)
+            if tuple(noise.shape) != (T - 1, n, c, S, S):
+                raise ValueError(f"noise must be [T-1, n, c, S, S] = {(T - 1, n, c, S, S)}, got {tuple(noise.shape)}")
+        out_dtype = torch.float32 if return_float else torch.uint8
+        out = torch.empty((n, c, S, S), dtype=out_dtype, device=self.device)
+        self.gpu_launches = 0
+        for lo in range(0, n, micro_batch):
+            hi = min(n, lo + micro_batch)
+            nz = None if noise is None else noise[:, lo:hi].contiguous()
+            self._sample_chunk(model, labels[lo:hi], float(cfg_scale), nz, seed, sample_base + lo, out[lo:hi],
+                               use_graph, max_steps)
+        return out
+
+    def _sample_chunk(self, model, labels, cfg, noise, seed, sample_base, out, use_graph, max_steps):
+        n = len(labels)
+        T = self.noise_steps
+        rows = 2 * n if cfg > 0 else n
+        plan = model.plan(n_src=n, rows=rows, S=self.img_size, use_step=True)
+        x = plan.x_in  # the sampler state lives in the plan's input buffer: no copy per step
+        plan.y.fill_(-1)
+        plan.y[:n].copy_(labels)
+
+        def one_step():
+            plan.run()
+            ops.cfg_update(x, plan.eps, self._coef, plan.step, cfg_scale=cfg, noise=noise, seed=seed,
+                           sample_base=sample_base)
+            ops.step_advance(plan.step)
+
+        launches_per_step = plan.n_launches + 2
+        if not getattr(plan, "_warm", False):
+            plan.step.fill_(T - 1)
+            one_step()  # loads the kernels' modules and sets their attributes outside of graph capture
+            torch.cuda.synchronize(self.device)
+            plan._warm = True
+            self.gpu_launches += launches_per_step
+        # x_T (:418) and the step counter i = T-1
+        if noise is not None:
+            x.copy_(noise[0])
+        else:
+            ops.philox_normal(x, seed=seed, sample_base=sample_base, step_tag=T)
+            self.gpu_launches += 1
+        plan.step.fill_(T - 1)
+        iters = T - 1 if max_steps is None else min(T - 1, max_steps)
+        if use_graph and iters > 0:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                one_step()
+            # capture does not execute: state is still (x_T, T-1)
+            for _ in range(iters):
+                g.replay()
+        else:
+            for _ in range(iters):
+                one_step()
+        self.gpu_launches += iters * launches_per_step
+        if out.dtype == torch.uint8:
+            ops.to_uint8(x, out)
+            self.gpu_launches += 1
+        else:
+            out.copy_(x)

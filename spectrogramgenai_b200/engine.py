@@ -1,0 +1,311 @@
+"""Host-side execution plan of UNet_conditional.forward on the sgb200 kernels.
+
+`PackedWeights` repacks a reference-schema state_dict (183 tensors, /root/reference/src/diff_modules.py:75-217)
+once into kernel layouts; `UNetPlan` pre-allocates every activation buffer for a fixed (rows, S) geometry and
+records the launch sequence as a flat list of closures, so that running the plan performs no allocation, no
+host<->device traffic and no synchronisation -- which is what makes it capturable in a CUDA graph.
+
+Data layout in HBM: activations are channels-last [rows, H, W, C] so that (a) SelfAttention's
+NCHW -> [n, L, C] transpose (:66) is free, (b) a 3x3 tap is a rectangular TMA box and (c) the implicit GEMM's
+K dimension (channels) is contiguous.  The residual stream (block outputs, skips) stays fp32; in the
+tensor-core modes every GEMM operand is additionally written as a 16-bit copy by the producing kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi, ops
+from ._cabi import SG_ENGINE_SIMT, SG_ENGINE_TC
+
+MODES = {"fp32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+EMB_BLOCKS = ("down1", "down2", "down3", "up1", "up2", "up3")  # order of the concatenated emb_layer projection
+TIME_DIM = 256
+
+
+def _pack_conv(w: torch.Tensor, dtype, device):
+    """[Cout, Cin, 3, 3] -> [9 taps (dy, dx), Cout, Cin], K (= Cin) contiguous."""
+    co, ci, kh, kw = w.shape
+    return w.detach().to(device=device, dtype=torch.float32).permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous().to(dtype)
+
+
+def _pack_linear(w: torch.Tensor, dtype, device):
+    return w.detach().to(device=device, dtype=torch.float32).reshape(1, *w.shape).contiguous().to(dtype)
+
+
+class PackedWeights:
+    """Kernel-layout copy of a UNet_conditional state_dict.  Derived data: rebuild after load_state_dict."""
+
+    def __init__(self, sd, device, mode: str):
+        if mode not in MODES:
+            raise ValueError(f"mode must be one of {sorted(MODES)}")
+        self.mode = mode
+        self.act = MODES[mode]
+        self.device = torch.device(device)
+        self.c_in = sd["inc.double_conv.0.weight"].shape[1]
+        self.c_out = sd["outc.weight"].shape[0]
+        self.deep = "bot2.double_conv.0.weight" in sd
+        f32 = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()  # noqa: E731
+        self.t = {}
+        for k, v in sd.items():
+            if k == "inc.double_conv.0.weight":
+                self.t[k] = f32(k)  # direct fp32 conv, reference layout [64, c_in, 3, 3]
+            elif k.endswith(".weight") and v.dim() == 4 and v.shape[-1] == 3:
+                self.t[k] = _pack_conv(v, self.act, self.device)
+            elif k.endswith("in_proj_weight") or k.endswith("out_proj.weight") or ".ff_self.1.weight" in k or ".ff_self.3.weight" in k:
+                self.t[k] = _pack_linear(v, self.act, self.device)
+            elif ".emb_layer." in k or k == "label_emb.weight":
+                continue
+            elif k == "outc.weight":
+                self.t[k] = f32(k).reshape(self.c_out, -1).contiguous()
+            else:
+                self.t[k] = f32(k)  # norm affines, biases
+        self.w_emb = torch.cat([f32(f"{b}.emb_layer.1.weight") for b in EMB_BLOCKS], 0).contiguous()
+        self.b_emb = torch.cat([f32(f"{b}.emb_layer.1.bias") for b in EMB_BLOCKS], 0).contiguous()
+        self.emb_off = {}
+        off = 0
+        for b in EMB_BLOCKS:
+            n = sd[f"{b}.emb_layer.1.bias"].shape[0]
+            self.emb_off[b] = (off, n)
+            off += n
+        self.emb_total = off
+        self.label = f32("label_emb.weight") if "label_emb.weight" in sd else None
+        self.num_classes = None if self.label is None else self.label.shape[0]
+        # exactly the reference expression (diff_modules.py:169), evaluated on the CPU like the oracle
+        self.inv_freq = (1.0 / (10000 ** (torch.arange(0, TIME_DIM, 2).float() / TIME_DIM))).to(self.device)
+
+    def __getitem__(self, k):
+        return self.t[k]
+
+
+class UNetPlan:
+    """Launch plan for `rows` batch rows at S x S.  Inputs live in plan-owned buffers:
+    x_in fp32 NCHW [n_src, c_in, S, S] (row r reads sample r % n_src), t fp32 [rows] or the device step
+    counter, y int64 [rows] (negative = unconditional).  Output: eps fp32 NCHW [rows, c_out, S, S]."""
+
+    def __init__(self, weights: PackedWeights, *, n_src: int, rows: int, S: int, use_step: bool = False,
+                 debug: bool = False):
+        if S < 16 or S & (S - 1):
+            raise ValueError(f"img size {S}: the sgb200 kernels need a power-of-two size >= 16")
+        if rows % n_src:
+            raise ValueError("rows must be a multiple of n_src")
+        self.W = weights
+        self.dev = weights.device
+        _cabi.require_b200(self.dev)
+        self.tc = weights.mode != "fp32"
+        self.act = weights.act
+        self.engine = SG_ENGINE_TC if self.tc else SG_ENGINE_SIMT
+        self.rows, self.n_src, self.S = rows, n_src, S
+        self.use_step = use_step
+        self.debug = debug  # keep every buffer alive and expose per-block outputs in self.taps
+        self._pool = {}
+        self.nbytes = 0
+        self.ops = []
+        self.n_launches = 0
+        f32, dev = torch.float32, self.dev
+        self.x_in = torch.zeros((n_src, weights.c_in, S, S), dtype=f32, device=dev)
+        self.t = torch.zeros((rows,), dtype=f32, device=dev)
+        self.y = torch.full((rows,), -1, dtype=torch.int64, device=dev)
+        self.step = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.temb = torch.empty((rows, TIME_DIM), dtype=f32, device=dev)
+        self.emb = torch.empty((rows, weights.emb_total), dtype=f32, device=dev)
+        self.eps = torch.empty((rows, weights.c_out, S, S), dtype=f32, device=dev)
+        self.taps = {}  # debug only: block name -> fp32 NHWC output buffer
+        self._build()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= s
+        key = (n * torch.empty((), dtype=dtype).element_size(), dtype)
+        lst = self._pool.get(key)
+        if lst:
+            return lst.pop().view(shape)
+        t = torch.empty(shape, dtype=dtype, device=self.dev)
+        self.nbytes += t.numel() * t.element_size()
+        return t
+
+    def _free(self, *ts):
+        if self.debug:
+            return
+        for t in ts:
+            if t is None:
+                continue
+            key = (t.numel() * t.element_size(), t.dtype)
+            self._pool.setdefault(key, []).append(t)
+
+    def _op(self, fn, *a, **kw):
+        self.ops.append((fn, a, kw))
+        self.n_launches += 1
+
+    def _pair(self, shape, want_f32=True, want_act=True):
+        """(fp32 buffer, GEMM-operand buffer) for one logical tensor; in fp32 mode they are the same buffer."""
+        if not self.tc:
+            b = self._alloc(shape, torch.float32)
+            return b, b
+        return (self._alloc(shape, torch.float32) if want_f32 else None,
+                self._alloc(shape, self.act) if want_act else None)
+
+    def _free_pair(self, p):
+        if p[0] is p[1]:
+            self._free(p[0])
+        else:
+            self._free(p[0], p[1])
+
+    # ------------------------------------------------------------------ blocks
+    def _conv(self, a_act, wname, rows, H, W):
+        """3x3 conv (no bias) -> (raw fp32 [rows,H,W,Cout], GroupNorm partials)."""
+        w = self.W[wname]
+        cout = w.shape[1]
+        raw = self._alloc((rows, H, W, cout), torch.float32)
+        P = ops.igemm_partials(self.engine, H, W, cout)
+        part = self._alloc((rows, P, 2), torch.float32)
+        args = ops.make_igemm_args(a_act, w, rows=rows, H=H, W=W, out_f32=raw, partials=part)
+        self._op(ops.igemm_launch, args)
+        return raw, part
+
+    def _double_conv(self, p, x, rows, H, W, *, residual=False, emb=None, want_f32=True, want_act=True, from_input=False):
+        """DoubleConv (:75-93).  x = (fp32, act) pair of the input (or None when from_input).  Returns a pair."""
+        W_ = self.W
+        if from_input:
+            raw1 = self._alloc((rows, H, W, 64), torch.float32)
+            part1 = self._alloc((rows, ops.conv_in_partials(H), 2), torch.float32)
+            self._op(ops.conv_in, self.x_in, W_[f"{p}.double_conv.0.weight"], raw1, part1)
+        else:
+            raw1, part1 = self._conv(x[1], f"{p}.double_conv.0.weight", rows, H, W)
+        mid = self._pair(raw1.shape, want_f32=False, want_act=True)
+        self._op(ops.gn_apply, raw1, part1, W_[f"{p}.double_conv.1.weight"], W_[f"{p}.double_conv.1.bias"], mode=1,
+                 out_f32=None if self.tc else mid[0], out_act=mid[1] if self.tc else None)
+        self._free(raw1, part1)
+        raw2, part2 = self._conv(mid[1], f"{p}.double_conv.3.weight", rows, H, W)
+        self._free_pair(mid)
+        out = self._pair(raw2.shape, want_f32, want_act)
+        self._op(ops.gn_apply, raw2, part2, W_[f"{p}.double_conv.4.weight"], W_[f"{p}.double_conv.4.bias"],
+                 mode=2 if residual else 0, residual=x[0] if residual else None, emb=emb,
+                 out_f32=out[0], out_act=out[1] if self.tc else None)
+        self._free(raw2, part2)
+        return out
+
+    def _emb_slice(self, block):
+        off, n = self.W.emb_off[block]
+        return self.emb[:, off:off + n]
+
+    def _self_attention(self, p, x, rows, H, W, C, *, want_act):
+        """SelfAttention (:52-72) on the fp32 residual stream x [rows, H, W, C] (tokens are already row-major)."""
+        W_ = self.W
+        L = H * W
+        M = rows * L
+        f32 = torch.float32
+        ln1 = self._alloc((M, C), self.act)
+        self._op(ops.layernorm, x, W_[f"{p}.ln.weight"], W_[f"{p}.ln.bias"], ln1)
+        qkv = self._alloc((M, 3 * C), f32)  # SIMT attention core reads fp32 q/k/v
+        self._op(ops.igemm_launch, ops.make_igemm_args(ln1, W_[f"{p}.mha.in_proj_weight"], rows=rows, H=H, W=W,
+                                                       bias=W_[f"{p}.mha.in_proj_bias"], out_f32=qkv))
+        self._free(ln1)
+        att = self._alloc((M, C), self.act)
+        self._op(ops.attention, qkv, att, rows=rows, L=L, C=C, engine=SG_ENGINE_SIMT)
+        self._free(qkv)
+        a = self._alloc((rows, H, W, C), f32)
+        self._op(ops.igemm_launch, ops.make_igemm_args(att, W_[f"{p}.mha.out_proj.weight"], rows=rows, H=H, W=W,
+                                                       bias=W_[f"{p}.mha.out_proj.bias"], residual=x, out_f32=a))
+        self._free(att)
+        ln2 = self._alloc((M, C), self.act)
+        self._op(ops.layernorm, a, W_[f"{p}.ff_self.0.weight"], W_[f"{p}.ff_self.0.bias"], ln2)
+        f1 = self._alloc((M, C), self.act)
+        self._op(ops.igemm_launch, ops.make_igemm_args(
+            ln2, W_[f"{p}.ff_self.1.weight"], rows=rows, H=H, W=W, bias=W_[f"{p}.ff_self.1.bias"], gelu=True,
+            **({"out_act": f1} if self.tc else {"out_f32": f1})))
+        self._free(ln2)
+        out = self._pair((rows, H, W, C), True, want_act)
+        self._op(ops.igemm_launch, ops.make_igemm_args(
+            f1, W_[f"{p}.ff_self.3.weight"], rows=rows, H=H, W=W, bias=W_[f"{p}.ff_self.3.bias"], residual=a,
+            out_f32=out[0], out_act=out[1] if self.tc else None))
+        self._free(f1, a)
+        return out
+
+    def _down(self, p, x, rows, H, W, C):
+        h, w = H // 2, W // 2
+        pooled = self._pair((rows, h, w, C))
+        self._op(ops.maxpool2, x[0], out_f32=pooled[0], out_act=pooled[1] if self.tc else None)
+        d1 = self._double_conv(f"{p}.maxpool_conv.1", pooled, rows, h, w, residual=True, want_f32=False)
+        self._free_pair(pooled)
+        d2 = self._double_conv(f"{p}.maxpool_conv.2", d1, rows, h, w, emb=self._emb_slice(p), want_act=False)
+        self._free_pair(d1)
+        return d2
+
+    def _up(self, p, x, skip, rows, h, w):
+        H, W = 2 * h, 2 * w
+        ct = x[0].shape[-1] + skip[0].shape[-1]
+        cat = self._pair((rows, H, W, ct))
+        self._op(ops.upsample_cat, x[0], skip[0], out_f32=cat[0], out_act=cat[1] if self.tc else None)
+        u1 = self._double_conv(f"{p}.conv.0", cat, rows, H, W, residual=True, want_f32=False)
+        self._free_pair(cat)
+        u2 = self._double_conv(f"{p}.conv.1", u1, rows, H, W, emb=self._emb_slice(p), want_act=False)
+        self._free_pair(u1)
+        return u2
+
+    # ------------------------------------------------------------------ whole network (:175-196)
+    def _build(self):
+        W_, rows, S = self.W, self.rows, self.S
+        keep = self.taps
+        self._op(ops.time_embed, None if self.use_step else self.t, self.step if self.use_step else None,
+                 self.y if W_.label is not None else None,
+                 W_.inv_freq, W_.label, W_.w_emb, W_.b_emb, self.temb, self.emb)
+        x1 = self._double_conv("inc", None, rows, S, S, from_input=True, want_act=False)
+        keep["inc"] = x1[0]
+        d = self._down("down1", x1, rows, S, S, 64)
+        keep["down1"] = d[0]
+        x2 = self._self_attention("sa1", d[0], rows, S // 2, S // 2, 128, want_act=False)
+        self._free_pair(d)
+        keep["sa1"] = x2[0]
+        d = self._down("down2", x2, rows, S // 2, S // 2, 128)
+        keep["down2"] = d[0]
+        x3 = self._self_attention("sa2", d[0], rows, S // 4, S // 4, 256, want_act=False)
+        self._free_pair(d)
+        keep["sa2"] = x3[0]
+        d = self._down("down3", x3, rows, S // 4, S // 4, 256)
+        keep["down3"] = d[0]
+        x4 = self._self_attention("sa3", d[0], rows, S // 8, S // 8, 256, want_act=True)
+        self._free_pair(d)
+        keep["sa3"] = x4[0]
+        s8 = S // 8
+        b = self._double_conv("bot1", x4, rows, s8, s8, want_f32=self.debug)
+        keep["bot1"] = b[0]
+        self._free_pair(x4)
+        if W_.deep:
+            b2 = self._double_conv("bot2", b, rows, s8, s8, want_f32=self.debug)
+            keep["bot2"] = b2[0]
+            self._free_pair(b)
+            b = b2
+        b3 = self._double_conv("bot3", b, rows, s8, s8, want_act=False)
+        keep["bot3"] = b3[0]
+        self._free_pair(b)
+        u = self._up("up1", b3, x3, rows, s8, s8)
+        self._free_pair(b3)
+        self._free_pair(x3)
+        keep["up1"] = u[0]
+        a = self._self_attention("sa4", u[0], rows, S // 4, S // 4, 128, want_act=False)
+        self._free_pair(u)
+        keep["sa4"] = a[0]
+        u = self._up("up2", a, x2, rows, S // 4, S // 4)
+        self._free_pair(a)
+        self._free_pair(x2)
+        keep["up2"] = u[0]
+        a = self._self_attention("sa5", u[0], rows, S // 2, S // 2, 64, want_act=False)
+        self._free_pair(u)
+        keep["sa5"] = a[0]
+        u = self._up("up3", a, x1, rows, S // 2, S // 2)
+        self._free_pair(a)
+        self._free_pair(x1)
+        keep["up3"] = u[0]
+        a = self._self_attention("sa6", u[0], rows, S, S, 64, want_act=False)
+        self._free_pair(u)
+        keep["sa6"] = a[0]
+        self._op(ops.conv_out, a[0].view(rows, S * S, 64), W_["outc.weight"], W_["outc.bias"], self.eps)
+        self._free_pair(a)
+        self._pool.clear()
+
+    def run(self):
+        """Issue the whole forward on torch's current stream (graph-capturable)."""
+        for fn, a, kw in self.ops:
+            fn(*a, **kw)

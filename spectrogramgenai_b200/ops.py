@@ -1,0 +1,170 @@
+"""Tensor-level wrappers over the C-ABI kernels (include/sgb200.h).
+
+Each function takes CUDA tensors, checks shapes/dtypes, and launches the kernel on
+torch's current stream through ctypes.  Outputs are caller-visible tensors; nothing here
+computes on the host and nothing falls back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+from ._cabi import SG_ENGINE_SIMT, SG_ENGINE_TC, IgemmArgs, check, dtype_code, ptr, stream_ptr
+
+HEADS = 4  # nn.MultiheadAttention(channels, 4) -- /root/reference/src/diff_modules.py:56
+
+
+def _lib():
+    return _cabi.load()
+
+
+def _f32(t, name):
+    if t is not None and (t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous CUDA fp32 tensor")
+    return t
+
+
+def _engine_of(dt: torch.dtype) -> int:
+    return SG_ENGINE_SIMT if dt == torch.float32 else SG_ENGINE_TC
+
+
+def time_embed(t, step, y, inv_freq, label, w_emb, b_emb, temb, emb):
+    """K5.  t fp32 [rows] or None (then step int32[1] is used); y int64 [rows] or None."""
+    rows = temb.shape[0]
+    num_classes = 0 if label is None else label.shape[0]
+    check(_lib().sg_time_embed(ptr(t), ptr(step), ptr(y), ptr(inv_freq), ptr(label), num_classes, ptr(w_emb),
+                               ptr(b_emb), w_emb.shape[0], rows, ptr(temb), ptr(emb), stream_ptr()), "sg_time_embed")
+
+
+def conv_in_partials(S: int) -> int:
+    return _lib().sg_conv_in_partials(S)
+
+
+def conv_in(x, w, raw, partials):
+    """inc.double_conv.0.  x fp32 NCHW [n_src,c,S,S]; raw fp32 [rows,S,S,64]; partials fp32 [rows,P,2]."""
+    n_src, c_in, S, _ = x.shape
+    rows = raw.shape[0]
+    check(_lib().sg_conv_in(ptr(_f32(x, "x")), n_src, c_in, S, ptr(_f32(w, "w")), rows, ptr(raw), ptr(partials),
+                            stream_ptr()), "sg_conv_in")
+
+
+def igemm_partials(engine: int, H: int, W: int, Cout: int) -> int:
+    return _lib().sg_igemm_partials(engine, H, W, Cout)
+
+
+def make_igemm_args(a, w, *, rows, H, W, bias=None, residual=None, out_f32=None, out_act=None, partials=None,
+                    gelu=False) -> IgemmArgs:
+    """a: act [rows,H,W,Cin] (any view with that many elements); w: act [taps,Cout,Cin]."""
+    taps, Cout, Cin = w.shape
+    if a.dtype != w.dtype:
+        raise ValueError("activation / weight dtype mismatch")
+    if a.numel() != rows * H * W * Cin:
+        raise ValueError(f"igemm: a has {a.numel()} elements, expected {rows}x{H}x{W}x{Cin}")
+    M = rows * H * W
+    for t, nm in ((residual, "residual"), (out_f32, "out_f32")):
+        if t is not None and (t.dtype != torch.float32 or t.numel() != M * Cout):
+            raise ValueError(f"igemm: {nm} must be fp32 with {M}x{Cout} elements")
+    if out_act is not None and (out_act.dtype != a.dtype or out_act.numel() != M * Cout):
+        raise ValueError("igemm: out_act must have the activation dtype and M x Cout elements")
+    args = IgemmArgs(ptr(a), ptr(w), ptr(bias), ptr(residual), ptr(out_f32), ptr(out_act), ptr(partials), rows, H, W,
+                     Cin, Cout, taps, 1 if gelu else 0, _engine_of(a.dtype), dtype_code(a.dtype))
+    args._keepalive = (a, w, bias, residual, out_f32, out_act, partials)
+    return args
+
+
+def igemm_launch(args: IgemmArgs):
+    check(_lib().sg_igemm(args, stream_ptr()), "sg_igemm")
+
+
+def igemm(a, w, **kw):
+    """K1 implicit GEMM (3x3 conv for taps=9, Linear for taps=1); see make_igemm_args."""
+    igemm_launch(make_igemm_args(a, w, **kw))
+
+
+def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f32=None, out_act=None):
+    """K2.  raw fp32 [rows,HW,C] (any shape with rows first, C last); emb: fp32 view [rows, C] (row stride kept)."""
+    rows, C = raw.shape[0], raw.shape[-1]
+    HW = raw.numel() // (rows * C)
+    P = partials.shape[1]
+    emb_stride = 0
+    if emb is not None:
+        if emb.dtype != torch.float32 or emb.shape != (rows, C) or emb.stride(1) != 1:
+            raise ValueError("gn_apply: emb must be an fp32 [rows, C] view with unit inner stride")
+        emb_stride = emb.stride(0)
+    adt = dtype_code(out_act.dtype) if out_act is not None else 0
+    check(_lib().sg_gn_apply(ptr(_f32(raw, "raw")), ptr(partials), P, ptr(gamma), ptr(beta), rows, HW, C, mode,
+                             ptr(_f32(residual, "residual")), ptr(emb), emb_stride, ptr(_f32(out_f32, "out_f32")),
+                             ptr(out_act), adt, stream_ptr()), "sg_gn_apply")
+
+
+def maxpool2(x, *, out_f32=None, out_act=None):
+    """K3a.  x fp32 [rows,H,W,C]."""
+    rows, H, W, Cc = x.shape
+    adt = dtype_code(out_act.dtype) if out_act is not None else 0
+    check(_lib().sg_maxpool2(ptr(_f32(x, "x")), rows, H, W, Cc, ptr(_f32(out_f32, "out_f32")), ptr(out_act), adt,
+                             stream_ptr()), "sg_maxpool2")
+
+
+def upsample_cat(x, skip, *, out_f32=None, out_act=None):
+    """K3b.  x fp32 [rows,h,w,Cx], skip fp32 [rows,2h,2w,Cs] -> [rows,2h,2w,Cs+Cx]."""
+    rows, h, w, Cx = x.shape
+    Cs = skip.shape[-1]
+    if tuple(skip.shape[:3]) != (rows, 2 * h, 2 * w):
+        raise ValueError("upsample_cat: skip must be [rows, 2h, 2w, Cs]")
+    adt = dtype_code(out_act.dtype) if out_act is not None else 0
+    check(_lib().sg_upsample_cat(ptr(_f32(x, "x")), ptr(_f32(skip, "skip")), rows, h, w, Cx, Cs,
+                                 ptr(_f32(out_f32, "out_f32")), ptr(out_act), adt, stream_ptr()), "sg_upsample_cat")
+
+
+def layernorm(x, gamma, beta, out):
+    """LayerNorm over the last dim.  x fp32 [..., C] -> out (fp32 / bf16 / fp16) of the same shape."""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    check(_lib().sg_layernorm(ptr(_f32(x, "x")), ptr(gamma), ptr(beta), M, Cc, ptr(out), dtype_code(out.dtype),
+                              stream_ptr()), "sg_layernorm")
+
+
+def attention(qkv, out, *, rows, L, C, engine=None):
+    """K4.  qkv [rows*L, 3C]; out [rows*L, C].  SIMT engine: qkv fp32, out fp32/16-bit.  TC: both 16-bit."""
+    if engine is None:
+        engine = _engine_of(qkv.dtype)
+    if qkv.numel() != rows * L * 3 * C or out.numel() != rows * L * C:
+        raise ValueError("attention: bad qkv / out size")
+    check(_lib().sg_attention(ptr(qkv), ptr(out), rows, L, C, HEADS, engine, dtype_code(out.dtype), stream_ptr()),
+          "sg_attention")
+
+
+def conv_out(x, w, b, eps):
+    """outc.  x fp32 [rows,HW,64] -> eps fp32 NCHW [rows,c_out,S,S]."""
+    rows, c_out = eps.shape[0], eps.shape[1]
+    HW = eps.shape[2] * eps.shape[3]
+    check(_lib().sg_conv_out(ptr(_f32(x, "x")), ptr(w), ptr(b), rows, HW, c_out, ptr(eps), stream_ptr()), "sg_conv_out")
+
+
+def cfg_update(x, eps, coef, step, *, cfg_scale, noise=None, seed=0, sample_base=0):
+    """K6.  x fp32 [n,c,S,S] in/out; eps fp32 [2n or n, c,S,S]; coef fp32 [T,3]; step int32[1]."""
+    n = x.shape[0]
+    E = x.numel() // n
+    T = coef.shape[0]
+    need = 2 * n if cfg_scale > 0 else n
+    if eps.shape[0] < need:
+        raise ValueError(f"cfg_update: eps has {eps.shape[0]} rows, needs {need}")
+    if noise is not None and (noise.dtype != torch.float32 or noise.numel() != (T - 1) * n * E):
+        raise ValueError("cfg_update: injected noise must be fp32 [T-1, n, c, S, S]")
+    check(_lib().sg_cfg_update(ptr(_f32(x, "x")), ptr(_f32(eps, "eps")), n, E, float(cfg_scale), ptr(coef), T,
+                               ptr(step), ptr(noise), int(seed) & (2**64 - 1), int(sample_base), stream_ptr()),
+          "sg_cfg_update")
+
+
+def step_advance(step):
+    check(_lib().sg_step_advance(ptr(step), stream_ptr()), "sg_step_advance")
+
+
+def philox_normal(x, *, seed, sample_base, step_tag):
+    n = x.shape[0]
+    check(_lib().sg_philox_normal(ptr(_f32(x, "x")), n, x.numel() // n, int(seed) & (2**64 - 1), int(sample_base),
+                                  int(step_tag), stream_ptr()), "sg_philox_normal")
+
+
+def to_uint8(x, out):
+    check(_lib().sg_to_uint8(ptr(_f32(x, "x")), x.numel(), ptr(out), stream_ptr()), "sg_to_uint8")

@@ -1,0 +1,326 @@
+"""Per-kernel parity of the C-ABI CUDA kernels against the CPU oracle / torch fp32-fp64 restatements.
+
+All tests call through spectrogramgenai_b200.ops, i.e. through the ctypes binding of libsgb200.so.
+Tolerances: bit-exact for the sampler arithmetic and the uint8 tail; fp32 kernels within 2e-5 rel-L2 of an
+fp64 evaluation; tensor-core kernels within 2e-5 of an fp64 evaluation ON THE SAME 16-bit-rounded operands
+(so the test isolates kernel correctness from operand rounding, which the end-to-end tests bound).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ddpm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from spectrogramgenai_b200 import _cabi, ops as _ops
+
+    _cabi.require_b200(torch.device("cuda", torch.cuda.current_device()))
+    return _ops
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def pack_conv(w, dtype=torch.float32):
+    co, ci, kh, kw = w.shape
+    return w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous().to(dtype)
+
+
+# ------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize("cfg", [3.0, 0.3, 0.0])
+@pytest.mark.parametrize("i", [999, 500, 2, 1])
+def test_cfg_update_bit_exact(ops, cfg, i):
+    n, c, S, T = 3, 4, 16, 1000
+    g = gen(i)
+    x = torch.randn(n, c, S, S, generator=g)
+    eps = torch.randn(2 * n, c, S, S, generator=g)
+    noise = torch.randn(T - 1, n, c, S, S, generator=g)
+    beta, alpha, ah = O.noise_schedule(T)
+    c1, c2, c3 = O.posterior_coefficients(beta, alpha, ah)
+    e = O.cfg_combine(eps[:n], eps[n:], cfg) if cfg > 0 else eps[:n]
+    z = noise[T - i] if i > 1 else torch.zeros_like(x)
+    ref = O.posterior_update(x, e, c1[i], c2[i], c3[i], z)
+    coef = torch.stack([c1, c2, c3], 1).contiguous().to(DEV)
+    xd = x.to(DEV)
+    step = torch.tensor([i], dtype=torch.int32, device=DEV)
+    ops.cfg_update(xd, eps.to(DEV), coef, step, cfg_scale=cfg, noise=noise.to(DEV))
+    assert torch.equal(xd.cpu(), ref)
+    ops.step_advance(step)
+    assert int(step.item()) == i - 1
+
+
+@pytest.mark.parametrize("count", [0, 1, 3, 4, 1023, 4 * 16 * 16 * 5])
+def test_to_uint8_bit_exact(ops, count):
+    g = gen(count)
+    x = torch.randn(count, generator=g) * 0.8
+    if count >= 4:
+        x[:4] = torch.tensor([-1.0, 1.0, -7.0, 7.0])
+    if count > 8:
+        x[4:8] = torch.tensor([0.0, 0.999999, -0.999999, 0.5])
+    out = torch.zeros(max(count, 1), dtype=torch.uint8, device=DEV)
+    ops.to_uint8(x.to(DEV), out) if count else None
+    assert torch.equal(out.cpu()[:count], O.to_uint8(x))
+
+
+def test_philox_normal_statistics_and_sharding_invariance(ops):
+    n, E = 8, 4 * 64 * 64
+    a = torch.empty(n, E, device=DEV)
+    ops.philox_normal(a, seed=1234, sample_base=0, step_tag=1000)
+    v = a.double().cpu()
+    assert abs(float(v.mean())) < 5e-3 and abs(float(v.std()) - 1) < 5e-3
+    assert abs(float((v ** 3).mean())) < 2e-2 and abs(float((v ** 4).mean()) - 3) < 5e-2
+    assert torch.isfinite(a).all()
+    # the stream is keyed by the GLOBAL sample index: two half-batches == one batch
+    b = torch.empty(4, E, device=DEV)
+    ops.philox_normal(b, seed=1234, sample_base=4, step_tag=1000)
+    assert torch.equal(b, a[4:])
+    # different step / seed -> different numbers
+    ops.philox_normal(b, seed=1234, sample_base=4, step_tag=999)
+    assert not torch.equal(b, a[4:])
+    # cfg_update's in-kernel noise == philox_normal of the same (seed, sample, step)
+    T = 10
+    coef = torch.tensor([[1.0, 0.0, 1.0]] * T, device=DEV)
+    x = torch.zeros(4, E, device=DEV)
+    step = torch.tensor([7], dtype=torch.int32, device=DEV)
+    ops.cfg_update(x.view(4, 4, 64, 64), torch.zeros(8, 4, 64, 64, device=DEV), coef, step, cfg_scale=3.0, seed=1234,
+                   sample_base=4)
+    ops.philox_normal(b, seed=1234, sample_base=4, step_tag=7)
+    assert torch.equal(x, b)
+
+
+# ------------------------------------------------------------------------------------------ pool / upsample
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (3, 2, 2, 256), (1, 64, 64, 64)])
+def test_maxpool2(ops, shape):
+    x = torch.randn(shape, generator=gen(1))
+    ref = nhwc(F.max_pool2d(nchw(x), 2))
+    o32 = torch.empty(ref.shape, device=DEV)
+    o16 = torch.empty(ref.shape, device=DEV, dtype=torch.bfloat16)
+    ops.maxpool2(x.to(DEV), out_f32=o32, out_act=o16)
+    assert torch.equal(o32.cpu(), ref)
+    assert torch.equal(o16.cpu(), ref.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("h,cx,cs", [(2, 256, 256), (8, 128, 128), (32, 64, 64), (1, 64, 64)])
+def test_upsample_cat(ops, h, cx, cs):
+    rows = 2
+    x = torch.randn(rows, h, h, cx, generator=gen(2))
+    skip = torch.randn(rows, 2 * h, 2 * h, cs, generator=gen(3))
+    up = F.interpolate(nchw(x).double(), scale_factor=2, mode="bilinear", align_corners=True)
+    ref = nhwc(torch.cat([nchw(skip).double(), up], 1))
+    o32 = torch.empty(ref.shape, device=DEV)
+    o16 = torch.empty(ref.shape, device=DEV, dtype=torch.float16)
+    ops.upsample_cat(x.to(DEV), skip.to(DEV), out_f32=o32, out_act=o16)
+    assert float((o32.cpu().double() - ref).abs().max()) < 2e-6
+    assert float((o16.cpu().double() - ref).abs().max()) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------ time embedding
+def test_time_embed(ops):
+    rows, ncls = 11, 27
+    g = gen(4)
+    t = torch.tensor([999, 998, 500, 20, 2, 1, 0, 7, 300, 640, 999]).float()
+    y = torch.randint(0, ncls, (rows,), generator=g)
+    y[3] = -1
+    y[10] = -1
+    label = torch.randn(ncls, 256, generator=g)
+    w = torch.randn(896, 256, generator=g) / 16
+    b = torch.randn(896, generator=g)
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, 256, 2).float() / 256))
+    ref_t = O.pos_encoding(t)
+    ref_t = ref_t + torch.where((y >= 0)[:, None], label[y.clamp_min(0)], torch.zeros(1))
+    ref_e = F.linear(F.silu(ref_t.double()), w.double(), b.double())
+    temb = torch.empty(rows, 256, device=DEV)
+    emb = torch.empty(rows, 896, device=DEV)
+    ops.time_embed(t.to(DEV), None, y.to(DEV), inv_freq.to(DEV), label.to(DEV), w.to(DEV), b.to(DEV), temb, emb)
+    # sin/cos of arguments up to 999 rad: device sinf vs host sinf differ by <= 2 ulp of a value <= 1
+    assert float((temb.cpu() - ref_t).abs().max()) < 5e-7
+    assert O.rel_l2(emb.cpu(), ref_e) < 2e-6
+    # device step counter path == t path
+    step = torch.tensor([500], dtype=torch.int32, device=DEV)
+    temb2 = torch.empty(rows, 256, device=DEV)
+    ops.time_embed(None, step, None, inv_freq.to(DEV), None, w.to(DEV), b.to(DEV), temb2, emb)
+    assert float((temb2.cpu() - O.pos_encoding(torch.full((rows,), 500.0))).abs().max()) < 5e-7
+
+
+# ------------------------------------------------------------------------------------------ convolutions
+@pytest.mark.parametrize("c_in,S,rows,n_src", [(4, 16, 4, 2), (1, 32, 2, 2), (4, 64, 2, 1), (3, 16, 1, 1)])
+def test_conv_in(ops, c_in, S, rows, n_src):
+    g = gen(5)
+    x = torch.randn(n_src, c_in, S, S, generator=g)
+    w = torch.randn(64, c_in, 3, 3, generator=g) / 3
+    ref = nhwc(F.conv2d(x.double(), w.double(), padding=1))
+    ref = ref[torch.arange(rows) % n_src]
+    raw = torch.empty(rows, S, S, 64, device=DEV)
+    part = torch.empty(rows, ops.conv_in_partials(S), 2, device=DEV)
+    ops.conv_in(x.to(DEV), w.to(DEV), raw, part)
+    assert O.rel_l2(raw.cpu(), ref) < 1e-6
+    s = part.cpu().double().sum(1)
+    assert torch.allclose(s[:, 0], ref.sum((1, 2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (ref ** 2).sum((1, 2, 3)), rtol=1e-5)
+
+
+CONV_CASES = [  # rows, H, Cin, Cout
+    (2, 16, 64, 64), (4, 2, 256, 256), (3, 4, 256, 512), (2, 8, 128, 128), (1, 32, 128, 64), (2, 16, 192, 128),
+    (40, 2, 64, 64),
+]
+
+
+def _conv_ref(a, w):
+    return nhwc(F.conv2d(nchw(a.double()), w.double(), padding=1))
+
+
+@pytest.mark.parametrize("rows,H,cin,cout", CONV_CASES)
+def test_igemm_conv_simt_with_groupnorm(ops, rows, H, cin, cout):
+    from spectrogramgenai_b200._cabi import SG_ENGINE_SIMT
+
+    g = gen(6)
+    a = torch.randn(rows, H, H, cin, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)
+    ref = _conv_ref(a, w)
+    raw = torch.empty(rows, H, H, cout, device=DEV)
+    part = torch.full((rows, ops.igemm_partials(SG_ENGINE_SIMT, H, H, cout), 2), float("nan"), device=DEV)
+    ops.igemm(a.to(DEV), pack_conv(w).to(DEV), rows=rows, H=H, W=H, out_f32=raw, partials=part)
+    assert O.rel_l2(raw.cpu(), ref) < 2e-6
+    # GroupNorm(1, C) finalize + affine + GELU / residual / embedding
+    gamma = torch.randn(cout, generator=g)
+    beta = torch.randn(cout, generator=g)
+    res = torch.randn(rows, H, H, cout, generator=g)
+    emb = torch.randn(rows, cout + 64, generator=g)
+    gn = nhwc(F.group_norm(nchw(ref), 1, gamma.double(), beta.double(), 1e-5))
+    for mode, want in ((0, gn), (1, F.gelu(gn)), (2, F.gelu(gn + res.double()))):
+        out = torch.empty(rows, H, H, cout, device=DEV)
+        ops.gn_apply(raw, part, gamma.to(DEV), beta.to(DEV), mode=mode, residual=res.to(DEV) if mode == 2 else None,
+                     out_f32=out)
+        assert O.rel_l2(out.cpu(), want) < 3e-6, mode
+    out = torch.empty(rows, H, H, cout, device=DEV)
+    o16 = torch.empty(rows, H, H, cout, device=DEV, dtype=torch.bfloat16)
+    embd = emb.to(DEV)
+    ops.gn_apply(raw, part, gamma.to(DEV), beta.to(DEV), mode=0, emb=embd[:, 64:], out_f32=out, out_act=o16)
+    want = gn + emb[:, 64:].double()[:, None, None, :]
+    assert O.rel_l2(out.cpu(), want) < 3e-6
+    assert O.rel_l2(o16.cpu(), want) < 4e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,H,cin,cout", CONV_CASES + [(2, 64, 64, 64), (1, 64, 128, 128)])
+def test_igemm_conv_tensor_core(ops, rows, H, cin, cout, dtype):
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    g = gen(7)
+    a = torch.randn(rows, H, H, cin, generator=g).to(dtype)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(dtype)
+    ref = _conv_ref(a.float(), w.float())  # fp64 on the rounded operands
+    raw = torch.full((rows, H, H, cout), float("nan"), device=DEV)
+    o16 = torch.empty(rows, H, H, cout, device=DEV, dtype=dtype)
+    part = torch.full((rows, ops.igemm_partials(SG_ENGINE_TC, H, H, cout), 2), float("nan"), device=DEV)
+    ops.igemm(a.to(DEV), pack_conv(w.float(), dtype).to(DEV), rows=rows, H=H, W=H, out_f32=raw, out_act=o16,
+              partials=part)
+    torch.cuda.synchronize()
+    assert O.rel_l2(raw.cpu(), ref) < 2e-6
+    assert O.rel_l2(o16.cpu(), ref) < 4e-3
+    s = part.cpu().double().sum(1)
+    assert torch.allclose(s[:, 0], ref.sum((1, 2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (ref ** 2).sum((1, 2, 3)), rtol=1e-5)
+
+
+LIN_CASES = [(2, 4, 64, 192), (2, 8, 128, 384), (1, 16, 256, 768), (3, 2, 256, 256), (2, 32, 64, 64)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,H,cin,cout", LIN_CASES)
+def test_igemm_linear_epilogues(ops, rows, H, cin, cout, dtype):
+    g = gen(8)
+    M = rows * H * H
+    a = torch.randn(M, cin, generator=g).to(dtype)
+    w = (torch.randn(cout, cin, generator=g) / math.sqrt(cin)).to(dtype)
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(M, cout, generator=g)
+    lin = F.linear(a.double(), w.double(), b.double())
+    wp = w.reshape(1, cout, cin).contiguous().to(DEV)
+    out = torch.empty(M, cout, device=DEV)
+    ops.igemm(a.to(DEV), wp, rows=rows, H=H, W=H, bias=b.to(DEV), residual=res.to(DEV), out_f32=out)
+    assert O.rel_l2(out.cpu(), lin + res.double()) < 3e-6
+    if dtype == torch.float32:
+        ops.igemm(a.to(DEV), wp, rows=rows, H=H, W=H, bias=b.to(DEV), gelu=True, out_f32=out)
+        assert O.rel_l2(out.cpu(), F.gelu(lin)) < 3e-6
+    else:
+        o16 = torch.empty(M, cout, device=DEV, dtype=dtype)
+        ops.igemm(a.to(DEV), wp, rows=rows, H=H, W=H, bias=b.to(DEV), gelu=True, out_act=o16)
+        assert O.rel_l2(o16.cpu(), F.gelu(lin)) < 4e-3
+
+
+def test_conv_out(ops):
+    g = gen(9)
+    for c_out, rows, S in ((4, 3, 16), (1, 2, 32)):
+        x = torch.randn(rows, S * S, 64, generator=g)
+        w = torch.randn(c_out, 64, generator=g) / 8
+        b = torch.randn(c_out, generator=g)
+        ref = (x.double() @ w.double().T + b.double()).transpose(1, 2).reshape(rows, c_out, S, S)
+        eps = torch.empty(rows, c_out, S, S, device=DEV)
+        ops.conv_out(x.to(DEV), w.to(DEV), b.to(DEV), eps)
+        assert O.rel_l2(eps.cpu(), ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ norms / attention
+@pytest.mark.parametrize("C", [64, 128, 256])
+def test_layernorm(ops, C):
+    g = gen(10)
+    x = torch.randn(37, C, generator=g) * 3 + 1
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.layer_norm(x.double(), (C,), gamma.double(), beta.double(), 1e-5)
+    for dt, tol in ((torch.float32, 2e-6), (torch.bfloat16, 4e-3), (torch.float16, 6e-4)):
+        out = torch.empty(37, C, device=DEV, dtype=dt)
+        ops.layernorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), out)
+        assert O.rel_l2(out.cpu(), ref) < tol
+
+
+def _attention_ref(qkv, rows, L, C):
+    d = C // 4
+    q, k, v = qkv.double().reshape(rows, L, 3 * C).split(C, -1)
+    h = lambda z: z.reshape(rows, L, 4, d).transpose(1, 2)  # noqa: E731
+    att = torch.softmax(h(q) * d ** -0.5 @ h(k).transpose(-1, -2), -1) @ h(v)
+    return att.transpose(1, 2).reshape(rows * L, C)
+
+
+@pytest.mark.parametrize("rows,L,C", [(2, 4, 256), (3, 16, 256), (2, 64, 256), (2, 256, 128), (1, 1024, 64), (2, 200, 64)])
+def test_attention_simt(ops, rows, L, C):
+    from spectrogramgenai_b200._cabi import SG_ENGINE_SIMT
+
+    qkv = torch.randn(rows * L, 3 * C, generator=gen(11)) * 1.5
+    ref = _attention_ref(qkv, rows, L, C)
+    out = torch.empty(rows * L, C, device=DEV)
+    ops.attention(qkv.to(DEV), out, rows=rows, L=L, C=C, engine=SG_ENGINE_SIMT)
+    assert O.rel_l2(out.cpu(), ref) < 3e-6
+    o16 = torch.empty(rows * L, C, device=DEV, dtype=torch.float16)
+    ops.attention(qkv.to(DEV), o16, rows=rows, L=L, C=C, engine=SG_ENGINE_SIMT)
+    assert O.rel_l2(o16.cpu(), ref) < 6e-4
+
+
+def test_error_reporting(ops):
+    """Bad arguments come back as a status + message (no exception crosses the C ABI, no crash)."""
+    from spectrogramgenai_b200._cabi import SgError
+
+    x = torch.zeros(2, 4, 24, 24, device=DEV)  # 24 is not a power of two
+    with pytest.raises(SgError, match="power of two"):
+        ops.conv_in(x, torch.zeros(64, 4, 3, 3, device=DEV), torch.zeros(2, 24, 24, 64, device=DEV),
+                    torch.zeros(2, 9, 2, device=DEV))
+    with pytest.raises(SgError, match="head dim"):
+        ops.attention(torch.zeros(4, 3 * 32, device=DEV), torch.zeros(4, 32, device=DEV), rows=1, L=4, C=32)
