@@ -1,10 +1,327 @@
-// K4 (tensor-core engine): flash-style self-attention on tcgen05 -- placeholder until the kernel lands.
+// K4 (tensor-core engine): flash-style multi-head self-attention on tcgen05 / TMEM, fed by TMA.
+//
+// Replaces the scaled-dot-product inside nn.MultiheadAttention (/root/reference/src/diff_modules.py:56,:69)
+// without ever materialising the L x L matrix (the reference materialises it AND head-averages it, then
+// throws the average away).
+//
+// Work decomposition: the tokens of all batch rows form one flat sequence of M = rows*L tokens (NHWC makes
+// the reference's view/swapaxes free).  One CTA = one tile of 128 consecutive query tokens x one head.
+//   * L >= 128: the tile lies inside one batch row; it loops over that row's L/128 key tiles.
+//   * L <  128: the tile holds 128/L whole batch rows; a single key tile (the same tokens) is used with a
+//     block-diagonal mask.
+// Per key tile:   S = Q K^T          tcgen05.mma  M=128 (queries) x N=128 (keys) x K=d      -> TMEM
+//                 P = exp2(S*c - m*c) softmax warps: one query row per thread, two passes over TMEM
+//                                     (row max, then exp / row sum / 16-bit pack) -> swizzled smem
+//                 O_j = P V           tcgen05.mma  M=128 x N=d x K=128 keys, V consumed MN-major -> TMEM
+//                 o = o*alpha + O_j   running output, max and sum stay in registers (fp32)
+// TMEM use is 128 columns (O_j aliases the dead S columns), so up to four CTAs share an SM and overlap each
+// other's MMA / MUFU / TMA phases; inside a CTA the phases are serial.
+// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax + epilogue.
 #include "tc_common.cuh"
 
 namespace sg {
-int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cudaStream_t stream) {
-  (void)qkv; (void)out; (void)rows; (void)L; (void)C; (void)heads; (void)act_dtype; (void)stream;
-  set_error("sg_attention: the tcgen05 attention kernel is not built into this library yet");
-  return SG_ERR_ARG;
+namespace tc {
+
+constexpr int ATT_BM = 128;   // queries per CTA
+constexpr int ATT_BN = 128;   // keys per tile
+constexpr int P_BYTES = ATT_BM * ATT_BN * 2;  // 32 KB: two SWIZZLE_128B atoms of 64 keys
+
+// generic K-/MN-major descriptor for tiles whose rows are one swizzle span of `row_bytes` (32 / 64 / 128)
+__device__ __forceinline__ uint64_t make_desc_rows(uint32_t saddr, int row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                          // LBO: single atom along the other dimension -> unused
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;     // SBO: 8 rows
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
 }
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttGeom {
+  int64_t M;          // rows * L tokens
+  int L, logL, C, heads;
+  int nkv;            // key tiles per query tile
+  float c;            // softmax scale * log2(e)
+  uint32_t tile_bytes;  // bytes of one TMA box (d*2 * min(128, M))
+  uint32_t idesc_s, idesc_o;
+  int act_dtype;
+};
+
+template <int D>
+constexpr int att_smem_bytes() {
+  return 1024 + ATT_BM * D * 2 /*Q*/ + 2 * 2 * ATT_BN * D * 2 /*K,V x 2 stages*/ + P_BYTES + 256;
+}
+
+template <int D>
+__global__ void __launch_bounds__(192, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
+  constexpr int ROWB = D * 2;              // bytes per token row of a head slice = the swizzle span
+  constexpr int TILE = ATT_BN * ROWB;      // one Q / K / V tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE;        // [2 stages]
+  uint8_t* sV = sK + 2 * TILE;    // [2 stages]
+  uint8_t* sP = sV + 2 * TILE;    // 1024-aligned: TILE is a multiple of 4096
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint64_t* o_read = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int64_t m0 = (int64_t)blockIdx.x * ATT_BM;
+  const int64_t kv0 = g.L >= ATT_BN ? (m0 >> g.logL) << g.logL : m0;  // first key token of this tile's row(s)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_read, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: Q once, then the K / V ring =====
+      mbar_arrive_expect_tx(q_full, g.tile_bytes);
+      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
+      for (int j = 0; j < g.nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
+        const int tok = (int)(kv0 + (int64_t)j * ATT_BN);
+        tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
+        tma_load_2d(sV + s * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < g.nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
+        if (j > 0) mbar_wait(o_read, (uint32_t)(j - 1) & 1u);  // O_{j-1} (aliasing S) has been consumed
+        tc_fence_after();
+        // S = Q K^T : K-major A and B, K = D in steps of 16 (32 bytes inside the swizzle span)
+        const uint64_t qd = make_desc_rows(smem_u32(sQ), ROWB);
+        const uint64_t kd = make_desc_rows(smem_u32(sK + s * TILE), ROWB);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
+        umma_commit(s_full);
+        // O_j = P V : A = P (K-major, two 64-key SWIZZLE_128B atoms), B = V consumed MN-major (d contiguous)
+        mbar_wait(p_ready, (uint32_t)j & 1u);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP);
+        const uint32_t va = smem_u32(sV + s * TILE);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k) {
+          const uint64_t pd = make_desc_k128(pa + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
+          const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
+          umma_ss(tmem_base, pd, vd, g.idesc_o, k != 0);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ===== softmax + epilogue: thread = one query row (TMEM lane quadrant = warp % 4) =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int64_t tok = m0 + r;
+    const bool row_valid = tok < g.M;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool masked = g.L < ATT_BN;  // block-diagonal tile (several batch rows) and/or ragged tail
+    const int64_t my_row = tok >> g.logL;
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    float mx = -INFINITY, l = 0.f;
+    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+    for (int j = 0; j < g.nkv; ++j) {
+      mbar_wait(s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      const int64_t key0 = kv0 + (int64_t)j * ATT_BN;
+      // ---- pass 1: row max ----
+      float tmax = -INFINITY;
+#pragma unroll 1
+      for (int cch = 0; cch < 4; ++cch) {
+        uint32_t v[32];
+        tmem_ld32(t_row + cch * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float sv = __uint_as_float(v[i]);
+          if (masked) {
+            const int64_t kt = key0 + cch * 32 + i;
+            if (row_valid && (kt >= g.M || (kt >> g.logL) != my_row)) sv = -INFINITY;
+          }
+          tmax = fmaxf(tmax, sv);
+        }
+      }
+      const float m_new = fmaxf(mx, tmax);
+      const float alpha = ex2((mx - m_new) * g.c);  // first tile: ex2(-inf) = 0
+      const float mc = m_new * g.c;
+      // ---- pass 2: p = exp2(s*c - m*c), row sum, pack to 16-bit, swizzled st.shared ----
+      float psum = 0.f;
+#pragma unroll 1
+      for (int cch = 0; cch < 4; ++cch) {
+        uint32_t v[32];
+        tmem_ld32(t_row + cch * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+          float p0 = ex2(fmaf(s0, g.c, -mc)), p1 = ex2(fmaf(s1, g.c, -mc));
+          if (masked) {
+            const int64_t kt = key0 + cch * 32 + i;
+            if (row_valid && (kt >= g.M || (kt >> g.logL) != my_row)) p0 = 0.f;
+            if (row_valid && (kt + 1 >= g.M || ((kt + 1) >> g.logL) != my_row)) p1 = 0.f;
+          }
+          const uint32_t w = pack16(p0, p1, g.act_dtype);
+          pk[i >> 1] = w;
+          // the row sum uses the ROUNDED probabilities, i.e. exactly what the P V product sees
+          const float2 pr = unpack16(w, g.act_dtype);
+          psum += pr.x + pr.y;
+        }
+        // 32 keys = 64 bytes = four 16-byte chunks jj = cch*4 .. cch*4+3 of this row's 256-byte P row
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = cch * 4 + u;
+          const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + (uint32_t)(((jj & 7) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
+                       "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
+                       : "memory");
+        }
+      }
+      l = l * alpha + psum;
+      mx = m_new;
+      tc_fence_before();    // our tcgen05.ld of S precede the MMA that overwrites those columns
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(p_ready);
+      // ---- O_j ----
+      mbar_wait(o_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      if constexpr (D == 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int cch = 0; cch < D / 32; ++cch) {
+          uint32_t v[32];
+          tmem_ld32(t_row + cch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[cch * 32 + i] = fmaf(o[cch * 32 + i], alpha, __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_read);
+    }
+    if (row_valid) {
+      const float inv = 1.0f / l;
+      uint16_t* dst = out + tok * g.C + head * D;
+#pragma unroll
+      for (int i = 0; i < D; i += 8) {
+        uint4 w;
+        w.x = pack16(o[i] * inv, o[i + 1] * inv, g.act_dtype);
+        w.y = pack16(o[i + 2] * inv, o[i + 3] * inv, g.act_dtype);
+        w.z = pack16(o[i + 4] * inv, o[i + 5] * inv, g.act_dtype);
+        w.w = pack16(o[i + 6] * inv, o[i + 7] * inv, g.act_dtype);
+        *reinterpret_cast<uint4*>(dst + i) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+template <int D>
+static int launch_att(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = att_smem_bytes<D>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("sg_attention(tc): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
+      return SG_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  attention_tc_kernel<D><<<grid, 192, smem, stream>>>(tm, g, out);
+  return launch_status("sg_attention(tc)");
+}
+
+}  // namespace tc
+
+int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cudaStream_t stream) {
+  using namespace tc;
+  SG_REQUIRE(act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_attention(tc): act_dtype must be SG_BF16 or SG_F16");
+  SG_REQUIRE(L > 0 && (L & (L - 1)) == 0, "sg_attention(tc): L=%d must be a power of two", L);
+  SG_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "sg_attention(tc): qkv / out must be 16-byte aligned");
+  const int d = C / heads;
+  AttGeom g;
+  g.M = (int64_t)rows * L;
+  SG_REQUIRE(g.M < (1ll << 31), "sg_attention(tc): too many tokens");
+  g.L = L;
+  g.logL = 0;
+  while ((1 << g.logL) < L) ++g.logL;
+  g.C = C;
+  g.heads = heads;
+  g.nkv = L >= ATT_BN ? L / ATT_BN : 1;
+  g.c = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
+  const uint32_t box_rows = (uint32_t)(g.M < 128 ? g.M : 128);
+  g.tile_bytes = box_rows * (uint32_t)d * 2u;
+  g.idesc_s = make_idesc(act_dtype, 128, ATT_BN, 0, 0);
+  g.idesc_o = make_idesc(act_dtype, 128, d, 0, 1);  // B = V is MN-major
+  g.act_dtype = act_dtype;
+  CUtensorMap tm;
+  const uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)g.M};
+  const uint64_t strides[1] = {(uint64_t)3 * C * 2};
+  const uint32_t box[2] = {(uint32_t)d, box_rows};
+  const CUtensorMapSwizzle sw = d == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (d == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  int rc = make_tmap(&tm, act_dtype, 2, qkv, dims, strides, box, sw);
+  if (rc) return rc;
+  SG_REQUIRE(heads <= 65535, "sg_attention(tc): too many heads");
+  dim3 grid((unsigned)cdiv(g.M, ATT_BM), (unsigned)heads);
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  if (d == 16) return launch_att<16>(tm, g, o, grid, stream);
+  if (d == 32) return launch_att<32>(tm, g, o, grid, stream);
+  return launch_att<64>(tm, g, o, grid, stream);
+}
+
 }  // namespace sg

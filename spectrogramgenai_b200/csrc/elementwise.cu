@@ -7,13 +7,15 @@ namespace sg {
 
 // ------------------------------------------------------------------------------------------------
 // K6  (/root/reference/src/diff_modules.py:426-439)
-//   eps = lerp(eps_u, eps_c, s)            ATen evaluates |s| >= 0.5 as eps_c - (eps_c - eps_u) * (1 - s)
+//   eps = lerp(eps_u, eps_c, s)            ATen (cpu/LerpKernel.cpp lerp_vec): fma(s < 0.5 ? s : s - 1, eps_c - eps_u,
+//                                          s < 0.5 ? eps_u : eps_c) -- one fused multiply-add
 //   x   = c1 * (x - c2 * eps) + c3 * z     every product / sum rounded separately (torch runs them as
 //                                          separate elementwise ops), hence the __f*_rn intrinsics
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float lerp_aten(float u, float c, float w) {
   const float d = __fsub_rn(c, u);
-  return (fabsf(w) < 0.5f) ? __fadd_rn(u, __fmul_rn(w, d)) : __fsub_rn(c, __fmul_rn(d, __fsub_rn(1.0f, w)));
+  const bool small = fabsf(w) < 0.5f;
+  return __fmaf_rn(small ? w : __fsub_rn(w, 1.0f), d, small ? u : c);
 }
 __device__ __forceinline__ float posterior(float x, float e, float c1, float c2, float c3, float z) {
   return __fadd_rn(__fmul_rn(c1, __fsub_rn(x, __fmul_rn(c2, e))), __fmul_rn(c3, z));

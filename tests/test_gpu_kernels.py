@@ -128,7 +128,11 @@ def test_upsample_cat(ops, h, cx, cs):
     o32 = torch.empty(ref.shape, device=DEV)
     o16 = torch.empty(ref.shape, device=DEV, dtype=torch.float16)
     ops.upsample_cat(x.to(DEV), skip.to(DEV), out_f32=o32, out_act=o16)
-    assert float((o32.cpu().double() - ref).abs().max()) < 2e-6
+    # fp32 source coordinates (dst * (in-1)/(out-1)) as torch computes them: compare with torch fp32 tightly,
+    # with the fp64 evaluation loosely
+    ref32 = nhwc(torch.cat([nchw(skip), F.interpolate(nchw(x), scale_factor=2, mode="bilinear", align_corners=True)], 1))
+    assert float((o32.cpu() - ref32).abs().max()) < 2e-6
+    assert float((o32.cpu().double() - ref).abs().max()) < 3e-5
     assert float((o16.cpu().double() - ref).abs().max()) < 4e-3
 
 
@@ -234,7 +238,7 @@ def test_igemm_conv_tensor_core(ops, rows, H, cin, cout, dtype):
     ops.igemm(a.to(DEV), pack_conv(w.float(), dtype).to(DEV), rows=rows, H=H, W=H, out_f32=raw, out_act=o16,
               partials=part)
     torch.cuda.synchronize()
-    assert O.rel_l2(raw.cpu(), ref) < 2e-6
+    assert O.rel_l2(raw.cpu(), ref) < 5e-6  # fp32 accumulation over K up to 9*256
     assert O.rel_l2(o16.cpu(), ref) < 4e-3
     s = part.cpu().double().sum(1)
     assert torch.allclose(s[:, 0], ref.sum((1, 2, 3)), rtol=1e-4, atol=1e-2)
