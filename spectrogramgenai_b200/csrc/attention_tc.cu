@@ -100,6 +100,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (g.M < ATT_BM) {
+    // tiny problems: the TMA box is clamped to M rows, so clear the tiles once (0 * stale-NaN would poison P V)
+    for (int i = threadIdx.x; i < 5 * TILE / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -12,6 +12,8 @@ tensor-core modes every GEMM operand is additionally written as a 16-bit copy by
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _cabi, ops
@@ -96,6 +98,7 @@ class UNetPlan:
         self.engine = SG_ENGINE_TC if self.tc else SG_ENGINE_SIMT
         self.rows, self.n_src, self.S = rows, n_src, S
         self.use_step = use_step
+        self.attention_engine = os.environ.get("SGB200_ATTENTION", "tc")  # "simt": fp32 core in the 16-bit modes
         self.debug = debug  # keep every buffer alive and expose per-block outputs in self.taps
         self._pool = {}
         self.nbytes = 0
@@ -198,12 +201,15 @@ class UNetPlan:
         f32 = torch.float32
         ln1 = self._alloc((M, C), self.act)
         self._op(ops.layernorm, x, W_[f"{p}.ln.weight"], W_[f"{p}.ln.bias"], ln1)
-        qkv = self._alloc((M, 3 * C), f32)  # SIMT attention core reads fp32 q/k/v
-        self._op(ops.igemm_launch, ops.make_igemm_args(ln1, W_[f"{p}.mha.in_proj_weight"], rows=rows, H=H, W=W,
-                                                       bias=W_[f"{p}.mha.in_proj_bias"], out_f32=qkv))
+        tc_attn = self.tc and self.attention_engine == "tc"
+        # tcgen05 attention consumes 16-bit q/k/v; the SIMT core reads fp32
+        qkv = self._alloc((M, 3 * C), self.act if tc_attn else f32)
+        self._op(ops.igemm_launch, ops.make_igemm_args(
+            ln1, W_[f"{p}.mha.in_proj_weight"], rows=rows, H=H, W=W, bias=W_[f"{p}.mha.in_proj_bias"],
+            **({"out_act": qkv} if tc_attn else {"out_f32": qkv})))
         self._free(ln1)
         att = self._alloc((M, C), self.act)
-        self._op(ops.attention, qkv, att, rows=rows, L=L, C=C, engine=SG_ENGINE_SIMT)
+        self._op(ops.attention, qkv, att, rows=rows, L=L, C=C, engine=SG_ENGINE_TC if tc_attn else SG_ENGINE_SIMT)
         self._free(qkv)
         a = self._alloc((rows, H, W, C), f32)
         self._op(ops.igemm_launch, ops.make_igemm_args(att, W_[f"{p}.mha.out_proj.weight"], rows=rows, H=H, W=W,

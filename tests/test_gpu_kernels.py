@@ -318,6 +318,27 @@ def test_attention_simt(ops, rows, L, C):
     assert O.rel_l2(o16.cpu(), ref) < 6e-4
 
 
+ATT_TC_CASES = [(2, 4, 256), (5, 16, 256), (3, 64, 256), (2, 256, 256), (2, 256, 128), (2, 1024, 128), (1, 1024, 64),
+                (2, 4096, 64), (40, 4, 256), (1, 16, 128)]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,L,C", ATT_TC_CASES)
+def test_attention_tensor_core(ops, rows, L, C, dtype):
+    """tcgen05 flash attention vs fp64 softmax(QK^T/sqrt(d))V on the same 16-bit q/k/v.  The only rounding the
+    kernel adds is P -> 16 bit before P V (2^-9 bf16 / 2^-12 f16 per element) and the 16-bit output."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    qkv = (torch.randn(rows * L, 3 * C, generator=gen(12)) * 1.5).to(dtype)
+    ref = _attention_ref(qkv.float(), rows, L, C)
+    out = torch.full((rows * L, C), float("nan"), device=DEV, dtype=dtype)
+    ops.attention(qkv.to(DEV), out, rows=rows, L=L, C=C, engine=SG_ENGINE_TC)
+    torch.cuda.synchronize()
+    err = O.rel_l2(out.cpu(), ref)
+    print(f"attention tc rows={rows} L={L} C={C} {dtype}: rel-L2 {err:.3e}")
+    assert err < (6e-3 if dtype == torch.bfloat16 else 1e-3)
+
+
 def test_error_reporting(ops):
     """Bad arguments come back as a status + message (no exception crosses the C ABI, no crash)."""
     from spectrogramgenai_b200._cabi import SgError
