@@ -17,6 +17,8 @@
 // TMEM use is 128 columns (O_j aliases the dead S columns), so up to four CTAs share an SM and overlap each
 // other's MMA / MUFU / TMA phases; inside a CTA the phases are serial.
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax + epilogue.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace sg {
@@ -36,6 +38,15 @@ __device__ __forceinline__ uint64_t make_desc_rows(uint32_t saddr, int row_bytes
   d |= (uint64_t)1 << 46;
   d |= layout << 61;
   return d;
+}
+
+// two fp32 -> one packed 16-bit pair (lo = a), format fixed at compile time: one F2FP instruction
+template <int DT>
+__device__ __forceinline__ uint32_t pack_pair(float a, float b) {
+  uint32_t w;
+  if constexpr (DT == SG_BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+  return w;
 }
 
 __device__ __forceinline__ float ex2(float x) {
@@ -59,7 +70,7 @@ constexpr int att_smem_bytes() {
   return 1024 + ATT_BM * D * 2 /*Q*/ + 2 * 2 * ATT_BN * D * 2 /*K,V x 2 stages*/ + P_BYTES + 256;
 }
 
-template <int D>
+template <int D, int DT>
 __global__ void __launch_bounds__(192, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
   constexpr int ROWB = D * 2;              // bytes per token row of a head slice = the swizzle span
@@ -209,11 +220,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
             if (row_valid && (kt >= g.M || (kt >> g.logL) != my_row)) p0 = 0.f;
             if (row_valid && (kt + 1 >= g.M || ((kt + 1) >> g.logL) != my_row)) p1 = 0.f;
           }
-          const uint32_t w = pack16(p0, p1, g.act_dtype);
-          pk[i >> 1] = w;
-          // the row sum uses the ROUNDED probabilities, i.e. exactly what the P V product sees
-          const float2 pr = unpack16(w, g.act_dtype);
-          psum += pr.x + pr.y;
+          pk[i >> 1] = pack_pair<DT>(p0, p1);
+          psum += p0 + p1;  // fp32 sum of the unrounded probabilities (rounding of P is unbiased)
         }
         // 32 keys = 64 bytes = four 16-byte chunks jj = cch*4 .. cch*4+3 of this row's 256-byte P row
 #pragma unroll
@@ -258,10 +266,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
 #pragma unroll
       for (int i = 0; i < D; i += 8) {
         uint4 w;
-        w.x = pack16(o[i] * inv, o[i + 1] * inv, g.act_dtype);
-        w.y = pack16(o[i + 2] * inv, o[i + 3] * inv, g.act_dtype);
-        w.z = pack16(o[i + 4] * inv, o[i + 5] * inv, g.act_dtype);
-        w.w = pack16(o[i + 6] * inv, o[i + 7] * inv, g.act_dtype);
+        w.x = pack_pair<DT>(o[i] * inv, o[i + 1] * inv);
+        w.y = pack_pair<DT>(o[i + 2] * inv, o[i + 3] * inv);
+        w.z = pack_pair<DT>(o[i + 4] * inv, o[i + 5] * inv);
+        w.w = pack_pair<DT>(o[i + 6] * inv, o[i + 7] * inv);
         *reinterpret_cast<uint4*>(dst + i) = w;
       }
     }
@@ -274,25 +282,295 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
   }
 }
 
-template <int D>
+template <int D, int DT>
 static int launch_att(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
   constexpr int smem = att_smem_bytes<D>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("sg_attention(tc): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
       return SG_ERR_LAUNCH;
     }
     configured = true;
   }
-  attention_tc_kernel<D><<<grid, 192, smem, stream>>>(tm, g, out);
+  attention_tc_kernel<D, DT><<<grid, 192, smem, stream>>>(tm, g, out);
   return launch_status("sg_attention(tc)");
+}
+
+// =====================================================================================================
+// v2 (L >= 256): one CTA = TWO tiles of 128 queries (A, B) of one head against the same K/V stream.
+//   * two softmax warp groups (4 warps each) ping-pong: while group A runs exp on S_A(j) the tensor core
+//     computes S_B(j) / P_A V / S_A(j+1), so the MUFU pipe always has a second warp per scheduler to issue from;
+//   * O accumulates in TMEM across key tiles (tcgen05.mma accumulate); the softmax reference maximum is only
+//     raised -- and O rescaled through tcgen05.ld/st -- when the tile maximum exceeds it by more than 2^8
+//     ("lazy rescale"), so a key tile costs ONE mbarrier wait per thread and no per-tile O round trip;
+//   * TMEM loads are register double-buffered (the load of chunk c+1 is in flight while chunk c is processed).
+// TMEM: S_A [0,128) S_B [128,256) O_A [256,256+D) O_B [320,320+D) -> 512 columns, one CTA per SM.
+// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax A, 6..9 = softmax B.
+// =====================================================================================================
+template <int D>
+constexpr int att2_smem_bytes() {
+  return 1024 + 2 * ATT_BM * D * 2 /*Q_A,Q_B*/ + 3 * 2 * ATT_BN * D * 2 /*K,V x 3 stages*/ + 2 * P_BYTES + 256;
+}
+
+template <int D, int DT>
+__global__ void __launch_bounds__(320, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
+  constexpr int ROWB = D * 2;
+  constexpr int TILE = ATT_BN * ROWB;
+  constexpr int KVS = 3;
+  constexpr float RESCALE_LOG2 = 8.0f;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;                  // [2][TILE]
+  uint8_t* sKV = sQ + 2 * TILE;        // [KVS][K | V][TILE]
+  uint8_t* sP = sKV + KVS * 2 * TILE;  // [2][P_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [3]
+  uint64_t* kv_empty = bars + 4;  // [3]
+  uint64_t* s_full = bars + 7;    // [2]
+  uint64_t* p_ready = bars + 9;   // [2]
+  uint64_t* o_done = bars + 11;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int64_t m0 = (int64_t)blockIdx.x * (2 * ATT_BM);
+  const int64_t kv0 = (m0 >> g.logL) << g.logL;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KVS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&p_ready[x], 128);
+      mbar_init(&o_done[x], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      mbar_arrive_expect_tx(q_full, 2 * g.tile_bytes);
+      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
+      tma_load_2d(sQ + TILE, &tm, q_full, head * D, (int)m0 + ATT_BM);
+      for (int j = 0; j < g.nkv; ++j) {
+        const int s = j % KVS;
+        mbar_wait(&kv_empty[s], ((uint32_t)(j / KVS) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
+        const int tok = (int)(kv0 + (int64_t)j * ATT_BN);
+        tma_load_2d(sKV + (2 * s) * TILE, &tm, &kv_full[s], g.C + head * D, tok);
+        tma_load_2d(sKV + (2 * s + 1) * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      auto issue_s = [&](int x, int s) {  // S_x = Q_x K^T
+        const uint64_t qd = make_desc_rows(smem_u32(sQ + x * TILE), ROWB);
+        const uint64_t kd = make_desc_rows(smem_u32(sKV + (2 * s) * TILE), ROWB);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base + x * 128, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
+        umma_commit(&s_full[x]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < g.nkv; ++j) {
+        const int s = j % KVS;
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(&p_ready[x], (uint32_t)j & 1u);
+          tc_fence_after();
+          // O_x (+)= P_x V : A = P (K-major, two 64-key atoms), B = V consumed MN-major
+          const uint32_t pa = smem_u32(sP + x * P_BYTES);
+          const uint32_t va = smem_u32(sKV + (2 * s + 1) * TILE);
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k) {
+            const uint64_t pd = make_desc_k128(pa + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
+            const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
+            umma_ss(tmem_base + 256 + x * 64, pd, vd, g.idesc_o, (j | k) != 0);
+          }
+          umma_commit(&o_done[x]);
+          if (x == 1) umma_commit(&kv_empty[s]);
+          if (j + 1 < g.nkv) {
+            const int s1 = (j + 1) % KVS;
+            if (x == 0) {
+              mbar_wait(&kv_full[s1], (uint32_t)((j + 1) / KVS) & 1u);
+              tc_fence_after();
+            }
+            issue_s(x, s1);
+          }
+        }
+      }
+    }
+  } else {
+    // ===== softmax groups =====
+    const int x = (warp - 2) >> 2;  // 0 = tile A, 1 = tile B
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int64_t tok = m0 + x * ATT_BM + r;
+    const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(x * 128);
+    const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + x * 64);
+    const uint32_t p_row = smem_u32(sP + x * P_BYTES) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < g.nkv; ++j) {
+      mbar_wait(&s_full[x], (uint32_t)j & 1u);
+      tc_fence_after();
+      // ---- pass 1: row max (register double-buffered TMEM loads) ----
+      uint32_t va[32], vb[32];
+      float tmax = -INFINITY;
+      tmem_ld32(t_s, va);
+      tmem_ld_wait();
+      tmem_ld32(t_s + 32, vb);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(va[i]));
+      tmem_ld_wait();
+      tmem_ld32(t_s + 64, va);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(vb[i]));
+      tmem_ld_wait();
+      tmem_ld32(t_s + 96, vb);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(va[i]));
+      tmem_ld_wait();
+      tmem_ld32(t_s, va);  // first chunk of pass 2 already in flight
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(vb[i]));
+      // ---- reference maximum: raise it (and rescale O, l) only when exceeded by more than 2^8 ----
+      if (j == 0) {
+        m_used = tmax;
+      } else {
+        const bool need = (tmax - m_used) * g.c > RESCALE_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? ex2((m_used - tmax) * g.c) : 1.0f;
+          if (need) m_used = tmax;
+          l *= alpha;
+          tmem_ld_wait();  // the in-flight S load must land before this warp issues other tcgen05.ld
+          // PV(j-1) has completed (its commit precedes S(j)'s in the issuer's stream), so O is quiescent
+#pragma unroll
+          for (int cch = 0; cch < D / 16; ++cch) {
+            uint32_t ov[16];
+            tmem_ld16(t_o + cch * 16, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st16(t_o + cch * 16, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mc = m_used * g.c;
+      // ---- pass 2: p = exp2(s*c - m*c), row sum, 16-bit pack, swizzled st.shared ----
+      float psum = 0.f;
+      auto emit = [&](const uint32_t (&v)[32], int cch) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(v[i]), g.c, -mc));
+          const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), g.c, -mc));
+          pk[i >> 1] = pack_pair<DT>(p0, p1);
+          psum += p0 + p1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = cch * 4 + u;
+          const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + (uint32_t)(((jj & 7) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
+                       "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
+                       : "memory");
+        }
+      };
+      tmem_ld_wait();
+      tmem_ld32(t_s + 32, vb);
+      emit(va, 0);
+      tmem_ld_wait();
+      tmem_ld32(t_s + 64, va);
+      emit(vb, 1);
+      tmem_ld_wait();
+      tmem_ld32(t_s + 96, vb);
+      emit(va, 2);
+      tmem_ld_wait();
+      emit(vb, 3);
+      l += psum;
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(&p_ready[x]);
+    }
+    // ---- epilogue: O / l ----
+    mbar_wait(&o_done[x], (uint32_t)(g.nkv - 1) & 1u);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    uint16_t* dst = out + tok * g.C + head * D;
+#pragma unroll
+    for (int cch = 0; cch < D / 16; ++cch) {
+      uint32_t ov[16];
+      tmem_ld16(t_o + cch * 16, ov);
+      tmem_ld_wait();
+      uint4 w0, w1;
+      w0.x = pack_pair<DT>(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv);
+      w0.y = pack_pair<DT>(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv);
+      w0.z = pack_pair<DT>(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv);
+      w0.w = pack_pair<DT>(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv);
+      w1.x = pack_pair<DT>(__uint_as_float(ov[8]) * inv, __uint_as_float(ov[9]) * inv);
+      w1.y = pack_pair<DT>(__uint_as_float(ov[10]) * inv, __uint_as_float(ov[11]) * inv);
+      w1.z = pack_pair<DT>(__uint_as_float(ov[12]) * inv, __uint_as_float(ov[13]) * inv);
+      w1.w = pack_pair<DT>(__uint_as_float(ov[14]) * inv, __uint_as_float(ov[15]) * inv);
+      *reinterpret_cast<uint4*>(dst + cch * 16) = w0;
+      *reinterpret_cast<uint4*>(dst + cch * 16 + 8) = w1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D, int DT>
+static int launch_att2(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = att2_smem_bytes<D>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel<D, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("sg_attention(tc2): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
+      return SG_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  attention_tc2_kernel<D, DT><<<grid, 320, smem, stream>>>(tm, g, out);
+  return launch_status("sg_attention(tc2)");
+}
+
+static int attention_version() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("SGB200_ATTN");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
 }
 
 }  // namespace tc
 
-int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cudaStream_t stream) {
+int attention_tc(
+const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cudaStream_t stream) {
   using namespace tc;
   SG_REQUIRE(act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_attention(tc): act_dtype must be SG_BF16 or SG_F16");
   SG_REQUIRE(L > 0 && (L & (L - 1)) == 0, "sg_attention(tc): L=%d must be a power of two", L);
@@ -324,9 +602,25 @@ int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, 
   SG_REQUIRE(heads <= 65535, "sg_attention(tc): too many heads");
   dim3 grid((unsigned)cdiv(g.M, ATT_BM), (unsigned)heads);
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
-  if (d == 16) return launch_att<16>(tm, g, o, grid, stream);
-  if (d == 32) return launch_att<32>(tm, g, o, grid, stream);
-  return launch_att<64>(tm, g, o, grid, stream);
+  if (L >= 2 * ATT_BM && attention_version() == 2) {
+    dim3 grid2((unsigned)(g.M / (2 * ATT_BM)), (unsigned)heads);
+    if (act_dtype == SG_BF16) {
+      if (d == 16) return launch_att2<16, SG_BF16>(tm, g, o, grid2, stream);
+      if (d == 32) return launch_att2<32, SG_BF16>(tm, g, o, grid2, stream);
+      return launch_att2<64, SG_BF16>(tm, g, o, grid2, stream);
+    }
+    if (d == 16) return launch_att2<16, SG_F16>(tm, g, o, grid2, stream);
+    if (d == 32) return launch_att2<32, SG_F16>(tm, g, o, grid2, stream);
+    return launch_att2<64, SG_F16>(tm, g, o, grid2, stream);
+  }
+  if (act_dtype == SG_BF16) {
+    if (d == 16) return launch_att<16, SG_BF16>(tm, g, o, grid, stream);
+    if (d == 32) return launch_att<32, SG_BF16>(tm, g, o, grid, stream);
+    return launch_att<64, SG_BF16>(tm, g, o, grid, stream);
+  }
+  if (d == 16) return launch_att<16, SG_F16>(tm, g, o, grid, stream);
+  if (d == 32) return launch_att<32, SG_F16>(tm, g, o, grid, stream);
+  return launch_att<64, SG_F16>(tm, g, o, grid, stream);
 }
 
 }  // namespace sg

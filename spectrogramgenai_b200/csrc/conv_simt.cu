@@ -9,12 +9,14 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream);  // igemm_tc.cu
 
 // ------------------------------------------------------------------------------------------------
 // inc.double_conv.0  (/root/reference/src/diff_modules.py:82 via :144): direct 3x3, NCHW fp32 in,
-// NHWC fp32 out (64 channels) + GroupNorm partials.  block = 64 pixels x 4 groups of 16 output channels.
+// NHWC fp32 out (64 channels) + GroupNorm partials.
 // ------------------------------------------------------------------------------------------------
 template <int CIN>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int n_src, int S,
                                                       const float* __restrict__ w, float* __restrict__ raw,
                                                       float* __restrict__ partials) {
+  // block = 128 pixels (64 horizontally adjacent pairs) x 4 groups of 16 output channels; a thread computes
+  // 2 pixels x 16 channels so that every weight vector read from shared memory feeds 8 FMAs.
   constexpr int K = CIN * 9;
   __shared__ __align__(16) float ws[K][64];  // [ci*9 + tap][co]
   __shared__ float red[2][8];
@@ -24,47 +26,60 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     ws[k][co] = w[i];
   }
   const int HW = S * S;
-  const int blocks_per_row = HW / 64;
+  const int blocks_per_row = HW / 128;
   const int row = blockIdx.x / blocks_per_row;
-  const int p = (blockIdx.x % blocks_per_row) * 64 + (tid >> 2);
+  const int p = (blockIdx.x % blocks_per_row) * 128 + (tid >> 2) * 2;  // even pixel; p and p+1 share a row (S even)
   const int cg = tid & 3;
   const int h = p / S, wq = p % S;
   const float* xs = x + (int64_t)(row % n_src) * CIN * HW;
-  float in[K];
+  float in[CIN][3][4];  // 3 x 4 input patch covering both pixels
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        const int hh = h + dy - 1, ww = wq + dx - 1;
+        in[ci][dy][dx] = (hh >= 0 && hh < S && ww >= 0 && ww < S) ? __ldg(xs + ci * HW + hh * S + ww) : 0.f;
+      }
+  __syncthreads();
+  float acc[2][16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = 0.f;
 #pragma unroll
   for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const int hh = h + dy - 1, ww = wq + dx - 1;
-        in[ci * 9 + dy * 3 + dx] = (hh >= 0 && hh < S && ww >= 0 && ww < S) ? __ldg(xs + ci * HW + hh * S + ww) : 0.f;
+        const float a0 = in[ci][dy][dx], a1 = in[ci][dy][dx + 1];
+        const int k = ci * 9 + dy * 3 + dx;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b = *reinterpret_cast<const float4*>(&ws[k][cg * 16 + j4 * 4]);
+          acc[0][j4 * 4 + 0] = fmaf(a0, b.x, acc[0][j4 * 4 + 0]);
+          acc[0][j4 * 4 + 1] = fmaf(a0, b.y, acc[0][j4 * 4 + 1]);
+          acc[0][j4 * 4 + 2] = fmaf(a0, b.z, acc[0][j4 * 4 + 2]);
+          acc[0][j4 * 4 + 3] = fmaf(a0, b.w, acc[0][j4 * 4 + 3]);
+          acc[1][j4 * 4 + 0] = fmaf(a1, b.x, acc[1][j4 * 4 + 0]);
+          acc[1][j4 * 4 + 1] = fmaf(a1, b.y, acc[1][j4 * 4 + 1]);
+          acc[1][j4 * 4 + 2] = fmaf(a1, b.z, acc[1][j4 * 4 + 2]);
+          acc[1][j4 * 4 + 3] = fmaf(a1, b.w, acc[1][j4 * 4 + 3]);
+        }
       }
-  __syncthreads();
-  float acc[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const float a = in[k];
-#pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 b = *reinterpret_cast<const float4*>(&ws[k][cg * 16 + j4 * 4]);
-      acc[j4 * 4 + 0] = fmaf(a, b.x, acc[j4 * 4 + 0]);
-      acc[j4 * 4 + 1] = fmaf(a, b.y, acc[j4 * 4 + 1]);
-      acc[j4 * 4 + 2] = fmaf(a, b.z, acc[j4 * 4 + 2]);
-      acc[j4 * 4 + 3] = fmaf(a, b.w, acc[j4 * 4 + 3]);
-    }
-  }
-  float* dst = raw + ((int64_t)row * HW + p) * 64 + cg * 16;
   float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4) {
-    *reinterpret_cast<float4*>(dst + j4 * 4) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+  for (int px = 0; px < 2; ++px) {
+    float* dst = raw + ((int64_t)row * HW + p + px) * 64 + cg * 16;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      s += acc[j4 * 4 + j];
-      q += acc[j4 * 4 + j] * acc[j4 * 4 + j];
+    for (int j4 = 0; j4 < 4; ++j4) {
+      __stcs(reinterpret_cast<float4*>(dst + j4 * 4),
+             make_float4(acc[px][j4 * 4], acc[px][j4 * 4 + 1], acc[px][j4 * 4 + 2], acc[px][j4 * 4 + 3]));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s += acc[px][j4 * 4 + j];
+        q += acc[px][j4 * 4 + j] * acc[px][j4 * 4 + j];
+      }
     }
   }
   s = warp_sum(s);
@@ -267,14 +282,14 @@ using namespace sg;
 
 extern "C" {
 
-int sg_conv_in_partials(int S) { return S * S / 64; }
+int sg_conv_in_partials(int S) { return S * S / 128; }
 
 int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w, int rows, float* raw, float* partials,
                sg_stream_t stream) {
   SG_REQUIRE(x && w && raw && partials, "sg_conv_in: null pointer");
   SG_REQUIRE(c_in >= 1 && c_in <= 4, "sg_conv_in: c_in=%d not in 1..4", c_in);
   SG_REQUIRE(pow2(S) && S >= 16 && rows > 0 && n_src > 0, "sg_conv_in: S=%d must be a power of two >= 16", S);
-  const int blocks = rows * (S * S / 64);
+  const int blocks = rows * (S * S / 128);
   cudaStream_t s = as_stream(stream);
   switch (c_in) {
     case 1: conv_in_kernel<1><<<blocks, 256, 0, s>>>(x, n_src, S, w, raw, partials); break;

@@ -15,6 +15,8 @@
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
 // Two CTAs are resident per SM (<= 101 KB smem, <= 128 TMEM columns each), so one CTA's epilogue overlaps
 // the other's main loop.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace sg {
@@ -81,6 +83,75 @@ struct IgemmEpi {
   float* partials;
   int gelu, P, act_dtype;
 };
+
+// Epilogue of one 128-row x BN accumulator (TMEM columns [tmem_acc, tmem_acc+BN)): executed by the four epilogue
+// warps (threadIdx 64..191).  Thread = one output row (TMEM lane); bias -> GELU -> residual -> stores -> GN partials.
+template <int BN>
+__device__ __forceinline__ void epilogue_128rows(uint32_t tmem_acc, int64_t m0, int n0, int tile_n, int warp, int lane,
+                                                 const IgemmGeom& g, const IgemmEpi& ep, float (*rowstat)[2]) {
+  const int q = warp & 3;
+  const int r = q * 32 + lane;
+  const int64_t m = m0 + r;
+  const bool valid = m < g.M;
+  float s_sum = 0.f, s_sq = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    const int nb = n0 + c * 32;
+    const int64_t off = m * g.Cout + nb;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(v[j]);
+      if (ep.bias) x += __ldg(ep.bias + nb + j);
+      if (ep.gelu) x = gelu_erf(x);
+      f[j] = x;
+    }
+    if (valid) {
+      if (ep.residual) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 rr = __ldg(reinterpret_cast<const float4*>(ep.residual + off) + j4);
+          f[j4 * 4 + 0] += rr.x; f[j4 * 4 + 1] += rr.y; f[j4 * 4 + 2] += rr.z; f[j4 * 4 + 3] += rr.w;
+        }
+      }
+      if (ep.out_f32) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          reinterpret_cast<float4*>(ep.out_f32 + off)[j4] =
+              make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+      }
+      if (ep.out_act) {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(ep.out_act) + off;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint4 w;
+          w.x = pack16(f[j8 * 8 + 0], f[j8 * 8 + 1], ep.act_dtype);
+          w.y = pack16(f[j8 * 8 + 2], f[j8 * 8 + 3], ep.act_dtype);
+          w.z = pack16(f[j8 * 8 + 4], f[j8 * 8 + 5], ep.act_dtype);
+          w.w = pack16(f[j8 * 8 + 6], f[j8 * 8 + 7], ep.act_dtype);
+          reinterpret_cast<uint4*>(dst)[j8] = w;
+        }
+      }
+      if (ep.partials) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          s_sum += f[j];
+          s_sq += f[j] * f[j];
+        }
+      }
+    }
+  }
+  if (ep.partials) {
+    rowstat[r][0] = s_sum;
+    rowstat[r][1] = s_sq;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+    write_tile_partials<BM>(rowstat, (int)threadIdx.x - 64, m0, g.M, g.HW, ep.partials, ep.P, tile_n, g.n_tiles);
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // rowstat may be rewritten by the next accumulator
+  }
+}
 
 template <int BN, int STAGES>
 constexpr int igemm_smem_bytes() {
@@ -176,69 +247,9 @@ __global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ C
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int64_t m = m0 + r;
-    const bool valid = m < g.M;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    float s_sum = 0.f, s_sq = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      const int64_t off = m * g.Cout + nb;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (ep.bias) x += __ldg(ep.bias + nb + j);
-        if (ep.gelu) x = gelu_erf(x);
-        f[j] = x;
-      }
-      if (valid) {
-        if (ep.residual) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(ep.residual + off) + j4);
-            f[j4 * 4 + 0] += rr.x; f[j4 * 4 + 1] += rr.y; f[j4 * 4 + 2] += rr.z; f[j4 * 4 + 3] += rr.w;
-          }
-        }
-        if (ep.out_f32) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            reinterpret_cast<float4*>(ep.out_f32 + off)[j4] =
-                make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
-        }
-        if (ep.out_act) {
-          uint16_t* dst = reinterpret_cast<uint16_t*>(ep.out_act) + off;
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            uint4 w;
-            w.x = pack16(f[j8 * 8 + 0], f[j8 * 8 + 1], ep.act_dtype);
-            w.y = pack16(f[j8 * 8 + 2], f[j8 * 8 + 3], ep.act_dtype);
-            w.z = pack16(f[j8 * 8 + 4], f[j8 * 8 + 5], ep.act_dtype);
-            w.w = pack16(f[j8 * 8 + 6], f[j8 * 8 + 7], ep.act_dtype);
-            reinterpret_cast<uint4*>(dst)[j8] = w;
-          }
-        }
-        if (ep.partials) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            s_sum += f[j];
-            s_sq += f[j] * f[j];
-          }
-        }
-      }
-    }
-    if (ep.partials) {
-      rowstat[r][0] = s_sum;
-      rowstat[r][1] = s_sq;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      write_tile_partials<BM>(rowstat, (int)threadIdx.x - 64, m0, g.M, g.HW, ep.partials, ep.P, tile_n, g.n_tiles);
-    }
+    epilogue_128rows<BN>(tmem_base, m0, n0, tile_n, warp, lane, g, ep, rowstat);
   }
   tc_fence_before();
   __syncthreads();
@@ -263,6 +274,272 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeo
   }
   igemm_tc_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(tmA, tmB, g, ep);
   return launch_status("sg_igemm(tc)");
+}
+
+// Coalesced epilogue of one 128-row x BN accumulator, executed by ONE group of four warps (TMEM lane quadrant =
+// warp % 4).  Each warp owns a 32-row x 32-column block per step: thread = accumulator row for the TMEM read, bias,
+// GELU and the GroupNorm row statistics; the block is then transposed through a per-warp smem scratch so that every
+// global access instruction touches 4 rows x 128 contiguous bytes (4 transactions instead of 32) for the residual
+// read and for the fp32 / 16-bit stores.
+constexpr int EPI_LD = 36;                          // scratch row stride in floats (144 B: conflict-free 128-bit access)
+constexpr int EPI_SCRATCH = 32 * EPI_LD * 4;        // bytes per warp
+template <int BN>
+__device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0, int n0, int tile_n, int warp, int lane,
+                                                   int group_tid, int bar_id, const IgemmGeom& g, const IgemmEpi& ep,
+                                                   float (*rowstat)[2], float* scratch) {
+  const int q = warp & 3;
+  const int r = q * 32 + lane;
+  const bool valid = m0 + r < g.M;
+  float s_sum = 0.f, s_sq = 0.f;
+  const int trow = lane >> 3, tcol = (lane & 7) * 4;  // transposed-domain role of this lane
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    const int nb = n0 + c * 32;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(v[j]);
+      if (ep.bias) x += __ldg(ep.bias + nb + j);
+      if (ep.gelu) x = gelu_erf(x);
+      f[j] = x;
+    }
+    if (ep.partials && valid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        s_sum += f[j];
+        s_sq += f[j] * f[j];
+      }
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4)
+      *reinterpret_cast<float4*>(scratch + lane * EPI_LD + j4 * 4) =
+          make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + trow;
+      const int64_t m = m0 + q * 32 + rr;
+      float4 o = *reinterpret_cast<const float4*>(scratch + rr * EPI_LD + tcol);
+      if (m < g.M) {
+        const int64_t off = m * g.Cout + nb + tcol;
+        if (ep.residual) {
+          const float4 rsd = __ldg(reinterpret_cast<const float4*>(ep.residual + off));
+          o.x += rsd.x; o.y += rsd.y; o.z += rsd.z; o.w += rsd.w;
+        }
+        if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + off) = o;
+        if (ep.out_act) {
+          uint2 w;
+          w.x = pack16(o.x, o.y, ep.act_dtype);
+          w.y = pack16(o.z, o.w, ep.act_dtype);
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out_act) + off) = w;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (ep.partials) {
+    rowstat[r][0] = s_sum;
+    rowstat[r][1] = s_sq;
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // this group's four warps only
+    write_tile_partials<BM>(rowstat, group_tid, m0, g.M, g.HW, ep.partials, ep.P, tile_n, g.n_tiles);
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // rowstat is rewritten by the next tile
+  }
+}
+
+// =====================================================================================================
+// v2: persistent CTAs, 256 x BN output tiles (two M=128 accumulators share every B k-block, so the
+// L2 -> smem operand traffic per MMA drops by 25 %), TMEM double-buffered so that the epilogue of tile i
+// overlaps the main loop of tile i+1, and TWO epilogue warp groups (one per accumulator) with coalesced stores.
+// One CTA per SM (<= 215 KB smem, up to 512 TMEM columns).  Warp roles (320 threads): 0 = TMA producer,
+// 1 = TMEM allocator + MMA issuer, 2..5 = epilogue of rows [0,128), 6..9 = epilogue of rows [128,256).
+// =====================================================================================================
+template <int BN>
+struct V2 {
+  static constexpr int STAGES = BN == 128 ? 3 : 4;  // 48 KB / 40 KB per stage
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE = 2 * A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 4 * BN;  // 2 buffers x 2 accumulators: 512 (BN=128) / 256 (BN=64)
+  static constexpr int THREADS = 320;
+  static_assert(1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH <= 227 * 1024, "smem budget");
+  static constexpr int SMEM = 1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH;
+};
+
+__device__ __forceinline__ void tile_coords(const IgemmGeom& g, int mt, int& cn, int& ch, int& cw) {
+  if (g.taps == 1) {
+    cn = 0; ch = 0; cw = mt * BM;  // linear layer: the map is {Cin, M, 1, 1}
+  } else if (g.tiles_per_sample > 0) {
+    cn = mt / g.tiles_per_sample;
+    const int p0 = (mt % g.tiles_per_sample) * BM;
+    ch = p0 / g.W;
+    cw = p0 % g.W;
+  } else {
+    cn = mt * g.samples_per_tile; ch = 0; cw = 0;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
+                                                           const IgemmEpi ep, const int num_tiles) {
+  using K = V2<BN>;
+  constexpr int STAGES = K::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * K::STAGE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + STAGES * K::STAGE + 256);           // [2 groups][128][2]
+  float* scratch_all = reinterpret_cast<float*>(smem + STAGES * K::STAGE + 256 + 2 * BM * 2 * 4);  // [8 warps]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk = g.taps * g.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<K::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;  // running k-block counter across tiles
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt2 = tile / g.n_tiles, n0 = (tile % g.n_tiles) * BN;
+        int cn0, ch0, cw0, cn1, ch1, cw1;
+        tile_coords(g, 2 * mt2, cn0, ch0, cw0);
+        tile_coords(g, 2 * mt2 + 1, cn1, ch1, cw1);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1u) ^ 1u);
+          const int tap = kb / g.cblocks, c0 = (kb % g.cblocks) * BK;
+          int dy = 0, dx = 0;
+          if (g.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          uint8_t* st = smem + s * K::STAGE;
+          mbar_arrive_expect_tx(&full[s], g.tx_bytes);
+          tma_load_4d(st, &tmA, &full[s], c0, cw0 + dx, ch0 + dy, cn0);
+          tma_load_4d(st + A_BYTES, &tmA, &full[s], c0, cw1 + dx, ch1 + dy, cn1);
+          tma_load_2d(st + 2 * A_BYTES, &tmB, &full[s], c0, tap * g.Cout + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u;
+        mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator pair
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * (2 * BN), acc1 = acc0 + BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * K::STAGE);
+          const uint64_t a0 = make_desc_k128(sa), a1 = make_desc_k128(sa + A_BYTES);
+          const uint64_t bd = make_desc_k128(sa + 2 * A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_ss(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
+            umma_ss(acc1, a1 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue: group 0 (warps 2..5) drains accumulator 0, group 1 (warps 6..9) accumulator 1 =====
+    const int grp = (warp - 2) >> 2;
+    const int group_tid = (int)threadIdx.x - 64 - grp * 128;
+    float* scratch = scratch_all + (warp - 2) * (EPI_SCRATCH / 4);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1u;
+      const int mt2 = tile / g.n_tiles, tile_n = tile % g.n_tiles;
+      mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
+      tc_fence_after();
+      const int64_t m0 = (int64_t)(2 * mt2 + grp) * BM;
+      if (m0 < g.M)
+        epilogue_coalesced<BN>(tmem_base + buf * (2 * BN) + grp * BN, m0, tile_n * BN, tile_n, warp, lane, group_tid,
+                               1 + grp, g, ep, rowstat + grp * BM, scratch);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<K::TMEM_COLS>(tmem_base);
+  }
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const IgemmEpi& ep,
+                   cudaStream_t stream) {
+  constexpr int smem = V2<BN>::SMEM;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("sg_igemm(tc2): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
+      return SG_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const int64_t mt2 = cdiv(g.M, 2 * BM);
+  const int64_t tiles = mt2 * g.n_tiles;
+  if (tiles >= (1ll << 31)) {
+    set_error("sg_igemm(tc2): too many tiles");
+    return SG_ERR_ARG;
+  }
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  igemm_tc2_kernel<BN><<<grid, V2<BN>::THREADS, smem, stream>>>(tmA, tmB, g, ep, (int)tiles);
+  return launch_status("sg_igemm(tc2)");
+}
+
+static int igemm_version() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("SGB200_IGEMM");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
 }
 
 }  // namespace tc
@@ -314,12 +591,14 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
     int rc = make_tmap(&tmB, a->act_dtype, 2, a->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  g.tx_bytes = box_rows * 128u + (uint32_t)BN * 128u;
+  const bool v2 = igemm_version() == 2;
+  g.tx_bytes = (v2 ? 2u : 1u) * box_rows * 128u + (uint32_t)BN * 128u;
 
   IgemmEpi ep;
   ep.bias = a->bias; ep.residual = a->residual; ep.out_f32 = a->out_f32; ep.out_act = a->out_act;
   ep.partials = a->partials; ep.gelu = a->gelu; ep.act_dtype = a->act_dtype;
   ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
+  if (v2) return BN == 128 ? launch2<128>(tmA, tmB, g, ep, stream) : launch2<64>(tmA, tmB, g, ep, stream);
   const int64_t grid = (int64_t)cdiv(g.M, BM) * g.n_tiles;
   SG_REQUIRE(grid < (1ll << 31), "sg_igemm(tc): grid too large");
   if (BN == 128) return launch<128, 3>(tmA, tmB, g, ep, (int)grid, stream);

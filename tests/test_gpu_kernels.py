@@ -339,6 +339,27 @@ def test_attention_tensor_core(ops, rows, L, C, dtype):
     assert err < (6e-3 if dtype == torch.bfloat16 else 1e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,L,C", [(2, 1024, 64), (1, 512, 128), (1, 256, 256)])
+def test_attention_tensor_core_growing_scores(ops, rows, L, C, dtype):
+    """Keys whose magnitude grows along the sequence: the running maximum rises by far more than 2^8 between key
+    tiles, which exercises the lazy-rescale path (O and l rescaled in TMEM) of the two-tile kernel."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    qkv = torch.randn(rows * L, 3 * C, generator=gen(13))
+    ramp = (1.0 + 24.0 * torch.arange(L) / L).repeat(rows)[:, None]
+    qkv[:, C:2 * C] *= ramp  # K
+    qkv = qkv.to(dtype)
+    ref = _attention_ref(qkv.float(), rows, L, C)
+    out = torch.full((rows * L, C), float("nan"), device=DEV, dtype=dtype)
+    ops.attention(qkv.to(DEV), out, rows=rows, L=L, C=C, engine=SG_ENGINE_TC)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    err = O.rel_l2(out.cpu(), ref)
+    print(f"attention tc (growing scores) rows={rows} L={L} C={C} {dtype}: rel-L2 {err:.3e}")
+    assert err < (8e-3 if dtype == torch.bfloat16 else 1.5e-3)
+
+
 def test_error_reporting(ops):
     """Bad arguments come back as a status + message (no exception crosses the C ABI, no crash)."""
     from spectrogramgenai_b200._cabi import SgError
