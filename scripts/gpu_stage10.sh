@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== attention kernel tests"; timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -s -k "attention_tensor_core" 2>&1 | grep -E "rel-L2|passed|failed|Error|error" | tail -32
+for p in 0 4 2; do echo "=== microbench attention poly=$p"; SGB200_ATTN_POLY=$p python scripts/prof_kernels.py attention 128 2>&1 | tail -3; done
+echo "=== poly=2 accuracy"; SGB200_ATTN_POLY=2 timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -s -k "attention_tensor_core" 2>&1 | grep -E "passed|failed" | tail -3
+echo "=== model 16-bit"; timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q -s -k "bf16 or f16 or philox" 2>&1 | grep -E "eps rel|traj|passed|failed|Error" | tail -24
+echo "=== bench"; timeout 1200 python bench.py --no-cpu-baseline > gpurun_out/bench_r1_i.json 2> gpurun_out/bench_r1_i.err; echo rc=$?; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_r1_i.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])
+for k,v in list(d['kernels'].items())[:5]: print(k, v)
+PY
+tail -3 gpurun_out/bench_r1_i.err

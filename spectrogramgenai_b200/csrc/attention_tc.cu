@@ -55,22 +55,37 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel. error 7.5e-5 -- far below
+// the 2^-9 / 2^-12 rounding P receives anyway).  Used for a fraction of the elements so that the MUFU pipe
+// (16 ex2 / clk / SM), which bounds d = 16 attention, is not the only unit producing probabilities.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05517145f, 0.24261084f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992812f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 struct AttGeom {
   int64_t M;          // rows * L tokens
   int L, logL, C, heads;
   int nkv;            // key tiles per query tile
   float c;            // softmax scale * log2(e)
   uint32_t tile_bytes;  // bytes of one TMA box (d*2 * min(128, M))
-  uint32_t idesc_s, idesc_o;
+  uint32_t idesc_s, idesc_o, idesc_1;
   int act_dtype;
+  float redo_log2;  // largest tolerated (tile max - reference max) * c before the tile is recomputed
 };
 
+constexpr int ONES_BYTES = 2048;  // a [16 x 64] 16-bit K-major tile of 1.0: B operand of the row-sum MMA
 template <int D>
 constexpr int att_smem_bytes() {
-  return 1024 + ATT_BM * D * 2 /*Q*/ + 2 * 2 * ATT_BN * D * 2 /*K,V x 2 stages*/ + P_BYTES + 256;
+  return 1024 + ATT_BM * D * 2 /*Q*/ + 2 * 2 * ATT_BN * D * 2 /*K,V x 2 stages*/ + P_BYTES + ONES_BYTES + 256;
 }
 
-template <int D, int DT>
+template <int D, int DT, int POLY>
 __global__ void __launch_bounds__(192, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
   constexpr int ROWB = D * 2;              // bytes per token row of a head slice = the swizzle span
@@ -82,7 +97,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
   uint8_t* sK = sQ + TILE;        // [2 stages]
   uint8_t* sV = sK + 2 * TILE;    // [2 stages]
   uint8_t* sP = sV + 2 * TILE;    // 1024-aligned: TILE is a multiple of 4096
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint8_t* sOnes = sP + P_BYTES;  // 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -111,6 +127,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<128>(tmem_slot);
+  {
+    const uint32_t one2 = DT == SG_BF16 ? 0x3F803F80u : 0x3C003C00u;  // two 1.0 values
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = one2;
+    fence_proxy_async();
+  }
   if (g.M < ATT_BM) {
     // tiny problems: the TMA box is clamped to M rows, so clear the tiles once (0 * stale-NaN would poison P V)
     for (int i = threadIdx.x; i < 5 * TILE / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -128,7 +149,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
       tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
       for (int j = 0; j < g.nkv; ++j) {
         const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        mbar_wait_spin(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
         const int tok = (int)(kv0 + (int64_t)j * ATT_BN);
         tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
@@ -138,11 +159,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      mbar_wait(q_full, 0);
+      mbar_wait_spin(q_full, 0);
       for (int j = 0; j < g.nkv; ++j) {
         const int s = j & 1;
-        mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
-        if (j > 0) mbar_wait(o_read, (uint32_t)(j - 1) & 1u);  // O_{j-1} (aliasing S) has been consumed
+        mbar_wait_spin(&kv_full[s], (uint32_t)(j >> 1) & 1u);
+        if (j > 0) mbar_wait_spin(o_read, (uint32_t)(j - 1) & 1u);  // O_{j-1} (aliasing S) has been consumed
         tc_fence_after();
         // S = Q K^T : K-major A and B, K = D in steps of 16 (32 bytes inside the swizzle span)
         const uint64_t qd = make_desc_rows(smem_u32(sQ), ROWB);
@@ -151,7 +172,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
         for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
         umma_commit(s_full);
         // O_j = P V : A = P (K-major, two 64-key SWIZZLE_128B atoms), B = V consumed MN-major (d contiguous)
-        mbar_wait(p_ready, (uint32_t)j & 1u);
+        mbar_wait_spin(p_ready, (uint32_t)j & 1u);
         tc_fence_after();
         const uint32_t pa = smem_u32(sP);
         const uint32_t va = smem_u32(sV + s * TILE);
@@ -160,6 +181,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
           const uint64_t pd = make_desc_k128(pa + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
           const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
           umma_ss(tmem_base, pd, vd, g.idesc_o, k != 0);
+        }
+        // row sums on the tensor core: [P . 1] into the 16 columns after O_j (every column = sum_k P[row, k],
+        // taken over the ROUNDED probabilities, i.e. exactly what P V used)
+        const uint64_t od = make_desc_k128(smem_u32(sOnes));
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k) {
+          const uint64_t pd = make_desc_k128(pa + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
+          umma_ss(tmem_base + D, pd, od + 2 * (k & 3), g.idesc_1, k != 0);
         }
         umma_commit(&kv_empty[s]);
         umma_commit(o_full);
@@ -177,76 +206,86 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
     float o[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) o[i] = 0.f;
-    float mx = -INFINITY, l = 0.f;
+    float m_ref = -INFINITY, l = 0.f;  // reference maximum of the exponent; running row sum (relative to m_ref)
     const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
     for (int j = 0; j < g.nkv; ++j) {
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
       const int64_t key0 = kv0 + (int64_t)j * ATT_BN;
-      // ---- pass 1: row max ----
-      float tmax = -INFINITY;
+      // ---- ONE sweep over S: p = exp2(s*c - m_ref*c) against the maximum known BEFORE this tile, and the tile
+      // maximum as a by-product.  Exact algebra (o, l are rescaled afterwards); the sweep is only repeated when the
+      // tile maximum exceeds the reference by more than redo_log2 (overflow guard; always on the first tile).
+      float tmax;
+      bool redo;
+      do {
+        const float mc = m_ref * g.c;
+        tmax = -INFINITY;
 #pragma unroll 1
-      for (int cch = 0; cch < 4; ++cch) {
-        uint32_t v[32];
-        tmem_ld32(t_row + cch * 32, v);
-        tmem_ld_wait();
+        for (int cch = 0; cch < 4; ++cch) {
+          uint32_t v[32];
+          tmem_ld32(t_row + cch * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sv = __uint_as_float(v[i]);
-          if (masked) {
-            const int64_t kt = key0 + cch * 32 + i;
-            if (row_valid && (kt >= g.M || (kt >> g.logL) != my_row)) sv = -INFINITY;
+          for (int i = 0; i < 32; i += 2) {
+            float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+            bool k0 = true, k1 = true;
+            if (masked) {
+              const int64_t kt = key0 + cch * 32 + i;
+              k0 = !(row_valid && (kt >= g.M || (kt >> g.logL) != my_row));
+              k1 = !(row_valid && (kt + 1 >= g.M || ((kt + 1) >> g.logL) != my_row));
+              if (!k0) s0 = -INFINITY;
+              if (!k1) s1 = -INFINITY;
+            }
+            tmax = fmaxf(tmax, fmaxf(s0, s1));
+            float p0, p1;
+            if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+              p0 = ex2_poly(fmaf(s0, g.c, -mc));
+              p1 = ex2_poly(fmaf(s1, g.c, -mc));
+            } else {
+              p0 = ex2(fmaf(s0, g.c, -mc));
+              p1 = ex2(fmaf(s1, g.c, -mc));
+            }
+            if (masked) {
+              if (!k0) p0 = 0.f;
+              if (!k1) p1 = 0.f;
+            }
+            pk[i >> 1] = pack_pair<DT>(p0, p1);
           }
-          tmax = fmaxf(tmax, sv);
-        }
-      }
-      const float m_new = fmaxf(mx, tmax);
-      const float alpha = ex2((mx - m_new) * g.c);  // first tile: ex2(-inf) = 0
-      const float mc = m_new * g.c;
-      // ---- pass 2: p = exp2(s*c - m*c), row sum, pack to 16-bit, swizzled st.shared ----
-      float psum = 0.f;
-#pragma unroll 1
-      for (int cch = 0; cch < 4; ++cch) {
-        uint32_t v[32];
-        tmem_ld32(t_row + cch * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+          // 32 keys = 64 bytes = four 16-byte chunks jj = cch*4 .. cch*4+3 of this row's 256-byte P row
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-          float p0 = ex2(fmaf(s0, g.c, -mc)), p1 = ex2(fmaf(s1, g.c, -mc));
-          if (masked) {
-            const int64_t kt = key0 + cch * 32 + i;
-            if (row_valid && (kt >= g.M || (kt >> g.logL) != my_row)) p0 = 0.f;
-            if (row_valid && (kt + 1 >= g.M || ((kt + 1) >> g.logL) != my_row)) p1 = 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const int jj = cch * 4 + u;
+            const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + (uint32_t)(((jj & 7) ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
+                         "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
+                         : "memory");
           }
-          pk[i >> 1] = pack_pair<DT>(p0, p1);
-          psum += p0 + p1;  // fp32 sum of the unrounded probabilities (rounding of P is unbiased)
         }
-        // 32 keys = 64 bytes = four 16-byte chunks jj = cch*4 .. cch*4+3 of this row's 256-byte P row
+        const bool over = (tmax - m_ref) * g.c > g.redo_log2;  // also true while m_ref == -inf
+        redo = __any_sync(0xffffffffu, over);
+        if (over) {
+          const float a0 = ex2((m_ref - tmax) * g.c);  // 0 on the first tile
+          l *= a0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int jj = cch * 4 + u;
-          const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + (uint32_t)(((jj & 7) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                       "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                       : "memory");
+          for (int i = 0; i < D; ++i) o[i] *= a0;
+          m_ref = tmax;
         }
-      }
-      l = l * alpha + psum;
-      mx = m_new;
+      } while (redo);
       tc_fence_before();    // our tcgen05.ld of S precede the MMA that overwrites those columns
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(p_ready);
-      // ---- O_j ----
+      // ---- O_j and the row sum, both relative to m_ref ----
       mbar_wait(o_full, (uint32_t)j & 1u);
       tc_fence_after();
+      float psum;
       if constexpr (D == 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row, v);
+        uint32_t v[32];
+        tmem_ld32(t_row, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
+        for (int i = 0; i < 16; ++i) o[i] += __uint_as_float(v[i]);
+        psum = __uint_as_float(v[16]);
       } else {
 #pragma unroll
         for (int cch = 0; cch < D / 32; ++cch) {
@@ -254,11 +293,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
           tmem_ld32(t_row + cch * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[cch * 32 + i] = fmaf(o[cch * 32 + i], alpha, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) o[cch * 32 + i] += __uint_as_float(v[i]);
         }
+        uint32_t v[16];
+        tmem_ld16(t_row + D, v);
+        tmem_ld_wait();
+        psum = __uint_as_float(v[0]);
       }
+      l += psum;
       tc_fence_before();
       mbar_arrive(o_read);
+      // ---- raise the reference to the new running maximum (exact rescale of o, l) ----
+      if (tmax > m_ref) {
+        const float a1 = ex2((m_ref - tmax) * g.c);
+        l *= a1;
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] *= a1;
+        m_ref = tmax;
+      }
     }
     if (row_valid) {
       const float inv = 1.0f / l;
@@ -282,19 +334,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
   }
 }
 
-template <int D, int DT>
+template <int D, int DT, int POLY>
 static int launch_att(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
   constexpr int smem = att_smem_bytes<D>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D, DT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("sg_attention(tc): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
       return SG_ERR_LAUNCH;
     }
     configured = true;
   }
-  attention_tc_kernel<D, DT><<<grid, 192, smem, stream>>>(tm, g, out);
+  attention_tc_kernel<D, DT, POLY><<<grid, 192, smem, stream>>>(tm, g, out);
   return launch_status("sg_attention(tc)");
 }
 
@@ -369,7 +421,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
       tma_load_2d(sQ + TILE, &tm, q_full, head * D, (int)m0 + ATT_BM);
       for (int j = 0; j < g.nkv; ++j) {
         const int s = j % KVS;
-        mbar_wait(&kv_empty[s], ((uint32_t)(j / KVS) & 1u) ^ 1u);
+        mbar_wait_spin(&kv_empty[s], ((uint32_t)(j / KVS) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
         const int tok = (int)(kv0 + (int64_t)j * ATT_BN);
         tma_load_2d(sKV + (2 * s) * TILE, &tm, &kv_full[s], g.C + head * D, tok);
@@ -386,15 +438,15 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
         for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base + x * 128, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
         umma_commit(&s_full[x]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      mbar_wait_spin(q_full, 0);
+      mbar_wait_spin(&kv_full[0], 0);
       tc_fence_after();
       issue_s(0, 0);
       issue_s(1, 0);
       for (int j = 0; j < g.nkv; ++j) {
         const int s = j % KVS;
         for (int x = 0; x < 2; ++x) {
-          mbar_wait(&p_ready[x], (uint32_t)j & 1u);
+          mbar_wait_spin(&p_ready[x], (uint32_t)j & 1u);
           tc_fence_after();
           // O_x (+)= P_x V : A = P (K-major, two 64-key atoms), B = V consumed MN-major
           const uint32_t pa = smem_u32(sP + x * P_BYTES);
@@ -410,7 +462,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
           if (j + 1 < g.nkv) {
             const int s1 = (j + 1) % KVS;
             if (x == 0) {
-              mbar_wait(&kv_full[s1], (uint32_t)((j + 1) / KVS) & 1u);
+              mbar_wait_spin(&kv_full[s1], (uint32_t)((j + 1) / KVS) & 1u);
               tc_fence_after();
             }
             issue_s(x, s1);
@@ -558,11 +610,22 @@ static int launch_att2(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, d
   return launch_status("sg_attention(tc2)");
 }
 
+// fraction of exponentials evaluated by the FMA-pipe polynomial: SGB200_ATTN_POLY = 0 (none), 4 (1/4), 2 (1/2)
+static int attention_poly() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SGB200_ATTN_POLY");
+    v = e ? atoi(e) : 4;
+    if (v != 0 && v != 2 && v != 4) v = 0;
+  }
+  return v;
+}
+
 static int attention_version() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("SGB200_ATTN");
-    v = (e && e[0] == '1') ? 1 : 2;
+    v = (e && e[0] == '2') ? 2 : 1;  // v1 (4 CTAs/SM) measured faster than the two-tile kernel on B200
   }
   return v;
 }
@@ -591,6 +654,8 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
   g.tile_bytes = box_rows * (uint32_t)d * 2u;
   g.idesc_s = make_idesc(act_dtype, 128, ATT_BN, 0, 0);
   g.idesc_o = make_idesc(act_dtype, 128, d, 0, 1);  // B = V is MN-major
+  g.idesc_1 = make_idesc(act_dtype, 128, 16, 0, 0);
+  g.redo_log2 = act_dtype == SG_BF16 ? 60.0f : 13.0f;  // p <= 2^60 (bf16/fp32 range) / 2^13 (fp16 max 65504)
   g.act_dtype = act_dtype;
   CUtensorMap tm;
   const uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)g.M};
@@ -613,14 +678,22 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
     if (d == 32) return launch_att2<32, SG_F16>(tm, g, o, grid2, stream);
     return launch_att2<64, SG_F16>(tm, g, o, grid2, stream);
   }
+  const int poly = attention_poly();
+#define SG_ATT_DISPATCH(DD, TT)                                                  \
+  do {                                                                           \
+    if (poly == 2) return launch_att<DD, TT, 2>(tm, g, o, grid, stream);         \
+    if (poly == 4) return launch_att<DD, TT, 4>(tm, g, o, grid, stream);         \
+    return launch_att<DD, TT, 0>(tm, g, o, grid, stream);                        \
+  } while (0)
   if (act_dtype == SG_BF16) {
-    if (d == 16) return launch_att<16, SG_BF16>(tm, g, o, grid, stream);
-    if (d == 32) return launch_att<32, SG_BF16>(tm, g, o, grid, stream);
-    return launch_att<64, SG_BF16>(tm, g, o, grid, stream);
+    if (d == 16) SG_ATT_DISPATCH(16, SG_BF16);
+    if (d == 32) SG_ATT_DISPATCH(32, SG_BF16);
+    SG_ATT_DISPATCH(64, SG_BF16);
   }
-  if (d == 16) return launch_att<16, SG_F16>(tm, g, o, grid, stream);
-  if (d == 32) return launch_att<32, SG_F16>(tm, g, o, grid, stream);
-  return launch_att<64, SG_F16>(tm, g, o, grid, stream);
+  if (d == 16) SG_ATT_DISPATCH(16, SG_F16);
+  if (d == 32) SG_ATT_DISPATCH(32, SG_F16);
+  SG_ATT_DISPATCH(64, SG_F16);
+#undef SG_ATT_DISPATCH
 }
 
 }  // namespace sg

@@ -318,22 +318,27 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
       *reinterpret_cast<float4*>(scratch + lane * EPI_LD + j4 * 4) =
           make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
     __syncwarp();
+    // all residual loads are issued before the first store (stores may alias them as far as the compiler knows)
+    float4 o[8], rsd[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + trow;
-      const int64_t m = m0 + q * 32 + rr;
-      float4 o = *reinterpret_cast<const float4*>(scratch + rr * EPI_LD + tcol);
+      o[it] = *reinterpret_cast<const float4*>(scratch + rr * EPI_LD + tcol);
+      rsd[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.residual && m0 + q * 32 + rr < g.M)
+        rsd[it] = __ldg(reinterpret_cast<const float4*>(ep.residual + (m0 + q * 32 + rr) * g.Cout + nb + tcol));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int64_t m = m0 + q * 32 + it * 4 + trow;
       if (m < g.M) {
         const int64_t off = m * g.Cout + nb + tcol;
-        if (ep.residual) {
-          const float4 rsd = __ldg(reinterpret_cast<const float4*>(ep.residual + off));
-          o.x += rsd.x; o.y += rsd.y; o.z += rsd.z; o.w += rsd.w;
-        }
-        if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + off) = o;
+        const float4 v4 = make_float4(o[it].x + rsd[it].x, o[it].y + rsd[it].y, o[it].z + rsd[it].z, o[it].w + rsd[it].w);
+        if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + off) = v4;
         if (ep.out_act) {
           uint2 w;
-          w.x = pack16(o.x, o.y, ep.act_dtype);
-          w.y = pack16(o.z, o.w, ep.act_dtype);
+          w.x = pack16(v4.x, v4.y, ep.act_dtype);
+          w.y = pack16(v4.z, v4.w, ep.act_dtype);
           *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out_act) + off) = w;
         }
       }
@@ -341,11 +346,46 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
     __syncwarp();
   }
   if (ep.partials) {
-    rowstat[r][0] = s_sum;
-    rowstat[r][1] = s_sq;
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // this group's four warps only
-    write_tile_partials<BM>(rowstat, group_tid, m0, g.M, g.HW, ep.partials, ep.P, tile_n, g.n_tiles);
-    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // rowstat is rewritten by the next tile
+    // Deterministic GroupNorm partials without a serial tail: xor-shuffle within the sample's rows of this warp,
+    // then (samples spanning several warps) a 4-entry smem combine.  group = rows of one sample inside the tile.
+    const int group = g.HW < BM ? g.HW : BM;
+    const int span = group < 32 ? group : 32;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (o < span) {
+        s_sum += __shfl_xor_sync(0xffffffffu, s_sum, o);
+        s_sq += __shfl_xor_sync(0xffffffffu, s_sq, o);
+      }
+    }
+    if (group < 32) {
+      if ((lane & (group - 1)) == 0 && valid) {
+        const int64_t sample = (m0 + r) / g.HW;
+        float* pp = ep.partials + (sample * ep.P + tile_n) * 2;
+        pp[0] = s_sum;
+        pp[1] = s_sq;
+      }
+    } else {
+      if (lane == 0) {
+        rowstat[q][0] = s_sum;
+        rowstat[q][1] = s_sq;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // this group's four warps only
+      const int wpg = group >> 5;  // warps per sample: 1, 2 or 4
+      if (group_tid < 4 / wpg && m0 + group_tid * group < g.M) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < wpg; ++w) {
+          a += rowstat[group_tid * wpg + w][0];
+          b += rowstat[group_tid * wpg + w][1];
+        }
+        const int64_t row0 = m0 + group_tid * group;
+        const int64_t sample = row0 / g.HW;
+        const int tile_in_sample = g.HW < BM ? 0 : (int)((row0 % g.HW) / BM);
+        float* pp = ep.partials + (sample * ep.P + tile_in_sample * g.n_tiles + tile_n) * 2;
+        pp[0] = a;
+        pp[1] = b;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // rowstat is rewritten by the next tile
+    }
   }
 }
 
@@ -430,7 +470,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
         tile_coords(g, 2 * mt2 + 1, cn1, ch1, cw1);
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&empty[s], ((it / STAGES) & 1u) ^ 1u);
+          mbar_wait_spin(&empty[s], ((it / STAGES) & 1u) ^ 1u);
           const int tap = kb / g.cblocks, c0 = (kb % g.cblocks) * BK;
           int dy = 0, dx = 0;
           if (g.taps == 9) {
@@ -451,12 +491,12 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const uint32_t buf = lt & 1u;
-        mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator pair
+        mbar_wait_spin(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator pair
         tc_fence_after();
         const uint32_t acc0 = tmem_base + buf * (2 * BN), acc1 = acc0 + BN;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&full[s], (it / STAGES) & 1u);
+          mbar_wait_spin(&full[s], (it / STAGES) & 1u);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * K::STAGE);
           const uint64_t a0 = make_desc_k128(sa), a1 = make_desc_k128(sa + A_BYTES);
@@ -480,7 +520,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const uint32_t buf = lt & 1u;
       const int mt2 = tile / g.n_tiles, tile_n = tile % g.n_tiles;
-      mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
+      mbar_wait_spin(&tmem_full[buf], (lt >> 1) & 1u);
       tc_fence_after();
       const int64_t m0 = (int64_t)(2 * mt2 + grp) * BM;
       if (m0 < g.M)

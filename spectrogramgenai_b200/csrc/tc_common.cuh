@@ -53,11 +53,25 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 }
 // Bounded wait: a protocol bug must surface as a launch error (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i)
+    if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
-  while (!mbar_try_wait_hint(bar, parity, 200000u)) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (++spins > (1u << 16)) {
       printf("sgb200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// Low-latency variant for the single-thread roles (TMA producer, MMA issuer): one polling lane costs almost no
+// issue bandwidth, and its reaction time is on the critical path of every hand-off.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("sgb200: mbarrier spin-wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
   }
