@@ -573,11 +573,194 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGe
   return launch_status("sg_igemm(tc2)");
 }
 
+// =====================================================================================================
+// v3 ("halo" mode, 3x3 convs with 16 <= W <= 64 and H*W >= 256): same persistent / double-buffered-TMEM /
+// two-group-epilogue skeleton as v2, but the A operand is loaded ONCE PER COLUMN SHIFT instead of once per tap.
+// A 256-pixel tile is R = 256/W whole image rows; for a fixed dx the three taps (dy = -1, 0, +1) read row-shifted
+// views of the same (R+2)-row halo slab, and because the slab's row pitch is exactly W pixels (the x shift and
+// both paddings are done by TMA coordinates / out-of-bounds fill), every shifted view is a 1024-byte aligned,
+// uniformly strided K-major UMMA tile: descriptor start = slab + (dy + half*R/2) * W * 128 bytes.
+// L2 -> smem A traffic drops from 9 x 256 to 3 x (256 + 2W) pixel rows per channel block (2.2x - 2.6x less), which
+// is what bounds these kernels (measured ~11-13 TB/s operand ceiling).
+// smem: A ring 2 x 48 KB (one slab per (channel block, dx)), B ring 4 x BN*128 B (one weight tile per tap).
+// =====================================================================================================
+template <int BN>
+struct V3 {
+  static constexpr int A_STAGES = 2, B_STAGES = 4;
+  static constexpr int A_SLAB = 48 * 1024;  // (R + 2) * W * 128 B <= 48 KB for W in {16, 32, 64}
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int TMEM_COLS = 4 * BN;
+  static constexpr int THREADS = 320;
+  static constexpr int BAR_OFF = 1024 * 0 + A_STAGES * A_SLAB + B_STAGES * B_BYTES;
+  static constexpr int SMEM = 1024 + BAR_OFF + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH;
+  static_assert(SMEM <= 227 * 1024, "smem budget");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1) igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
+                                                           const IgemmEpi ep, const int num_tiles) {
+  using K = V3<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + K::A_STAGES * K::A_SLAB;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + K::BAR_OFF);
+  uint64_t* a_empty = a_full + K::A_STAGES;
+  uint64_t* b_full = a_empty + K::A_STAGES;
+  uint64_t* b_empty = b_full + K::B_STAGES;
+  uint64_t* tmem_full = b_empty + K::B_STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + K::BAR_OFF + 256);
+  float* scratch_all = reinterpret_cast<float*>(smem + K::BAR_OFF + 256 + 2 * BM * 2 * 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = 256 / g.W;                        // image rows per tile
+  const int tiles_per_sample = g.HW / 256;
+  const uint32_t row_bytes = (uint32_t)g.W * 128u;
+  const uint32_t slab_bytes = (uint32_t)(R + 2) * row_bytes;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < K::A_STAGES; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < K::B_STAGES; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<K::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt2 = tile / g.n_tiles, n0 = (tile % g.n_tiles) * BN;
+        const int cn = mt2 / tiles_per_sample, h0 = (mt2 % tiles_per_sample) * R;
+        for (int cb = 0; cb < g.cblocks; ++cb) {
+          for (int dx = 0; dx < 3; ++dx, ++ia) {
+            const int as = ia % K::A_STAGES;
+            mbar_wait_spin(&a_empty[as], ((ia / K::A_STAGES) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&a_full[as], slab_bytes);
+            tma_load_4d(sA + as * K::A_SLAB, &tmA, &a_full[as], cb * BK, dx - 1, h0 - 1, cn);
+            for (int dy = 0; dy < 3; ++dy, ++ib) {
+              const int bs = ib % K::B_STAGES;
+              mbar_wait_spin(&b_empty[bs], ((ib / K::B_STAGES) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)K::B_BYTES);
+              tma_load_2d(sB + bs * K::B_BYTES, &tmB, &b_full[bs], cb * BK, (dy * 3 + dx) * g.Cout + n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      uint32_t ia = 0, ib = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u;
+        mbar_wait_spin(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * (2 * BN), acc1 = acc0 + BN;
+        uint32_t first = 1;
+        for (int cb = 0; cb < g.cblocks; ++cb) {
+          for (int dx = 0; dx < 3; ++dx, ++ia) {
+            const int as = ia % K::A_STAGES;
+            mbar_wait_spin(&a_full[as], (ia / K::A_STAGES) & 1u);
+            tc_fence_after();
+            const uint32_t slab = smem_u32(sA + as * K::A_SLAB);
+            for (int dy = 0; dy < 3; ++dy, ++ib) {
+              const int bs = ib % K::B_STAGES;
+              mbar_wait_spin(&b_full[bs], (ib / K::B_STAGES) & 1u);
+              tc_fence_after();
+              const uint64_t a0 = make_desc_k128(slab + (uint32_t)dy * row_bytes);
+              const uint64_t a1 = make_desc_k128(slab + (uint32_t)(dy + R / 2) * row_bytes);
+              const uint64_t bd = make_desc_k128(smem_u32(sB + bs * K::B_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t accum = (first && k == 0) ? 0u : 1u;
+                umma_ss(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, accum);
+                umma_ss(acc1, a1 + 2 * k, bd + 2 * k, g.idesc, accum);
+              }
+              first = 0;
+              umma_commit(&b_empty[bs]);
+            }
+            umma_commit(&a_empty[as]);
+          }
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue (identical to v2) =====
+    const int grp = (warp - 2) >> 2;
+    const int group_tid = (int)threadIdx.x - 64 - grp * 128;
+    float* scratch = scratch_all + (warp - 2) * (EPI_SCRATCH / 4);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1u;
+      const int mt2 = tile / g.n_tiles, tile_n = tile % g.n_tiles;
+      mbar_wait_spin(&tmem_full[buf], (lt >> 1) & 1u);
+      tc_fence_after();
+      const int64_t m0 = (int64_t)(2 * mt2 + grp) * BM;
+      if (m0 < g.M)
+        epilogue_coalesced<BN>(tmem_base + buf * (2 * BN) + grp * BN, m0, tile_n * BN, tile_n, warp, lane, group_tid,
+                               1 + grp, g, ep, rowstat + grp * BM, scratch);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<K::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const IgemmEpi& ep,
+                   cudaStream_t stream) {
+  constexpr int smem = V3<BN>::SMEM;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("sg_igemm(tc3): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
+      return SG_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const int64_t tiles = (g.M / 256) * g.n_tiles;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  igemm_tc3_kernel<BN><<<grid, V3<BN>::THREADS, smem, stream>>>(tmA, tmB, g, ep, (int)tiles);
+  return launch_status("sg_igemm(tc3)");
+}
+
 static int igemm_version() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("SGB200_IGEMM");
-    v = (e && e[0] == '1') ? 1 : 2;
+    // 1 = one tile per CTA, 2 = persistent 256 x BN (default), 3 = v2 + halo-slab A reuse for 3x3 convs.
+    // Measured on B200: v3 moves 2.3x fewer bytes L2 -> smem yet is not faster (128->128 @64x64: 777 vs 906 TFLOP/s),
+    // i.e. these kernels are bound by the shared-memory port (SS-mode MMA operand reads + TMA writes), not by L2.
+    v = e ? atoi(e) : 2;
+    if (v < 1 || v > 3) v = 2;
   }
   return v;
 }
@@ -631,13 +814,23 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
     int rc = make_tmap(&tmB, a->act_dtype, 2, a->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  const bool v2 = igemm_version() == 2;
+  const bool halo = igemm_version() == 3 && a->taps == 9 && a->W >= 16 && a->W <= 64 && HW >= 256;
+  const bool v2 = igemm_version() >= 2;
   g.tx_bytes = (v2 ? 2u : 1u) * box_rows * 128u + (uint32_t)BN * 128u;
 
   IgemmEpi ep;
   ep.bias = a->bias; ep.residual = a->residual; ep.out_f32 = a->out_f32; ep.out_act = a->out_act;
   ep.partials = a->partials; ep.gelu = a->gelu; ep.act_dtype = a->act_dtype;
   ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
+  if (halo) {
+    // A map with the slab box {64, W, 256/W + 2, 1}; x shift and zero padding come from the TMA coordinates
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->rows};
+    const uint64_t strides[3] = {cb, cb * a->W, cb * a->W * a->H};
+    const uint32_t box[4] = {64, (uint32_t)a->W, (uint32_t)(256 / a->W + 2), 1};
+    int rc = make_tmap(&tmA, a->act_dtype, 4, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    return BN == 128 ? launch3<128>(tmA, tmB, g, ep, stream) : launch3<64>(tmA, tmB, g, ep, stream);
+  }
   if (v2) return BN == 128 ? launch2<128>(tmA, tmB, g, ep, stream) : launch2<64>(tmA, tmB, g, ep, stream);
   const int64_t grid = (int64_t)cdiv(g.M, BM) * g.n_tiles;
   SG_REQUIRE(grid < (1ll << 31), "sg_igemm(tc): grid too large");
