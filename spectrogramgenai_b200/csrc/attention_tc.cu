@@ -122,9 +122,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
       mbar_init(&kv_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 4);  // one elected lane per softmax warp
     mbar_init(o_full, 1);
-    mbar_init(o_read, 128);
+    mbar_init(o_read, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<128>(tmem_slot);
@@ -271,7 +271,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
       } while (redo);
       tc_fence_before();    // our tcgen05.ld of S precede the MMA that overwrites those columns
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(p_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
       // ---- O_j and the row sum, both relative to m_ref ----
       mbar_wait(o_full, (uint32_t)j & 1u);
       tc_fence_after();
@@ -285,7 +286,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
       }
       l += psum;
       tc_fence_before();
-      mbar_arrive(o_read);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_read);
       // ---- raise the reference to the new running maximum (exact rescale of o, l) ----
       if (tmax > m_ref) {
         const float a1 = ex2((m_ref - tmax) * g.c);
@@ -652,7 +654,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&kv_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 4);
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
@@ -801,7 +803,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       l += psum;
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(p_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
     }
     // ---- epilogue: O / l ----
     mbar_wait(o_done, (uint32_t)(nkv - 1) & 1u);

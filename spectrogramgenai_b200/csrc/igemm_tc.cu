@@ -283,10 +283,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeo
 // read and for the fp32 / 16-bit stores.
 constexpr int EPI_LD = 36;                          // scratch row stride in floats (144 B: conflict-free 128-bit access)
 constexpr int EPI_SCRATCH = 32 * EPI_LD * 4;        // bytes per warp
+constexpr int MAX_COUT = 1024;                      // bias staged in smem
+constexpr int BIAS_BYTES = MAX_COUT * 4;
 template <int BN>
 __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0, int n0, int tile_n, int warp, int lane,
                                                    int group_tid, int bar_id, const IgemmGeom& g, const IgemmEpi& ep,
-                                                   float (*rowstat)[2], float* scratch) {
+                                                   float (*rowstat)[2], float* scratch, const float* s_bias) {
   const int q = warp & 3;
   const int r = q * 32 + lane;
   const bool valid = m0 + r < g.M;
@@ -294,17 +296,31 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
   const int trow = lane >> 3, tcol = (lane & 7) * 4;  // transposed-domain role of this lane
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
+    const int nb = n0 + c * 32;
+    // residual loads first: their HBM latency overlaps the TMEM read, the bias / GELU math and the transposition
+    float4 rsd[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + trow;
+      rsd[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.residual && m0 + q * 32 + rr < g.M)
+        rsd[it] = __ldg(reinterpret_cast<const float4*>(ep.residual + (m0 + q * 32 + rr) * g.Cout + nb + tcol));
+    }
     uint32_t v[32];
     tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
     tmem_ld_wait();
-    const int nb = n0 + c * 32;
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(v[j]);
-      if (ep.bias) x += __ldg(ep.bias + nb + j);
-      if (ep.gelu) x = gelu_erf(x);
-      f[j] = x;
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + nb + j4 * 4);  // smem broadcast (zeros if no bias)
+      f[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
+      f[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
+      f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
+      f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+    }
+    if (ep.gelu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
     }
     if (ep.partials && valid) {
 #pragma unroll
@@ -318,16 +334,9 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
       *reinterpret_cast<float4*>(scratch + lane * EPI_LD + j4 * 4) =
           make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
     __syncwarp();
-    // all residual loads are issued before the first store (stores may alias them as far as the compiler knows)
-    float4 o[8], rsd[8];
+    float4 o[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + trow;
-      o[it] = *reinterpret_cast<const float4*>(scratch + rr * EPI_LD + tcol);
-      rsd[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ep.residual && m0 + q * 32 + rr < g.M)
-        rsd[it] = __ldg(reinterpret_cast<const float4*>(ep.residual + (m0 + q * 32 + rr) * g.Cout + nb + tcol));
-    }
+    for (int it = 0; it < 8; ++it) o[it] = *reinterpret_cast<const float4*>(scratch + (it * 4 + trow) * EPI_LD + tcol);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int64_t m = m0 + q * 32 + it * 4 + trow;
@@ -403,8 +412,8 @@ struct V2 {
   static constexpr int STAGE = 2 * A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 4 * BN;  // 2 buffers x 2 accumulators: 512 (BN=128) / 256 (BN=64)
   static constexpr int THREADS = 320;
-  static_assert(1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH <= 227 * 1024, "smem budget");
-  static constexpr int SMEM = 1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH;
+  static_assert(1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES <= 227 * 1024, "smem budget");
+  static constexpr int SMEM = 1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES;
 };
 
 __device__ __forceinline__ void tile_coords(const IgemmGeom& g, int mt, int& cn, int& ch, int& cw) {
@@ -436,6 +445,8 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + STAGES * K::STAGE + 256);           // [2 groups][128][2]
   float* scratch_all = reinterpret_cast<float*>(smem + STAGES * K::STAGE + 256 + 2 * BM * 2 * 4);  // [8 warps]
+  float* s_bias = scratch_all + 8 * (EPI_SCRATCH / 4);
+  for (int i = threadIdx.x; i < g.Cout; i += blockDim.x) s_bias[i] = ep.bias ? __ldg(ep.bias + i) : 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = g.taps * g.cblocks;
@@ -525,7 +536,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
       const int64_t m0 = (int64_t)(2 * mt2 + grp) * BM;
       if (m0 < g.M)
         epilogue_coalesced<BN>(tmem_base + buf * (2 * BN) + grp * BN, m0, tile_n * BN, tile_n, warp, lane, group_tid,
-                               1 + grp, g, ep, rowstat + grp * BM, scratch);
+                               1 + grp, g, ep, rowstat + grp * BM, scratch, s_bias);
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
     }
@@ -592,7 +603,7 @@ struct V3 {
   static constexpr int TMEM_COLS = 4 * BN;
   static constexpr int THREADS = 320;
   static constexpr int BAR_OFF = 1024 * 0 + A_STAGES * A_SLAB + B_STAGES * B_BYTES;
-  static constexpr int SMEM = 1024 + BAR_OFF + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH;
+  static constexpr int SMEM = 1024 + BAR_OFF + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES;
   static_assert(SMEM <= 227 * 1024, "smem budget");
 };
 
@@ -615,6 +626,8 @@ __global__ void __launch_bounds__(320, 1) igemm_tc3_kernel(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + K::BAR_OFF + 256);
   float* scratch_all = reinterpret_cast<float*>(smem + K::BAR_OFF + 256 + 2 * BM * 2 * 4);
+  float* s_bias = scratch_all + 8 * (EPI_SCRATCH / 4);
+  for (int i = threadIdx.x; i < g.Cout; i += blockDim.x) s_bias[i] = ep.bias ? __ldg(ep.bias + i) : 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = 256 / g.W;                        // image rows per tile
@@ -720,7 +733,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc3_kernel(const __grid_constant
       const int64_t m0 = (int64_t)(2 * mt2 + grp) * BM;
       if (m0 < g.M)
         epilogue_coalesced<BN>(tmem_base + buf * (2 * BN) + grp * BN, m0, tile_n * BN, tile_n, warp, lane, group_tid,
-                               1 + grp, g, ep, rowstat + grp * BM, scratch);
+                               1 + grp, g, ep, rowstat + grp * BM, scratch, s_bias);
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
     }
@@ -784,6 +797,7 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
   g.samples_per_tile = HW >= 128 ? 0 : 128 / HW;
   g.idesc = make_idesc(a->act_dtype, 128, BN, 0, 0);
   SG_REQUIRE(g.M < (1ll << 31), "sg_igemm(tc): M too large");
+  SG_REQUIRE(a->Cout <= MAX_COUT, "sg_igemm(tc): Cout=%d > %d", a->Cout, MAX_COUT);
 
   CUtensorMap tmA, tmB;
   uint32_t box_rows;
