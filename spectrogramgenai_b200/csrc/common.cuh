@@ -14,6 +14,7 @@ namespace sg {
 // ---- error plumbing (thread-local last-error string, returned through the C ABI) -------------
 void set_error(const char* fmt, ...);
 int launch_status(const char* what);  // cudaGetLastError -> SG_OK / SG_ERR_LAUNCH
+int num_sms();                        // SM count of the current device (persistent-kernel grid sizing)
 
 #define SG_REQUIRE(cond, ...)        \
   do {                               \

@@ -11,74 +11,59 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream);  // igemm_tc.cu
 // inc.double_conv.0  (/root/reference/src/diff_modules.py:82 via :144): direct 3x3, NCHW fp32 in,
 // NHWC fp32 out (64 channels) + GroupNorm partials.
 // ------------------------------------------------------------------------------------------------
+// The 64 x c_in x 3 x 3 weights (<= 9216 B) live in constant memory: with one pixel x all 64 output channels per
+// thread every weight index is a compile-time constant, so each FMA takes its weight straight from the constant bank
+// (no shared-memory staging, no load instructions; the first version was bound by LDS.128 wavefronts at 1.4 ms).
+// sg_conv_in refreshes the bank with a stream-ordered repack kernel ([co][k] -> [k][co], so that four weights arrive per
+// LDCU.128), so calls on ONE stream may use different weights; concurrent calls on different streams must use the same
+// weights.
+__constant__ __align__(16) float c_conv_in_w[36 * 64];
+
+__global__ void conv_in_pack_kernel(const float* __restrict__ w, float* __restrict__ dst, int K) {
+  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) dst[(i % K) * 64 + i / K] = w[i];  // w is [co][ci][3][3]
+}
+
 template <int CIN>
-__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int n_src, int S,
-                                                      const float* __restrict__ w, float* __restrict__ raw,
-                                                      float* __restrict__ partials) {
-  // block = 128 pixels (64 horizontally adjacent pairs) x 4 groups of 16 output channels; a thread computes
-  // 2 pixels x 16 channels so that every weight vector read from shared memory feeds 8 FMAs.
+__global__ void __launch_bounds__(128, 4) conv_in_kernel(const float* __restrict__ x, int n_src, int S,
+                                                         float* __restrict__ raw, float* __restrict__ partials) {
   constexpr int K = CIN * 9;
-  __shared__ __align__(16) float ws[K][64];  // [ci*9 + tap][co]
-  __shared__ float red[2][8];
+  __shared__ float red[2][4];
   const int tid = threadIdx.x;
-  for (int i = tid; i < 64 * K; i += 256) {
-    const int co = i / K, k = i % K;  // w is [co][ci][3][3] == [co][k]
-    ws[k][co] = w[i];
-  }
   const int HW = S * S;
   const int blocks_per_row = HW / 128;
   const int row = blockIdx.x / blocks_per_row;
-  const int p = (blockIdx.x % blocks_per_row) * 128 + (tid >> 2) * 2;  // even pixel; p and p+1 share a row (S even)
-  const int cg = tid & 3;
+  const int p = (blockIdx.x % blocks_per_row) * 128 + tid;
   const int h = p / S, wq = p % S;
   const float* xs = x + (int64_t)(row % n_src) * CIN * HW;
-  float in[CIN][3][4];  // 3 x 4 input patch covering both pixels
-#pragma unroll
-  for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 4; ++dx) {
-        const int hh = h + dy - 1, ww = wq + dx - 1;
-        in[ci][dy][dx] = (hh >= 0 && hh < S && ww >= 0 && ww < S) ? __ldg(xs + ci * HW + hh * S + ww) : 0.f;
-      }
-  __syncthreads();
-  float acc[2][16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = 0.f;
+  float in[K];
 #pragma unroll
   for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const float a0 = in[ci][dy][dx], a1 = in[ci][dy][dx + 1];
-        const int k = ci * 9 + dy * 3 + dx;
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b = *reinterpret_cast<const float4*>(&ws[k][cg * 16 + j4 * 4]);
-          acc[0][j4 * 4 + 0] = fmaf(a0, b.x, acc[0][j4 * 4 + 0]);
-          acc[0][j4 * 4 + 1] = fmaf(a0, b.y, acc[0][j4 * 4 + 1]);
-          acc[0][j4 * 4 + 2] = fmaf(a0, b.z, acc[0][j4 * 4 + 2]);
-          acc[0][j4 * 4 + 3] = fmaf(a0, b.w, acc[0][j4 * 4 + 3]);
-          acc[1][j4 * 4 + 0] = fmaf(a1, b.x, acc[1][j4 * 4 + 0]);
-          acc[1][j4 * 4 + 1] = fmaf(a1, b.y, acc[1][j4 * 4 + 1]);
-          acc[1][j4 * 4 + 2] = fmaf(a1, b.z, acc[1][j4 * 4 + 2]);
-          acc[1][j4 * 4 + 3] = fmaf(a1, b.w, acc[1][j4 * 4 + 3]);
-        }
+        const int hh = h + dy - 1, ww = wq + dx - 1;
+        in[ci * 9 + dy * 3 + dx] = (hh >= 0 && hh < S && ww >= 0 && ww < S) ? __ldg(xs + ci * HW + hh * S + ww) : 0.f;
       }
+  float* dst = raw + ((int64_t)row * HW + p) * 64;
   float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int px = 0; px < 2; ++px) {
-    float* dst = raw + ((int64_t)row * HW + p + px) * 64 + cg * 16;
+  for (int c0 = 0; c0 < 64; c0 += 16) {  // 16 channels at a time keeps the accumulators + patch under 128 registers
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(in[k], c_conv_in_w[k * 64 + c0 + j], acc[j]);
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
-      __stcs(reinterpret_cast<float4*>(dst + j4 * 4),
-             make_float4(acc[px][j4 * 4], acc[px][j4 * 4 + 1], acc[px][j4 * 4 + 2], acc[px][j4 * 4 + 3]));
+      __stcs(reinterpret_cast<float4*>(dst + c0 + j4 * 4),
+             make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]));
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        s += acc[px][j4 * 4 + j];
-        q += acc[px][j4 * 4 + j] * acc[px][j4 * 4 + j];
+        s += acc[j4 * 4 + j];
+        q += acc[j4 * 4 + j] * acc[j4 * 4 + j];
       }
     }
   }
@@ -90,14 +75,9 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
   __syncthreads();
   if (tid == 0) {
-    float ts = 0.f, tq = 0.f;
-    for (int i = 0; i < 8; ++i) {
-      ts += red[0][i];
-      tq += red[1][i];
-    }
-    float* pp = partials + ((int64_t)row * blocks_per_row + (blockIdx.x % blocks_per_row)) * 2;
-    pp[0] = ts;
-    pp[1] = tq;
+    float* pp = partials + (int64_t)blockIdx.x * 2;
+    pp[0] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    pp[1] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
   }
 }
 
@@ -240,23 +220,37 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const float* __restrict
 // outc (:166, :195): 1x1 conv 64 -> c_out (+bias); NHWC fp32 in, NCHW fp32 out.  AI ~ 4 FLOP/B: HBM-bound.
 // One thread per pixel: 256 B contiguous read, coalesced per-channel writes.
 // ------------------------------------------------------------------------------------------------
+constexpr int CO_LD = 68;  // padded row (floats): 16-byte aligned, and 8 consecutive rows start 4 banks apart
 __global__ void __launch_bounds__(128) conv_out_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                        const float* __restrict__ b, int64_t total, int HW, int c_out,
                                                        float* __restrict__ eps) {
+  // tile = 128 pixels x 64 channels (32 KB), staged through shared memory so that the global read is one fully
+  // coalesced stream (the first version had every thread walk its own 256-byte pixel row: half of each 32-byte
+  // sector was wasted, 1.7 TB/s); then one thread per pixel, coalesced per-channel writes.
   __shared__ __align__(16) float ws[8][64];
   __shared__ float bs[8];
+  __shared__ __align__(16) float tile[128 * CO_LD];
   for (int i = threadIdx.x; i < c_out * 64; i += blockDim.x) ws[i / 64][i % 64] = w[i];
   if (threadIdx.x < c_out) bs[threadIdx.x] = b[threadIdx.x];
+  const int64_t m0 = (int64_t)blockIdx.x * 128;
+  const float4* src = reinterpret_cast<const float4*>(in + m0 * 64);
+  const int64_t left = total - m0;
+  const int npx = left < 128 ? (int)left : 128;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < npx * 16; i += 128) {
+    const float4 v = __ldcs(src + i);
+    *reinterpret_cast<float4*>(&tile[(i >> 4) * CO_LD + (i & 15) * 4]) = v;
+  }
   __syncthreads();
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= total) return;
+  if ((int)threadIdx.x >= npx) return;
+  const int64_t m = m0 + threadIdx.x;
   float acc[8];
 #pragma unroll
   for (int co = 0; co < 8; ++co) acc[co] = 0.f;
-  const float4* src = reinterpret_cast<const float4*>(in + m * 64);
+  const float* trow = &tile[threadIdx.x * CO_LD];
 #pragma unroll
   for (int k4 = 0; k4 < 16; ++k4) {
-    const float4 v = __ldcs(src + k4);
+    const float4 v = *reinterpret_cast<const float4*>(trow + k4 * 4);
 #pragma unroll
     for (int co = 0; co < 8; ++co) {
       if (co < c_out) {
@@ -289,13 +283,24 @@ int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w, int r
   SG_REQUIRE(x && w && raw && partials, "sg_conv_in: null pointer");
   SG_REQUIRE(c_in >= 1 && c_in <= 4, "sg_conv_in: c_in=%d not in 1..4", c_in);
   SG_REQUIRE(pow2(S) && S >= 16 && rows > 0 && n_src > 0, "sg_conv_in: S=%d must be a power of two >= 16", S);
-  const int blocks = rows * (S * S / 128);
+  const int64_t ntiles = (int64_t)rows * (S * S / 128);
+  SG_REQUIRE(ntiles < (1ll << 31), "sg_conv_in: too many tiles");
   cudaStream_t s = as_stream(stream);
+  static float* bank = nullptr;  // global address of the constant bank (constant memory is written through it)
+  if (!bank) {
+    cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&bank), c_conv_in_w);
+    if (e != cudaSuccess) {
+      set_error("sg_conv_in: cudaGetSymbolAddress: %s", cudaGetErrorString(e));
+      return SG_ERR_LAUNCH;
+    }
+  }
+  conv_in_pack_kernel<<<1, 256, 0, s>>>(w, bank, 9 * c_in);
+  const int blocks = (int)ntiles;
   switch (c_in) {
-    case 1: conv_in_kernel<1><<<blocks, 256, 0, s>>>(x, n_src, S, w, raw, partials); break;
-    case 2: conv_in_kernel<2><<<blocks, 256, 0, s>>>(x, n_src, S, w, raw, partials); break;
-    case 3: conv_in_kernel<3><<<blocks, 256, 0, s>>>(x, n_src, S, w, raw, partials); break;
-    default: conv_in_kernel<4><<<blocks, 256, 0, s>>>(x, n_src, S, w, raw, partials); break;
+    case 1: conv_in_kernel<1><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials); break;
+    case 2: conv_in_kernel<2><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials); break;
+    case 3: conv_in_kernel<3><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials); break;
+    default: conv_in_kernel<4><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials); break;
   }
   return launch_status("sg_conv_in");
 }

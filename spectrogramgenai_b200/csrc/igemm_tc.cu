@@ -549,17 +549,6 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   }
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 template <int BN>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const IgemmEpi& ep,
                    cudaStream_t stream) {
