@@ -168,6 +168,14 @@ def classify(fn, a, kw):
         return name, 0.0, by
     if name == "layernorm":
         return "layernorm", 0.0, a[0].numel() * 4 + a[3].numel() * a[3].element_size()
+    if name == "ln_inproj":  # x fp32 in, qkv 16-bit out; one [M,C] x [C,3C] GEMM
+        x, qkv = a[0], a[5]
+        Cc = x.shape[-1]
+        return "sa_ln_inproj_fused", 2.0 * x.numel() * 3 * Cc, x.numel() * 4 + qkv.numel() * qkv.element_size()
+    if name == "attn_tail":  # att 16-bit + x fp32 in, out fp32; three [M,C] x [C,C] GEMMs
+        att, x, out = a[0], a[1], a[10]
+        Cc = x.shape[-1]
+        return "sa_tail_fused", 3 * 2.0 * x.numel() * Cc, att.numel() * att.element_size() + x.numel() * 4 + out.numel() * 4
     if name == "conv_in":
         x, w, raw, part = a
         return "conv_in", 2.0 * raw.numel() * x.shape[1] * 9, raw.shape[0] * x[0].numel() * 4 + raw.numel() * 4

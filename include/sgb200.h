@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 2
+#define SG_ABI_VERSION 3
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -120,6 +120,26 @@ int sg_upsample_cat(const float* x, const float* skip, int rows, int h, int w, i
 
 /* ---- LayerNorm over C (:57 self.ln, :59 ff_self.0).  in fp32 [M,C] -> act [M,C]; C in {64,128,256} ---- */
 int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t M, int C, void* out_act,
+                 int act_dtype, sg_stream_t stream);
+
+/* ---- SelfAttention head, fused (tcgen05 engine, C = 64): qkv = LayerNorm(x) Win^T + bin ----
+ * replaces self.ln (:57,:67) + the in_proj of nn.MultiheadAttention (:56,:69).
+ * x fp32 [M,C] (the residual stream, tokens row-major) -> qkv act [M,3C].  w_in act [3C,C] (torch layout),
+ * b_in fp32 [3C].  One pass over x, one over qkv; the LayerNorm of a token is register math of the thread that
+ * owns its accumulator row.  C != 64 is SG_ERR_ARG: callers use sg_layernorm + sg_igemm there.
+ */
+int sg_ln_inproj(const float* x, const float* ln_g, const float* ln_b, const void* w_in, const float* b_in, int64_t M,
+                 int C, void* qkv, int act_dtype, sg_stream_t stream);
+
+/* ---- SelfAttention tail, fused (tcgen05 engine, C = 64) ----
+ * replaces out_proj + residual (:69-70), ff_self = LayerNorm -> Linear -> GELU -> Linear (:58-63) and the second
+ * residual (:71):   a = att Wo^T + bo + x;   out = GELU(LayerNorm(a) W1^T + b1) W2^T + b2 + a.
+ * att act [M,C] (attention core output), x fp32 [M,C], wo/w1/w2 act [C,C] (torch layout: [out, in]),
+ * biases and LayerNorm affine fp32 [C]; out fp32 [M,C] (may alias x: a tile is read completely before it is written).
+ * Three chained tcgen05 GEMMs per 128-token tile, operands handed from epilogue to GEMM through shared memory.
+ */
+int sg_attn_tail(const void* att, const float* x, const void* wo, const float* bo, const float* ln_g, const float* ln_b,
+                 const void* w1, const float* b1, const void* w2, const float* b2, int64_t M, int C, float* out,
                  int act_dtype, sg_stream_t stream);
 
 /* ---- K4: multi-head self-attention core, never materialising the L x L matrix ----

@@ -14,7 +14,7 @@ from . import build as _build
 
 SG_F32, SG_BF16, SG_F16 = 0, 1, 2
 SG_ENGINE_SIMT, SG_ENGINE_TC = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
 
@@ -45,6 +45,8 @@ PROTOTYPES = {
     "sg_maxpool2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sg_upsample_cat": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sg_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
+    "sg_ln_inproj": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
+    "sg_attn_tail": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
     "sg_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sg_conv_out": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "sg_cfg_update": (_i, [_vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp, _u64, _i64, _vp]),

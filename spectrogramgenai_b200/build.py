@@ -28,6 +28,7 @@ SOURCES = [
     "attention_simt.cu",
     "igemm_tc.cu",
     "attention_tc.cu",
+    "token_mlp_tc.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

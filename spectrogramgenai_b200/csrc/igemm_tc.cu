@@ -48,7 +48,8 @@ int make_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const uin
     es[i] = 1;
     if (i + 1 < rank) gs[i] = strides[i];
   }
-  const CUtensorMapDataType dt = dtype == SG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType dt = dtype == SG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : (dtype == SG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

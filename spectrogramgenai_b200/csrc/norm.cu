@@ -99,50 +99,65 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm over C (:57, :59; eps 1e-5).  One warp per token; the token's C values live in registers
-// (C/32 per lane), two-pass mean / variance like torch.
+// LayerNorm over C (:57, :59; eps 1e-5).  C/4 lanes (at most 32) hold one token as float4's, so a warp instruction
+// moves 512 contiguous bytes (the first version, one warp per token with 2 values per lane, reached 3.0 TB/s); four
+// passes are unrolled so that every lane has four independent 16-byte loads in flight.  Two-pass mean / variance
+// like torch, reductions by xor-shuffles inside the token's lane group.
 // ------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int64_t M,
                                                         float* __restrict__ o32, void* __restrict__ o16, int dtype) {
-  constexpr int V = C / 32;  // 2, 4 or 8 values per lane, contiguous
+  constexpr int LPT = C / 4 < 32 ? C / 4 : 32;  // lanes per token: 16 (C = 64), 32 (C = 128, 256)
+  constexpr int NV = C / (4 * LPT);             // float4's per lane: 1, 1, 2
+  constexpr int TPW = 32 / LPT;                 // tokens per warp pass: 2, 1, 1
+  constexpr int U = 4;                          // passes in flight
   const int lane = threadIdx.x & 31;
-  const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tok >= M) return;
-  float v[V];
-  const float* src = in + tok * C + lane * V;
-  if constexpr (V == 2) {
-    const float2 t = *reinterpret_cast<const float2*>(src);
-    v[0] = t.x; v[1] = t.y;
-  } else {
+  const int sub = lane % LPT, tsel = lane / LPT;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t tok0 = wid * (U * TPW) + tsel;
+  float4 gm[NV], bt[NV];
 #pragma unroll
-    for (int j = 0; j < V / 4; ++j) {
-      const float4 t = *reinterpret_cast<const float4*>(src + 4 * j);
-      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  for (int j = 0; j < NV; ++j) {
+    gm[j] = __ldg(reinterpret_cast<const float4*>(gamma) + j * LPT + sub);
+    bt[j] = __ldg(reinterpret_cast<const float4*>(beta) + j * LPT + sub);
+  }
+  float4 v[U][NV];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t tok = tok0 + u * TPW;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      v[u][j] = tok < M ? __ldcs(reinterpret_cast<const float4*>(in + tok * C) + j * LPT + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t tok = tok0 + u * TPW;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
+#pragma unroll
+    for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float d0 = v[u][j].x - mean, d1 = v[u][j].y - mean, d2 = v[u][j].z - mean, d3 = v[u][j].w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
     }
-  }
-  float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < V; ++j) s += v[j];
-  const float mean = warp_sum(s) * (1.0f / C);
-  float q = 0.f;
+    for (int o = LPT / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / C) + 1e-5f);
+    if (tok < M) {
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const float d = v[j] - mean;
-    q += d * d;
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
-  float y[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) y[j] = (v[j] - mean) * rstd * __ldg(gamma + lane * V + j) + __ldg(beta + lane * V + j);
-  const int64_t off = tok * C + lane * V;
-  if constexpr (V == 2) {
-    if (o32) *reinterpret_cast<float2*>(o32 + off) = make_float2(y[0], y[1]);
-    if (o16) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(o16) + off) = pack16(y[0], y[1], dtype);
-  } else {
-#pragma unroll
-    for (int j = 0; j < V / 4; ++j) store4_dual(o32, o16, dtype, off + 4 * j, y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      for (int j = 0; j < NV; ++j) {
+        const float y0 = (v[u][j].x - mean) * rstd * gm[j].x + bt[j].x;
+        const float y1 = (v[u][j].y - mean) * rstd * gm[j].y + bt[j].y;
+        const float y2 = (v[u][j].z - mean) * rstd * gm[j].z + bt[j].z;
+        const float y3 = (v[u][j].w - mean) * rstd * gm[j].w + bt[j].w;
+        store4_dual(o32, o16, dtype, tok * C + (j * LPT + sub) * 4, y0, y1, y2, y3);
+      }
+    }
   }
 }
 
@@ -179,7 +194,8 @@ int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t
   SG_REQUIRE(M > 0, "sg_layernorm: M=%lld", (long long)M);
   float* o32 = act_dtype == SG_F32 ? reinterpret_cast<float*>(out_act) : nullptr;
   void* o16 = act_dtype == SG_F32 ? nullptr : out_act;
-  const int blocks = cdiv(M, 8);
+  const int tok_per_block = 8 * 4 * (C == 64 ? 2 : 1);  // 8 warps x 4 passes x tokens per pass
+  const int blocks = cdiv(M, tok_per_block);
   cudaStream_t s = as_stream(stream);
   switch (C) {
     case 64: layernorm_kernel<64><<<blocks, 256, 0, s>>>(in, gamma, beta, M, o32, o16, act_dtype); break;

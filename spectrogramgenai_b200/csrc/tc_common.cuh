@@ -210,7 +210,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();  // igemm_tc.cu; nullptr (with sg_last_error set) when the driver lacks it
 
-// rank-`rank` 16-bit tensor map, zero OOB fill.  dims/box innermost first; strides[i] = byte stride of dim i+1.
+// rank-`rank` tensor map (SG_BF16 / SG_F16 / SG_F32 elements), zero OOB fill.  dims/box innermost first; strides[i] = byte stride of dim i+1.
 int make_tmap(CUtensorMap* out, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
               const uint32_t* box, CUtensorMapSwizzle swizzle);
 

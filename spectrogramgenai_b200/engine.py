@@ -199,18 +199,32 @@ class UNetPlan:
         L = H * W
         M = rows * L
         f32 = torch.float32
-        ln1 = self._alloc((M, C), self.act)
-        self._op(ops.layernorm, x, W_[f"{p}.ln.weight"], W_[f"{p}.ln.bias"], ln1)
         tc_attn = self.tc and self.attention_engine == "tc"
+        fused = tc_attn and C in ops.FUSED_TOKEN_C and os.environ.get("SGB200_FUSED_SA", "1") != "0"
         # tcgen05 attention consumes 16-bit q/k/v; the SIMT core reads fp32
         qkv = self._alloc((M, 3 * C), self.act if tc_attn else f32)
-        self._op(ops.igemm_launch, ops.make_igemm_args(
-            ln1, W_[f"{p}.mha.in_proj_weight"], rows=rows, H=H, W=W, bias=W_[f"{p}.mha.in_proj_bias"],
-            **({"out_act": qkv} if tc_attn else {"out_f32": qkv})))
-        self._free(ln1)
+        if fused:
+            # LayerNorm + in_proj in one pass over x (sg_ln_inproj)
+            self._op(ops.ln_inproj, x, W_[f"{p}.ln.weight"], W_[f"{p}.ln.bias"], W_[f"{p}.mha.in_proj_weight"],
+                     W_[f"{p}.mha.in_proj_bias"], qkv)
+        else:
+            ln1 = self._alloc((M, C), self.act)
+            self._op(ops.layernorm, x, W_[f"{p}.ln.weight"], W_[f"{p}.ln.bias"], ln1)
+            self._op(ops.igemm_launch, ops.make_igemm_args(
+                ln1, W_[f"{p}.mha.in_proj_weight"], rows=rows, H=H, W=W, bias=W_[f"{p}.mha.in_proj_bias"],
+                **({"out_act": qkv} if tc_attn else {"out_f32": qkv})))
+            self._free(ln1)
         att = self._alloc((M, C), self.act)
         self._op(ops.attention, qkv, att, rows=rows, L=L, C=C, engine=SG_ENGINE_TC if tc_attn else SG_ENGINE_SIMT)
         self._free(qkv)
+        if fused and not want_act:
+            # out_proj + residual + LayerNorm + FFN + residual in one pass (sg_attn_tail)
+            out = self._pair((rows, H, W, C), True, False)
+            self._op(ops.attn_tail, att, x, W_[f"{p}.mha.out_proj.weight"], W_[f"{p}.mha.out_proj.bias"],
+                     W_[f"{p}.ff_self.0.weight"], W_[f"{p}.ff_self.0.bias"], W_[f"{p}.ff_self.1.weight"],
+                     W_[f"{p}.ff_self.1.bias"], W_[f"{p}.ff_self.3.weight"], W_[f"{p}.ff_self.3.bias"], out[0])
+            self._free(att)
+            return out
         a = self._alloc((rows, H, W, C), f32)
         self._op(ops.igemm_launch, ops.make_igemm_args(att, W_[f"{p}.mha.out_proj.weight"], rows=rows, H=H, W=W,
                                                        bias=W_[f"{p}.mha.out_proj.bias"], residual=x, out_f32=a))

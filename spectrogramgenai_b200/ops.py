@@ -124,6 +124,26 @@ def layernorm(x, gamma, beta, out):
                               stream_ptr()), "sg_layernorm")
 
 
+FUSED_TOKEN_C = (64,)  # channel counts the fused SelfAttention head / tail kernels are built for
+
+
+def ln_inproj(x, ln_g, ln_b, w_in, b_in, qkv):
+    """Fused LayerNorm + in_proj (tcgen05).  x fp32 [M, C]; w_in 16-bit [.., 3C, C]; qkv 16-bit [M, 3C]."""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    check(_lib().sg_ln_inproj(ptr(_f32(x, "x")), ptr(ln_g), ptr(ln_b), ptr(w_in), ptr(b_in), M, Cc, ptr(qkv),
+                              dtype_code(qkv.dtype), stream_ptr()), "sg_ln_inproj")
+
+
+def attn_tail(att, x, wo, bo, ln_g, ln_b, w1, b1, w2, b2, out):
+    """Fused out_proj + residual + LayerNorm + FFN + residual (tcgen05).  att 16-bit [M, C]; x, out fp32 [M, C]."""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    check(_lib().sg_attn_tail(ptr(att), ptr(_f32(x, "x")), ptr(wo), ptr(bo), ptr(ln_g), ptr(ln_b), ptr(w1), ptr(b1),
+                              ptr(w2), ptr(b2), M, Cc, ptr(_f32(out, "out")), dtype_code(att.dtype), stream_ptr()),
+          "sg_attn_tail")
+
+
 def attention(qkv, out, *, rows, L, C, engine=None):
     """K4.  qkv [rows*L, 3C]; out [rows*L, C].  SIMT engine: qkv fp32, out fp32/16-bit.  TC: both 16-bit."""
     if engine is None:

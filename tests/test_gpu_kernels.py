@@ -284,16 +284,73 @@ def test_conv_out(ops):
 
 
 # ------------------------------------------------------------------------------------------ norms / attention
+@pytest.mark.parametrize("M", [37, 1, 64, 4099])
 @pytest.mark.parametrize("C", [64, 128, 256])
-def test_layernorm(ops, C):
+def test_layernorm(ops, C, M):
+    """Ragged token counts: every lane group / unrolled pass of the vectorised kernel sees a partial tail."""
     g = gen(10)
-    x = torch.randn(37, C, generator=g) * 3 + 1
+    x = torch.randn(M, C, generator=g) * 3 + 1
     gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
     ref = F.layer_norm(x.double(), (C,), gamma.double(), beta.double(), 1e-5)
     for dt, tol in ((torch.float32, 2e-6), (torch.bfloat16, 4e-3), (torch.float16, 6e-4)):
-        out = torch.empty(37, C, device=DEV, dtype=dt)
-        ops.layernorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), out)
-        assert O.rel_l2(out.cpu(), ref) < tol
+        out = torch.full((M + 3, C), float("nan"), device=DEV, dtype=dt)
+        ops.layernorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), out[:M])
+        assert O.rel_l2(out[:M].cpu(), ref) < tol
+        assert torch.isnan(out[M:].float()).all()  # nothing written past the last token
+
+
+def _sa_weights(C, g):
+    w = lambda *s: torch.randn(*s, generator=g) / s[-1] ** 0.5  # noqa: E731
+    return dict(ln_g=1 + 0.2 * torch.randn(C, generator=g), ln_b=0.2 * torch.randn(C, generator=g),
+                w_in=w(3 * C, C), b_in=0.3 * torch.randn(3 * C, generator=g),
+                wo=w(C, C), bo=0.3 * torch.randn(C, generator=g),
+                ln2_g=1 + 0.2 * torch.randn(C, generator=g), ln2_b=0.2 * torch.randn(C, generator=g),
+                w1=w(C, C), b1=0.3 * torch.randn(C, generator=g), w2=w(C, C), b2=0.3 * torch.randn(C, generator=g))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M", [128, 4096 + 128, 200, 100000])
+def test_ln_inproj_fused(ops, M, dtype):
+    """Fused LayerNorm + in_proj vs fp64 torch on the same 16-bit weights.  Rounding added by the kernel: LN output
+    and qkv to 16 bit (what the unfused path does too).  M = 200 exercises the TMA-clipped last tile."""
+    C = 64
+    g = gen(21)
+    W = _sa_weights(C, g)
+    x = torch.randn(M, C, generator=g) * 2 + 0.5
+    w16 = W["w_in"].to(dtype)
+    ln = F.layer_norm(x.double(), (C,), W["ln_g"].double(), W["ln_b"].double(), 1e-5)
+    ref = ln @ w16.double().T + W["b_in"].double()
+    qkv = torch.full((M + 1, 3 * C), float("nan"), device=DEV, dtype=dtype)
+    ops.ln_inproj(x.to(DEV), W["ln_g"].to(DEV), W["ln_b"].to(DEV), w16.to(DEV), W["b_in"].to(DEV), qkv[:M])
+    torch.cuda.synchronize()
+    err = O.rel_l2(qkv[:M].cpu(), ref)
+    print(f"ln_inproj M={M} {dtype}: rel-L2 {err:.3e}")
+    assert err < (6e-3 if dtype == torch.bfloat16 else 8e-4)
+    assert torch.isnan(qkv[M:].float()).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M", [128, 4096 + 128, 200, 100000])
+def test_attn_tail_fused(ops, M, dtype):
+    """Fused out_proj + residual + LayerNorm + FFN + residual vs fp64 torch on the same 16-bit att / weights."""
+    C = 64
+    g = gen(22)
+    W = _sa_weights(C, g)
+    x = torch.randn(M, C, generator=g) * 2
+    att = torch.randn(M, C, generator=g).to(dtype)
+    wo, w1, w2 = (W[k].to(dtype) for k in ("wo", "w1", "w2"))
+    a = att.double() @ wo.double().T + W["bo"].double() + x.double()
+    h = F.gelu(F.layer_norm(a, (C,), W["ln2_g"].double(), W["ln2_b"].double(), 1e-5) @ w1.double().T + W["b1"].double())
+    ref = h @ w2.double().T + W["b2"].double() + a
+    out = torch.full((M + 1, C), float("nan"), device=DEV)
+    d = lambda t: t.to(DEV)  # noqa: E731
+    ops.attn_tail(d(att), d(x), d(wo), d(W["bo"]), d(W["ln2_g"]), d(W["ln2_b"]), d(w1), d(W["b1"]), d(w2), d(W["b2"]),
+                  out[:M])
+    torch.cuda.synchronize()
+    err = O.rel_l2(out[:M].cpu(), ref)
+    print(f"attn_tail M={M} {dtype}: rel-L2 {err:.3e}")
+    assert err < (3e-3 if dtype == torch.bfloat16 else 4e-4)
+    assert torch.isnan(out[M:]).all()
 
 
 def _attention_ref(qkv, rows, L, C):
