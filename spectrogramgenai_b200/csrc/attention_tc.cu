@@ -1808,31 +1808,50 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Issue helpers: called by ALL lanes of warp 0 (convergent); one elected lane executes the TMA / MMA instructions.
+  const uint64_t q_desc = make_desc_rows(smem_u32(sQ), ROWB);
+  const uint64_t p_desc = make_desc_k128(smem_u32(sP));
   auto load_tile = [&](int t) {
     const int s = t & 1;
-    mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
     const int tok = (int)(kv0 + (int64_t)t * ATT_BN);
-    tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
-    tma_load_2d(sV + s * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
+      tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
+      tma_load_2d(sV + s * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
+    }
   };
   auto issue_s = [&](int t) {  // S = Q K_t^T
     mbar_wait_spin(&kv_full[t & 1], (uint32_t)(t >> 1) & 1u);
     tc_fence_after();
-    const uint64_t qd = make_desc_rows(smem_u32(sQ), ROWB);
     const uint64_t kd = make_desc_rows(smem_u32(sK + (t & 1) * TILE), ROWB);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
-    umma_commit(s_full);
+      for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base, q_desc + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
+      umma_commit(s_full);
+    }
   };
-  if (leader) {
-    mbar_arrive_expect_tx(q_full, g.tile_bytes);
-    tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
+  auto issue_pv = [&](int t) {  // O_t = P V_t : A = P (K-major, two SWIZZLE_128B atoms of 64 keys), B = V MN-major
+    tc_fence_after();
+    const uint64_t vd = make_desc_rows(smem_u32(sV + (t & 1) * TILE), ROWB);
+    if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < ATT_BN / 16; ++k)
+        umma_ss(tmem_base + (uint32_t)((k % NACC) * D), p_desc + (uint64_t)((k >> 2) * (ATT_BM * 128 / 16) + (k & 3) * 2),
+                vd + (uint64_t)(k * 16 * ROWB / 16), g.idesc_o, k >= NACC);
+      umma_commit(o_full);
+    }
+  };
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, g.tile_bytes);
+      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
+    }
     load_tile(0);
     if (nkv > 1) load_tile(1);
     mbar_wait_spin(q_full, 0);
     issue_s(0);
+    __syncwarp();
   }
-  __syncwarp();
 
   const int r = warp * 32 + lane;
   const int64_t tok = m0 + r;
@@ -1936,18 +1955,7 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
     if (g.dbg & 2) {
     } else if (warp == 0) {
       named_bar_sync<1, 128>();
-      if (lane == 0) {
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP);
-        const uint32_t va = smem_u32(sV + (j & 1) * TILE);
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k) {
-          const uint64_t pd = make_desc_k128(pa + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
-          const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
-          umma_ss(tmem_base + (uint32_t)((k % NACC) * D), pd, vd, g.idesc_o, k >= NACC);
-        }
-        umma_commit(o_full);
-      }
+      issue_pv(j);
       __syncwarp();
     } else {
       named_bar_arrive<1, 128>();
@@ -1980,11 +1988,9 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
     if (j + 1 < nkv && !(g.dbg & 2)) {
       if (warp == 0) {
         named_bar_sync<2, 128>();
-        if (lane == 0) {
-          // o_full(j) has been observed: every MMA that read K/V stage j&1 is complete -> refill it with tile j+2
-          issue_s(j + 1);
-          if (j + 2 < nkv) load_tile(j + 2);
-        }
+        // o_full(j) has been observed: every MMA that read K/V stage j&1 is complete -> it can be refilled with tile j+2
+        issue_s(j + 1);
+        if (j + 2 < nkv) load_tile(j + 2);
         __syncwarp();
       } else {
         named_bar_arrive<2, 128>();

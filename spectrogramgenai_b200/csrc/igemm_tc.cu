@@ -472,47 +472,48 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t it = 0;  // running k-block counter across tiles
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt2 = tile / g.n_tiles, n0 = (tile % g.n_tiles) * BN;
-        int cn0, ch0, cw0, cn1, ch1, cw1;
-        tile_coords(g, 2 * mt2, cn0, ch0, cw0);
-        tile_coords(g, 2 * mt2 + 1, cn1, ch1, cw1);
-        for (int kb = 0; kb < nk; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait_spin(&empty[s], ((it / STAGES) & 1u) ^ 1u);
-          const int tap = kb / g.cblocks, c0 = (kb % g.cblocks) * BK;
-          int dy = 0, dx = 0;
-          if (g.taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
-          }
-          uint8_t* st = smem + s * K::STAGE;
+    // ===== TMA producer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
+    uint32_t it = 0;  // running k-block counter across tiles
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt2 = tile / g.n_tiles, n0 = (tile % g.n_tiles) * BN;
+      int cn0, ch0, cw0, cn1, ch1, cw1;
+      tile_coords(g, 2 * mt2, cn0, ch0, cw0);
+      tile_coords(g, 2 * mt2 + 1, cn1, ch1, cw1);
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait_spin(&empty[s], ((it / STAGES) & 1u) ^ 1u);
+        const int tap = kb / g.cblocks, c0 = (kb % g.cblocks) * BK;
+        int dy = 0, dx = 0;
+        if (g.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        uint8_t* st = smem + s * K::STAGE;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], g.tx_bytes);
           tma_load_4d(st, &tmA, &full[s], c0, cw0 + dx, ch0 + dy, cn0);
           tma_load_4d(st + A_BYTES, &tmA, &full[s], c0, cw1 + dx, ch1 + dy, cn1);
           tma_load_2d(st + 2 * A_BYTES, &tmB, &full[s], c0, tap * g.Cout + n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1u;
-        mbar_wait_spin(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator pair
+    // ===== MMA issuer: warp-uniform loop, descriptors in uniform registers, one elected lane issues =====
+    uint32_t it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1u;
+      mbar_wait_spin(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator pair
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * (2 * BN), acc1 = acc0 + BN;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait_spin(&full[s], (it / STAGES) & 1u);
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * (2 * BN), acc1 = acc0 + BN;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait_spin(&full[s], (it / STAGES) & 1u);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * K::STAGE);
-          const uint64_t a0 = make_desc_k128(sa), a1 = make_desc_k128(sa + A_BYTES);
-          const uint64_t bd = make_desc_k128(sa + 2 * A_BYTES);
+        const uint32_t sa = smem_u32(smem + s * K::STAGE);
+        const uint64_t a0 = make_desc_k128(sa), a1 = make_desc_k128(sa + A_BYTES);
+        const uint64_t bd = make_desc_k128(sa + 2 * A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             umma_ss(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
@@ -520,8 +521,10 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
           }
           umma_commit(&empty[s]);
         }
-        umma_commit(&tmem_full[buf]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&tmem_full[buf]);
+      __syncwarp();
     }
   } else {
     // ===== epilogue: group 0 (warps 2..5) drains accumulator 0, group 1 (warps 6..9) accumulator 1 =====

@@ -118,6 +118,21 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp (t
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a CONVERGENT warp (the same lane every time).  Issuing tcgen05 / TMA instructions as
+//   if (elect_one()) umma_ss(...);
+// from warp-uniform code lets ptxas keep descriptors and addresses in uniform registers; inside an `if (lane == 0)`
+// region every MMA costs ~15 single-lane instructions (64-bit descriptor math in vector registers, R2UR moves, a
+// compiler-inserted ELECT), which sat on the critical path of each attention hand-off.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread.
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                         uint32_t accumulate) {

@@ -160,7 +160,8 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
   const uint32_t aA = smem_u32(sA), aX = smem_u32(sX), aW = smem_u32(sW);
   const int r = tid;
 
-  if (leader) {
+  // TMA / MMA instructions are issued by one elected lane of the CONVERGENT warp 0 (descriptors stay in uniform registers)
+  if (warp == 0 && elect_one()) {
     mbar_arrive_expect_tx(w_full, 3 * W_TILE);
     tma_load_2d(sW, &tm_wo, w_full, 0, 0);
     tma_load_2d(sW + W_TILE, &tm_w1, w_full, 0, 0);
@@ -170,20 +171,24 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
   bool first = true;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int m0 = tile * TM;
-    if (leader) {
-      tma_store_wait_read();  // the previous tile's output (staged in sX) has left shared memory
-      mbar_arrive_expect_tx(in_full, A_TILE + X_TILE);
-      tma_load_2d(sA, &tm_att, in_full, 0, m0);
-      tma_load_2d(sX, &tm_x, in_full, 0, m0);
-      tma_load_2d(sX + TM * 128, &tm_x, in_full, 32, m0);
+    if (warp == 0) {
+      if (elect_one()) {
+        tma_store_wait_read();  // the previous tile's output (staged in sX) has left shared memory
+        mbar_arrive_expect_tx(in_full, A_TILE + X_TILE);
+        tma_load_2d(sA, &tm_att, in_full, 0, m0);
+        tma_load_2d(sX, &tm_x, in_full, 0, m0);
+        tma_load_2d(sX + TM * 128, &tm_x, in_full, 32, m0);
+      }
       if (first) mbar_wait_spin(w_full, 0);
       mbar_wait_spin(in_full, in_ph);
       tc_fence_after();
-      gemm_k64(tmem_base, aA, aW, p.idesc);  // att Wo^T
-      umma_commit(mma_done);
+      if (elect_one()) {
+        gemm_k64(tmem_base, aA, aW, p.idesc);  // att Wo^T
+        umma_commit(mma_done);
+      }
+      __syncwarp();
     }
     first = false;
-    __syncwarp();
     // ---- a = att Wo^T + bo + x ; LN(a) -> operand ----
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
@@ -210,12 +215,14 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     tc_fence_before();
     fence_proxy_async();
     __syncthreads();
-    if (leader) {
+    if (warp == 0) {
       tc_fence_after();
-      gemm_k64(tmem_base + 64, aA, aW + W_TILE, p.idesc);  // LN(a) W1^T
-      umma_commit(mma_done);
+      if (elect_one()) {
+        gemm_k64(tmem_base + 64, aA, aW + W_TILE, p.idesc);  // LN(a) W1^T
+        umma_commit(mma_done);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     // ---- h = GELU(. + b1) -> operand ----
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
@@ -243,12 +250,14 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     tc_fence_before();
     fence_proxy_async();
     __syncthreads();
-    if (leader) {
+    if (warp == 0) {
       tc_fence_after();
-      gemm_k64(tmem_base, aA, aW + 2 * W_TILE, p.idesc);  // h W2^T
-      umma_commit(mma_done);
+      if (elect_one()) {
+        gemm_k64(tmem_base, aA, aW + 2 * W_TILE, p.idesc);  // h W2^T
+        umma_commit(mma_done);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     // ---- out = . + b2 + a -> fp32 tile (over this thread's own x row) -> TMA store ----
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
@@ -272,13 +281,13 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     tc_fence_before();
     fence_proxy_async();
     __syncthreads();
-    if (leader) {
+    if (warp == 0 && elect_one()) {
       tma_store_2d(&tm_out, sX, 0, m0);
       tma_store_2d(&tm_out, sX + TM * 128, 32, m0);
       tma_store_commit();
     }
   }
-  if (leader) tma_store_wait_all();
+  if (warp == 0 && elect_one()) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -340,7 +349,7 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const uint32_t aA = smem_u32(sA), aX = smem_u32(sX), aW = smem_u32(sW);
   const int r = tid;
 
-  if (leader) {
+  if (warp == 0 && elect_one()) {
     mbar_arrive_expect_tx(w_full, 3 * W_TILE);
     tma_load_2d(sW, &tm_w, w_full, 0, 0);
   }
@@ -348,7 +357,7 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   bool first = true;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int m0 = tile * TM;
-    if (leader) {
+    if (warp == 0 && elect_one()) {
       tma_store_wait_read();  // the previous tile's qkv boxes (staged in sX | sA) have left shared memory
       mbar_arrive_expect_tx(in_full, X_TILE);
       tma_load_2d(sX, &tm_x, in_full, 0, m0);
@@ -369,14 +378,16 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     ln_row_to_operand<DT>(a, sPar, sPar + TC, aA, r);
     fence_proxy_async();
     __syncthreads();
-    if (leader) {
+    if (warp == 0) {
       if (first) mbar_wait_spin(w_full, 0);
       tc_fence_after();
-      gemm_k64(tmem_base, aA, aW, p.idesc);  // one M128 x N192 accumulator
-      umma_commit(mma_done);
+      if (elect_one()) {
+        gemm_k64(tmem_base, aA, aW, p.idesc);  // one M128 x N192 accumulator
+        umma_commit(mma_done);
+      }
+      __syncwarp();
     }
     first = false;
-    __syncwarp();
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
     tc_fence_after();
@@ -404,14 +415,14 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     tc_fence_before();
     fence_proxy_async();
     __syncthreads();
-    if (leader) {
+    if (warp == 0 && elect_one()) {
       tma_store_2d(&tm_qkv, sX, 0, m0);
       tma_store_2d(&tm_qkv, sX + A_TILE, 64, m0);
       tma_store_2d(&tm_qkv, sX + 2 * A_TILE, 128, m0);
       tma_store_commit();
     }
   }
-  if (leader) tma_store_wait_all();
+  if (warp == 0 && elect_one()) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
