@@ -145,7 +145,7 @@ def classify(fn, a, kw):
         fl = 2.0 * M * g.Cin * g.Cout * g.taps
         esz = 4 if g.act_dtype == 0 else 2
         by = M * g.Cin * esz + g.taps * g.Cin * g.Cout * esz + M * g.Cout * (4 if g.out_f32 else 0) \
-            + M * g.Cout * (esz if g.out_act else 0) + (M * g.Cout * 4 if g.residual else 0)
+            + M * g.Cout * ((2 if g.out_dtype else esz) if g.out_act else 0) + (M * g.Cout * 4 if g.residual else 0)
         eng = "tc" if g.engine == 1 else "simt"
         return (f"igemm_{eng}_conv3x3" if g.taps == 9 else f"igemm_{eng}_linear"), fl, by
     if name == "attention":
@@ -153,7 +153,7 @@ def classify(fn, a, kw):
         return "attention", 4.0 * rows * L * L * C, rows * L * C * (3 * a[0].element_size() + a[1].element_size())
     if name == "gn_apply":
         raw = a[0]
-        by = raw.numel() * 4
+        by = raw.numel() * raw.element_size()
         for k in ("out_f32", "out_act", "residual"):
             t = kw.get(k)
             if t is not None:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 3
+#define SG_ABI_VERSION 4
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -93,7 +93,10 @@ typedef struct {
   float* partials;       /* fp32 [rows, P, 2] GroupNorm partial sums or NULL    */
   int32_t rows, H, W, Cin, Cout, taps, gelu;
   int32_t engine;        /* sg_engine                                           */
-  int32_t act_dtype;     /* sg_dtype of a, w and out_act                        */
+  int32_t act_dtype;     /* sg_dtype of a, w and (unless out_dtype says otherwise) out_act */
+  int32_t out_dtype;     /* 0: out_act has act_dtype.  SG_F16 / SG_BF16: out_act is stored in that 16-bit type
+                            whatever the operand type (tcgen05 engine only) -- used to keep the raw conv output that
+                            feeds GroupNorm in fp16 (saturating, 11-bit mantissa) instead of fp32              */
 } sg_igemm_args;
 int sg_igemm_partials(int engine, int H, int W, int Cout); /* P for the given geometry */
 int sg_igemm(const sg_igemm_args* args, sg_stream_t stream);
@@ -103,8 +106,10 @@ int sg_igemm(const sg_igemm_args* args, sg_stream_t stream);
  * the broadcast "x + emb" of Down/Up (:113,:136).  mode: 0 = affine only, 1 = GELU(affine),
  * 2 = GELU(residual + affine) (residual fp32 [rows,HW,C] required).  emb (fp32, row stride
  * emb_stride, already offset to this layer's slice) is added last when non-NULL.
+ * raw is fp32 (raw_dtype SG_F32) or fp16 (SG_F16, written by sg_igemm with out_dtype = SG_F16); the statistics in
+ * `partials` always come from the fp32 accumulators.
  */
-int sg_gn_apply(const float* raw, const float* partials, int P, const float* gamma, const float* beta,
+int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, const float* gamma, const float* beta,
                 int rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride,
                 float* out_f32, void* out_act, int act_dtype, sg_stream_t stream);
 

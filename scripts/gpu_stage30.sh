@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "=== kernel tests"; timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x 2>&1 | tail -5
+echo "=== model tests"; timeout 1200 python -m pytest tests/test_gpu_model.py -m gpu -q -x -s 2>&1 | grep -E "passed|failed|rel|err" | tail -30
+echo "=== bench"; timeout 1200 python bench.py --no-cpu-baseline > gpurun_out/bench_r1_q.json 2> gpurun_out/bench_r1_q.err; echo rc=$?; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_r1_q.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])
+for k,v in list(d['kernels'].items()): print(k, v)
+PY
+tail -3 gpurun_out/bench_r1_q.err

@@ -14,7 +14,7 @@ from . import build as _build
 
 SG_F32, SG_BF16, SG_F16 = 0, 1, 2
 SG_ENGINE_SIMT, SG_ENGINE_TC = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
 
@@ -27,6 +27,7 @@ class IgemmArgs(C.Structure):
         ("partials", _vp),
         ("rows", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
         ("taps", C.c_int32), ("gelu", C.c_int32), ("engine", C.c_int32), ("act_dtype", C.c_int32),
+        ("out_dtype", C.c_int32),
     ]
 
 
@@ -41,7 +42,7 @@ PROTOTYPES = {
     "sg_conv_in": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "sg_igemm_partials": (_i, [_i, _i, _i, _i]),
     "sg_igemm": (_i, [C.POINTER(IgemmArgs), _vp]),
-    "sg_gn_apply": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "sg_gn_apply": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "sg_maxpool2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sg_upsample_cat": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sg_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),

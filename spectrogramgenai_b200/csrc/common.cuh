@@ -77,8 +77,9 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int dtype) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t w;  // saturating: a raw fp16 value beyond +-65504 must not become inf (it feeds a normalisation)
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+  return w;
 }
 __device__ __forceinline__ float2 unpack16(uint32_t w, int dtype) {
   if (dtype == SG_BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));

@@ -322,7 +322,7 @@ int sg_igemm(const sg_igemm_args* a, sg_stream_t stream) {
   SG_REQUIRE(a->Cout % 64 == 0, "sg_igemm: Cout=%d %% 64 != 0", a->Cout);
   if (a->engine == SG_ENGINE_TC) return igemm_tc(a, as_stream(stream));
   SG_REQUIRE(a->engine == SG_ENGINE_SIMT, "sg_igemm: engine %d", a->engine);
-  SG_REQUIRE(a->act_dtype == SG_F32, "sg_igemm: the SIMT engine computes in fp32");
+  SG_REQUIRE(a->act_dtype == SG_F32 && a->out_dtype == 0, "sg_igemm: the SIMT engine computes and stores in fp32");
   SG_REQUIRE(a->Cin % 16 == 0, "sg_igemm: Cin=%d %% 16 != 0", a->Cin);
   float* out = a->out_f32 ? a->out_f32 : reinterpret_cast<float*>(a->out_act);
   const int64_t M = (int64_t)a->rows * a->H * a->W;

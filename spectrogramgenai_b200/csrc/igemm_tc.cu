@@ -776,6 +776,7 @@ static int igemm_version() {
 int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
   using namespace tc;
   SG_REQUIRE(a->act_dtype == SG_BF16 || a->act_dtype == SG_F16, "sg_igemm(tc): act_dtype must be SG_BF16 or SG_F16");
+  SG_REQUIRE(a->out_dtype == 0 || a->out_dtype == SG_BF16 || a->out_dtype == SG_F16, "sg_igemm(tc): out_dtype %d", a->out_dtype);
   SG_REQUIRE(a->Cin % 64 == 0, "sg_igemm(tc): Cin=%d %% 64 != 0", a->Cin);
   SG_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
              "sg_igemm(tc): operands must be 16-byte aligned");
@@ -827,7 +828,7 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
 
   IgemmEpi ep;
   ep.bias = a->bias; ep.residual = a->residual; ep.out_f32 = a->out_f32; ep.out_act = a->out_act;
-  ep.partials = a->partials; ep.gelu = a->gelu; ep.act_dtype = a->act_dtype;
+  ep.partials = a->partials; ep.gelu = a->gelu; ep.act_dtype = a->out_dtype ? a->out_dtype : a->act_dtype;
   ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
   if (halo) {
     // A map with the slab box {64, W, 256/W + 2, 1}; x shift and zero padding come from the TMA coordinates

@@ -11,15 +11,20 @@ namespace sg {
 // then streams its slice of the row.
 // grid = (chunks, rows); one thread handles 4 consecutive channels of one pixel per iteration.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ raw, const float* __restrict__ partials,
+// RAW16: the raw tensor is fp16 (tensor-core modes).  MODE >= 0 fixes the mode at compile time and lets a thread keep
+// the folded per-channel scale / shift of its 8 channels in registers (valid when the grid stride is a multiple of C,
+// which the launcher checks); MODE = -1 is the general runtime-mode path.
+template <bool RAW16, int MODE>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ raw_v, const float* __restrict__ partials,
                                                        int P, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int64_t per_row4, int C4,
-                                                       int mode, const float* __restrict__ residual,
+                                                       int mode_rt, const float* __restrict__ residual,
                                                        const float* __restrict__ emb, int emb_stride,
                                                        float* __restrict__ o32, void* __restrict__ o16, int dtype) {
   __shared__ double red[2][8];
   __shared__ float stat[2];
   const int row = blockIdx.y;
+  const int mode = MODE >= 0 ? MODE : mode_rt;
   {
     double s = 0.0, q = 0.0;
     const float2* pp = reinterpret_cast<const float2*>(partials) + (int64_t)row * P;
@@ -55,45 +60,165 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   }
   const float mean = stat[0], rstd = stat[1];
   const int64_t base4 = (int64_t)row * per_row4;
-  const float4* r4 = reinterpret_cast<const float4*>(raw) + base4;
   const float4* res4 = residual ? reinterpret_cast<const float4*>(residual) + base4 : nullptr;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
   const float4* e4 = emb ? reinterpret_cast<const float4*>(emb + (int64_t)row * emb_stride) : nullptr;
-  // 4 independent 16-byte loads in flight per thread (the single-load loop was latency-bound at 57 % of HBM peak)
-  constexpr int U = 4;
+  auto norm4 = [&](float4 v, float4 r, int c4) {  // 4 consecutive channels starting at channel 4*c4
+    const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4);
+    float4 y;
+    y.x = (v.x - mean) * rstd * g.x + b.x;
+    y.y = (v.y - mean) * rstd * g.y + b.y;
+    y.z = (v.z - mean) * rstd * g.z + b.z;
+    y.w = (v.w - mean) * rstd * g.w + b.w;
+    if (mode == 2) {
+      y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+    }
+    if (mode >= 1) {
+      y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w);
+    }
+    if (e4) {
+      const float4 e = __ldg(e4 + c4);
+      y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+    }
+    return y;
+  };
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < per_row4; i0 += stride * U) {
-    float4 v[U], r[U];
+  if constexpr (RAW16 && MODE >= 0) {
+    // fp16 raw, compile-time mode, grid stride a multiple of C/8: this thread always sees the same 8 channels, so
+    // y = v * sc + sh with sc = rstd * gamma, sh = beta - mean * sc (+ emb when nothing follows the affine) is one FMA
+    constexpr int U = 4;
+    const uint4* h8 = reinterpret_cast<const uint4*>(raw_v) + base4 / 2;
+    const int64_t per_row8 = per_row4 / 2;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = (int)((2 * first) % C4);
+    float sc[8], sh[8], ev[8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i < per_row4) {
-        v[u] = __ldcs(r4 + i);
-        if (mode == 2) r[u] = __ldcs(res4 + i);
+    for (int h = 0; h < 2; ++h) {
+      const float4 g = __ldg(g4 + c4 + h), b = __ldg(b4 + c4 + h);
+      const float4 e = e4 ? __ldg(e4 + c4 + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w}, ee[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sc[h * 4 + j] = rstd * gg[j];
+        sh[h * 4 + j] = bb[j] - mean * sc[h * 4 + j] + (MODE == 0 ? ee[j] : 0.f);
+        ev[h * 4 + j] = ee[j];
       }
     }
+    for (int64_t i0 = first; i0 < per_row8; i0 += stride * U) {
+      uint4 h[U];
+      float4 r[U][2];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i >= per_row4) break;
-      const int c4 = (int)(i % C4);
-      const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4);
-      float y0 = (v[u].x - mean) * rstd * g.x + b.x;
-      float y1 = (v[u].y - mean) * rstd * g.y + b.y;
-      float y2 = (v[u].z - mean) * rstd * g.z + b.z;
-      float y3 = (v[u].w - mean) * rstd * g.w + b.w;
-      if (mode == 2) {
-        y0 += r[u].x; y1 += r[u].y; y2 += r[u].z; y3 += r[u].w;
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < per_row8) {
+          h[u] = __ldcs(h8 + i);
+          if (MODE == 2) {
+            r[u][0] = __ldcs(res4 + 2 * i);
+            r[u][1] = __ldcs(res4 + 2 * i + 1);
+          }
+        }
       }
-      if (mode >= 1) {
-        y0 = gelu_erf(y0); y1 = gelu_erf(y1); y2 = gelu_erf(y2); y3 = gelu_erf(y3);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i >= per_row8) break;
+        const float2 a0 = unpack16(h[u].x, SG_F16), a1 = unpack16(h[u].y, SG_F16);
+        const float2 a2 = unpack16(h[u].z, SG_F16), a3 = unpack16(h[u].w, SG_F16);
+        float y[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], sc[j], sh[j]);
+        if (MODE == 2) {
+          y[0] += r[u][0].x; y[1] += r[u][0].y; y[2] += r[u][0].z; y[3] += r[u][0].w;
+          y[4] += r[u][1].x; y[5] += r[u][1].y; y[6] += r[u][1].z; y[7] += r[u][1].w;
+        }
+        if (MODE >= 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = gelu_erf(y[j]);
+          if (e4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] += ev[j];
+          }
+        }
+        const int64_t off = (base4 + 2 * i) * 4;
+        if (o32) {
+          *reinterpret_cast<float4*>(o32 + off) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(o32 + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+        if (o16) {  // 8 values = one 16-byte store
+          uint4 w;
+          w.x = pack16(y[0], y[1], dtype);
+          w.y = pack16(y[2], y[3], dtype);
+          w.z = pack16(y[4], y[5], dtype);
+          w.w = pack16(y[6], y[7], dtype);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(o16) + off) = w;
+        }
       }
-      if (e4) {
-        const float4 e = __ldg(e4 + c4);
-        y0 += e.x; y1 += e.y; y2 += e.z; y3 += e.w;
+    }
+  } else if constexpr (RAW16) {
+    // fp16 raw: one thread = 8 consecutive channels = one 16-byte load; U independent loads in flight per thread
+    constexpr int U = 4;
+    const uint4* h8 = reinterpret_cast<const uint4*>(raw_v) + base4 / 2;
+    const int64_t per_row8 = per_row4 / 2;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < per_row8; i0 += stride * U) {
+      uint4 h[U];
+      float4 r[U][2];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < per_row8) {
+          h[u] = __ldcs(h8 + i);
+          if (mode == 2) {
+            r[u][0] = __ldcs(res4 + 2 * i);
+            r[u][1] = __ldcs(res4 + 2 * i + 1);
+          }
+        }
       }
-      store4_dual(o32, o16, dtype, (base4 + i) * 4, y0, y1, y2, y3);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i >= per_row8) break;
+        const int c4 = (int)((2 * i) % C4);
+        const float2 a0 = unpack16(h[u].x, SG_F16), a1 = unpack16(h[u].y, SG_F16);
+        const float2 a2 = unpack16(h[u].z, SG_F16), a3 = unpack16(h[u].w, SG_F16);
+        const float4 y0 = norm4(make_float4(a0.x, a0.y, a1.x, a1.y), r[u][0], c4);
+        const float4 y1 = norm4(make_float4(a2.x, a2.y, a3.x, a3.y), r[u][1], c4 + 1);
+        const int64_t off = (base4 + 2 * i) * 4;
+        if (o32) {
+          *reinterpret_cast<float4*>(o32 + off) = y0;
+          *reinterpret_cast<float4*>(o32 + off + 4) = y1;
+        }
+        if (o16) {  // 8 values = one 16-byte store
+          uint4 w;
+          w.x = pack16(y0.x, y0.y, dtype);
+          w.y = pack16(y0.z, y0.w, dtype);
+          w.z = pack16(y1.x, y1.y, dtype);
+          w.w = pack16(y1.z, y1.w, dtype);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(o16) + off) = w;
+        }
+      }
+    }
+  } else {
+    // 4 independent 16-byte loads in flight per thread (the single-load loop was latency-bound at 57 % of HBM peak)
+    constexpr int U = 4;
+    const float4* r4 = reinterpret_cast<const float4*>(raw_v) + base4;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < per_row4; i0 += stride * U) {
+      float4 v[U], r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < per_row4) {
+          v[u] = __ldcs(r4 + i);
+          if (mode == 2) r[u] = __ldcs(res4 + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i >= per_row4) break;
+        const float4 y = norm4(v[u], r[u], (int)(i % C4));
+        store4_dual(o32, o16, dtype, (base4 + i) * 4, y.x, y.y, y.z, y.w);
+      }
     }
   }
 }
@@ -167,11 +292,13 @@ using namespace sg;
 
 extern "C" {
 
-int sg_gn_apply(const float* raw, const float* partials, int P, const float* gamma, const float* beta, int rows,
-                int HW, int C, int mode, const float* residual, const float* emb, int emb_stride, float* out_f32,
+int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, const float* gamma, const float* beta,
+                int rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride, float* out_f32,
                 void* out_act, int act_dtype, sg_stream_t stream) {
+  SG_REQUIRE(raw_dtype == SG_F32 || raw_dtype == SG_F16, "sg_gn_apply: raw_dtype must be SG_F32 or SG_F16");
   SG_REQUIRE(raw && partials && gamma && beta && (out_f32 || out_act), "sg_gn_apply: null pointer");
   SG_REQUIRE(rows > 0 && HW > 0 && C % 4 == 0 && P > 0, "sg_gn_apply: bad shape rows=%d HW=%d C=%d P=%d", rows, HW, C, P);
+  SG_REQUIRE(raw_dtype == SG_F32 || C % 8 == 0, "sg_gn_apply: fp16 raw needs C %% 8 == 0 (C=%d)", C);
   SG_REQUIRE(mode >= 0 && mode <= 2, "sg_gn_apply: mode %d", mode);
   SG_REQUIRE(mode != 2 || residual, "sg_gn_apply: mode 2 needs a residual");
   SG_REQUIRE(!emb || emb_stride % 4 == 0, "sg_gn_apply: emb stride must be a multiple of 4");
@@ -183,8 +310,21 @@ int sg_gn_apply(const float* raw, const float* partials, int P, const float* gam
   if (chunks > want) chunks = want > 1 ? want : 1;
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, rows);
-  gn_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(raw, partials, P, gamma, beta, per_row4, C / 4, mode, residual,
-                                                       emb, emb_stride, out_f32, out_act, act_dtype);
+  cudaStream_t st = as_stream(stream);
+#define SG_GN_LAUNCH(R16, MD)                                                                                          \
+  gn_apply_kernel<R16, MD><<<grid, 256, 0, st>>>(raw, partials, P, gamma, beta, per_row4, C / 4, mode, residual, emb, \
+                                                 emb_stride, out_f32, out_act, act_dtype)
+  if (raw_dtype == SG_F16) {
+    // fixed-channel fast path: every thread of the grid-stride loop must land on the same 8 channels each pass
+    const bool fixed = ((int64_t)chunks * 256 * 8) % C == 0;
+    if (fixed && mode == 0) SG_GN_LAUNCH(true, 0);
+    else if (fixed && mode == 1) SG_GN_LAUNCH(true, 1);
+    else if (fixed && mode == 2) SG_GN_LAUNCH(true, 2);
+    else SG_GN_LAUNCH(true, -1);
+  } else {
+    SG_GN_LAUNCH(false, -1);
+  }
+#undef SG_GN_LAUNCH
   return launch_status("sg_gn_apply");
 }
 

@@ -99,6 +99,7 @@ class UNetPlan:
         self.rows, self.n_src, self.S = rows, n_src, S
         self.use_step = use_step
         self.attention_engine = os.environ.get("SGB200_ATTENTION", "tc")  # "simt": fp32 core in the 16-bit modes
+        self.raw16 = os.environ.get("SGB200_RAW16", "1") != "0"  # fp16 raw conv outputs in the tensor-core modes
         self.debug = debug  # keep every buffer alive and expose per-block outputs in self.taps
         self._pool = {}
         self.nbytes = 0
@@ -160,10 +161,14 @@ class UNetPlan:
         """3x3 conv (no bias) -> (raw fp32 [rows,H,W,Cout], GroupNorm partials)."""
         w = self.W[wname]
         cout = w.shape[1]
-        raw = self._alloc((rows, H, W, cout), torch.float32)
+        # tensor-core modes keep the raw conv output (it is only ever read by GroupNorm-apply) in fp16: half the
+        # bytes of the conv epilogue and of the normalisation pass; the statistics come from the fp32 accumulators
+        raw16 = self.tc and self.raw16
+        raw = self._alloc((rows, H, W, cout), torch.float16 if raw16 else torch.float32)
         P = ops.igemm_partials(self.engine, H, W, cout)
         part = self._alloc((rows, P, 2), torch.float32)
-        args = ops.make_igemm_args(a_act, w, rows=rows, H=H, W=W, out_f32=raw, partials=part)
+        args = ops.make_igemm_args(a_act, w, rows=rows, H=H, W=W, partials=part,
+                                   **({"out_act": raw} if raw16 else {"out_f32": raw}))
         self._op(ops.igemm_launch, args)
         return raw, part
 

@@ -64,10 +64,16 @@ def make_igemm_args(a, w, *, rows, H, W, bias=None, residual=None, out_f32=None,
     for t, nm in ((residual, "residual"), (out_f32, "out_f32")):
         if t is not None and (t.dtype != torch.float32 or t.numel() != M * Cout):
             raise ValueError(f"igemm: {nm} must be fp32 with {M}x{Cout} elements")
-    if out_act is not None and (out_act.dtype != a.dtype or out_act.numel() != M * Cout):
-        raise ValueError("igemm: out_act must have the activation dtype and M x Cout elements")
+    out_dtype = 0
+    if out_act is not None:
+        if out_act.numel() != M * Cout:
+            raise ValueError("igemm: out_act must have M x Cout elements")
+        if out_act.dtype != a.dtype:
+            if a.dtype == torch.float32 or out_act.dtype not in (torch.float16, torch.bfloat16):
+                raise ValueError("igemm: out_act must have the activation dtype (or be a 16-bit tensor in the tensor-core modes)")
+            out_dtype = dtype_code(out_act.dtype)
     args = IgemmArgs(ptr(a), ptr(w), ptr(bias), ptr(residual), ptr(out_f32), ptr(out_act), ptr(partials), rows, H, W,
-                     Cin, Cout, taps, 1 if gelu else 0, _engine_of(a.dtype), dtype_code(a.dtype))
+                     Cin, Cout, taps, 1 if gelu else 0, _engine_of(a.dtype), dtype_code(a.dtype), out_dtype)
     args._keepalive = (a, w, bias, residual, out_f32, out_act, partials)
     return args
 
@@ -82,7 +88,7 @@ def igemm(a, w, **kw):
 
 
 def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f32=None, out_act=None):
-    """K2.  raw fp32 [rows,HW,C] (any shape with rows first, C last); emb: fp32 view [rows, C] (row stride kept)."""
+    """K2.  raw fp32 or fp16 [rows,HW,C] (any shape with rows first, C last); emb: fp32 view [rows, C] (row stride kept)."""
     rows, C = raw.shape[0], raw.shape[-1]
     HW = raw.numel() // (rows * C)
     P = partials.shape[1]
@@ -92,7 +98,9 @@ def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f
             raise ValueError("gn_apply: emb must be an fp32 [rows, C] view with unit inner stride")
         emb_stride = emb.stride(0)
     adt = dtype_code(out_act.dtype) if out_act is not None else 0
-    check(_lib().sg_gn_apply(ptr(_f32(raw, "raw")), ptr(partials), P, ptr(gamma), ptr(beta), rows, HW, C, mode,
+    if raw.dtype not in (torch.float32, torch.float16):
+        raise ValueError("gn_apply: raw must be fp32 or fp16")
+    check(_lib().sg_gn_apply(ptr(raw), dtype_code(raw.dtype), ptr(partials), P, ptr(gamma), ptr(beta), rows, HW, C, mode,
                              ptr(_f32(residual, "residual")), ptr(emb), emb_stride, ptr(_f32(out_f32, "out_f32")),
                              ptr(out_act), adt, stream_ptr()), "sg_gn_apply")
 

@@ -245,6 +245,43 @@ def test_igemm_conv_tensor_core(ops, rows, H, cin, cout, dtype):
     assert torch.allclose(s[:, 1], (ref ** 2).sum((1, 2, 3)), rtol=1e-5)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,H,cin,cout", [(2, 16, 64, 128), (3, 8, 256, 256), (1, 64, 64, 64)])
+def test_conv_fp16_raw_then_groupnorm(ops, rows, H, cin, cout, dtype):
+    """The tensor-core modes keep the raw conv output in fp16 whatever the operand type (sg_igemm out_dtype): the
+    GroupNorm statistics still come from the fp32 accumulators, the stored value carries 2^-12 relative rounding,
+    and a value beyond the fp16 range saturates instead of becoming inf."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    g = gen(17)
+    a = torch.randn(rows, H, H, cin, generator=g).to(dtype)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(dtype)
+    ref = _conv_ref(a.float(), w.float())
+    raw16 = torch.full((rows, H, H, cout), float("nan"), device=DEV, dtype=torch.float16)
+    part = torch.full((rows, ops.igemm_partials(SG_ENGINE_TC, H, H, cout), 2), float("nan"), device=DEV)
+    ops.igemm(a.to(DEV), pack_conv(w.float(), dtype).to(DEV), rows=rows, H=H, W=H, out_act=raw16, partials=part)
+    torch.cuda.synchronize()
+    assert O.rel_l2(raw16.cpu(), ref) < 4e-4
+    s = part.cpu().double().sum(1)
+    assert torch.allclose(s[:, 1], (ref ** 2).sum((1, 2, 3)), rtol=1e-5)  # statistics are those of the fp32 result
+    gamma, beta = torch.randn(cout, generator=g), torch.randn(cout, generator=g)
+    res = torch.randn(rows, H, H, cout, generator=g)
+    gn = nhwc(F.group_norm(nchw(ref), 1, gamma.double(), beta.double(), 1e-5))
+    for mode, want in ((0, gn), (1, F.gelu(gn)), (2, F.gelu(gn + res.double()))):
+        out = torch.empty(rows, H, H, cout, device=DEV)
+        ops.gn_apply(raw16, part, gamma.to(DEV), beta.to(DEV), mode=mode, residual=res.to(DEV) if mode == 2 else None,
+                     out_f32=out)
+        assert O.rel_l2(out.cpu(), want) < 6e-4, mode
+    # saturation: weights scaled so that the result leaves the fp16 range
+    big = torch.full((1, 8, 8, 64), 200.0).to(dtype)
+    wbig = torch.full((64, 64, 3, 3), 1.0).to(dtype)
+    rawb = torch.empty(1, 8, 8, 64, device=DEV, dtype=torch.float16)
+    partb = torch.empty(1, ops.igemm_partials(SG_ENGINE_TC, 8, 8, 64), 2, device=DEV)
+    ops.igemm(big.to(DEV), pack_conv(wbig.float(), dtype).to(DEV), rows=1, H=8, W=8, out_act=rawb, partials=partb)
+    torch.cuda.synchronize()
+    assert torch.isfinite(rawb.float()).all() and float(rawb.float().max()) == 65504.0
+
+
 LIN_CASES = [(2, 4, 64, 192), (2, 8, 128, 384), (1, 16, 256, 768), (3, 2, 256, 256), (2, 32, 64, 64)]
 
 
