@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 4
+#define SG_ABI_VERSION 5
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -72,7 +72,7 @@ int sg_time_embed(const float* t, const int32_t* step, const int64_t* y, const f
  */
 int sg_conv_in_partials(int S);
 int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w /*[64,c_in,3,3]*/, int rows,
-               float* raw, float* partials, sg_stream_t stream);
+               void* raw, int raw_dtype /* SG_F32 or SG_F16 (saturating) */, float* partials, sg_stream_t stream);
 
 /* ---- K1: implicit-GEMM 3x3 (taps=9, pad 1) or 1x1 (taps=1; Linear) over NHWC activations ----
  * replaces nn.Conv2d(.,.,3,padding=1,bias=False) (:82,:85) and the Linear layers of

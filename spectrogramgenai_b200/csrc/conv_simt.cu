@@ -23,9 +23,9 @@ __global__ void conv_in_pack_kernel(const float* __restrict__ w, float* __restri
   for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) dst[(i % K) * 64 + i / K] = w[i];  // w is [co][ci][3][3]
 }
 
-template <int CIN>
+template <int CIN, bool RAW16>
 __global__ void __launch_bounds__(128, 4) conv_in_kernel(const float* __restrict__ x, int n_src, int S,
-                                                         float* __restrict__ raw, float* __restrict__ partials) {
+                                                         void* __restrict__ raw_v, float* __restrict__ partials) {
   constexpr int K = CIN * 9;
   __shared__ float red[2][4];
   const int tid = threadIdx.x;
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(128, 4) conv_in_kernel(const float* __restrict
         const int hh = h + dy - 1, ww = wq + dx - 1;
         in[ci * 9 + dy * 3 + dx] = (hh >= 0 && hh < S && ww >= 0 && ww < S) ? __ldg(xs + ci * HW + hh * S + ww) : 0.f;
       }
-  float* dst = raw + ((int64_t)row * HW + p) * 64;
+  float* dst = reinterpret_cast<float*>(raw_v) + ((int64_t)row * HW + p) * 64;
+  uint16_t* dst16 = reinterpret_cast<uint16_t*>(raw_v) + ((int64_t)row * HW + p) * 64;
   float s = 0.f, q = 0.f;
 #pragma unroll
   for (int c0 = 0; c0 < 64; c0 += 16) {  // 16 channels at a time keeps the accumulators + patch under 128 registers
@@ -56,15 +57,26 @@ __global__ void __launch_bounds__(128, 4) conv_in_kernel(const float* __restrict
     for (int k = 0; k < K; ++k)
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = fmaf(in[k], c_conv_in_w[k * 64 + c0 + j], acc[j]);
+    if constexpr (RAW16) {  // statistics from the fp32 values, storage in (saturating) fp16: 2 x 16 bytes
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      __stcs(reinterpret_cast<float4*>(dst + c0 + j4 * 4),
-             make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s += acc[j4 * 4 + j];
-        q += acc[j4 * 4 + j] * acc[j4 * 4 + j];
+      for (int j8 = 0; j8 < 2; ++j8) {
+        uint4 w;
+        w.x = pack16(acc[j8 * 8 + 0], acc[j8 * 8 + 1], SG_F16);
+        w.y = pack16(acc[j8 * 8 + 2], acc[j8 * 8 + 3], SG_F16);
+        w.z = pack16(acc[j8 * 8 + 4], acc[j8 * 8 + 5], SG_F16);
+        w.w = pack16(acc[j8 * 8 + 6], acc[j8 * 8 + 7], SG_F16);
+        __stcs(reinterpret_cast<uint4*>(dst16 + c0 + j8 * 8), w);
       }
+    } else {
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4)
+        __stcs(reinterpret_cast<float4*>(dst + c0 + j4 * 4),
+               make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      s += acc[j];
+      q += acc[j] * acc[j];
     }
   }
   s = warp_sum(s);
@@ -278,8 +290,9 @@ extern "C" {
 
 int sg_conv_in_partials(int S) { return S * S / 128; }
 
-int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w, int rows, float* raw, float* partials,
-               sg_stream_t stream) {
+int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w, int rows, void* raw, int raw_dtype,
+               float* partials, sg_stream_t stream) {
+  SG_REQUIRE(raw_dtype == SG_F32 || raw_dtype == SG_F16, "sg_conv_in: raw_dtype must be SG_F32 or SG_F16");
   SG_REQUIRE(x && w && raw && partials, "sg_conv_in: null pointer");
   SG_REQUIRE(c_in >= 1 && c_in <= 4, "sg_conv_in: c_in=%d not in 1..4", c_in);
   SG_REQUIRE(pow2(S) && S >= 16 && rows > 0 && n_src > 0, "sg_conv_in: S=%d must be a power of two >= 16", S);
@@ -296,12 +309,18 @@ int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w, int r
   }
   conv_in_pack_kernel<<<1, 256, 0, s>>>(w, bank, 9 * c_in);
   const int blocks = (int)ntiles;
+#define SG_CONV_IN(CI)                                                                              \
+  do {                                                                                              \
+    if (raw_dtype == SG_F16) conv_in_kernel<CI, true><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials);  \
+    else conv_in_kernel<CI, false><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials);              \
+  } while (0)
   switch (c_in) {
-    case 1: conv_in_kernel<1><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials); break;
-    case 2: conv_in_kernel<2><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials); break;
-    case 3: conv_in_kernel<3><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials); break;
-    default: conv_in_kernel<4><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials); break;
+    case 1: SG_CONV_IN(1); break;
+    case 2: SG_CONV_IN(2); break;
+    case 3: SG_CONV_IN(3); break;
+    default: SG_CONV_IN(4); break;
   }
+#undef SG_CONV_IN
   return launch_status("sg_conv_in");
 }
 

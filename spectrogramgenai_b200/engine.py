@@ -176,7 +176,7 @@ class UNetPlan:
         """DoubleConv (:75-93).  x = (fp32, act) pair of the input (or None when from_input).  Returns a pair."""
         W_ = self.W
         if from_input:
-            raw1 = self._alloc((rows, H, W, 64), torch.float32)
+            raw1 = self._alloc((rows, H, W, 64), torch.float16 if (self.tc and self.raw16) else torch.float32)
             part1 = self._alloc((rows, ops.conv_in_partials(H), 2), torch.float32)
             self._op(ops.conv_in, self.x_in, W_[f"{p}.double_conv.0.weight"], raw1, part1)
         else:

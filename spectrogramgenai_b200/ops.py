@@ -41,11 +41,13 @@ def conv_in_partials(S: int) -> int:
 
 
 def conv_in(x, w, raw, partials):
-    """inc.double_conv.0.  x fp32 NCHW [n_src,c,S,S]; raw fp32 [rows,S,S,64]; partials fp32 [rows,P,2]."""
+    """inc.double_conv.0.  x fp32 NCHW [n_src,c,S,S]; raw fp32 or fp16 [rows,S,S,64]; partials fp32 [rows,P,2]."""
     n_src, c_in, S, _ = x.shape
     rows = raw.shape[0]
-    check(_lib().sg_conv_in(ptr(_f32(x, "x")), n_src, c_in, S, ptr(_f32(w, "w")), rows, ptr(raw), ptr(partials),
-                            stream_ptr()), "sg_conv_in")
+    if raw.dtype not in (torch.float32, torch.float16):
+        raise ValueError("conv_in: raw must be fp32 or fp16")
+    check(_lib().sg_conv_in(ptr(_f32(x, "x")), n_src, c_in, S, ptr(_f32(w, "w")), rows, ptr(raw), dtype_code(raw.dtype),
+                            ptr(partials), stream_ptr()), "sg_conv_in")
 
 
 def igemm_partials(engine: int, H: int, W: int, Cout: int) -> int:

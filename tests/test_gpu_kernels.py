@@ -179,6 +179,12 @@ def test_conv_in(ops, c_in, S, rows, n_src):
     s = part.cpu().double().sum(1)
     assert torch.allclose(s[:, 0], ref.sum((1, 2, 3)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(s[:, 1], (ref ** 2).sum((1, 2, 3)), rtol=1e-5)
+    # fp16 raw output (tensor-core modes): same fp32 statistics, stored value rounded to 11 bits
+    raw16 = torch.empty(rows, S, S, 64, device=DEV, dtype=torch.float16)
+    part16 = torch.empty_like(part)
+    ops.conv_in(x.to(DEV), w.to(DEV), raw16, part16)
+    assert O.rel_l2(raw16.cpu(), ref) < 4e-4
+    assert torch.equal(part16, part)
 
 
 CONV_CASES = [  # rows, H, Cin, Cout
