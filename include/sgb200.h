@@ -28,10 +28,13 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 5
+#define SG_ABI_VERSION 6
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
+/* sg_igemm epilogue activation: GELU is applied after the bias and BEFORE the residual add (ff_self, :61);
+ * RELU_POST after the residual add (the VQAE decoder's relu(conv(x) + x), :343-348). */
+typedef enum { SG_ACT_NONE = 0, SG_ACT_GELU = 1, SG_ACT_RELU_POST = 2 } sg_act;
 
 enum {
   SG_OK = 0,
@@ -91,7 +94,8 @@ typedef struct {
   float* out_f32;        /* fp32 [M, Cout] or NULL                              */
   void* out_act;         /* act  [M, Cout] or NULL                              */
   float* partials;       /* fp32 [rows, P, 2] GroupNorm partial sums or NULL    */
-  int32_t rows, H, W, Cin, Cout, taps, gelu;
+  int32_t rows, H, W, Cin, Cout, taps;
+  int32_t act;           /* sg_act: applied as described below                  */
   int32_t engine;        /* sg_engine                                           */
   int32_t act_dtype;     /* sg_dtype of a, w and (unless out_dtype says otherwise) out_act */
   int32_t out_dtype;     /* 0: out_act has act_dtype.  SG_F16 / SG_BF16: out_act is stored in that 16-bit type
@@ -180,6 +184,25 @@ int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base,
 
 /* ---- K8: (clamp(x,-1,1)+1)/2*255 -> truncating uint8 cast (:440-441) ---- */
 int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream);
+
+/* ---- DiffusionVAE decode tail (:702-706) ----
+ * sg_vq_quantize: [clamp(-1,1) +] VQEmbeddingEMA.forward in eval mode (:290-318) over `count` fp32 values taken in
+ *   groups of 4 consecutive elements (the reference's reshape(-1, 4) of the NCHW latent); codebook fp32 [n_codes, 4];
+ *   quantized = x + (q - x) exactly as :313 writes it; indices int32 [count/4] or NULL.
+ * sg_dec_in_proj: Decoder.in_proj (:330): 1x1 conv 4 -> Cout + bias; z fp32 NCHW [n,4,S,S], w fp32 [Cout,4],
+ *   out NHWC [n,S,S,Cout] as fp32 and/or act.
+ * sg_tconv2_u8: Decoder.strided_t_conv_2 (:336) + image tail (:704-705).  t = output of the first ConvTranspose2d
+ *   computed by sg_igemm as a Linear and left un-shuffled: [2 (a)][n*S*S][2 (b) * C] of dtype t_dtype (fp32 or 16-bit),
+ *   i.e. pixel (2h+a, 2w+b) of the 2S x 2S map; w2 fp32 [C,1,2,2], b2 fp32 [1].  out_u8 uint8 [n,1,4S,4S] =
+ *   ((y+1)/2*255) truncated to int32 and reduced mod 256 (the un-clamped cast of the reference), out_f32 = y (either
+ *   may be NULL).
+ */
+int sg_vq_quantize(const float* x, int64_t count, const float* codebook, int n_codes, int clamp, float* quantized,
+                   int32_t* indices, sg_stream_t stream);
+int sg_dec_in_proj(const float* z, const float* w, const float* b, int n, int S, int Cout, float* out_f32, void* out_act,
+                   int act_dtype, sg_stream_t stream);
+int sg_tconv2_u8(const void* t, int t_dtype, int n, int S, int C, const float* w2, const float* b2, uint8_t* out_u8,
+                 float* out_f32, sg_stream_t stream);
 
 #ifdef __cplusplus
 }

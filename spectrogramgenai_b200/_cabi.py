@@ -14,7 +14,8 @@ from . import build as _build
 
 SG_F32, SG_BF16, SG_F16 = 0, 1, 2
 SG_ENGINE_SIMT, SG_ENGINE_TC = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
+SG_ACT_NONE, SG_ACT_GELU, SG_ACT_RELU_POST = 0, 1, 2
 
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
 
@@ -26,7 +27,7 @@ class IgemmArgs(C.Structure):
         ("a", _vp), ("w", _vp), ("bias", _vp), ("residual", _vp), ("out_f32", _vp), ("out_act", _vp),
         ("partials", _vp),
         ("rows", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
-        ("taps", C.c_int32), ("gelu", C.c_int32), ("engine", C.c_int32), ("act_dtype", C.c_int32),
+        ("taps", C.c_int32), ("act", C.c_int32), ("engine", C.c_int32), ("act_dtype", C.c_int32),
         ("out_dtype", C.c_int32),
     ]
 
@@ -54,6 +55,9 @@ PROTOTYPES = {
     "sg_step_advance": (_i, [_vp, _vp]),
     "sg_philox_normal": (_i, [_vp, _i, _i, _u64, _i64, _i, _vp]),
     "sg_to_uint8": (_i, [_vp, _i64, _vp, _vp]),
+    "sg_vq_quantize": (_i, [_vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
+    "sg_dec_in_proj": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sg_tconv2_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -29,6 +29,7 @@ SOURCES = [
     "igemm_tc.cu",
     "attention_tc.cu",
     "token_mlp_tc.cu",
+    "vae_decode.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

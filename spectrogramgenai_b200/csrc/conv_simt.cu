@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const float* __restrict
                                                          const float* __restrict__ bias,
                                                          const float* __restrict__ residual, float* __restrict__ out,
                                                          float* __restrict__ partials, int64_t M, int H, int W, int Cin,
-                                                         int Cout, int taps, int gelu, int P) {
+                                                         int Cout, int taps, int act, int P) {
   __shared__ float As[2][SBK][SLDA];
   __shared__ __align__(16) float Bs[2][SBK][SLDB];
   __shared__ float rowstat[SBM][2];
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const float* __restrict
     const int r = ty + 16 * i;
     const int64_t m = m0 + r;
     float v0 = acc[i][0] + bv.x, v1 = acc[i][1] + bv.y, v2 = acc[i][2] + bv.z, v3 = acc[i][3] + bv.w;
-    if (gelu) {
+    if (act == SG_ACT_GELU) {
       v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
     }
     float s = 0.f, q = 0.f;
@@ -205,6 +205,9 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const float* __restrict
       if (residual) {
         const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + off));
         v0 += rr.x; v1 += rr.y; v2 += rr.z; v3 += rr.w;
+      }
+      if (act == SG_ACT_RELU_POST) {
+        v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
       }
       *reinterpret_cast<float4*>(out + off) = make_float4(v0, v1, v2, v3);
       s = v0 + v1 + v2 + v3;
@@ -350,7 +353,7 @@ int sg_igemm(const sg_igemm_args* a, sg_stream_t stream) {
   igemm_simt_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(a->a),
                                                          reinterpret_cast<const float*>(a->w), a->bias, a->residual,
                                                          out, a->partials, M, a->H, a->W, a->Cin, a->Cout, a->taps,
-                                                         a->gelu, P);
+                                                         a->act, P);
   return launch_status("sg_igemm(simt)");
 }
 

@@ -82,7 +82,7 @@ struct IgemmEpi {
   float* out_f32;
   void* out_act;
   float* partials;
-  int gelu, P, act_dtype;
+  int act, P, act_dtype;  // act: sg_act
 };
 
 // Epilogue of one 128-row x BN accumulator (TMEM columns [tmem_acc, tmem_acc+BN)): executed by the four epilogue
@@ -107,7 +107,7 @@ __device__ __forceinline__ void epilogue_128rows(uint32_t tmem_acc, int64_t m0, 
     for (int j = 0; j < 32; ++j) {
       float x = __uint_as_float(v[j]);
       if (ep.bias) x += __ldg(ep.bias + nb + j);
-      if (ep.gelu) x = gelu_erf(x);
+      if (ep.act == SG_ACT_GELU) x = gelu_erf(x);
       f[j] = x;
     }
     if (valid) {
@@ -117,6 +117,10 @@ __device__ __forceinline__ void epilogue_128rows(uint32_t tmem_acc, int64_t m0, 
           const float4 rr = __ldg(reinterpret_cast<const float4*>(ep.residual + off) + j4);
           f[j4 * 4 + 0] += rr.x; f[j4 * 4 + 1] += rr.y; f[j4 * 4 + 2] += rr.z; f[j4 * 4 + 3] += rr.w;
         }
+      }
+      if (ep.act == SG_ACT_RELU_POST) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
       }
       if (ep.out_f32) {
 #pragma unroll
@@ -319,7 +323,7 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
       f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
       f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
     }
-    if (ep.gelu) {
+    if (ep.act == SG_ACT_GELU) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
     }
@@ -343,7 +347,8 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
       const int64_t m = m0 + q * 32 + it * 4 + trow;
       if (m < g.M) {
         const int64_t off = m * g.Cout + nb + tcol;
-        const float4 v4 = make_float4(o[it].x + rsd[it].x, o[it].y + rsd[it].y, o[it].z + rsd[it].z, o[it].w + rsd[it].w);
+        float4 v4 = make_float4(o[it].x + rsd[it].x, o[it].y + rsd[it].y, o[it].z + rsd[it].z, o[it].w + rsd[it].w);
+        if (ep.act == SG_ACT_RELU_POST) v4 = make_float4(fmaxf(v4.x, 0.f), fmaxf(v4.y, 0.f), fmaxf(v4.z, 0.f), fmaxf(v4.w, 0.f));
         if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + off) = v4;
         if (ep.out_act) {
           uint2 w;
@@ -828,7 +833,7 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
 
   IgemmEpi ep;
   ep.bias = a->bias; ep.residual = a->residual; ep.out_f32 = a->out_f32; ep.out_act = a->out_act;
-  ep.partials = a->partials; ep.gelu = a->gelu; ep.act_dtype = a->out_dtype ? a->out_dtype : a->act_dtype;
+  ep.partials = a->partials; ep.act = a->act; ep.act_dtype = a->out_dtype ? a->out_dtype : a->act_dtype;
   ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
   if (halo) {
     // A map with the slab box {64, W, 256/W + 2, 1}; x shift and zero padding come from the TMA coordinates

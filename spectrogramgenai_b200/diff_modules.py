@@ -25,8 +25,9 @@ import torch.nn as nn
 
 from . import _cabi, ops
 from .engine import MODES, TIME_DIM, PackedWeights, UNetPlan
+from .vae import VqaeDecoder
 
-__all__ = ["UNet_conditional", "Diffusion", "EMA", "state_dict_schema"]
+__all__ = ["UNet_conditional", "Diffusion", "DiffusionVAE", "EMA", "state_dict_schema"]
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -321,3 +322,34 @@ class Diffusion:
             self.gpu_launches += 1
         else:
             out.copy_(x)
+
+
+class DiffusionVAE(Diffusion):
+    """Latent-space variant (reference :578-706): the UNet denoises [n, 4, S/4, S/4] latents and the VQAE codebook +
+    decoder turn them into [n, 1, S, S] spectrograms.  Same constructor as the reference; `vqae_path` is loaded with
+    torch.load(weights_only=True) unless `vqae_state_dict` (ours, keyword-only) is given.  Only the decode side of
+    the VQAE is on the sampling path; `sav_denoise_path` (per-50-step PNG dumps, :661-700) is not implemented."""
+
+    def __init__(self, noise_steps=1000, beta_start=1e-4, beta_end=0.02, img_size=256, num_classes=10, c_in=1, c_out=1,
+                 device="cuda", vqae_path="models/VQAE/ckpt.pt", sav_denoise_path=None, class_names=(), *,
+                 vqae_state_dict=None, **kwargs):
+        if sav_denoise_path:
+            raise NotImplementedError("sav_denoise_path (denoise-trajectory PNG dumps) is outside the B200 sampling path")
+        latent_dim = 4  # (:611); the reference builds UNet_conditional(latent_dim, latent_dim) at img_size // 4 (:624-627)
+        super().__init__(noise_steps, beta_start, beta_end, img_size // 4, num_classes, latent_dim, latent_dim, device,
+                         **kwargs)
+        if vqae_state_dict is None:
+            vqae_state_dict = torch.load(vqae_path, map_location="cpu", weights_only=True)
+        self.vqae = VqaeDecoder(vqae_state_dict, self.device, self.model.compute_dtype)
+        self.class_names = list(class_names)
+
+    @torch.no_grad()
+    def sample(self, use_ema, labels, cfg_scale=3, *legacy, decode_micro_batch=64, **kw):
+        """sample(use_ema, labels, cfg_scale=3) -> uint8 [n, 1, 4*img_size, 4*img_size] (:630-706)."""
+        if kw.pop("return_float", False):
+            raise TypeError("DiffusionVAE.sample returns the decoded uint8 image; use Diffusion.sample for latents")
+        x = super().sample(use_ema, labels, cfg_scale, *legacy, return_float=True, **kw)
+        launches = self.gpu_launches
+        out = self.vqae.decode(x, micro_batch=decode_micro_batch)
+        self.gpu_launches = launches + self.vqae.gpu_launches
+        return out

@@ -55,7 +55,7 @@ def igemm_partials(engine: int, H: int, W: int, Cout: int) -> int:
 
 
 def make_igemm_args(a, w, *, rows, H, W, bias=None, residual=None, out_f32=None, out_act=None, partials=None,
-                    gelu=False) -> IgemmArgs:
+                    gelu=False, relu_post=False) -> IgemmArgs:
     """a: act [rows,H,W,Cin] (any view with that many elements); w: act [taps,Cout,Cin]."""
     taps, Cout, Cin = w.shape
     if a.dtype != w.dtype:
@@ -75,7 +75,8 @@ def make_igemm_args(a, w, *, rows, H, W, bias=None, residual=None, out_f32=None,
                 raise ValueError("igemm: out_act must have the activation dtype (or be a 16-bit tensor in the tensor-core modes)")
             out_dtype = dtype_code(out_act.dtype)
     args = IgemmArgs(ptr(a), ptr(w), ptr(bias), ptr(residual), ptr(out_f32), ptr(out_act), ptr(partials), rows, H, W,
-                     Cin, Cout, taps, 1 if gelu else 0, _engine_of(a.dtype), dtype_code(a.dtype), out_dtype)
+                     Cin, Cout, taps, 1 if gelu else (2 if relu_post else 0), _engine_of(a.dtype), dtype_code(a.dtype),
+                     out_dtype)
     args._keepalive = (a, w, bias, residual, out_f32, out_act, partials)
     return args
 
@@ -132,6 +133,28 @@ def layernorm(x, gamma, beta, out):
     M = x.numel() // Cc
     check(_lib().sg_layernorm(ptr(_f32(x, "x")), ptr(gamma), ptr(beta), M, Cc, ptr(out), dtype_code(out.dtype),
                               stream_ptr()), "sg_layernorm")
+
+
+def vq_quantize(x, codebook, quantized, indices=None, *, clamp=True):
+    """[clamp(-1,1) +] nearest-codeword quantisation of groups of 4 consecutive fp32 values (VQEmbeddingEMA.forward)."""
+    check(_lib().sg_vq_quantize(ptr(_f32(x, "x")), x.numel(), ptr(_f32(codebook, "codebook")), codebook.shape[0],
+                                1 if clamp else 0, ptr(_f32(quantized, "quantized")), ptr(indices), stream_ptr()),
+          "sg_vq_quantize")
+
+
+def dec_in_proj(z, w, b, *, out_f32=None, out_act=None):
+    """Decoder.in_proj: z fp32 NCHW [n,4,S,S] -> NHWC [n,S,S,Cout]."""
+    n, _, S, _ = z.shape
+    adt = dtype_code(out_act.dtype) if out_act is not None else 0
+    check(_lib().sg_dec_in_proj(ptr(_f32(z, "z")), ptr(_f32(w, "w")), ptr(b), n, S, w.shape[0], ptr(out_f32), ptr(out_act),
+                                adt, stream_ptr()), "sg_dec_in_proj")
+
+
+def tconv2_u8(t, w2, b2, *, n, S, out_u8=None, out_f32=None):
+    """Decoder.strided_t_conv_2 + uint8 image tail on the un-shuffled first transposed conv t [2, n*S*S, 2*C]."""
+    Cc = w2.shape[0]
+    check(_lib().sg_tconv2_u8(ptr(t), dtype_code(t.dtype), n, S, Cc, ptr(_f32(w2, "w2")), ptr(b2), ptr(out_u8),
+                              ptr(out_f32), stream_ptr()), "sg_tconv2_u8")
 
 
 FUSED_TOKEN_C = (64,)  # channel counts the fused SelfAttention head / tail kernels are built for
