@@ -266,6 +266,9 @@ def main():
 
     import torch.distributed as dist
 
+    # stdout carries exactly ONE JSON line: NCCL's own banner / debug output (it writes to stdout) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
     from spectrogramgenai_b200 import ops
     from spectrogramgenai_b200.diff_modules import Diffusion
     from spectrogramgenai_b200.sharding import gather_shards
@@ -380,6 +383,25 @@ def main():
             ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
             roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"],
                         "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "traffic": None}
+        # DRAM traffic per launch of the dominant family from the committed `ncu --set full` capture of this command
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic_r1.json")) as f:
+                tr = json.load(f).get(dom)
+            if tr and int(tr.get("batch_per_gpu", -1)) == n and tr.get("mode") == args.mode:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tr["source"]
+        except (OSError, ValueError):
+            pass
+        if dom == "attention":
+            # d = 16 heads: a score tile is 0.5 M tensor MACs but 16 K exponentials, so the binding unit is the MUFU
+            # pipe (16 ex2/clk/SM, measured 15.8), not the tensor pipe: report that roofline beside the tensor one
+            exps = sum(float(kw["rows"]) * 4 * kw["L"] * kw["L"] for fn, a, kw in plan.ops if fn.__name__ == "attention")
+            sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+            mufu_peak = 16.0 * 148 * sm_mhz * 1e6
+            roofline["binding_unit"] = {
+                "unit": "MUFU ex2 (16/clk/SM at the sampled SM clock); 1/4 of the exponentials run on the FMA pipe",
+                "exp_per_s": round(exps / (v["ms"] * 1e-3), 1), "mufu_peak_exp_per_s": mufu_peak,
+                "frac_all_on_mufu": round(exps / (v["ms"] * 1e-3) / mufu_peak, 4)}
         roofline["peak_source"] = peaks["source"]
         roofline["launches_per_step"] = round(v["launches"])
         roofline["avg_launch_ms"] = round(v["ms"] / max(v["launches"], 1), 4)

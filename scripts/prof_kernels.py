@@ -57,6 +57,16 @@ if what in ("linear", "all"):
         args = ops.make_igemm_args(a, w, rows=rows, H=int(math.isqrt(L)), W=int(math.isqrt(L)), bias=b, residual=res, out_f32=o32)
         timeit(f"linear M={M} {cin}->{cout}", lambda: ops.igemm_launch(args), flops=2.0 * M * cin * cout,
                nbytes=a.numel() * 2 + 2 * o32.numel() * 4)
+if what in ("linear16",):
+    for (L, cin, cout) in ((4096, 64, 192), (1024, 128, 384)):
+        M = rows * L
+        a = torch.randn(M, cin, device=dev, generator=g).to(dt)
+        w = (torch.randn(1, cout, cin, device=dev, generator=g) / math.sqrt(cin)).to(dt)
+        b = torch.randn(cout, device=dev, generator=g)
+        o16 = torch.empty(M, cout, device=dev, dtype=dt)
+        args = ops.make_igemm_args(a, w, rows=rows, H=int(math.isqrt(L)), W=int(math.isqrt(L)), bias=b, out_act=o16)
+        timeit(f"linear16 M={M} {cin}->{cout}", lambda: ops.igemm_launch(args), flops=2.0 * M * cin * cout,
+               nbytes=a.numel() * 2 + o16.numel() * 2)
 if what in ("gn", "all"):
     H, C = 64, 128
     raw = torch.randn(rows, H, H, C, device=dev, generator=g)

@@ -1879,7 +1879,8 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   };
   for (int j = 0; j < nkv; ++j) {
     const uint32_t ph = (uint32_t)j & 1u;
-    if (!(g.dbg & 1)) mbar_wait(s_full, ph);
+    if (g.dbg & 4) mbar_wait_spin(s_full, ph);
+    else if (!(g.dbg & 1)) mbar_wait(s_full, ph);
     tc_fence_after();
     if (j == 0) m_ref = tile_max();
     // The reference m_ref is NOT tracked per tile (that costs an FMNMX per pair): p = exp2((s - m_ref) c) may exceed 1.
@@ -1963,7 +1964,8 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
     float ps0, ps1;
     un2(psum2, ps0, ps1);
     l += ps0 + ps1;
-    if (!(g.dbg & 1)) mbar_wait(o_full, ph);
+    if (g.dbg & 4) mbar_wait_spin(o_full, ph);
+    else if (!(g.dbg & 1)) mbar_wait(o_full, ph);
     tc_fence_after();
     if constexpr (NACC * D >= 32) {
 #pragma unroll
