@@ -16,7 +16,11 @@
 //                 o = o*alpha + O_j   running output, max and sum stay in registers (fp32)
 // TMEM use is 128 columns (O_j aliases the dead S columns), so up to four CTAs share an SM and overlap each
 // other's MMA / MUFU / TMA phases; inside a CTA the phases are serial.
-// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax + epilogue.
+// Three kernels live here: v8 (default for L >= 128; four softmax warps, named-barrier hand-offs, packed fp32 body,
+// part of the exponentials on the FMA pipe), v1 (the first tcgen05 kernel: 192 threads, warp 0 = TMA producer,
+// warp 1 = MMA issuer, warps 2..5 = softmax; still used for L < 128, where a tile holds several batch rows and needs
+// the block-diagonal mask) and v3 (TMEM-resident output, kept selectable).  The measured history of the other variants
+// is in attention_version() below and in profiles/README.md.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -77,7 +81,6 @@ struct AttGeom {
   uint32_t idesc_s, idesc_o, idesc_1;
   int act_dtype;
   float redo_log2;  // largest tolerated (tile max - reference max) * c before the tile is recomputed
-  int dbg;          // timing experiments only (SGB200_ATTN_DBG): 1 = softmax does not wait for the products, 2 = no hand-offs at all
 };
 
 constexpr int ONES_BYTES = 2048;  // a [16 x 64] 16-bit K-major tile of 1.0: B operand of the row-sum MMA
@@ -335,267 +338,6 @@ static int launch_att(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, di
   attention_tc_kernel<D, DT, POLY><<<grid, 192, smem, stream>>>(tm, g, out);
   return launch_status("sg_attention(tc)");
 }
-
-// =====================================================================================================
-// v2 (L >= 256): one CTA = TWO tiles of 128 queries (A, B) of one head against the same K/V stream.
-//   * two softmax warp groups (4 warps each) ping-pong: while group A runs exp on S_A(j) the tensor core
-//     computes S_B(j) / P_A V / S_A(j+1), so the MUFU pipe always has a second warp per scheduler to issue from;
-//   * O accumulates in TMEM across key tiles (tcgen05.mma accumulate); the softmax reference maximum is only
-//     raised -- and O rescaled through tcgen05.ld/st -- when the tile maximum exceeds it by more than 2^8
-//     ("lazy rescale"), so a key tile costs ONE mbarrier wait per thread and no per-tile O round trip;
-//   * TMEM loads are register double-buffered (the load of chunk c+1 is in flight while chunk c is processed).
-// TMEM: S_A [0,128) S_B [128,256) O_A [256,256+D) O_B [320,320+D) -> 512 columns, one CTA per SM.
-// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax A, 6..9 = softmax B.
-// =====================================================================================================
-template <int D>
-constexpr int att2_smem_bytes() {
-  return 1024 + 2 * ATT_BM * D * 2 /*Q_A,Q_B*/ + 3 * 2 * ATT_BN * D * 2 /*K,V x 3 stages*/ + 2 * P_BYTES + 256;
-}
-
-template <int D, int DT>
-__global__ void __launch_bounds__(320, 1)
-attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
-  constexpr int ROWB = D * 2;
-  constexpr int TILE = ATT_BN * ROWB;
-  constexpr int KVS = 3;
-  constexpr float RESCALE_LOG2 = 8.0f;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;                  // [2][TILE]
-  uint8_t* sKV = sQ + 2 * TILE;        // [KVS][K | V][TILE]
-  uint8_t* sP = sKV + KVS * 2 * TILE;  // [2][P_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [3]
-  uint64_t* kv_empty = bars + 4;  // [3]
-  uint64_t* s_full = bars + 7;    // [2]
-  uint64_t* p_ready = bars + 9;   // [2]
-  uint64_t* o_done = bars + 11;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * (2 * ATT_BM);
-  const int64_t kv0 = (m0 >> g.logL) << g.logL;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tm);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KVS; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1);
-      mbar_init(&p_ready[x], 128);
-      mbar_init(&o_done[x], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      mbar_arrive_expect_tx(q_full, 2 * g.tile_bytes);
-      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
-      tma_load_2d(sQ + TILE, &tm, q_full, head * D, (int)m0 + ATT_BM);
-      for (int j = 0; j < g.nkv; ++j) {
-        const int s = j % KVS;
-        mbar_wait_spin(&kv_empty[s], ((uint32_t)(j / KVS) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
-        const int tok = (int)(kv0 + (int64_t)j * ATT_BN);
-        tma_load_2d(sKV + (2 * s) * TILE, &tm, &kv_full[s], g.C + head * D, tok);
-        tma_load_2d(sKV + (2 * s + 1) * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      auto issue_s = [&](int x, int s) {  // S_x = Q_x K^T
-        const uint64_t qd = make_desc_rows(smem_u32(sQ + x * TILE), ROWB);
-        const uint64_t kd = make_desc_rows(smem_u32(sKV + (2 * s) * TILE), ROWB);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base + x * 128, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
-        umma_commit(&s_full[x]);
-      };
-      mbar_wait_spin(q_full, 0);
-      mbar_wait_spin(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      for (int j = 0; j < g.nkv; ++j) {
-        const int s = j % KVS;
-        for (int x = 0; x < 2; ++x) {
-          mbar_wait_spin(&p_ready[x], (uint32_t)j & 1u);
-          tc_fence_after();
-          // O_x (+)= P_x V : A = P (K-major, two 64-key atoms), B = V consumed MN-major
-          const uint32_t pa = smem_u32(sP + x * P_BYTES);
-          const uint32_t va = smem_u32(sKV + (2 * s + 1) * TILE);
-#pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k) {
-            const uint64_t pd = make_desc_k128(pa + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
-            const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
-            umma_ss(tmem_base + 256 + x * 64, pd, vd, g.idesc_o, (j | k) != 0);
-          }
-          umma_commit(&o_done[x]);
-          if (x == 1) umma_commit(&kv_empty[s]);
-          if (j + 1 < g.nkv) {
-            const int s1 = (j + 1) % KVS;
-            if (x == 0) {
-              mbar_wait_spin(&kv_full[s1], (uint32_t)((j + 1) / KVS) & 1u);
-              tc_fence_after();
-            }
-            issue_s(x, s1);
-          }
-        }
-      }
-    }
-  } else {
-    // ===== softmax groups =====
-    const int x = (warp - 2) >> 2;  // 0 = tile A, 1 = tile B
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int64_t tok = m0 + x * ATT_BM + r;
-    const uint32_t t_s = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(x * 128);
-    const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + x * 64);
-    const uint32_t p_row = smem_u32(sP + x * P_BYTES) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < g.nkv; ++j) {
-      mbar_wait(&s_full[x], (uint32_t)j & 1u);
-      tc_fence_after();
-      // ---- pass 1: row max (register double-buffered TMEM loads) ----
-      uint32_t va[32], vb[32];
-      float tmax = -INFINITY;
-      tmem_ld32(t_s, va);
-      tmem_ld_wait();
-      tmem_ld32(t_s + 32, vb);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(va[i]));
-      tmem_ld_wait();
-      tmem_ld32(t_s + 64, va);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(vb[i]));
-      tmem_ld_wait();
-      tmem_ld32(t_s + 96, vb);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(va[i]));
-      tmem_ld_wait();
-      tmem_ld32(t_s, va);  // first chunk of pass 2 already in flight
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(vb[i]));
-      // ---- reference maximum: raise it (and rescale O, l) only when exceeded by more than 2^8 ----
-      if (j == 0) {
-        m_used = tmax;
-      } else {
-        const bool need = (tmax - m_used) * g.c > RESCALE_LOG2;
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? ex2((m_used - tmax) * g.c) : 1.0f;
-          if (need) m_used = tmax;
-          l *= alpha;
-          tmem_ld_wait();  // the in-flight S load must land before this warp issues other tcgen05.ld
-          // PV(j-1) has completed (its commit precedes S(j)'s in the issuer's stream), so O is quiescent
-#pragma unroll
-          for (int cch = 0; cch < D / 16; ++cch) {
-            uint32_t ov[16];
-            tmem_ld16(t_o + cch * 16, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st16(t_o + cch * 16, ov);
-          }
-          tmem_st_wait();
-        }
-      }
-      const float mc = m_used * g.c;
-      // ---- pass 2: p = exp2(s*c - m*c), row sum, 16-bit pack, swizzled st.shared ----
-      float psum = 0.f;
-      auto emit = [&](const uint32_t (&v)[32], int cch) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(v[i]), g.c, -mc));
-          const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), g.c, -mc));
-          pk[i >> 1] = pack_pair<DT>(p0, p1);
-          psum += p0 + p1;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int jj = cch * 4 + u;
-          const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + (uint32_t)(((jj & 7) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                       "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                       : "memory");
-        }
-      };
-      tmem_ld_wait();
-      tmem_ld32(t_s + 32, vb);
-      emit(va, 0);
-      tmem_ld_wait();
-      tmem_ld32(t_s + 64, va);
-      emit(vb, 1);
-      tmem_ld_wait();
-      tmem_ld32(t_s + 96, vb);
-      emit(va, 2);
-      tmem_ld_wait();
-      emit(vb, 3);
-      l += psum;
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(&p_ready[x]);
-    }
-    // ---- epilogue: O / l ----
-    mbar_wait(&o_done[x], (uint32_t)(g.nkv - 1) & 1u);
-    tc_fence_after();
-    const float inv = 1.0f / l;
-    uint16_t* dst = out + tok * g.C + head * D;
-#pragma unroll
-    for (int cch = 0; cch < D / 16; ++cch) {
-      uint32_t ov[16];
-      tmem_ld16(t_o + cch * 16, ov);
-      tmem_ld_wait();
-      uint4 w0, w1;
-      w0.x = pack_pair<DT>(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv);
-      w0.y = pack_pair<DT>(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv);
-      w0.z = pack_pair<DT>(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv);
-      w0.w = pack_pair<DT>(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv);
-      w1.x = pack_pair<DT>(__uint_as_float(ov[8]) * inv, __uint_as_float(ov[9]) * inv);
-      w1.y = pack_pair<DT>(__uint_as_float(ov[10]) * inv, __uint_as_float(ov[11]) * inv);
-      w1.z = pack_pair<DT>(__uint_as_float(ov[12]) * inv, __uint_as_float(ov[13]) * inv);
-      w1.w = pack_pair<DT>(__uint_as_float(ov[14]) * inv, __uint_as_float(ov[15]) * inv);
-      *reinterpret_cast<uint4*>(dst + cch * 16) = w0;
-      *reinterpret_cast<uint4*>(dst + cch * 16 + 8) = w1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-template <int D, int DT>
-static int launch_att2(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = att2_smem_bytes<D>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel<D, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc2): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  attention_tc2_kernel<D, DT><<<grid, 320, smem, stream>>>(tm, g, out);
-  return launch_status("sg_attention(tc2)");
-}
-
 
 // =====================================================================================================
 // v3 (L >= 256): the occupancy of v1 (128 TMEM columns, four CTAs per SM) with the short hand-off chain of v2.
@@ -867,270 +609,14 @@ static int launch_att3(const void* qkv, const AttGeom& g0, int act_dtype, uint16
   return launch_status("sg_attention(tc3)");
 }
 
-// =====================================================================================================
-// v4 (L >= 128): v1's footprint (128 TMEM columns, four CTAs per SM, output accumulated in registers) with the key
-// tile software-pipelined in two 64-key halves a / b that live in the two halves of the CTA's TMEM:
-//     issuer :  S_a S_b | PV_a      PV_b | S_a' S_b' | ...
-//     softmax:  sweep a | sweep b | O_a   O_b | sweep a' | ...
-// While the softmax warps sweep half a the tensor core already holds S_b; P_a V runs under sweep b; the next S_a
-// is issued as soon as O_a has been read.  Per 128 keys the only exposed hand-off is the tail of P_b V.
-// The exponent reference m_ref lags (it is the maximum known BEFORE a half is swept) and is raised only when a half's
-// maximum exceeds it by more than redo_log2 (then that half is swept again); o, l are kept relative to the current
-// m_ref, and a pending O_x computed under an older reference is rescaled when it is read.
-// =====================================================================================================
+// shared-memory footprint of the 128-key-tile kernels: Q + two K/V stages + the 16-bit P tile + barriers
 template <int D>
 constexpr int att4_smem_bytes() {
   return 1024 + ATT_BM * D * 2 /*Q*/ + 2 * 2 * ATT_BN * D * 2 /*K,V x 2 stages*/ + P_BYTES + 256;
 }
 
-template <int D, int DT>
-__global__ void __launch_bounds__(192, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
-attention_tc4_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
-  constexpr int ROWB = D * 2;
-  constexpr int TILE = ATT_BN * ROWB;
-  constexpr int HK = ATT_BN / 2;  // 64 keys per half
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE;      // [2 stages]
-  uint8_t* sV = sK + 2 * TILE;  // [2 stages]
-  uint8_t* sP = sV + 2 * TILE;  // atom 0 = half a, atom 1 = half b
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    // [2] halves
-  uint64_t* p_ready = bars + 7;   // [2]
-  uint64_t* o_full = bars + 9;    // [2]
-  uint64_t* o_read = bars + 11;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * ATT_BM;
-  const int64_t kv0 = (m0 >> g.logL) << g.logL;
-  const int nkv = g.L / ATT_BN;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tm);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 4);
-      mbar_init(&o_full[s], 1);
-      mbar_init(&o_read[s], 4);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      mbar_arrive_expect_tx(q_full, g.tile_bytes);
-      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait_spin(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
-        const int tok = (int)(kv0 + (int64_t)j * ATT_BN);
-        tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
-        tma_load_2d(sV + s * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      auto issue_s = [&](int h, int s) {  // S_h = Q K_h^T into TMEM columns [64h, 64h+64)
-        const uint64_t qd = make_desc_rows(smem_u32(sQ), ROWB);
-        const uint64_t kd = make_desc_rows(smem_u32(sK + s * TILE + h * HK * ROWB), ROWB);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base + h * HK, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
-        umma_commit(&s_full[h]);
-      };
-      auto issue_pv = [&](int h, int s) {  // O_h = P_h V_h into TMEM columns [64h, 64h+D) (the dead S_h columns)
-        const uint32_t pa = smem_u32(sP) + h * (ATT_BM * 128);
-        const uint32_t va = smem_u32(sV + s * TILE + h * HK * ROWB);
-#pragma unroll
-        for (int k = 0; k < HK / 16; ++k) {
-          const uint64_t pd = make_desc_k128(pa + k * 32);
-          const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
-          umma_ss(tmem_base + h * HK, pd, vd, g.idesc_o, k != 0);
-        }
-        umma_commit(&o_full[h]);
-      };
-      mbar_wait_spin(q_full, 0);
-      mbar_wait_spin(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)j & 1u;
-        mbar_wait_spin(&p_ready[0], ph);
-        tc_fence_after();
-        issue_pv(0, s);
-        mbar_wait_spin(&p_ready[1], ph);
-        tc_fence_after();
-        issue_pv(1, s);
-        umma_commit(&kv_empty[s]);
-        if (j + 1 < nkv) {
-          mbar_wait_spin(&kv_full[s ^ 1], (uint32_t)((j + 1) >> 1) & 1u);
-          mbar_wait_spin(&o_read[0], ph);
-          tc_fence_after();
-          issue_s(0, s ^ 1);
-          mbar_wait_spin(&o_read[1], ph);
-          tc_fence_after();
-          issue_s(1, s ^ 1);
-        }
-      }
-    }
-  } else {
-    // ===== softmax + epilogue =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int64_t tok = m0 + r;
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
-    float m_ref = -INFINITY, l = 0.f;
-    float m_used[2] = {0.f, 0.f};
-    for (int j = 0; j < nkv; ++j) {
-      const uint32_t ph = (uint32_t)j & 1u;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(&s_full[h], ph);
-        tc_fence_after();
-        float tmax, psum;
-        bool redo;
-        do {
-          const float mc = m_ref * g.c;
-          tmax = -INFINITY;
-          psum = 0.f;
-#pragma unroll 1
-          for (int cch = 0; cch < 2; ++cch) {
-            uint32_t v[32];
-            tmem_ld32(t_row + h * HK + cch * 32, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-              tmax = fmaxf(tmax, fmaxf(s0, s1));
-              const float p0 = ex2(fmaf(s0, g.c, -mc)), p1 = ex2(fmaf(s1, g.c, -mc));
-              pk[i >> 1] = pack_pair<DT>(p0, p1);
-              psum += p0 + p1;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int jj = cch * 4 + u;  // 16-byte chunk inside this half's 128-byte P row
-              const uint32_t addr = p_row + (uint32_t)h * (ATT_BM * 128) + (uint32_t)((jj ^ (r & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                           "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                           : "memory");
-            }
-          }
-          const bool over = (tmax - m_ref) * g.c > g.redo_log2;  // also true while m_ref == -inf
-          redo = __any_sync(0xffffffffu, over);
-          if (over) {
-            const float a0 = ex2((m_ref - tmax) * g.c);  // 0 on the very first sweep
-            l *= a0;
-#pragma unroll
-            for (int i = 0; i < D; ++i) o[i] *= a0;
-            m_ref = tmax;
-          }
-        } while (redo);
-        l += psum;
-        m_used[h] = m_ref;
-        tc_fence_before();
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[h]);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(&o_full[h], ph);
-        tc_fence_after();
-        // O_h was produced under reference m_used[h]; o is relative to the current m_ref
-        const float sc = (m_used[h] == m_ref) ? 1.0f : ex2((m_used[h] - m_ref) * g.c);
-        if constexpr (D == 16) {
-          uint32_t v[16];
-          tmem_ld16(t_row + h * HK, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = fmaf(__uint_as_float(v[i]), sc, o[i]);
-        } else {
-#pragma unroll
-          for (int cch = 0; cch < D / 32; ++cch) {
-            uint32_t v[32];
-            tmem_ld32(t_row + h * HK + cch * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[cch * 32 + i] = fmaf(__uint_as_float(v[i]), sc, o[cch * 32 + i]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_read[h]);
-      }
-    }
-    const float inv = 1.0f / l;
-    uint16_t* dst = out + tok * g.C + head * D;
-#pragma unroll
-    for (int i = 0; i < D; i += 8) {
-      uint4 w;
-      w.x = pack_pair<DT>(o[i] * inv, o[i + 1] * inv);
-      w.y = pack_pair<DT>(o[i + 2] * inv, o[i + 3] * inv);
-      w.z = pack_pair<DT>(o[i + 4] * inv, o[i + 5] * inv);
-      w.w = pack_pair<DT>(o[i + 6] * inv, o[i + 7] * inv);
-      *reinterpret_cast<uint4*>(dst + i) = w;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc<128>(tmem_base);
-  }
-}
-
-template <int D, int DT>
-static int launch_att4(const CUtensorMap& tm, const AttGeom& g0, int act_dtype, uint16_t* out, dim3 grid,
-                       cudaStream_t stream) {
-  constexpr int smem = att4_smem_bytes<D>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc4_kernel<D, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc4): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  AttGeom g = g0;
-  g.idesc_s = make_idesc(act_dtype, 128, ATT_BN / 2, 0, 0);
-  attention_tc4_kernel<D, DT><<<grid, 192, smem, stream>>>(tm, g, out);
-  return launch_status("sg_attention(tc4)");
-}
-
-// =====================================================================================================
-// v5 (L >= 128): v1's protocol and footprint (128 TMEM columns, four CTAs per SM) with an inner body built for
-// ISSUE SLOTS.  ncu on v1: the XU (MUFU) pipe is 67 % busy while the issue slots are 61 % busy -- v1 spends ~7 issue
-// slots per exponential, so with 8 MUFU clocks per warp-instruction the two limits nearly coincide.  v5 halves the
-// non-MUFU work with the packed fp32 instructions of sm_100 (FFMA2 / FADD2: two lanes of fp32 per issue slot) and
-// the three-input FMNMX3, reads S in double-buffered 16-column chunks so the TMEM latency is covered inside the
-// warp, and can route POLY/8 of the pairs through a packed Cody-Waite polynomial exp2 on the FMA pipe so that the
-// MUFU pipe is no longer the only unit producing probabilities.
-// =====================================================================================================
+// packed fp32 arithmetic of sm_100 (two lanes per instruction: half the issue slots of the scalar forms), the
+// three-input maximum, and the FMA-pipe exp2 used for a fraction of the softmax exponentials
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -1191,557 +677,9 @@ __device__ __forceinline__ constexpr bool pair_is_poly(int pair) {
                      : (pair & 1) == 1;
 }
 
-template <int D, int DT, int POLY, int NACC>
-__global__ void __launch_bounds__(192, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
-attention_tc5_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
-  constexpr int ROWB = D * 2;
-  constexpr int TILE = ATT_BN * ROWB;
-  static_assert(NACC * D <= 128 && (ATT_BN / 16) % NACC == 0, "accumulators must fit the dead S columns");
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE;      // [2 stages]
-  uint8_t* sV = sK + 2 * TILE;  // [2 stages]
-  uint8_t* sP = sV + 2 * TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint64_t* o_read = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * ATT_BM;
-  const int64_t kv0 = (m0 >> g.logL) << g.logL;
-  const int nkv = g.L / ATT_BN;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tm);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 4);
-    mbar_init(o_full, 1);
-    mbar_init(o_read, 4);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, g.tile_bytes);
-      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait_spin(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
-        const int tok = (int)(kv0 + (int64_t)j * ATT_BN);
-        tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
-        tma_load_2d(sV + s * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait_spin(q_full, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait_spin(&kv_full[s], (uint32_t)(j >> 1) & 1u);
-        if (j > 0) mbar_wait_spin(o_read, (uint32_t)(j - 1) & 1u);
-        tc_fence_after();
-        const uint64_t qd = make_desc_rows(smem_u32(sQ), ROWB);
-        const uint64_t kd = make_desc_rows(smem_u32(sK + s * TILE), ROWB);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
-        umma_commit(s_full);
-        mbar_wait_spin(p_ready, (uint32_t)j & 1u);
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP);
-        const uint32_t va = smem_u32(sV + s * TILE);
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k) {
-          const uint64_t pd = make_desc_k128(pa + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
-          const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
-          umma_ss(tmem_base + (uint32_t)((k % NACC) * D), pd, vd, g.idesc_o, k >= NACC);
-        }
-        umma_commit(&kv_empty[s]);
-        umma_commit(o_full);
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int64_t tok = m0 + r;
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    const uint32_t rx = (uint32_t)(r & 7);
-    uint64_t o2[D / 2];
-#pragma unroll
-    for (int i = 0; i < D / 2; ++i) o2[i] = 0ull;  // two +0.0f
-    float m_ref = -INFINITY, l = 0.f;
-    const uint64_t c2 = pk2(g.c, g.c);
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      float tmax;
-      uint64_t psum2;
-      bool redo;
-      do {
-        const float nmc = -m_ref * g.c;
-        const uint64_t nmc2 = pk2(nmc, nmc);
-        tmax = -INFINITY;
-        psum2 = 0ull;
-        uint32_t va[16], vb[16];
-        tmem_ld16(t_row, va);
-        tmem_ld_wait();
-        // one 16-column chunk: 8 pairs -> two 16-byte stores into this row's swizzled P row
-        auto chunk = [&](const uint32_t(&v)[16], int ch) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-            tmax = max3(tmax, s0, s1);
-            const uint64_t x2 = fma2(pk2(s0, s1), c2, nmc2);
-            float p0, p1;
-            if (pair_is_poly<POLY>(i >> 1)) {
-              ex2_poly2(x2, p0, p1);
-            } else {
-              float x0, x1;
-              un2(x2, x0, x1);
-              p0 = ex2(x0);
-              p1 = ex2(x1);
-            }
-            pk[i >> 1] = pack_pair<DT>(p0, p1);
-            psum2 = add2(psum2, pk2(p0, p1));
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int jj = ch * 2 + u;  // 16-byte chunk index inside the 256-byte P row
-            const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + ((((uint32_t)jj & 7u) ^ rx) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                         "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                         : "memory");
-          }
-        };
-#pragma unroll
-        for (int ch = 0; ch < 8; ch += 2) {
-          tmem_ld16(t_row + (ch + 1) * 16, vb);  // in flight while chunk ch is processed
-          chunk(va, ch);
-          tmem_ld_wait();
-          if (ch + 2 < 8) tmem_ld16(t_row + (ch + 2) * 16, va);
-          chunk(vb, ch + 1);
-          if (ch + 2 < 8) tmem_ld_wait();
-        }
-        const bool over = (tmax - m_ref) * g.c > g.redo_log2;  // also true while m_ref == -inf
-        redo = __any_sync(0xffffffffu, over);
-        if (over) {
-          const float a0 = ex2((m_ref - tmax) * g.c);  // 0 on the first tile
-          l *= a0;
-          const uint64_t a2 = pk2(a0, a0);
-#pragma unroll
-          for (int i = 0; i < D / 2; ++i) o2[i] = mul2(o2[i], a2);
-          m_ref = tmax;
-        }
-      } while (redo);
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
-      float ps0, ps1;
-      un2(psum2, ps0, ps1);
-      l += ps0 + ps1;
-      mbar_wait(o_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      if constexpr (NACC * D >= 32) {
-#pragma unroll
-        for (int cch = 0; cch < NACC * D / 32; ++cch) {
-          uint32_t v[32];
-          tmem_ld32(t_row + cch * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int e = ((cch * 32 + i) % D) >> 1;
-            o2[e] = add2(o2[e], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          }
-        }
-      } else {
-        uint32_t v[16];
-        tmem_ld16(t_row, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) o2[i >> 1] = add2(o2[i >> 1], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_read);
-      if (tmax > m_ref) {
-        const float a1 = ex2((m_ref - tmax) * g.c);
-        l *= a1;
-        const uint64_t a2 = pk2(a1, a1);
-#pragma unroll
-        for (int i = 0; i < D / 2; ++i) o2[i] = mul2(o2[i], a2);
-        m_ref = tmax;
-      }
-    }
-    const float inv = 1.0f / l;
-    uint16_t* dst = out + tok * g.C + head * D;
-#pragma unroll
-    for (int i = 0; i < D; i += 8) {
-      float f[8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) un2(o2[(i >> 1) + u], f[2 * u], f[2 * u + 1]);
-      uint4 w;
-      w.x = pack_pair<DT>(f[0] * inv, f[1] * inv);
-      w.y = pack_pair<DT>(f[2] * inv, f[3] * inv);
-      w.z = pack_pair<DT>(f[4] * inv, f[5] * inv);
-      w.w = pack_pair<DT>(f[6] * inv, f[7] * inv);
-      *reinterpret_cast<uint4*>(dst + i) = w;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc<128>(tmem_base);
-  }
-}
-
-template <int D, int DT, int POLY, int NACC>
-static int launch_att5(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = att4_smem_bytes<D>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc5_kernel<D, DT, POLY, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc5): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  attention_tc5_kernel<D, DT, POLY, NACC><<<grid, 192, smem, stream>>>(tm, g, out);
-  return launch_status("sg_attention(tc5)");
-}
-
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
-}
-
-template <int D, int DT>
-static int dispatch_att5(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
-  static const int poly = env_int("SGB200_ATTN_POLY8", 0);  // eighths of the pairs evaluated by the polynomial
-  static const int nacc = env_int("SGB200_ATTN_NACC", 2);
-  constexpr int NA = D == 64 ? 2 : 4;
-#define SG_ATT5(P)                                                                        \
-  do {                                                                                    \
-    if (nacc == 1) return launch_att5<D, DT, P, 1>(tm, g, out, grid, stream);             \
-    if (nacc == 2) return launch_att5<D, DT, P, 2>(tm, g, out, grid, stream);             \
-    return launch_att5<D, DT, P, NA>(tm, g, out, grid, stream);                           \
-  } while (0)
-  if (poly == 1) SG_ATT5(1);
-  if (poly == 2) SG_ATT5(2);
-  if (poly == 3) SG_ATT5(3);
-  if (poly == 4) SG_ATT5(4);
-  SG_ATT5(0);
-#undef SG_ATT5
-}
-
-// =====================================================================================================
-// v7 (L >= 128, d <= 32): the key sequence is processed in QUARTER tiles of 32 keys through a ring of four 32-column
-// TMEM buffers, so that no hand-off between the tensor core and the softmax warps is ever waited for:
-//     step i (softmax):  sweep S_i -> P_i | arrive p_ready_i | read O_{i-2} | arrive o_read_{i-2}
-//     step i (issuer) :  wait p_ready_i -> P_i V_i into buffer i%4 (over the dead S_i) | wait o_read_{i-2} ->
-//                        S_{i+2} = Q K_{i+2}^T into buffer (i+2)%4 (over the consumed O_{i-2})
-// Every product is issued at least one whole quarter sweep before its consumer needs it (S_{i+2} during step i,
-// O_i read during step i+2).  v1 exposed two round trips per 128 keys (ncu: 32 % of the softmax warps' time sat in
-// mbarrier waits), v4 one.  Other changes against v1/v5:
-//   * ONE single-lane role: the MMA issuer also drives TMA.  With three K/V stages the slot of tile t+1 is known to be
-//     free when S of tile t starts (the o_read it has just observed implies every P V of tile t-2 is complete), so the
-//     kv_empty barriers disappear, and so does one of the two polling lanes (ncu: the two spin loops were 57 % of all
-//     issued instructions and shared their schedulers with half of the softmax warps).
-//   * warps 0..3 are the softmax warps (one per scheduler), warp 4 the issuer: 160 threads, <= 102 registers at
-//     four CTAs per SM.
-//   * inner body as v5: FFMA2 / FADD2 / FMNMX3, POLY/8 of the pairs through the FMA-pipe polynomial.
-//   * the exponent reference m_ref is initialised from the first quarter's maximum and afterwards only raised when a
-//     quarter's maximum exceeds it by more than redo_log2 (that quarter is swept again); a pending O computed under
-//     an older reference is rescaled when it is read.
-// =====================================================================================================
-constexpr int ATT_QK = 32;  // keys per quarter tile
-template <int D>
-constexpr int att7_smem_bytes() {
-  return 1024 + ATT_BM * D * 2 /*Q*/ + 3 * 2 * ATT_BN * D * 2 /*K,V x 3 stages*/ + P_BYTES + 256;
-}
-
-template <int D, int DT, int POLY>
-__global__ void __launch_bounds__(160, 4)
-attention_tc7_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
-  static_assert(D == 16 || D == 32, "O_i must fit a 32-column quarter buffer");
-  constexpr int ROWB = D * 2;
-  constexpr int TILE = ATT_BN * ROWB;
-  constexpr int KVS = 3;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE;        // [KVS]
-  uint8_t* sV = sK + KVS * TILE;  // [KVS]
-  uint8_t* sP = sV + KVS * TILE;  // 1024-aligned (TILE is a multiple of 4096); quarter q = 64-byte column q of the
-                                  // two SWIZZLE_128B atoms of the 128-key P tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [3]
-  uint64_t* s_full = bars + 4;    // [4]
-  uint64_t* p_ready = bars + 8;   // [4]
-  uint64_t* o_full = bars + 12;   // [4]
-  uint64_t* o_read = bars + 16;   // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * ATT_BM;
-  const int64_t kv0 = (m0 >> g.logL) << g.logL;
-  const int nkv = g.L / ATT_BN;
-  const int nq = 4 * nkv;
-
-  if (warp == 4 && lane == 0) {
-    prefetch_tensormap(&tm);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KVS; ++s) mbar_init(&kv_full[s], 1);
-    for (int b = 0; b < 4; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&p_ready[b], 4);
-      mbar_init(&o_full[b], 1);
-      mbar_init(&o_read[b], 4);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 4) tmem_alloc<128>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      // ===== TMA producer + MMA issuer =====
-      auto load_tile = [&](int t) {
-        const int s = t % KVS;
-        mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
-        const int tok = (int)(kv0 + (int64_t)t * ATT_BN);
-        tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
-        tma_load_2d(sV + s * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
-      };
-      const uint64_t qd = make_desc_rows(smem_u32(sQ), ROWB);
-      auto issue_s = [&](int i) {  // S_i = Q K_i^T (M128 x N32 x K=D) into buffer i % 4
-        const int t = i >> 2, qq = i & 3;
-        if (qq == 0) {
-          if (t + 1 < nkv) load_tile(t + 1);  // its slot held tile t-2: every P V of that tile is known to be complete
-          mbar_wait_spin(&kv_full[t % KVS], (uint32_t)(t / KVS) & 1u);
-          tc_fence_after();
-        }
-        const uint64_t kd = make_desc_rows(smem_u32(sK + (t % KVS) * TILE + qq * ATT_QK * ROWB), ROWB);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base + (uint32_t)(qq * ATT_QK), qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
-        umma_commit(&s_full[qq]);
-      };
-      mbar_arrive_expect_tx(q_full, g.tile_bytes);
-      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
-      load_tile(0);
-      mbar_wait_spin(q_full, 0);
-      issue_s(0);
-      issue_s(1);
-      for (int i = 0; i < nq; ++i) {
-        const int b = i & 3, t = i >> 2;
-        // O_i = P_i V_i (M128 x N=D x K32) over the dead S_i
-        mbar_wait_spin(&p_ready[b], (uint32_t)t & 1u);
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP) + (uint32_t)(b >> 1) * (ATT_BM * 128) + (uint32_t)(b & 1) * 64u;
-        const uint32_t va = smem_u32(sV + (t % KVS) * TILE + b * ATT_QK * ROWB);
-#pragma unroll
-        for (int k = 0; k < ATT_QK / 16; ++k) {
-          const uint64_t pd = make_desc_k128(pa + k * 32);
-          const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
-          umma_ss(tmem_base + (uint32_t)(b * ATT_QK), pd, vd, g.idesc_o, k != 0);
-        }
-        umma_commit(&o_full[b]);
-        if (i + 2 < nq) {
-          if (i >= 2) {
-            mbar_wait_spin(&o_read[(i - 2) & 3], (uint32_t)((i - 2) >> 2) & 1u);
-            tc_fence_after();
-          }
-          issue_s(i + 2);
-        }
-      }
-    }
-  } else {
-    // ===== softmax + epilogue: thread = one query row (TMEM lane quadrant = warp) =====
-    const int r = warp * 32 + lane;
-    const int64_t tok = m0 + r;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    const uint32_t rx = (uint32_t)(r & 7);
-    const uint64_t c2 = pk2(g.c, g.c);
-    uint64_t o2[D / 2];
-#pragma unroll
-    for (int e = 0; e < D / 2; ++e) o2[e] = 0ull;  // two +0.0f
-    float m_ref = 0.f, l = 0.f;
-    float m_used[4] = {0.f, 0.f, 0.f, 0.f};
-
-    auto read_o = [&](int b, uint32_t parity) {  // o += O_b * 2^((m_used[b] - m_ref) c)
-      mbar_wait(&o_full[b], parity);
-      tc_fence_after();
-      uint32_t v[D];
-      if constexpr (D == 16) tmem_ld16(t_row + b * ATT_QK, reinterpret_cast<uint32_t(&)[16]>(v));
-      else tmem_ld32(t_row + b * ATT_QK, reinterpret_cast<uint32_t(&)[32]>(v));
-      tmem_ld_wait();
-      const float sc = ex2((m_used[b] - m_ref) * g.c);  // exactly 1.0f while the reference has not moved
-      const uint64_t sc2 = pk2(sc, sc);
-#pragma unroll
-      for (int e = 0; e < D / 2; ++e)
-        o2[e] = fma2(pk2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sc2, o2[e]);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_read[b]);
-    };
-
-    for (int t = 0; t < nkv; ++t) {
-      const uint32_t ph = (uint32_t)t & 1u;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        mbar_wait(&s_full[b], ph);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(t_row + b * ATT_QK, v);
-        tmem_ld_wait();
-        if (t == 0 && b == 0) {  // the reference starts at the first quarter's row maximum
-          float mx = __uint_as_float(v[0]);
-#pragma unroll
-          for (int i = 1; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[i]), __uint_as_float(v[(i + 1) & 31]));
-          m_ref = mx;
-        }
-        float tmax;
-        uint64_t psum2;
-        bool redo;
-        do {
-          const float nmc = -m_ref * g.c;
-          const uint64_t nmc2 = pk2(nmc, nmc);
-          tmax = -INFINITY;
-          psum2 = 0ull;
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-            tmax = max3(tmax, s0, s1);
-            const uint64_t x2 = fma2(pk2(s0, s1), c2, nmc2);
-            float p0, p1;
-            if (pair_is_poly<POLY>(i >> 1)) {
-              ex2_poly2(x2, p0, p1);
-            } else {
-              float x0, x1;
-              un2(x2, x0, x1);
-              p0 = ex2(x0);
-              p1 = ex2(x1);
-            }
-            pk[i >> 1] = pack_pair<DT>(p0, p1);
-            psum2 = add2(psum2, pk2(p0, p1));
-          }
-          // 32 keys = 64 bytes = 16-byte chunks jj = 4b .. 4b+3 of this row's 256-byte P row
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int jj = b * 4 + u;
-            const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + ((((uint32_t)jj & 7u) ^ rx) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                         "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                         : "memory");
-          }
-          const bool over = (tmax - m_ref) * g.c > g.redo_log2;
-          redo = __any_sync(0xffffffffu, over);
-          if (over) {  // raise the reference: exact rescale of what has been accumulated, then sweep again
-            const float a0 = ex2((m_ref - tmax) * g.c);
-            l *= a0;
-            const uint64_t a2 = pk2(a0, a0);
-#pragma unroll
-            for (int e = 0; e < D / 2; ++e) o2[e] = mul2(o2[e], a2);
-            m_ref = tmax;
-          }
-        } while (redo);
-        m_used[b] = m_ref;
-        tc_fence_before();    // our tcgen05.ld of S_i precede the MMA that overwrites those columns
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[b]);
-        float ps0, ps1;
-        un2(psum2, ps0, ps1);
-        l += ps0 + ps1;
-        // O of two quarters ago: buffer (b + 2) % 4, of this tile for b >= 2, of the previous tile otherwise
-        if (b >= 2) read_o(b - 2, ph);
-        else if (t > 0) read_o(b + 2, ph ^ 1u);
-      }
-    }
-    read_o(2, (uint32_t)(nkv - 1) & 1u);
-    read_o(3, (uint32_t)(nkv - 1) & 1u);
-    const float inv = 1.0f / l;
-    uint16_t* dst = out + tok * g.C + head * D;
-#pragma unroll
-    for (int i = 0; i < D; i += 8) {
-      float f[8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) un2(o2[(i >> 1) + u], f[2 * u], f[2 * u + 1]);
-      uint4 w;
-      w.x = pack_pair<DT>(f[0] * inv, f[1] * inv);
-      w.y = pack_pair<DT>(f[2] * inv, f[3] * inv);
-      w.z = pack_pair<DT>(f[4] * inv, f[5] * inv);
-      w.w = pack_pair<DT>(f[6] * inv, f[7] * inv);
-      *reinterpret_cast<uint4*>(dst + i) = w;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    __syncwarp();
-    tmem_dealloc<128>(tmem_base);
-  }
-}
-
-template <int D, int DT, int POLY>
-static int launch_att7(const CUtensorMap& tm, const AttGeom& g0, int act_dtype, uint16_t* out, dim3 grid,
-                       cudaStream_t stream) {
-  constexpr int smem = att7_smem_bytes<D>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc7_kernel<D, DT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc7): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  AttGeom g = g0;
-  g.idesc_s = make_idesc(act_dtype, 128, ATT_QK, 0, 0);
-  attention_tc7_kernel<D, DT, POLY><<<grid, 160, smem, stream>>>(tm, g, out);
-  return launch_status("sg_attention(tc7)");
-}
-
-template <int D, int DT>
-static int dispatch_att7(const CUtensorMap& tm, const AttGeom& g, int act_dtype, uint16_t* out, dim3 grid,
-                         cudaStream_t stream) {
-  static const int poly = env_int("SGB200_ATTN_POLY8", 2);  // eighths of the pairs evaluated by the polynomial
-  if (poly == 0) return launch_att7<D, DT, 0>(tm, g, act_dtype, out, grid, stream);
-  if (poly == 1) return launch_att7<D, DT, 1>(tm, g, act_dtype, out, grid, stream);
-  if (poly == 3) return launch_att7<D, DT, 3>(tm, g, act_dtype, out, grid, stream);
-  if (poly == 4) return launch_att7<D, DT, 4>(tm, g, act_dtype, out, grid, stream);
-  return launch_att7<D, DT, 2>(tm, g, act_dtype, out, grid, stream);
 }
 
 // =====================================================================================================
@@ -1879,8 +817,7 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   };
   for (int j = 0; j < nkv; ++j) {
     const uint32_t ph = (uint32_t)j & 1u;
-    if (g.dbg & 4) mbar_wait_spin(s_full, ph);
-    else if (!(g.dbg & 1)) mbar_wait(s_full, ph);
+    mbar_wait(s_full, ph);
     tc_fence_after();
     if (j == 0) m_ref = tile_max();
     // The reference m_ref is NOT tracked per tile (that costs an FMNMX per pair): p = exp2((s - m_ref) c) may exceed 1.
@@ -1953,8 +890,7 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
     } while (redo);
     tc_fence_before();    // our tcgen05.ld of S precede the MMA that overwrites those columns
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    if (g.dbg & 2) {
-    } else if (warp == 0) {
+    if (warp == 0) {
       named_bar_sync<1, 128>();
       issue_pv(j);
       __syncwarp();
@@ -1964,8 +900,7 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
     float ps0, ps1;
     un2(psum2, ps0, ps1);
     l += ps0 + ps1;
-    if (g.dbg & 4) mbar_wait_spin(o_full, ph);
-    else if (!(g.dbg & 1)) mbar_wait(o_full, ph);
+    mbar_wait(o_full, ph);
     tc_fence_after();
     if constexpr (NACC * D >= 32) {
 #pragma unroll
@@ -1987,7 +922,7 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
       for (int i = 0; i < 16; i += 2) o2[i >> 1] = add2(o2[i >> 1], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
     }
     tc_fence_before();
-    if (j + 1 < nkv && !(g.dbg & 2)) {
+    if (j + 1 < nkv) {
       if (warp == 0) {
         named_bar_sync<2, 128>();
         // o_full(j) has been observed: every MMA that read K/V stage j&1 is complete -> it can be refilled with tile j+2
@@ -2046,311 +981,6 @@ static int dispatch_att8(const CUtensorMap& tm, const AttGeom& g, uint16_t* out,
   return launch_att8<D, DT, 2, 2>(tm, g, out, grid, stream);
 }
 
-// =====================================================================================================
-// v9 (L >= 128, d <= 32): zero exposed hand-offs at v8's footprint (128 TMEM columns, four CTAs per SM).
-// ncu on v8: the softmax warps spend 31 % of their time waiting for S = Q K^T and O_j = P V (the kernel runs at 1.91 ms
-// instead of 2.40 ms at sa6 when those waits are removed).  Here
-//   * the key tile is 48 keys, S is DOUBLE-BUFFERED in TMEM columns [0,48) / [48,96) and the output accumulates in
-//     TMEM columns [96, 96+d) across all key tiles (tcgen05.mma accumulate), so a step of a softmax warp is just
-//         wait s_full[i&1] (issued two steps ago) | sweep S_i -> P_i | bar.arrive
-//     with no per-tile read of O and nothing to wait for in steady state;
-//   * a fifth warp sleeps on the named barrier (bar.sync, no polling) and then issues, in order, P_i V_i (3 MMAs,
-//     accumulating), S_{i+2} = Q K_{i+2}^T into the buffer the sweep has just released, and the TMA load of tile i+3.
-//     tcgen05.commit tracks every MMA issued before it by the thread, so a softmax thread that has observed
-//     s_full of step i knows P_{i-2} V_{i-2} is complete: the P buffer (ring of 2) and the K/V stage (ring of 5) it
-//     is about to reuse are free without any further barrier;
-//   * the exponent reference m_ref is the first tile's row maximum and is raised only if a tile exceeds it by more
-//     than redo_log2 (then O's row is rescaled in place through tcgen05.ld / st and the tile swept again);
-//   * L is a power of two, so the last tile holds 16 or 32 valid keys: its sweep covers only those chunks and its
-//     P V is issued with K = 16 / 32, so nothing beyond the row's keys is ever read by a product that is used.
-// =====================================================================================================
-constexpr int ATT9_BN = 48;
-template <int D>
-struct Att9 {
-  static constexpr int ROWB = D * 2;
-  static constexpr int QT = ATT_BM * ROWB;
-  static constexpr int KVT = ATT9_BN * ROWB;  // 1536 / 3072: a multiple of the 32B / 64B swizzle period (256 / 512)
-  static constexpr int KVS = 5;
-  static constexpr int PT = ATT_BM * 128;     // one SWIZZLE_128B atom column: 128 rows x 128 bytes (96 used)
-  static constexpr int SMEM = 1024 + QT + 2 * PT + 2 * KVS * KVT + 256;
-};
-
-template <int D, int DT, int POLY>
-__global__ void __launch_bounds__(160, (D == 32 ? 3 : 4))
-attention_tc9_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                     const AttGeom g, uint16_t* __restrict__ out) {
-  static_assert(D == 16 || D == 32, "O must fit TMEM columns [96, 128)");
-  using A = Att9<D>;
-  constexpr int ROWB = A::ROWB, KVS = A::KVS;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;
-  uint8_t* sP = sQ + A::QT;       // [2], 1024-aligned
-  uint8_t* sK = sP + 2 * A::PT;   // [KVS]
-  uint8_t* sV = sK + KVS * A::KVT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KVS * A::KVT);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;  // [5]
-  uint64_t* s_full = bars + 6;   // [2]
-  uint64_t* pv_done = bars + 8;  // one phase per step
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * ATT_BM;
-  const int64_t kv0 = (m0 >> g.logL) << g.logL;
-  const int nst = (g.L + ATT9_BN - 1) / ATT9_BN;       // >= 3
-  const int rem16 = (g.L - (nst - 1) * ATT9_BN) >> 4;  // 16-key chunks of the last tile: 1, 2 (or 3)
-
-  if (warp == 4 && lane == 0) {
-    prefetch_tensormap(&tmQ);
-    prefetch_tensormap(&tmKV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KVS; ++s) mbar_init(&kv_full[s], 1);
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(pv_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 4) {
-    __syncwarp();
-    tmem_alloc<128>(tmem_slot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 2 * ATT9_BN;
-
-  if (warp == 4) {
-    // ===== issuer warp: sleeps on the named barrier; lane 0 issues MMA + TMA =====
-    auto load_tile = [&](int t) {
-      const int s = t % KVS;
-      mbar_arrive_expect_tx(&kv_full[s], 2u * A::KVT);
-      const int tok = (int)(kv0 + (int64_t)t * ATT9_BN);
-      tma_load_2d(sK + s * A::KVT, &tmKV, &kv_full[s], g.C + head * D, tok);
-      tma_load_2d(sV + s * A::KVT, &tmKV, &kv_full[s], 2 * g.C + head * D, tok);
-    };
-    const uint64_t qd = make_desc_rows(smem_u32(sQ), ROWB);
-    auto issue_s = [&](int t) {  // S_t = Q K_t^T (M128 x N48 x K=D) into S buffer t & 1
-      mbar_wait_spin(&kv_full[t % KVS], (uint32_t)(t / KVS) & 1u);
-      tc_fence_after();
-      const uint64_t kd = make_desc_rows(smem_u32(sK + (t % KVS) * A::KVT), ROWB);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_ss(tmem_base + (uint32_t)((t & 1) * ATT9_BN), qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
-      umma_commit(&s_full[t & 1]);
-    };
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, (uint32_t)A::QT);
-      tma_load_2d(sQ, &tmQ, q_full, head * D, (int)m0);
-      load_tile(0);
-      load_tile(1);
-      load_tile(2);
-      mbar_wait_spin(q_full, 0);
-      issue_s(0);
-      issue_s(1);
-    }
-    __syncwarp();
-    for (int i = 0; i < nst; ++i) {
-      if (i & 1) named_bar_sync<2, 160>();
-      else named_bar_sync<1, 160>();
-      if (lane == 0) {
-        tc_fence_after();
-        // O += P_i V_i : A = P_i (K-major, SWIZZLE_128B rows of 48 keys), B = V_i consumed MN-major
-        const uint32_t pa = smem_u32(sP + (i & 1) * A::PT);
-        const uint32_t va = smem_u32(sV + (i % KVS) * A::KVT);
-        const int ksteps = (i == nst - 1) ? rem16 : ATT9_BN / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t pd = make_desc_k128(pa + k * 32);
-          const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
-          umma_ss(tmem_o, pd, vd, g.idesc_o, (i | k) != 0);
-        }
-        umma_commit(pv_done);
-        if (i + 2 < nst) issue_s(i + 2);
-        if (i + 3 < nst) load_tile(i + 3);  // its stage held tile i-2, whose P V the softmax warps have seen complete
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===== softmax warps: thread = one query row (TMEM lane quadrant = warp) =====
-    const int r = warp * 32 + lane;
-    const int64_t tok = m0 + r;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const uint32_t t_o = tmem_o + lane_base;
-    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    const uint32_t rx = (uint32_t)(r & 7);
-    const uint64_t c2 = pk2(g.c, g.c);
-    float m_ref = 0.f, l = 0.f;
-    for (int i = 0; i < nst; ++i) {
-      const int sb = i & 1;
-      const uint32_t t_s = tmem_base + lane_base + (uint32_t)(sb * ATT9_BN);
-      const uint32_t p_buf = p_row + (uint32_t)(sb * A::PT);
-      const int nch = (i == nst - 1) ? rem16 : ATT9_BN / 16;
-      mbar_wait(&s_full[sb], (uint32_t)(i >> 1) & 1u);
-      tc_fence_after();
-      if (i == 0) {  // the reference starts at the first tile's row maximum (a full tile: nst >= 3)
-        float mx = -INFINITY;
-#pragma unroll
-        for (int ch = 0; ch < ATT9_BN / 16; ++ch) {
-          uint32_t v[16];
-          tmem_ld16(t_s + ch * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-        }
-        m_ref = mx;
-      }
-      float tmax;
-      uint64_t psum2;
-      bool redo;
-      do {
-        const float nmc = -m_ref * g.c;
-        const uint64_t nmc2 = pk2(nmc, nmc);
-        tmax = -INFINITY;
-        psum2 = 0ull;
-        auto chunk = [&](const uint32_t(&v)[16], int ch) {  // 16 keys: 8 pairs -> two 16-byte stores of the P row
-          uint32_t pk[8];
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const float s0 = __uint_as_float(v[e]), s1 = __uint_as_float(v[e + 1]);
-            tmax = max3(tmax, s0, s1);
-            const uint64_t x2 = fma2(pk2(s0, s1), c2, nmc2);
-            float p0, p1;
-            if (pair_is_poly<POLY>(e >> 1)) {
-              ex2_poly2(x2, p0, p1);
-            } else {
-              float x0, x1;
-              un2(x2, x0, x1);
-              p0 = ex2(x0);
-              p1 = ex2(x1);
-            }
-            pk[e >> 1] = pack_pair<DT>(p0, p1);
-            psum2 = add2(psum2, pk2(p0, p1));
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t addr = p_buf + ((((uint32_t)(ch * 2 + u)) ^ rx) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                         "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                         : "memory");
-          }
-        };
-        uint32_t va[16], vb[16];
-        tmem_ld16(t_s, va);
-        tmem_ld_wait();
-        if (nch > 1) tmem_ld16(t_s + 16, vb);  // in flight while chunk 0 is processed
-        chunk(va, 0);
-        if (nch > 1) {
-          tmem_ld_wait();
-          if (nch > 2) tmem_ld16(t_s + 32, va);
-          chunk(vb, 1);
-          if (nch > 2) {
-            tmem_ld_wait();
-            chunk(va, 2);
-          }
-        }
-        const bool over = (tmax - m_ref) * g.c > g.redo_log2;
-        redo = __any_sync(0xffffffffu, over);
-        if (redo) {
-          // raise the reference (rare): exact rescale of l and of this row of O, then sweep the tile again
-          const float a0 = over ? ex2((m_ref - tmax) * g.c) : 1.0f;
-          if (i > 0) {
-            mbar_wait(pv_done, (uint32_t)(i - 1) & 1u);  // every P V issued so far has landed in O
-            tc_fence_after();
-            uint32_t ov[D];
-            if constexpr (D == 16) tmem_ld16(t_o, reinterpret_cast<uint32_t(&)[16]>(ov));
-            else tmem_ld32(t_o, reinterpret_cast<uint32_t(&)[32]>(ov));
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < D; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * a0);
-            if constexpr (D == 16) {
-              tmem_st16(t_o, reinterpret_cast<const uint32_t(&)[16]>(ov));
-            } else {
-              tmem_st16(t_o, reinterpret_cast<const uint32_t(&)[16]>(ov[0]));
-              tmem_st16(t_o + 16, reinterpret_cast<const uint32_t(&)[16]>(ov[16]));
-            }
-            tmem_st_wait();
-          }
-          if (over) {
-            l *= a0;
-            m_ref = tmax;
-          }
-        }
-      } while (redo);
-      tc_fence_before();    // our tcgen05.ld of S_i / st of O precede the MMAs issued after the barrier
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      if (sb) named_bar_arrive<2, 160>();
-      else named_bar_arrive<1, 160>();
-      float ps0, ps1;
-      un2(psum2, ps0, ps1);
-      l += ps0 + ps1;
-    }
-    mbar_wait(pv_done, (uint32_t)(nst - 1) & 1u);
-    tc_fence_after();
-    uint32_t ov[D];
-    if constexpr (D == 16) tmem_ld16(t_o, reinterpret_cast<uint32_t(&)[16]>(ov));
-    else tmem_ld32(t_o, reinterpret_cast<uint32_t(&)[32]>(ov));
-    tmem_ld_wait();
-    const float inv = 1.0f / l;
-    uint16_t* dst = out + tok * g.C + head * D;
-#pragma unroll
-    for (int e = 0; e < D; e += 8) {
-      uint4 w;
-      w.x = pack_pair<DT>(__uint_as_float(ov[e]) * inv, __uint_as_float(ov[e + 1]) * inv);
-      w.y = pack_pair<DT>(__uint_as_float(ov[e + 2]) * inv, __uint_as_float(ov[e + 3]) * inv);
-      w.z = pack_pair<DT>(__uint_as_float(ov[e + 4]) * inv, __uint_as_float(ov[e + 5]) * inv);
-      w.w = pack_pair<DT>(__uint_as_float(ov[e + 6]) * inv, __uint_as_float(ov[e + 7]) * inv);
-      *reinterpret_cast<uint4*>(dst + e) = w;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    __syncwarp();
-    tmem_dealloc<128>(tmem_base);
-  }
-}
-
-template <int D, int DT, int POLY>
-static int launch_att9(const void* qkv, const AttGeom& g0, int act_dtype, uint16_t* out, cudaStream_t stream) {
-  using A = Att9<D>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc9_kernel<D, DT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, A::SMEM);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc9): cudaFuncSetAttribute(%d B smem): %s", A::SMEM, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  AttGeom g = g0;
-  g.idesc_s = make_idesc(act_dtype, 128, ATT9_BN, 0, 0);
-  CUtensorMap tmQ, tmKV;
-  const uint64_t dims[2] = {(uint64_t)3 * g.C, (uint64_t)g.M};
-  const uint64_t strides[1] = {(uint64_t)3 * g.C * 2};
-  const uint32_t boxq[2] = {(uint32_t)D, 128u};
-  const uint32_t boxkv[2] = {(uint32_t)D, (uint32_t)ATT9_BN};
-  const CUtensorMapSwizzle sw = D == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-  int rc = make_tmap(&tmQ, act_dtype, 2, qkv, dims, strides, boxq, sw);
-  if (rc) return rc;
-  rc = make_tmap(&tmKV, act_dtype, 2, qkv, dims, strides, boxkv, sw);
-  if (rc) return rc;
-  dim3 grid((unsigned)(g.M / ATT_BM), (unsigned)g.heads);
-  attention_tc9_kernel<D, DT, POLY><<<grid, 160, A::SMEM, stream>>>(tmQ, tmKV, g, out);
-  return launch_status("sg_attention(tc9)");
-}
-
-template <int D, int DT>
-static int dispatch_att9(const void* qkv, const AttGeom& g, int act_dtype, uint16_t* out, cudaStream_t stream) {
-  static const int poly = env_int("SGB200_ATTN_POLY8", 2);  // eighths of the pairs evaluated by the polynomial
-  if (poly == 0) return launch_att9<D, DT, 0>(qkv, g, act_dtype, out, stream);
-  if (poly == 1) return launch_att9<D, DT, 1>(qkv, g, act_dtype, out, stream);
-  if (poly == 3) return launch_att9<D, DT, 3>(qkv, g, act_dtype, out, stream);
-  return launch_att9<D, DT, 2>(qkv, g, act_dtype, out, stream);
-}
-
 // fraction of exponentials evaluated by the FMA-pipe polynomial: SGB200_ATTN_POLY = 0 (none), 4 (1/4), 2 (1/2)
 static int attention_poly() {
   static int v = -1;
@@ -2363,16 +993,18 @@ static int attention_poly() {
 }
 
 static int attention_version() {
-  static int v = 0;
-  if (v == 0) {
+  static int v = -1;
+  if (v < 0) {
+    // SGB200_ATTN: 0 = auto (default): v8 for L >= 128, v1 below (block-diagonal tile over 128/L batch rows);
+    // 1 = v1 everywhere, 3 = v3 (TMEM-resident O, 128-d key tiles) for L >= 256, 8 = v8.
+    // Measured on B200 (rows=128, bf16, ms); v2/v4/v5/v7/v9/v10 were experiments, removed (see profiles/README.md):
+    //                           v1     v2    v3     v4     v5     v7     v8     v9     v10
+    //   d=16 L=4096 (sa6)       3.07   3.57  3.12   2.82   2.43   3.41   2.12   2.48   2.25
+    //   d=32 L=1024 (sa1)       0.347  -     0.267  0.234  0.227  0.348  0.188  0.220  0.184
+    //   d=16 L=1024 (sa5)       0.226  -     -      0.200  0.183  0.237  0.152  0.175  0.158
     const char* e = getenv("SGB200_ATTN");
-    // 0 = auto (default): v8 for L >= 128, v1 below.  1..8 force a version where it applies (v1 always for L < 128).
-    // measured on B200 (rows=128, bf16), ms:       v1     v2    v3    v4    v5    v7    v8
-    //   d=16 L=4096 (sa6)                          3.07   3.57  3.12  2.82  2.43  3.41  2.40
-    //   d=32 L=1024 (sa1)                          0.347  -     0.267 0.234 0.227 0.348 0.219
-    //   d=16 L=1024 (sa5)                          0.226  -     -     0.200 0.183 0.237 0.178
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 9) v = 0;
+    if (v != 1 && v != 3 && v != 8) v = 0;
   }
   return v;
 }
@@ -2404,10 +1036,6 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
   g.idesc_1 = make_idesc(act_dtype, 128, 16, 0, 0);
   g.redo_log2 = act_dtype == SG_BF16 ? 60.0f : 13.0f;  // p <= 2^60 (bf16/fp32 range) / 2^13 (fp16 max 65504)
   g.act_dtype = act_dtype;
-  {
-    static const int dbg = getenv("SGB200_ATTN_DBG") ? atoi(getenv("SGB200_ATTN_DBG")) : 0;
-    g.dbg = dbg;
-  }
   CUtensorMap tm;
   const uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)g.M};
   const uint64_t strides[1] = {(uint64_t)3 * C * 2};
@@ -2418,22 +1046,6 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
   SG_REQUIRE(heads <= 65535, "sg_attention(tc): too many heads");
   dim3 grid((unsigned)cdiv(g.M, ATT_BM), (unsigned)heads);
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
-  if (L >= ATT_BN && d <= 32 && attention_version() == 9) {
-    if (act_dtype == SG_BF16) {
-      if (d == 16) return dispatch_att9<16, SG_BF16>(qkv, g, act_dtype, o, stream);
-      return dispatch_att9<32, SG_BF16>(qkv, g, act_dtype, o, stream);
-    }
-    if (d == 16) return dispatch_att9<16, SG_F16>(qkv, g, act_dtype, o, stream);
-    return dispatch_att9<32, SG_F16>(qkv, g, act_dtype, o, stream);
-  }
-  if (L >= ATT_BN && d <= 32 && attention_version() == 7) {
-    if (act_dtype == SG_BF16) {
-      if (d == 16) return dispatch_att7<16, SG_BF16>(tm, g, act_dtype, o, grid, stream);
-      return dispatch_att7<32, SG_BF16>(tm, g, act_dtype, o, grid, stream);
-    }
-    if (d == 16) return dispatch_att7<16, SG_F16>(tm, g, act_dtype, o, grid, stream);
-    return dispatch_att7<32, SG_F16>(tm, g, act_dtype, o, grid, stream);
-  }
   if (L >= ATT_BN && (attention_version() == 8 || attention_version() == 0)) {
     if (act_dtype == SG_BF16) {
       if (d == 16) return dispatch_att8<16, SG_BF16>(tm, g, o, grid, stream);
@@ -2444,27 +1056,7 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
     if (d == 32) return dispatch_att8<32, SG_F16>(tm, g, o, grid, stream);
     return dispatch_att8<64, SG_F16>(tm, g, o, grid, stream);
   }
-  if (L >= ATT_BN && attention_version() == 5) {
-    if (act_dtype == SG_BF16) {
-      if (d == 16) return dispatch_att5<16, SG_BF16>(tm, g, o, grid, stream);
-      if (d == 32) return dispatch_att5<32, SG_BF16>(tm, g, o, grid, stream);
-      return dispatch_att5<64, SG_BF16>(tm, g, o, grid, stream);
-    }
-    if (d == 16) return dispatch_att5<16, SG_F16>(tm, g, o, grid, stream);
-    if (d == 32) return dispatch_att5<32, SG_F16>(tm, g, o, grid, stream);
-    return dispatch_att5<64, SG_F16>(tm, g, o, grid, stream);
-  }
-  if (L >= ATT_BN && attention_version() == 4) {
-    if (act_dtype == SG_BF16) {
-      if (d == 16) return launch_att4<16, SG_BF16>(tm, g, act_dtype, o, grid, stream);
-      if (d == 32) return launch_att4<32, SG_BF16>(tm, g, act_dtype, o, grid, stream);
-      return launch_att4<64, SG_BF16>(tm, g, act_dtype, o, grid, stream);
-    }
-    if (d == 16) return launch_att4<16, SG_F16>(tm, g, act_dtype, o, grid, stream);
-    if (d == 32) return launch_att4<32, SG_F16>(tm, g, act_dtype, o, grid, stream);
-    return launch_att4<64, SG_F16>(tm, g, act_dtype, o, grid, stream);
-  }
-  if (L >= 2 * ATT_BM && (attention_version() == 3 || (attention_version() == 0 && d >= 32))) {
+  if (L >= 2 * ATT_BM && attention_version() == 3) {
     if (act_dtype == SG_BF16) {
       if (d == 16) return launch_att3<16, SG_BF16>(qkv, g, act_dtype, o, stream);
       if (d == 32) return launch_att3<32, SG_BF16>(qkv, g, act_dtype, o, stream);
@@ -2473,17 +1065,6 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
     if (d == 16) return launch_att3<16, SG_F16>(qkv, g, act_dtype, o, stream);
     if (d == 32) return launch_att3<32, SG_F16>(qkv, g, act_dtype, o, stream);
     return launch_att3<64, SG_F16>(qkv, g, act_dtype, o, stream);
-  }
-  if (L >= 2 * ATT_BM && attention_version() == 2) {
-    dim3 grid2((unsigned)(g.M / (2 * ATT_BM)), (unsigned)heads);
-    if (act_dtype == SG_BF16) {
-      if (d == 16) return launch_att2<16, SG_BF16>(tm, g, o, grid2, stream);
-      if (d == 32) return launch_att2<32, SG_BF16>(tm, g, o, grid2, stream);
-      return launch_att2<64, SG_BF16>(tm, g, o, grid2, stream);
-    }
-    if (d == 16) return launch_att2<16, SG_F16>(tm, g, o, grid2, stream);
-    if (d == 32) return launch_att2<32, SG_F16>(tm, g, o, grid2, stream);
-    return launch_att2<64, SG_F16>(tm, g, o, grid2, stream);
   }
   const int poly = attention_poly();
 #define SG_ATT_DISPATCH(DD, TT)                                                  \
