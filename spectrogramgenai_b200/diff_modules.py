@@ -230,6 +230,53 @@ class Diffusion:
             self.ema_model = copy.deepcopy(self.model).eval().requires_grad_(False)
             self.ema_model.load_state_dict(torch.load(ema_path, weights_only=True))
 
+    def load_model(self, args):
+        """Reference `load_model(args)` (:525-546): loads models/<run_name>/ckpt.pt when args.load_model is set and
+        raises FileNotFoundError when a checkpoint is missing.  The reference also restores optim.pt into its AdamW
+        optimizer; sampling has no optimizer, so the file is only required to exist (same error as upstream)."""
+        if not args.load_model:
+            print("Starting model ftesh...")
+            return
+        model_path = os.path.join("models", args.run_name, "ckpt.pt")
+        if os.path.exists(model_path):
+            self.model.load_state_dict(torch.load(model_path, weights_only=True))
+            print(f"Model loaded successfully from {model_path}")
+        else:
+            raise FileNotFoundError(f"Model checkpoint not found at {model_path}")
+        optim_path = os.path.join("models", args.run_name, "optim.pt")
+        if not os.path.exists(optim_path):
+            raise FileNotFoundError(f"Optimizer checkpoint not found at {optim_path}")
+        print("Model loaded successfully")
+
+    # ------------------------------------------------------------------ generation driver (:759-775)
+    def gen_images(self, img_folder, samp_i, labels=None, *, colormap=None, **sample_kw):
+        """Reference `gen_images(img_folder, samp_i, labels=None)`: one sample per label, coloured with viridis and
+        written as RGBA PNG `{class_name}_gen_imgs_{i}_{samp_i}.png` (the name format src/helpers.py:602-610 parses).
+        `colormap` (ours): callable uint8 [H, W] -> float RGBA [H, W, 4]; default matplotlib.cm.viridis, imported
+        lazily (the reference imports matplotlib at module top).  Returns the list of files written."""
+        import numpy as np
+        from PIL import Image
+
+        if colormap is None:
+            try:
+                from matplotlib import cm
+            except ImportError as e:  # pragma: no cover - depends on the environment
+                raise ImportError("gen_images colours with matplotlib.cm.viridis (as the reference does); install "
+                                  "matplotlib or pass colormap=") from e
+            colormap = cm.viridis
+        class_names = getattr(self, "class_names", None) or [str(k) for k in range(self.num_classes or 0)]
+        if labels is None:
+            labels = torch.arange(self.num_classes).long().to(self.device)
+        sampled_images = self.sample(False, labels, **sample_kw)
+        paths = []
+        for i, (lab, img) in enumerate(zip(torch.as_tensor(labels).reshape(-1).tolist(), sampled_images)):
+            rgba = colormap(img.permute(1, 2, 0).cpu().numpy().squeeze())
+            rgba = (np.asarray(rgba) * 255).astype(np.uint8)
+            path = f"{img_folder}/{class_names[lab]}_gen_imgs_{i}_{samp_i}.png"
+            Image.fromarray(rgba).save(path)
+            paths.append(path)
+        return paths
+
     # ------------------------------------------------------------------ sampling (:411-442)
     @torch.no_grad()
     def sample(self, use_ema, labels, cfg_scale=3, *legacy, noise=None, seed=0, sample_base=0, micro_batch=512,

@@ -1,0 +1,64 @@
+"""Generation driver: the B200 counterpart of /root/reference/src/ddpm_conditional_generate.py (same flags, same
+output files).  One process per GPU; with torchrun the sample indices [start_idx, start_idx + num_samples) are split
+across ranks (each index is one `gen_images` call = one spectrogram per class), so no collective is needed: every rank
+writes its own PNG files.
+
+    python -m spectrogramgenai_b200.generate --run_name DDPM_conditional_VAE --num_samples 50 --img_folder diffusion_samples
+    torchrun --nproc-per-node 8 -m spectrogramgenai_b200.generate ...
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from types import SimpleNamespace
+
+import torch
+
+from .diff_modules import DiffusionVAE
+from .diff_utils import set_seed
+
+
+def parse_args(argv=None):
+    c = SimpleNamespace(run_name="DDPM_conditional_VAE", seed=42, num_classes=27, noise_steps=1000, img_size=256,
+                        dataset_path="Birdnet_conf_files_images_split", img_folder="diffusion_samples", train_folder="train",
+                        start_idx=0, num_samples=50, sav_denoise_path=None)
+    p = argparse.ArgumentParser(description="CFG-DDPM spectrogram generation on B200")
+    p.add_argument("--seed", type=int, default=c.seed)
+    p.add_argument("--img_size", type=int, default=c.img_size)
+    p.add_argument("--num_classes", type=int, default=c.num_classes)
+    p.add_argument("--noise_steps", type=int, default=c.noise_steps)
+    p.add_argument("--load_model", type=bool, default=True)
+    p.add_argument("--img_folder", type=str, default=c.img_folder)
+    p.add_argument("--num_samples", type=int, default=c.num_samples, help="number of samples per class")
+    p.add_argument("--run_name", type=str, default=c.run_name, help="run name (where to load model)")
+    p.add_argument("--dataset_path", type=str, default=c.dataset_path, help="class names = sorted(listdir(<path>/train))")
+    p.add_argument("--start_idx", type=int, default=c.start_idx)
+    p.add_argument("--sav_denoise_path", type=str, default=c.sav_denoise_path)
+    p.add_argument("--vqae_path", type=str, default="models/VQAE/ckpt.pt")
+    p.add_argument("--compute_dtype", type=str, default="bf16", choices=["bf16", "f16", "fp32"])
+    a = p.parse_args(argv)
+    for k, v in vars(a).items():
+        setattr(c, k, v)
+    return c
+
+
+def main(argv=None):
+    config = parse_args(argv)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    set_seed(config.seed)
+    os.makedirs(config.img_folder, exist_ok=True)
+    class_names = sorted(os.listdir(os.path.join(config.dataset_path, config.train_folder)))
+    diffuser = DiffusionVAE(config.noise_steps, img_size=config.img_size, num_classes=config.num_classes,
+                            device=f"cuda:{local}", vqae_path=config.vqae_path, sav_denoise_path=config.sav_denoise_path,
+                            class_names=class_names, compute_dtype=config.compute_dtype)
+    diffuser.load_model(config)
+    for samp_i in range(config.start_idx + rank, config.start_idx + config.num_samples, world):
+        # the Philox stream is keyed by (seed, global sample index): every samp_i gets its own noise on any rank count
+        diffuser.gen_images(config.img_folder, samp_i, seed=config.seed, sample_base=samp_i * config.num_classes)
+    print("done!")
+
+
+if __name__ == "__main__":
+    main()

@@ -112,3 +112,37 @@ def test_diffusion_vae_sample_end_to_end(mode):
     assert d.gpu_launches > 0
     with pytest.raises(NotImplementedError):
         DiffusionVAE(noise_steps=T, img_size=64, device=DEV, vqae_state_dict=vsd, sav_denoise_path="/tmp/x")
+
+
+def test_gen_images_writes_reference_named_pngs(tmp_path):
+    """gen_images (:759-775): RGBA PNG per label named {class}_gen_imgs_{i}_{samp_i}.png whose pixels are the colormap
+    of exactly what sample() returns (matplotlib is absent here, so a stand-in LUT is injected)."""
+    import types
+
+    import numpy as np
+    from PIL import Image
+
+    from oracle.weights import make_state_dict
+    from spectrogramgenai_b200.diff_modules import DiffusionVAE
+
+    T, S = 4, 16
+    names = ["blackbird", "wren", "robin"]
+    d = DiffusionVAE(noise_steps=T, img_size=4 * S, num_classes=27, device=DEV, class_names=names,
+                     vqae_state_dict=V.make_vqae_state_dict(VAE_SEED), compute_dtype="bf16")
+    d.model.load_state_dict(make_state_dict(1234, 4, 4, 27))
+    lut = np.stack([np.linspace(0, 1, 256), np.linspace(1, 0, 256), np.full(256, 0.5), np.ones(256)], 1)
+    labels = torch.tensor([2, 0])
+    paths = d.gen_images(str(tmp_path), 7, labels, colormap=lambda a: lut[a], seed=11)
+    assert [os.path.basename(p) for p in paths] == ["robin_gen_imgs_0_7.png", "blackbird_gen_imgs_1_7.png"]
+    want = d.sample(False, labels, seed=11).cpu().numpy()
+    for p, img in zip(paths, want):
+        im = Image.open(p)
+        assert im.mode == "RGBA" and im.size == (4 * S, 4 * S)
+        assert np.array_equal(np.asarray(im), (lut[img[0]] * 255).astype(np.uint8))
+        # the downstream parser (src/helpers.py:602-610): class = name.split("_")[0], int(last "_" field) < 250
+        stem = os.path.basename(p)[:-4]
+        assert stem.split("_")[0] in names and int(stem.split("_")[-1]) == 7
+    # load_model mirrors the reference's error behaviour
+    with pytest.raises(FileNotFoundError):
+        d.load_model(types.SimpleNamespace(load_model=True, run_name="does_not_exist"))
+    d.load_model(types.SimpleNamespace(load_model=False, run_name="x"))
