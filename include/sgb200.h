@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 6
+#define SG_ABI_VERSION 7
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -110,11 +110,14 @@ int sg_igemm(const sg_igemm_args* args, sg_stream_t stream);
  * the broadcast "x + emb" of Down/Up (:113,:136).  mode: 0 = affine only, 1 = GELU(affine),
  * 2 = GELU(residual + affine) (residual fp32 [rows,HW,C] required).  emb (fp32, row stride
  * emb_stride, already offset to this layer's slice) is added last when non-NULL.
+ * raw / partials hold raw_rows rows and output row r normalises raw row r % raw_rows (raw_rows == rows, or the
+ * label-independent prefix of the UNet computed once for the conditional and unconditional halves, raw_rows == rows/2:
+ * inc and down1's convolutions see no embedding, :187-188, :110-113).
  * raw is fp32 (raw_dtype SG_F32) or fp16 (SG_F16, written by sg_igemm with out_dtype = SG_F16); the statistics in
  * `partials` always come from the fp32 accumulators.
  */
 int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, const float* gamma, const float* beta,
-                int rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride,
+                int rows, int raw_rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride,
                 float* out_f32, void* out_act, int act_dtype, sg_stream_t stream);
 
 /* ---- K3a: MaxPool2d(2) (:100).  in fp32 [rows,H,W,C] -> fp32 and/or act [rows,H/2,W/2,C] ---- */
@@ -122,10 +125,11 @@ int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, 
                 sg_stream_t stream);
 
 /* ---- K3b: Upsample(x2, bilinear, align_corners=True) + cat([skip, x], dim=1) (:120,:132-133) ----
- * x fp32 [rows,h,w,Cx], skip fp32 [rows,2h,2w,Cs] -> [rows,2h,2w,Cs+Cx] (skip channels first).
+ * x fp32 [rows,h,w,Cx], skip fp32 [skip_rows,2h,2w,Cs] -> [rows,2h,2w,Cs+Cx] (skip channels first); output row r
+ * reads skip row r % skip_rows (skip_rows == rows, or the shared label-independent `inc` output, rows/2).
  */
-int sg_upsample_cat(const float* x, const float* skip, int rows, int h, int w, int Cx, int Cs, float* out_f32,
-                    void* out_act, int act_dtype, sg_stream_t stream);
+int sg_upsample_cat(const float* x, const float* skip, int rows, int skip_rows, int h, int w, int Cx, int Cs,
+                    float* out_f32, void* out_act, int act_dtype, sg_stream_t stream);
 
 /* ---- LayerNorm over C (:57 self.ln, :59 ff_self.0).  in fp32 [M,C] -> act [M,C]; C in {64,128,256} ---- */
 int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t M, int C, void* out_act,

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__
 // two independent 16-byte loads per source in flight, half the index arithmetic, one 16-byte 16-bit store).
 template <int V>
 __global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restrict__ x, const float* __restrict__ skip,
-                                                           int64_t total, int h, int w, int Cx4, int Cs4,
+                                                           int64_t total, int skip_rows, int h, int w, int Cx4, int Cs4,
                                                            float sh, float sw, float* __restrict__ o32,
                                                            void* __restrict__ o16, int dtype) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // in units of V float4's
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restri
   const int64_t r = p / H;
   float4 v[V];
   if (c4 < Cs4) {
-    const float4* src = reinterpret_cast<const float4*>(skip) + ((r * H + ho) * W + wo) * Cs4 + c4;
+    const float4* src = reinterpret_cast<const float4*>(skip) + (((r % skip_rows) * H + ho) * W + wo) * Cs4 + c4;
 #pragma unroll
     for (int u = 0; u < V; ++u) v[u] = __ldcs(src + u);
   } else {
@@ -231,8 +231,9 @@ int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, 
   return launch_status("sg_maxpool2");
 }
 
-int sg_upsample_cat(const float* x, const float* skip, int rows, int h, int w, int Cx, int Cs, float* out_f32,
-                    void* out_act, int act_dtype, sg_stream_t stream) {
+int sg_upsample_cat(const float* x, const float* skip, int rows, int skip_rows, int h, int w, int Cx, int Cs,
+                    float* out_f32, void* out_act, int act_dtype, sg_stream_t stream) {
+  SG_REQUIRE(skip_rows > 0 && rows % skip_rows == 0, "sg_upsample_cat: rows=%d must be a multiple of skip_rows=%d", rows, skip_rows);
   SG_REQUIRE(x && skip && (out_f32 || out_act), "sg_upsample_cat: null pointer");
   SG_REQUIRE(rows > 0 && h >= 1 && w >= 1 && Cx % 4 == 0 && Cs % 4 == 0, "sg_upsample_cat: bad shape");
   SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_upsample_cat: out_act needs a 16-bit dtype");
@@ -241,10 +242,10 @@ int sg_upsample_cat(const float* x, const float* skip, int rows, int h, int w, i
   const float sh = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
   const float sw = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
   if (Cx % 8 == 0 && Cs % 8 == 0)
-    upsample_cat_kernel<2><<<cdiv(total4 / 2, 256), 256, 0, as_stream(stream)>>>(x, skip, total4 / 2, h, w, Cx / 4, Cs / 4,
+    upsample_cat_kernel<2><<<cdiv(total4 / 2, 256), 256, 0, as_stream(stream)>>>(x, skip, total4 / 2, skip_rows, h, w, Cx / 4, Cs / 4,
                                                                                  sh, sw, out_f32, out_act, act_dtype);
   else
-    upsample_cat_kernel<1><<<cdiv(total4, 256), 256, 0, as_stream(stream)>>>(x, skip, total4, h, w, Cx / 4, Cs / 4, sh, sw,
+    upsample_cat_kernel<1><<<cdiv(total4, 256), 256, 0, as_stream(stream)>>>(x, skip, total4, skip_rows, h, w, Cx / 4, Cs / 4, sh, sw,
                                                                              out_f32, out_act, act_dtype);
   return launch_status("sg_upsample_cat");
 }

@@ -18,16 +18,17 @@ template <bool RAW16, int MODE>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ raw_v, const float* __restrict__ partials,
                                                        int P, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int64_t per_row4, int C4,
-                                                       int mode_rt, const float* __restrict__ residual,
+                                                       int raw_rows, int mode_rt, const float* __restrict__ residual,
                                                        const float* __restrict__ emb, int emb_stride,
                                                        float* __restrict__ o32, void* __restrict__ o16, int dtype) {
   __shared__ double red[2][8];
   __shared__ float stat[2];
   const int row = blockIdx.y;
+  const int rrow = row % raw_rows;  // raw / partials row (the label-independent prefix is stored once for both halves)
   const int mode = MODE >= 0 ? MODE : mode_rt;
   {
     double s = 0.0, q = 0.0;
-    const float2* pp = reinterpret_cast<const float2*>(partials) + (int64_t)row * P;
+    const float2* pp = reinterpret_cast<const float2*>(partials) + (int64_t)rrow * P;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
       const float2 v = pp[i];
       s += (double)v.x;
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
     __syncthreads();
   }
   const float mean = stat[0], rstd = stat[1];
-  const int64_t base4 = (int64_t)row * per_row4;
+  const int64_t base4 = (int64_t)row * per_row4;    // output / residual row
+  const int64_t rbase4 = (int64_t)rrow * per_row4;  // raw row
   const float4* res4 = residual ? reinterpret_cast<const float4*>(residual) + base4 : nullptr;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
     // fp16 raw, compile-time mode, grid stride a multiple of C/8: this thread always sees the same 8 channels, so
     // y = v * sc + sh with sc = rstd * gamma, sh = beta - mean * sc (+ emb when nothing follows the affine) is one FMA
     constexpr int U = 4;
-    const uint4* h8 = reinterpret_cast<const uint4*>(raw_v) + base4 / 2;
+    const uint4* h8 = reinterpret_cast<const uint4*>(raw_v) + rbase4 / 2;
     const int64_t per_row8 = per_row4 / 2;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int c4 = (int)((2 * first) % C4);
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
   } else if constexpr (RAW16) {
     // fp16 raw: one thread = 8 consecutive channels = one 16-byte load; U independent loads in flight per thread
     constexpr int U = 4;
-    const uint4* h8 = reinterpret_cast<const uint4*>(raw_v) + base4 / 2;
+    const uint4* h8 = reinterpret_cast<const uint4*>(raw_v) + rbase4 / 2;
     const int64_t per_row8 = per_row4 / 2;
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < per_row8; i0 += stride * U) {
       uint4 h[U];
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
   } else {
     // 4 independent 16-byte loads in flight per thread (the single-load loop was latency-bound at 57 % of HBM peak)
     constexpr int U = 4;
-    const float4* r4 = reinterpret_cast<const float4*>(raw_v) + base4;
+    const float4* r4 = reinterpret_cast<const float4*>(raw_v) + rbase4;
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < per_row4; i0 += stride * U) {
       float4 v[U], r[U];
 #pragma unroll
@@ -293,12 +295,13 @@ using namespace sg;
 extern "C" {
 
 int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, const float* gamma, const float* beta,
-                int rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride, float* out_f32,
+                int rows, int raw_rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride, float* out_f32,
                 void* out_act, int act_dtype, sg_stream_t stream) {
   SG_REQUIRE(raw_dtype == SG_F32 || raw_dtype == SG_F16, "sg_gn_apply: raw_dtype must be SG_F32 or SG_F16");
   SG_REQUIRE(raw && partials && gamma && beta && (out_f32 || out_act), "sg_gn_apply: null pointer");
   SG_REQUIRE(rows > 0 && HW > 0 && C % 4 == 0 && P > 0, "sg_gn_apply: bad shape rows=%d HW=%d C=%d P=%d", rows, HW, C, P);
   SG_REQUIRE(raw_dtype == SG_F32 || C % 8 == 0, "sg_gn_apply: fp16 raw needs C %% 8 == 0 (C=%d)", C);
+  SG_REQUIRE(raw_rows > 0 && rows % raw_rows == 0, "sg_gn_apply: rows=%d must be a multiple of raw_rows=%d", rows, raw_rows);
   SG_REQUIRE(mode >= 0 && mode <= 2, "sg_gn_apply: mode %d", mode);
   SG_REQUIRE(mode != 2 || residual, "sg_gn_apply: mode 2 needs a residual");
   SG_REQUIRE(!emb || emb_stride % 4 == 0, "sg_gn_apply: emb stride must be a multiple of 4");
@@ -312,7 +315,7 @@ int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, co
   dim3 grid(chunks, rows);
   cudaStream_t st = as_stream(stream);
 #define SG_GN_LAUNCH(R16, MD)                                                                                          \
-  gn_apply_kernel<R16, MD><<<grid, 256, 0, st>>>(raw, partials, P, gamma, beta, per_row4, C / 4, mode, residual, emb, \
+  gn_apply_kernel<R16, MD><<<grid, 256, 0, st>>>(raw, partials, P, gamma, beta, per_row4, C / 4, raw_rows, mode, residual, emb, \
                                                  emb_stride, out_f32, out_act, act_dtype)
   if (raw_dtype == SG_F16) {
     // fixed-channel fast path: every thread of the grid-stride loop must land on the same 8 channels each pass

@@ -100,6 +100,10 @@ class UNetPlan:
         self.use_step = use_step
         self.attention_engine = os.environ.get("SGB200_ATTENTION", "tc")  # "simt": fp32 core in the 16-bit modes
         self.raw16 = os.environ.get("SGB200_RAW16", "1") != "0"  # fp16 raw conv outputs in the tensor-core modes
+        # CFG batching puts the conditional rows in [0, n) and the unconditional ones in [n, 2n); both halves see the
+        # same x, and `inc` / the convolutions of `down1` take no embedding (:187-188, :110-113: emb is added AFTER the
+        # convs), so that prefix is computed once for n rows and broadcast where the embedding comes in
+        self.rows_p = n_src if (rows == 2 * n_src and os.environ.get("SGB200_SHARED_PREFIX", "1") != "0") else rows
         self.debug = debug  # keep every buffer alive and expose per-block outputs in self.taps
         self._pool = {}
         self.nbytes = 0
@@ -172,8 +176,10 @@ class UNetPlan:
         self._op(ops.igemm_launch, args)
         return raw, part
 
-    def _double_conv(self, p, x, rows, H, W, *, residual=False, emb=None, want_f32=True, want_act=True, from_input=False):
-        """DoubleConv (:75-93).  x = (fp32, act) pair of the input (or None when from_input).  Returns a pair."""
+    def _double_conv(self, p, x, rows, H, W, *, residual=False, emb=None, want_f32=True, want_act=True, from_input=False,
+                     out_rows=None):
+        """DoubleConv (:75-93).  x = (fp32, act) pair of the input (or None when from_input).  Returns a pair.
+        out_rows > rows: the last GroupNorm-apply (+emb) writes out_rows rows, row r from raw row r % rows."""
         W_ = self.W
         if from_input:
             raw1 = self._alloc((rows, H, W, 64), torch.float16 if (self.tc and self.raw16) else torch.float32)
@@ -187,7 +193,7 @@ class UNetPlan:
         self._free(raw1, part1)
         raw2, part2 = self._conv(mid[1], f"{p}.double_conv.3.weight", rows, H, W)
         self._free_pair(mid)
-        out = self._pair(raw2.shape, want_f32, want_act)
+        out = self._pair((out_rows or rows,) + tuple(raw2.shape[1:]), want_f32, want_act)
         self._op(ops.gn_apply, raw2, part2, W_[f"{p}.double_conv.4.weight"], W_[f"{p}.double_conv.4.bias"],
                  mode=2 if residual else 0, residual=x[0] if residual else None, emb=emb,
                  out_f32=out[0], out_act=out[1] if self.tc else None)
@@ -248,13 +254,14 @@ class UNetPlan:
         self._free(f1, a)
         return out
 
-    def _down(self, p, x, rows, H, W, C):
+    def _down(self, p, x, rows, H, W, C, *, out_rows=None):
         h, w = H // 2, W // 2
         pooled = self._pair((rows, h, w, C))
         self._op(ops.maxpool2, x[0], out_f32=pooled[0], out_act=pooled[1] if self.tc else None)
         d1 = self._double_conv(f"{p}.maxpool_conv.1", pooled, rows, h, w, residual=True, want_f32=False)
         self._free_pair(pooled)
-        d2 = self._double_conv(f"{p}.maxpool_conv.2", d1, rows, h, w, emb=self._emb_slice(p), want_act=False)
+        d2 = self._double_conv(f"{p}.maxpool_conv.2", d1, rows, h, w, emb=self._emb_slice(p), want_act=False,
+                               out_rows=out_rows)
         self._free_pair(d1)
         return d2
 
@@ -276,9 +283,10 @@ class UNetPlan:
         self._op(ops.time_embed, None if self.use_step else self.t, self.step if self.use_step else None,
                  self.y if W_.label is not None else None,
                  W_.inv_freq, W_.label, W_.w_emb, W_.b_emb, self.temb, self.emb)
-        x1 = self._double_conv("inc", None, rows, S, S, from_input=True, want_act=False)
+        rp = self.rows_p  # rows of the label-independent prefix (n when the CFG halves are batched, else rows)
+        x1 = self._double_conv("inc", None, rp, S, S, from_input=True, want_act=False)
         keep["inc"] = x1[0]
-        d = self._down("down1", x1, rows, S, S, 64)
+        d = self._down("down1", x1, rp, S, S, 64, out_rows=rows)
         keep["down1"] = d[0]
         x2 = self._self_attention("sa1", d[0], rows, S // 2, S // 2, 128, want_act=False)
         self._free_pair(d)

@@ -92,9 +92,13 @@ def igemm(a, w, **kw):
 
 def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f32=None, out_act=None):
     """K2.  raw fp32 or fp16 [rows,HW,C] (any shape with rows first, C last); emb: fp32 view [rows, C] (row stride kept)."""
-    rows, C = raw.shape[0], raw.shape[-1]
-    HW = raw.numel() // (rows * C)
+    raw_rows, C = raw.shape[0], raw.shape[-1]
+    HW = raw.numel() // (raw_rows * C)
     P = partials.shape[1]
+    out_any = out_f32 if out_f32 is not None else out_act
+    rows = out_any.shape[0] if out_any is not None else raw_rows  # > raw_rows: row r normalises raw row r % raw_rows
+    if rows % raw_rows or partials.shape[0] != raw_rows:
+        raise ValueError("gn_apply: output rows must be a multiple of the raw rows; partials must have the raw rows")
     emb_stride = 0
     if emb is not None:
         if emb.dtype != torch.float32 or emb.shape != (rows, C) or emb.stride(1) != 1:
@@ -103,7 +107,7 @@ def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f
     adt = dtype_code(out_act.dtype) if out_act is not None else 0
     if raw.dtype not in (torch.float32, torch.float16):
         raise ValueError("gn_apply: raw must be fp32 or fp16")
-    check(_lib().sg_gn_apply(ptr(raw), dtype_code(raw.dtype), ptr(partials), P, ptr(gamma), ptr(beta), rows, HW, C, mode,
+    check(_lib().sg_gn_apply(ptr(raw), dtype_code(raw.dtype), ptr(partials), P, ptr(gamma), ptr(beta), rows, raw_rows, HW, C, mode,
                              ptr(_f32(residual, "residual")), ptr(emb), emb_stride, ptr(_f32(out_f32, "out_f32")),
                              ptr(out_act), adt, stream_ptr()), "sg_gn_apply")
 
@@ -117,13 +121,15 @@ def maxpool2(x, *, out_f32=None, out_act=None):
 
 
 def upsample_cat(x, skip, *, out_f32=None, out_act=None):
-    """K3b.  x fp32 [rows,h,w,Cx], skip fp32 [rows,2h,2w,Cs] -> [rows,2h,2w,Cs+Cx]."""
+    """K3b.  x fp32 [rows,h,w,Cx], skip fp32 [skip_rows,2h,2w,Cs] -> [rows,2h,2w,Cs+Cx]; row r reads skip row
+    r % skip_rows (skip_rows == rows, or rows/2 for the shared label-independent prefix)."""
     rows, h, w, Cx = x.shape
     Cs = skip.shape[-1]
-    if tuple(skip.shape[:3]) != (rows, 2 * h, 2 * w):
-        raise ValueError("upsample_cat: skip must be [rows, 2h, 2w, Cs]")
+    skip_rows = skip.shape[0]
+    if tuple(skip.shape[1:3]) != (2 * h, 2 * w) or rows % skip_rows:
+        raise ValueError("upsample_cat: skip must be [skip_rows, 2h, 2w, Cs] with rows a multiple of skip_rows")
     adt = dtype_code(out_act.dtype) if out_act is not None else 0
-    check(_lib().sg_upsample_cat(ptr(_f32(x, "x")), ptr(_f32(skip, "skip")), rows, h, w, Cx, Cs,
+    check(_lib().sg_upsample_cat(ptr(_f32(x, "x")), ptr(_f32(skip, "skip")), rows, skip_rows, h, w, Cx, Cs,
                                  ptr(_f32(out_f32, "out_f32")), ptr(out_act), adt, stream_ptr()), "sg_upsample_cat")
 
 

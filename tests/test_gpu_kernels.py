@@ -164,6 +164,31 @@ def test_time_embed(ops):
     assert float((temb2.cpu() - O.pos_encoding(torch.full((rows,), 500.0))).abs().max()) < 5e-7
 
 
+def test_row_broadcast_of_the_shared_prefix(ops):
+    """CFG batching computes the label-independent prefix (inc, down1's convs) once for n rows: GroupNorm-apply and
+    upsample+concat then read raw / skip row r % n for output row r.  Must equal the same call on repeated inputs."""
+    g = gen(31)
+    n, H, C = 3, 8, 64
+    raw = torch.randn(n, H, H, C, generator=g).to(DEV)
+    part = torch.stack([raw.double().sum((1, 2, 3)), (raw.double() ** 2).sum((1, 2, 3))], -1).float().reshape(n, 1, 2).contiguous()
+    gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
+    emb = torch.randn(2 * n, C, generator=g).to(DEV)
+    for raw_t in (raw, raw.half()):
+        out_b = torch.empty(2 * n, H, H, C, device=DEV)
+        ops.gn_apply(raw_t, part, gamma, beta, mode=0, emb=emb, out_f32=out_b)
+        out_r = torch.empty(2 * n, H, H, C, device=DEV)
+        ops.gn_apply(raw_t.repeat(2, 1, 1, 1), part.repeat(2, 1, 1), gamma, beta, mode=0, emb=emb, out_f32=out_r)
+        assert torch.equal(out_b, out_r)
+        assert not torch.equal(out_b[:n], out_b[n:])  # the two halves differ by their embeddings
+    x = torch.randn(2 * n, 4, 4, 64, generator=g).to(DEV)
+    skip = torch.randn(n, 8, 8, 64, generator=g).to(DEV)
+    o_b = torch.empty(2 * n, 8, 8, 128, device=DEV)
+    o_r = torch.empty(2 * n, 8, 8, 128, device=DEV)
+    ops.upsample_cat(x, skip, out_f32=o_b)
+    ops.upsample_cat(x, skip.repeat(2, 1, 1, 1), out_f32=o_r)
+    assert torch.equal(o_b, o_r)
+
+
 # ------------------------------------------------------------------------------------------ convolutions
 @pytest.mark.parametrize("c_in,S,rows,n_src", [(4, 16, 4, 2), (1, 32, 2, 2), (4, 64, 2, 1), (3, 16, 1, 1)])
 def test_conv_in(ops, c_in, S, rows, n_src):

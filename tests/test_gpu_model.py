@@ -178,3 +178,29 @@ def test_bad_labels_raise():
     d = _diffusion("fp32", 16, 4)
     with pytest.raises(IndexError):
         d.sample(False, torch.tensor([0, NUM_CLASSES]))
+
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_shared_prefix_is_bit_identical(monkeypatch, mode):
+    """With the conditional and unconditional halves batched (rows = 2n) the label-independent prefix (inc and the
+    convolutions of down1) runs once for n rows; eps must be bit-identical to the plan that runs it for all 2n rows."""
+    m = build_model(mode)
+    n, S = 3, 32
+    x, y = golden_inputs(S, 4, n)
+    eps = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SGB200_SHARED_PREFIX", flag)
+        m.release_plans()
+        plan = m.plan(n_src=n, rows=2 * n, S=S, use_step=True)
+        assert plan.rows_p == (n if flag == "1" else 2 * n)
+        plan.x_in.copy_(x.to(DEV))
+        plan.y.fill_(-1)
+        plan.y[:n].copy_(y.to(DEV))
+        plan.step.fill_(321)
+        plan.run()
+        torch.cuda.synchronize()
+        eps[flag] = plan.eps.clone()
+    m.release_plans()
+    assert torch.equal(eps["1"], eps["0"])
+    assert not torch.equal(eps["1"][:n], eps["1"][n:])
