@@ -299,8 +299,73 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
   const bool valid = m0 + r < g.M;
   float s_sum = 0.f, s_sq = 0.f;
   const int trow = lane >> 3, tcol = (lane & 7) * 4;  // transposed-domain role of this lane
+  // Fast path for the two hottest epilogues -- raw fp16 conv output + GroupNorm statistics, and 16-bit Linear output
+  // with bias (+GELU) -- on full tiles: packed fp32 statistics, the 16-bit values (not fp32) go through the transposing
+  // scratch, no per-row predicates / residual slots.  (The generic loop below costs ~7 instructions per element on
+  // only eight epilogue warps and bounds the Cout = 64 convolutions and the 16-bit Linear layers.)
+  const bool fast = ep.out_act && !ep.out_f32 && !ep.residual && ep.act != SG_ACT_RELU_POST && m0 + BM <= g.M;
+  if (fast) {
+    uint32_t* sc32 = reinterpret_cast<uint32_t*>(scratch);  // [32 rows][20 words]: 64 B of 16-bit data per row + pad
+    uint16_t* outp = reinterpret_cast<uint16_t*>(ep.out_act) + (m0 + q * 32) * (int64_t)g.Cout + n0;
+    const bool has_bias = ep.bias != nullptr, gelu = ep.act == SG_ACT_GELU, stats = ep.partials != nullptr;
+    uint64_t s2 = 0ull, q2 = 0ull;
+    const int prow = lane >> 2, piece = lane & 3;  // store role: 8 rows x four 16-byte pieces per instruction
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (has_bias) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + c * 32 + j4 * 4);
+          f[j4 * 4 + 0] += b4.x; f[j4 * 4 + 1] += b4.y; f[j4 * 4 + 2] += b4.z; f[j4 * 4 + 3] += b4.w;
+        }
+      }
+      if (gelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+      }
+      if (stats) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          uint64_t p;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(f[j]), "f"(f[j + 1]));
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s2) : "l"(p));
+          asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(q2) : "l"(p));
+        }
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        uint4 w;
+        w.x = pack16(f[j4 * 8 + 0], f[j4 * 8 + 1], ep.act_dtype);
+        w.y = pack16(f[j4 * 8 + 2], f[j4 * 8 + 3], ep.act_dtype);
+        w.z = pack16(f[j4 * 8 + 4], f[j4 * 8 + 5], ep.act_dtype);
+        w.w = pack16(f[j4 * 8 + 6], f[j4 * 8 + 7], ep.act_dtype);
+        *reinterpret_cast<uint4*>(sc32 + lane * 20 + j4 * 4) = w;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 8 + prow;
+        const uint4 w = *reinterpret_cast<const uint4*>(sc32 + row * 20 + piece * 4);
+        *reinterpret_cast<uint4*>(outp + (int64_t)row * g.Cout + c * 32 + piece * 8) = w;
+      }
+      __syncwarp();
+    }
+    if (stats) {
+      float a0, a1, b0, b1;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(s2));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(q2));
+      s_sum = a0 + a1;
+      s_sq = b0 + b1;
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < (fast ? 0 : BN / 32); ++c) {
     const int nb = n0 + c * 32;
     // residual loads first: their HBM latency overlaps the TMEM read, the bias / GELU math and the transposition
     float4 rsd[8];
