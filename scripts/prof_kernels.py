@@ -41,11 +41,11 @@ if what in ("conv", "all"):
     for (H, cin, cout) in ((64, 128, 128), (32, 256, 256), (16, 512, 512), (64, 64, 64), (8, 512, 512)):
         a = torch.randn(rows, H, H, cin, device=dev, generator=g).to(dt)
         w = (torch.randn(9, cout, cin, device=dev, generator=g) / math.sqrt(9 * cin)).to(dt)
-        raw = torch.empty(rows, H, H, cout, device=dev)
+        raw = torch.empty(rows, H, H, cout, device=dev, dtype=torch.float16)  # fp16 raw output, as the engine keeps it
         part = torch.empty(rows, ops.igemm_partials(SG_ENGINE_TC, H, H, cout), 2, device=dev)
-        args = ops.make_igemm_args(a, w, rows=rows, H=H, W=H, out_f32=raw, partials=part)
+        args = ops.make_igemm_args(a, w, rows=rows, H=H, W=H, out_act=raw, partials=part)
         timeit(f"conv3x3 H={H} {cin}->{cout} rows={rows}", lambda: ops.igemm_launch(args),
-               flops=2.0 * rows * H * H * cin * cout * 9, nbytes=a.numel() * 2 + raw.numel() * 4)
+               flops=2.0 * rows * H * H * cin * cout * 9, nbytes=a.numel() * 2 + raw.numel() * 2)
 if what in ("linear", "all"):
     for (L, cin, cout) in ((4096, 64, 192), (4096, 64, 64), (1024, 128, 384)):
         M = rows * L
@@ -69,9 +69,9 @@ if what in ("linear16",):
                nbytes=a.numel() * 2 + o16.numel() * 2)
 if what in ("gn", "all"):
     H, C = 64, 128
-    raw = torch.randn(rows, H, H, C, device=dev, generator=g)
+    raw = torch.randn(rows, H, H, C, device=dev, generator=g).half()  # fp16 raw conv output, as in the tensor-core modes
     part = torch.rand(rows, 32, 2, device=dev, generator=g) * 1000 + 1000
     gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     o16 = torch.empty(rows, H, H, C, device=dev, dtype=dt)
-    timeit("gn_apply 64x64x128 -> bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=1, out_act=o16),
-           nbytes=raw.numel() * 6)
+    timeit("gn_apply 64x64x128 fp16 raw -> GELU -> bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=1, out_act=o16),
+           nbytes=raw.numel() * 4)

@@ -114,8 +114,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * ATT_BM;
+  // heads are the FASTEST grid dimension: the head slices of a token (d * 2 = 32..128 bytes) share 128-byte lines, so
+  // the heads of one query tile must run together to be served from L2 (with heads slowest, ncu showed 4x the
+  // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
+  const int head = blockIdx.x;
+  const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
   const int64_t kv0 = g.L >= ATT_BN ? (m0 >> g.logL) << g.logL : m0;  // first key token of this tile's row(s)
 
   if (warp == 0 && lane == 0) {
@@ -383,8 +386,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * ATT_BM;
+  // heads are the FASTEST grid dimension: the head slices of a token (d * 2 = 32..128 bytes) share 128-byte lines, so
+  // the heads of one query tile must run together to be served from L2 (with heads slowest, ncu showed 4x the
+  // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
+  const int head = blockIdx.x;
+  const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
   const int64_t kv0 = (m0 >> g.logL) << g.logL;
   const int nkv = (g.L + BN - 1) / BN;
 
@@ -604,7 +610,8 @@ static int launch_att3(const void* qkv, const AttGeom& g0, int act_dtype, uint16
   if (rc) return rc;
   rc = make_tmap(&tmKV, act_dtype, 2, qkv, dims, strides, boxkv, sw);
   if (rc) return rc;
-  dim3 grid((unsigned)(g.M / ATT_BM), (unsigned)g.heads);
+  const int64_t tiles3 = g.M / ATT_BM;
+  dim3 grid((unsigned)g.heads, (unsigned)(tiles3 < 32768 ? tiles3 : 32768), (unsigned)cdiv(tiles3, 32768));
   attention_tc3_kernel<D, DT><<<grid, 192, A::SMEM, stream>>>(tmQ, tmKV, g, out);
   return launch_status("sg_attention(tc3)");
 }
@@ -722,8 +729,11 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int64_t m0 = (int64_t)blockIdx.x * ATT_BM;
+  // heads are the FASTEST grid dimension: the head slices of a token (d * 2 = 32..128 bytes) share 128-byte lines, so
+  // the heads of one query tile must run together to be served from L2 (with heads slowest, ncu showed 4x the
+  // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
+  const int head = blockIdx.x;
+  const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
   const int64_t kv0 = (m0 >> g.logL) << g.logL;
   const int nkv = g.L / ATT_BN;
   const bool leader = threadIdx.x == 0;
@@ -1044,7 +1054,9 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
   int rc = make_tmap(&tm, act_dtype, 2, qkv, dims, strides, box, sw);
   if (rc) return rc;
   SG_REQUIRE(heads <= 65535, "sg_attention(tc): too many heads");
-  dim3 grid((unsigned)cdiv(g.M, ATT_BM), (unsigned)heads);
+  const int64_t tiles = cdiv(g.M, ATT_BM);
+  SG_REQUIRE(tiles <= 32768 || tiles % 32768 == 0, "sg_attention(tc): %lld query tiles (must be <= 32768 or a multiple of it)", (long long)tiles);
+  dim3 grid((unsigned)heads, (unsigned)(tiles < 32768 ? tiles : 32768), (unsigned)cdiv(tiles, 32768));
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
   if (L >= ATT_BN && (attention_version() == 8 || attention_version() == 0)) {
     if (act_dtype == SG_BF16) {
