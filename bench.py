@@ -255,7 +255,7 @@ def main():
     ap.add_argument("--channels", type=int, default=4)
     ap.add_argument("--mode", default="bf16", choices=["bf16", "f16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=8)
-    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=10, help="CPU-baseline sample: timesteps of n = cpu-batch (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     args = ap.parse_args()
