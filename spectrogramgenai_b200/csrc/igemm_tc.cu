@@ -298,6 +298,7 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
   const int r = q * 32 + lane;
   const bool valid = m0 + r < g.M;
   float s_sum = 0.f, s_sq = 0.f;
+  float s_even = 0.f, s_odd = 0.f, q_even = 0.f, q_odd = 0.f;  // generic path: per-parity chains (see below)
   const int trow = lane >> 3, tcol = (lane & 7) * 4;  // transposed-domain role of this lane
   // Fast path for the two hottest epilogues -- raw fp16 conv output + GroupNorm statistics, and 16-bit Linear output
   // with bias (+GELU) -- on full tiles: packed fp32 statistics, the 16-bit values (not fp32) go through the transposing
@@ -360,8 +361,8 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
       float a0, a1, b0, b1;
       asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(s2));
       asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(q2));
-      s_sum = a0 + a1;
-      s_sq = b0 + b1;
+      s_sum = __fadd_rn(a0, a1);
+      s_sq = __fadd_rn(b0, b1);
     }
   }
 #pragma unroll 1
@@ -393,10 +394,14 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
       for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
     }
     if (ep.partials && valid) {
+      // same summation order as the packed fast path (even / odd columns in two chains, combined at the end), so that
+      // a sample's GroupNorm statistics do not depend on whether its tile took the fast or the generic path
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        s_sum += f[j];
-        s_sq += f[j] * f[j];
+      for (int j = 0; j < 32; j += 2) {
+        s_even = __fadd_rn(s_even, f[j]);
+        s_odd = __fadd_rn(s_odd, f[j + 1]);
+        q_even = __fmaf_rn(f[j], f[j], q_even);
+        q_odd = __fmaf_rn(f[j + 1], f[j + 1], q_odd);
       }
     }
 #pragma unroll
@@ -424,6 +429,10 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
       }
     }
     __syncwarp();
+  }
+  if (!fast) {
+    s_sum = __fadd_rn(s_even, s_odd);
+    s_sq = __fadd_rn(q_even, q_odd);
   }
   if (ep.partials) {
     // Deterministic GroupNorm partials without a serial tail: xor-shuffle within the sample's rows of this warp,

@@ -68,19 +68,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
   const float4* e4 = emb ? reinterpret_cast<const float4*>(emb + (int64_t)row * emb_stride) : nullptr;
   auto norm4 = [&](float4 v, float4 r, int c4) {  // 4 consecutive channels starting at channel 4*c4
     const float4 g = __ldg(g4 + c4), b = __ldg(b4 + c4);
+    const float4 e = e4 ? __ldg(e4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 y;
-    y.x = (v.x - mean) * rstd * g.x + b.x;
-    y.y = (v.y - mean) * rstd * g.y + b.y;
-    y.z = (v.z - mean) * rstd * g.z + b.z;
-    y.w = (v.w - mean) * rstd * g.w + b.w;
+    if constexpr (RAW16) {
+      // the SAME folded arithmetic as the fixed-channel fast path below (y = v * sc + sh), so that a sample's result
+      // does not depend on which of the two paths the grid geometry of its batch selects
+      // explicit intrinsics: both paths must round identically whatever the compiler would contract
+      const float s0 = __fmul_rn(rstd, g.x), s1 = __fmul_rn(rstd, g.y), s2 = __fmul_rn(rstd, g.z), s3 = __fmul_rn(rstd, g.w);
+      y.x = __fmaf_rn(v.x, s0, __fadd_rn(__fmaf_rn(-mean, s0, b.x), mode == 0 ? e.x : 0.f));
+      y.y = __fmaf_rn(v.y, s1, __fadd_rn(__fmaf_rn(-mean, s1, b.y), mode == 0 ? e.y : 0.f));
+      y.z = __fmaf_rn(v.z, s2, __fadd_rn(__fmaf_rn(-mean, s2, b.z), mode == 0 ? e.z : 0.f));
+      y.w = __fmaf_rn(v.w, s3, __fadd_rn(__fmaf_rn(-mean, s3, b.w), mode == 0 ? e.w : 0.f));
+    } else {
+      y.x = (v.x - mean) * rstd * g.x + b.x;
+      y.y = (v.y - mean) * rstd * g.y + b.y;
+      y.z = (v.z - mean) * rstd * g.z + b.z;
+      y.w = (v.w - mean) * rstd * g.w + b.w;
+    }
     if (mode == 2) {
       y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
     }
     if (mode >= 1) {
       y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w);
     }
-    if (e4) {
-      const float4 e = __ldg(e4 + c4);
+    if (e4 && (!RAW16 || mode >= 1)) {
       y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
     }
     return y;
@@ -102,8 +113,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
       const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w}, ee[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        sc[h * 4 + j] = rstd * gg[j];
-        sh[h * 4 + j] = bb[j] - mean * sc[h * 4 + j] + (MODE == 0 ? ee[j] : 0.f);
+        sc[h * 4 + j] = __fmul_rn(rstd, gg[j]);
+        sh[h * 4 + j] = __fadd_rn(__fmaf_rn(-mean, sc[h * 4 + j], bb[j]), MODE == 0 ? ee[j] : 0.f);
         ev[h * 4 + j] = ee[j];
       }
     }
@@ -129,7 +140,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
         const float2 a2 = unpack16(h[u].z, SG_F16), a3 = unpack16(h[u].w, SG_F16);
         float y[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], sc[j], sh[j]);
+        for (int j = 0; j < 8; ++j) y[j] = __fmaf_rn(y[j], sc[j], sh[j]);
         if (MODE == 2) {
           y[0] += r[u][0].x; y[1] += r[u][0].y; y[2] += r[u][0].z; y[3] += r[u][0].w;
           y[4] += r[u][1].x; y[5] += r[u][1].y; y[6] += r[u][1].z; y[7] += r[u][1].w;

@@ -91,6 +91,24 @@ def test_forward_accepts_float_t_and_odd_batches():
     assert torch.equal(e_one[0], e_long[2])  # per-sample results do not depend on the batch they ride in
 
 
+@pytest.mark.parametrize("mode", ["bf16", "f16"])
+def test_tensor_core_modes_small_and_ragged_batches(mode):
+    """n = 1 and n = 5 at 16x16 latents: the deepest SelfAttention sees 64 .. 320 tokens, i.e. fewer than one
+    128-token tile and a ragged last tile in the fused head / tail kernels, the attention core and the GEMMs."""
+    m = build_model(mode)
+    sd = make_state_dict(WEIGHT_SEED, 4, 4, NUM_CLASSES)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(5, 4, 16, 16, generator=g)
+    y = torch.randint(0, NUM_CLASSES, (5,), generator=g)
+    t = torch.tensor([999, 3, 250, 1, 77])
+    want = O.unet_forward(sd, x, t, y)
+    e5 = m(x.to(DEV), t.to(DEV), y.to(DEV)).cpu()
+    assert O.rel_l2(e5, want) < EPS_TOL[mode]
+    e1 = m(x[2:3].to(DEV), t[2:3].to(DEV), y[2:3].to(DEV)).cpu()
+    assert O.rel_l2(e1, want[2:3]) < EPS_TOL[mode]
+    assert torch.equal(e1[0], e5[2])  # per-sample results do not depend on the batch they ride in
+
+
 def _diffusion(mode, s, T, c=4):
     from spectrogramgenai_b200.diff_modules import Diffusion
 
