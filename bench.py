@@ -159,6 +159,10 @@ def classify(fn, a, kw):
             if t is not None:
                 by += t.numel() * t.element_size()
         return "gn_apply", 0.0, by
+    if name == "gn_apply_vcat":
+        raw, part, gamma, beta, xs, skip, out = a
+        return "gn_apply", 0.0, raw.numel() * 2 + xs.numel() * 4 + skip.numel() * 4 * (raw.shape[0] // skip.shape[0]) \
+            + out.numel() * out.element_size()
     if name in ("maxpool2", "upsample_cat"):
         by = sum(t.numel() * t.element_size() for t in a)
         for k in ("out_f32", "out_act"):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 7
+#define SG_ABI_VERSION 8
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -119,6 +119,17 @@ int sg_igemm(const sg_igemm_args* args, sg_stream_t stream);
 int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, const float* gamma, const float* beta,
                 int rows, int raw_rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride,
                 float* out_f32, void* out_act, int act_dtype, sg_stream_t stream);
+
+/* ---- K2 + K3b: GELU(GroupNorm(raw) + cat([skip, upsample2x(x)])) -> act, residual recomputed from its sources ----
+ * The first DoubleConv of Up is residual (:88-91 with :132-134): its input -- the concatenation of the skip and the
+ * bilinearly upsampled x -- is added back after the second GroupNorm.  Instead of keeping an fp32 copy of that
+ * concatenation (written by sg_upsample_cat, read here), this variant of sg_gn_apply mode 2 recomputes it from x fp32
+ * [rows,h,w,Cx] and skip fp32 [skip_rows,2h,2w,Cs] (row r reads skip row r % skip_rows).  raw is fp16
+ * [rows,2h,2w,Cs+Cx] (sg_igemm out_dtype = SG_F16), out act of the same shape; Cx, Cs multiples of 8.
+ */
+int sg_gn_apply_vcat(const void* raw, const float* partials, int P, const float* gamma, const float* beta, int rows,
+                     const float* x, const float* skip, int skip_rows, int h, int w, int Cx, int Cs, void* out_act,
+                     int act_dtype, sg_stream_t stream);
 
 /* ---- K3a: MaxPool2d(2) (:100).  in fp32 [rows,H,W,C] -> fp32 and/or act [rows,H/2,W/2,C] ---- */
 int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, void* out_act, int act_dtype,

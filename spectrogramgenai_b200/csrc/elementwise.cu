@@ -117,65 +117,68 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__
 // two independent 16-byte loads per source in flight, half the index arithmetic, one 16-byte 16-bit store).
 template <int V>
 __global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restrict__ x, const float* __restrict__ skip,
-                                                           int64_t total, int skip_rows, int h, int w, int Cx4, int Cs4,
+                                                           unsigned per_row, int skip_rows, int h, int w, int Cx4, int Cs4,
                                                            float sh, float sw, float* __restrict__ o32,
                                                            void* __restrict__ o16, int dtype) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // in units of V float4's
-  if (idx >= total) return;
-  const int Ct = (Cx4 + Cs4) / V;
-  const int c4 = (int)(idx % Ct) * V;
-  int64_t p = idx / Ct;
-  const int H = 2 * h, W = 2 * w;
-  const int wo = (int)(p % W);
-  p /= W;
-  const int ho = (int)(p % H);
-  const int64_t r = p / H;
-  float4 v[V];
-  if (c4 < Cs4) {
-    const float4* src = reinterpret_cast<const float4*>(skip) + (((r % skip_rows) * H + ho) * W + wo) * Cs4 + c4;
+  // grid = (chunks, rows): 32-bit index arithmetic inside a row (the 64-bit div / mod chain of the flat version cost
+  // more than the loads); per_row counts units of V float4's
+  const unsigned row = blockIdx.y;
+  const unsigned Ct = (unsigned)(Cx4 + Cs4) / V;
+  const unsigned H = 2 * h, W = 2 * w;
+  const float4* xrow = reinterpret_cast<const float4*>(x) + (size_t)row * h * w * Cx4;
+  const float4* srow = reinterpret_cast<const float4*>(skip) + (size_t)(row % (unsigned)skip_rows) * H * W * Cs4;
+  const size_t obase = (size_t)row * per_row * (4 * V);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+    const unsigned p = i / Ct;
+    const unsigned c4 = (i - p * Ct) * V;
+    const unsigned ho = p / W, wo = p - ho * W;
+    float4 v[V];
+    if (c4 < (unsigned)Cs4) {
+      const float4* src = srow + (size_t)p * Cs4 + c4;
 #pragma unroll
-    for (int u = 0; u < V; ++u) v[u] = __ldcs(src + u);
-  } else {
-    const int cx = c4 - Cs4;
-    // align_corners=True: src = dst * (in-1)/(out-1)
-    const float fy = sh * (float)ho, fx = sw * (float)wo;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
-    const float hy = 1.0f - ly, hx = 1.0f - lx;
-    const float4* base = reinterpret_cast<const float4*>(x) + r * h * w * Cx4 + cx;
-    float4 a[V], b[V], c[V], d[V];
+      for (int u = 0; u < V; ++u) v[u] = __ldcs(src + u);
+    } else {
+      const unsigned cx = c4 - Cs4;
+      // align_corners=True: src = dst * (in-1)/(out-1)
+      const float fy = sh * (float)ho, fx = sw * (float)wo;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+      const float ly = fy - (float)y0, lx = fx - (float)x0;
+      const float hy = 1.0f - ly, hx = 1.0f - lx;
+      const float4* base = xrow + cx;
+      float4 a[V], b[V], c[V], d[V];
 #pragma unroll
-    for (int u = 0; u < V; ++u) {
-      a[u] = __ldg(base + ((int64_t)y0 * w + x0) * Cx4 + u);
-      b[u] = __ldg(base + ((int64_t)y0 * w + x1) * Cx4 + u);
-      c[u] = __ldg(base + ((int64_t)y1 * w + x0) * Cx4 + u);
-      d[u] = __ldg(base + ((int64_t)y1 * w + x1) * Cx4 + u);
-    }
+      for (int u = 0; u < V; ++u) {
+        a[u] = __ldg(base + (size_t)(y0 * w + x0) * Cx4 + u);
+        b[u] = __ldg(base + (size_t)(y0 * w + x1) * Cx4 + u);
+        c[u] = __ldg(base + (size_t)(y1 * w + x0) * Cx4 + u);
+        d[u] = __ldg(base + (size_t)(y1 * w + x1) * Cx4 + u);
+      }
 #pragma unroll
-    for (int u = 0; u < V; ++u) {
-      v[u].x = hy * (hx * a[u].x + lx * b[u].x) + ly * (hx * c[u].x + lx * d[u].x);
-      v[u].y = hy * (hx * a[u].y + lx * b[u].y) + ly * (hx * c[u].y + lx * d[u].y);
-      v[u].z = hy * (hx * a[u].z + lx * b[u].z) + ly * (hx * c[u].z + lx * d[u].z);
-      v[u].w = hy * (hx * a[u].w + lx * b[u].w) + ly * (hx * c[u].w + lx * d[u].w);
+      for (int u = 0; u < V; ++u) {
+        v[u].x = hy * (hx * a[u].x + lx * b[u].x) + ly * (hx * c[u].x + lx * d[u].x);
+        v[u].y = hy * (hx * a[u].y + lx * b[u].y) + ly * (hx * c[u].y + lx * d[u].y);
+        v[u].z = hy * (hx * a[u].z + lx * b[u].z) + ly * (hx * c[u].z + lx * d[u].z);
+        v[u].w = hy * (hx * a[u].w + lx * b[u].w) + ly * (hx * c[u].w + lx * d[u].w);
+      }
     }
-  }
-  const int64_t off = idx * (4 * V);
-  if constexpr (V == 2) {
-    if (o32) {
-      __stcs(reinterpret_cast<float4*>(o32 + off), v[0]);
-      __stcs(reinterpret_cast<float4*>(o32 + off + 4), v[1]);
+    const size_t off = obase + (size_t)i * (4 * V);
+    if constexpr (V == 2) {
+      if (o32) {
+        __stcs(reinterpret_cast<float4*>(o32 + off), v[0]);
+        __stcs(reinterpret_cast<float4*>(o32 + off + 4), v[1]);
+      }
+      if (o16) {
+        uint4 wv;
+        wv.x = pack16(v[0].x, v[0].y, dtype);
+        wv.y = pack16(v[0].z, v[0].w, dtype);
+        wv.z = pack16(v[1].x, v[1].y, dtype);
+        wv.w = pack16(v[1].z, v[1].w, dtype);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(o16) + off) = wv;
+      }
+    } else {
+      store4_dual(o32, o16, dtype, off, v[0].x, v[0].y, v[0].z, v[0].w);
     }
-    if (o16) {
-      uint4 wv;
-      wv.x = pack16(v[0].x, v[0].y, dtype);
-      wv.y = pack16(v[0].z, v[0].w, dtype);
-      wv.z = pack16(v[1].x, v[1].y, dtype);
-      wv.w = pack16(v[1].z, v[1].w, dtype);
-      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(o16) + off) = wv;
-    }
-  } else {
-    store4_dual(o32, o16, dtype, off, v[0].x, v[0].y, v[0].z, v[0].w);
   }
 }
 
@@ -237,16 +240,23 @@ int sg_upsample_cat(const float* x, const float* skip, int rows, int skip_rows, 
   SG_REQUIRE(x && skip && (out_f32 || out_act), "sg_upsample_cat: null pointer");
   SG_REQUIRE(rows > 0 && h >= 1 && w >= 1 && Cx % 4 == 0 && Cs % 4 == 0, "sg_upsample_cat: bad shape");
   SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_upsample_cat: out_act needs a 16-bit dtype");
-  const int64_t total4 = (int64_t)rows * (2 * h) * (2 * w) * ((Cx + Cs) / 4);
+  const int64_t row4 = (int64_t)(2 * h) * (2 * w) * ((Cx + Cs) / 4);  // float4's per row
+  SG_REQUIRE(row4 < (1ll << 31) && rows <= 65535, "sg_upsample_cat: row too large / too many rows");
   // torch: scale = (in - 1) / (out - 1) in fp32 (area_pixel_compute_scale, align_corners=True)
   const float sh = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
   const float sw = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
-  if (Cx % 8 == 0 && Cs % 8 == 0)
-    upsample_cat_kernel<2><<<cdiv(total4 / 2, 256), 256, 0, as_stream(stream)>>>(x, skip, total4 / 2, skip_rows, h, w, Cx / 4, Cs / 4,
-                                                                                 sh, sw, out_f32, out_act, act_dtype);
+  const int v = (Cx % 8 == 0 && Cs % 8 == 0) ? 2 : 1;
+  const int64_t per_row = row4 / v;
+  int chunks = (int)cdiv(per_row, 256 * 2);  // two elements per thread
+  const int want = (int)cdiv(148 * 8, rows);
+  if (chunks > want) chunks = want > 1 ? want : 1;
+  dim3 grid((unsigned)chunks, (unsigned)rows);
+  if (v == 2)
+    upsample_cat_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, skip, (unsigned)per_row, skip_rows, h, w, Cx / 4, Cs / 4, sh,
+                                                                sw, out_f32, out_act, act_dtype);
   else
-    upsample_cat_kernel<1><<<cdiv(total4, 256), 256, 0, as_stream(stream)>>>(x, skip, total4, skip_rows, h, w, Cx / 4, Cs / 4, sh, sw,
-                                                                             out_f32, out_act, act_dtype);
+    upsample_cat_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, skip, (unsigned)per_row, skip_rows, h, w, Cx / 4, Cs / 4, sh,
+                                                                sw, out_f32, out_act, act_dtype);
   return launch_status("sg_upsample_cat");
 }
 

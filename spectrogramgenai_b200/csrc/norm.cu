@@ -237,6 +237,129 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// GELU(GroupNorm(raw) + cat([skip, upsample2x(x)])) -> 16 bit: the second GroupNorm of Up's first DoubleConv
+// (:132-134 feeding the residual DoubleConv :88-91), with the residual RECOMPUTED from its sources instead of read
+// from an fp32 copy of the concatenated tensor.  Materialising that copy cost a 2.1 GB write in upsample_cat plus a
+// 2.1 GB read here at up3 (n = 512); the sources are 0.8 GB and mostly L2-resident.  Same bilinear expression as
+// upsample_cat_kernel (align_corners=True).  One thread = 8 channels of one pixel; fp16 raw only (tensor-core modes).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_apply_vcat_kernel(const uint4* __restrict__ raw8, const float* __restrict__ partials,
+                                                            int P, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int HW, int W2, int C8,
+                                                            int Cs8, const float* __restrict__ x,
+                                                            const float* __restrict__ skip, int skip_rows, int h, int w,
+                                                            float sh, float sw, void* __restrict__ o16, int dtype) {
+  __shared__ double red[2][8];
+  __shared__ float stat[2];
+  const int row = blockIdx.y;
+  const int64_t per_row8 = (int64_t)HW * C8;
+  {
+    double s = 0.0, q = 0.0;
+    const float2* pp = reinterpret_cast<const float2*>(partials) + (int64_t)row * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      const float2 v = pp[i];
+      s += (double)v.x;
+      q += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = s;
+      red[1][threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double ts = 0.0, tq = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+        ts += red[0][i];
+        tq += red[1][i];
+      }
+      const double cnt = (double)per_row8 * 8.0;
+      const double mean = ts / cnt;
+      double var = tq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stat[0] = (float)mean;
+      stat[1] = (float)(1.0 / sqrt(var + 1e-5));
+    }
+    __syncthreads();
+  }
+  const float mean = stat[0], rstd = stat[1];
+  const int Cx8 = C8 - Cs8;
+  const uint4* rrow = raw8 + (int64_t)row * per_row8;
+  uint4* orow = reinterpret_cast<uint4*>(o16) + (int64_t)row * per_row8;
+  const float4* skip4 = reinterpret_cast<const float4*>(skip) + (int64_t)(row % skip_rows) * HW * (Cs8 * 2);
+  const float4* x4 = reinterpret_cast<const float4*>(x) + (int64_t)row * h * w * (Cx8 * 2);
+  // One thread = one pixel x (8 skip channels k, 8 upsampled channels Cs8 + k): every lane runs both the skip load and
+  // the bilinear gather (a warp that mixed "skip lanes" and "x lanes" executed both branches with half its lanes idle).
+  // 32-bit index arithmetic; the launcher makes the grid stride a multiple of Cs8 (= Cx8, checked there), so a
+  // thread keeps its channels and the folded scale / shift of its 16 channels live in registers.
+  const unsigned nu = (unsigned)HW * (unsigned)Cs8, stride = gridDim.x * blockDim.x;
+  const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned k = first % (unsigned)Cs8;
+  float sc[16], sf[16];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const unsigned c4 = (u < 2 ? k * 2 + u : ((unsigned)Cs8 + k) * 2 + (u - 2));
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[u * 4 + j] = __fmul_rn(rstd, gg[j]);
+      sf[u * 4 + j] = __fmaf_rn(-mean, sc[u * 4 + j], bb[j]);  // same rounding as gn_apply_kernel
+    }
+  }
+  unsigned p = first / (unsigned)Cs8;
+  const unsigned dp = stride / (unsigned)Cs8;
+  for (unsigned i = first; i < nu; i += stride, p += dp) {
+    const size_t e_s = (size_t)p * C8 + k, e_x = e_s + Cs8;  // units of 8 channels inside the row
+    const uint4 h_s = __ldcs(rrow + e_s), h_x = __ldcs(rrow + e_x);
+    float r[16];
+    {
+      const float4 a = __ldg(skip4 + ((size_t)p * Cs8 + k) * 2), b = __ldg(skip4 + ((size_t)p * Cs8 + k) * 2 + 1);
+      r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+    }
+    {
+      const unsigned ho = p / (unsigned)W2, wo = p - ho * (unsigned)W2;
+      const float fy = sh * (float)ho, fx = sw * (float)wo;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+      const float ly = fy - (float)y0, lx = fx - (float)x0;
+      const float hy = 1.0f - ly, hx = 1.0f - lx;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float4 a = __ldg(x4 + (size_t)(y0 * w + x0) * (Cx8 * 2) + k * 2 + u);
+        const float4 b = __ldg(x4 + (size_t)(y0 * w + x1) * (Cx8 * 2) + k * 2 + u);
+        const float4 c = __ldg(x4 + (size_t)(y1 * w + x0) * (Cx8 * 2) + k * 2 + u);
+        const float4 d = __ldg(x4 + (size_t)(y1 * w + x1) * (Cx8 * 2) + k * 2 + u);
+        r[8 + u * 4 + 0] = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
+        r[8 + u * 4 + 1] = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
+        r[8 + u * 4 + 2] = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
+        r[8 + u * 4 + 3] = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const uint4 hraw = half ? h_x : h_s;
+      const float2 a0 = unpack16(hraw.x, SG_F16), a1 = unpack16(hraw.y, SG_F16);
+      const float2 a2 = unpack16(hraw.z, SG_F16), a3 = unpack16(hraw.w, SG_F16);
+      float y[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = gelu_erf(__fmaf_rn(y[j], sc[half * 8 + j], sf[half * 8 + j]) + r[half * 8 + j]);
+      uint4 wv;
+      wv.x = pack16(y[0], y[1], dtype);
+      wv.y = pack16(y[2], y[3], dtype);
+      wv.z = pack16(y[4], y[5], dtype);
+      wv.w = pack16(y[6], y[7], dtype);
+      orow[half ? e_x : e_s] = wv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm over C (:57, :59; eps 1e-5).  C/4 lanes (at most 32) hold one token as float4's, so a warp instruction
 // moves 512 contiguous bytes (the first version, one warp per token with 2 values per lane, reached 3.0 TB/s); four
 // passes are unrolled so that every lane has four independent 16-byte loads in flight.  Two-pass mean / variance
@@ -340,6 +463,33 @@ int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, co
   }
 #undef SG_GN_LAUNCH
   return launch_status("sg_gn_apply");
+}
+
+int sg_gn_apply_vcat(const void* raw, const float* partials, int P, const float* gamma, const float* beta, int rows,
+                     const float* x, const float* skip, int skip_rows, int h, int w, int Cx, int Cs, void* out_act,
+                     int act_dtype, sg_stream_t stream) {
+  SG_REQUIRE(raw && partials && gamma && beta && x && skip && out_act, "sg_gn_apply_vcat: null pointer");
+  SG_REQUIRE(rows > 0 && h >= 1 && w >= 1 && P > 0 && Cx % 8 == 0 && Cs % 8 == 0 && Cx > 0 && Cs > 0,
+             "sg_gn_apply_vcat: bad shape rows=%d h=%d w=%d Cx=%d Cs=%d", rows, h, w, Cx, Cs);
+  SG_REQUIRE(skip_rows > 0 && rows % skip_rows == 0, "sg_gn_apply_vcat: rows=%d must be a multiple of skip_rows=%d", rows, skip_rows);
+  SG_REQUIRE(act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_gn_apply_vcat: out_act needs a 16-bit dtype");
+  const int H2 = 2 * h, W2 = 2 * w, C = Cx + Cs;
+  const int64_t per_row8 = (int64_t)H2 * W2 * (C / 8);
+  SG_REQUIRE(per_row8 < (1ll << 31), "sg_gn_apply_vcat: row too large");
+  int chunks = cdiv(per_row8 / 2, 256);
+  const int want = cdiv(148 * 8, rows);
+  if (chunks > want) chunks = want > 1 ? want : 1;
+  if (chunks < 1) chunks = 1;
+  SG_REQUIRE(Cx == Cs, "sg_gn_apply_vcat: Cx=%d != Cs=%d (a thread pairs skip channel k with upsampled channel k)", Cx, Cs);
+  // the kernel keeps a thread on the same channels: the grid stride (chunks * 256 threads) must be a multiple of Cs/8
+  while (((int64_t)chunks * 256) % (Cs / 8) != 0) ++chunks;
+  // torch: scale = (in - 1) / (out - 1) in fp32 (area_pixel_compute_scale, align_corners=True), as sg_upsample_cat
+  const float sh = (H2 > 1) ? (float)(h - 1) / (float)(H2 - 1) : 0.f;
+  const float sw = (W2 > 1) ? (float)(w - 1) / (float)(W2 - 1) : 0.f;
+  gn_apply_vcat_kernel<<<dim3(chunks, rows), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint4*>(raw), partials, P, gamma, beta, H2 * W2, W2, C / 8, Cs / 8, x, skip, skip_rows, h, w,
+      sh, sw, out_act, act_dtype);
+  return launch_status("sg_gn_apply_vcat");
 }
 
 int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t M, int C, void* out_act, int act_dtype,

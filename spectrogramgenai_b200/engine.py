@@ -194,9 +194,15 @@ class UNetPlan:
         raw2, part2 = self._conv(mid[1], f"{p}.double_conv.3.weight", rows, H, W)
         self._free_pair(mid)
         out = self._pair((out_rows or rows,) + tuple(raw2.shape[1:]), want_f32, want_act)
-        self._op(ops.gn_apply, raw2, part2, W_[f"{p}.double_conv.4.weight"], W_[f"{p}.double_conv.4.bias"],
-                 mode=2 if residual else 0, residual=x[0] if residual else None, emb=emb,
-                 out_f32=out[0], out_act=out[1] if self.tc else None)
+        if isinstance(residual, tuple):
+            # Up's first DoubleConv: the residual is cat([skip, upsample(x)]), recomputed from (x, skip) in the kernel
+            _, x_src, skip_src = residual
+            self._op(ops.gn_apply_vcat, raw2, part2, W_[f"{p}.double_conv.4.weight"], W_[f"{p}.double_conv.4.bias"],
+                     x_src, skip_src, out[1])
+        else:
+            self._op(ops.gn_apply, raw2, part2, W_[f"{p}.double_conv.4.weight"], W_[f"{p}.double_conv.4.bias"],
+                     mode=2 if residual else 0, residual=x[0] if residual else None, emb=emb,
+                     out_f32=out[0], out_act=out[1] if self.tc else None)
         self._free(raw2, part2)
         return out
 
@@ -268,9 +274,14 @@ class UNetPlan:
     def _up(self, p, x, skip, rows, h, w):
         H, W = 2 * h, 2 * w
         ct = x[0].shape[-1] + skip[0].shape[-1]
-        cat = self._pair((rows, H, W, ct))
+        # tensor-core modes with fp16 raw tensors: only the 16-bit operand copy of the concatenation is materialised;
+        # the residual DoubleConv recomputes its fp32 residual from (x, skip) (sg_gn_apply_vcat)
+        vcat = (self.tc and self.raw16 and x[0].shape[-1] == skip[0].shape[-1]
+                and os.environ.get("SGB200_VCAT", "1") != "0")
+        cat = self._pair((rows, H, W, ct), want_f32=not vcat)
         self._op(ops.upsample_cat, x[0], skip[0], out_f32=cat[0], out_act=cat[1] if self.tc else None)
-        u1 = self._double_conv(f"{p}.conv.0", cat, rows, H, W, residual=True, want_f32=False)
+        u1 = self._double_conv(f"{p}.conv.0", cat, rows, H, W, residual=("vcat", x[0], skip[0]) if vcat else True,
+                               want_f32=False)
         self._free_pair(cat)
         u2 = self._double_conv(f"{p}.conv.1", u1, rows, H, W, emb=self._emb_slice(p), want_act=False)
         self._free_pair(u1)

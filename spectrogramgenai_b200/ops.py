@@ -112,6 +112,20 @@ def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f
                              ptr(out_act), adt, stream_ptr()), "sg_gn_apply")
 
 
+def gn_apply_vcat(raw, partials, gamma, beta, x, skip, out_act):
+    """GELU(GroupNorm(raw) + cat([skip, upsample2x(x)])) -> 16 bit (sg_gn_apply_vcat).  raw fp16 [rows,2h,2w,Cs+Cx];
+    x fp32 [rows,h,w,Cx]; skip fp32 [skip_rows,2h,2w,Cs]."""
+    rows, h, w, Cx = x.shape
+    Cs = skip.shape[-1]
+    if raw.dtype != torch.float16 or tuple(raw.shape) != (rows, 2 * h, 2 * w, Cs + Cx):
+        raise ValueError("gn_apply_vcat: raw must be fp16 [rows, 2h, 2w, Cs+Cx]")
+    if tuple(skip.shape[1:3]) != (2 * h, 2 * w) or rows % skip.shape[0]:
+        raise ValueError("gn_apply_vcat: skip must be [skip_rows, 2h, 2w, Cs] with rows a multiple of skip_rows")
+    check(_lib().sg_gn_apply_vcat(ptr(raw), ptr(partials), partials.shape[1], ptr(gamma), ptr(beta), rows,
+                                  ptr(_f32(x, "x")), ptr(_f32(skip, "skip")), skip.shape[0], h, w, Cx, Cs, ptr(out_act),
+                                  dtype_code(out_act.dtype), stream_ptr()), "sg_gn_apply_vcat")
+
+
 def maxpool2(x, *, out_f32=None, out_act=None):
     """K3a.  x fp32 [rows,H,W,C]."""
     rows, H, W, Cc = x.shape

@@ -189,6 +189,32 @@ def test_row_broadcast_of_the_shared_prefix(ops):
     assert torch.equal(o_b, o_r)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,skip_rows,h,cx,cs", [(2, 2, 4, 64, 64), (4, 2, 8, 128, 128), (2, 1, 16, 64, 64), (3, 3, 2, 256, 256), (1, 1, 1, 64, 64)])
+def test_gn_apply_vcat(ops, rows, skip_rows, h, cx, cs, dtype):
+    """GELU(GroupNorm(raw) + cat([skip, upsample(x)])) with the residual recomputed from its sources equals
+    sg_upsample_cat (fp32) followed by sg_gn_apply mode 2, bit for bit, and fp64 torch within 16-bit rounding."""
+    g = gen(41)
+    C = cx + cs
+    x = torch.randn(rows, h, h, cx, generator=g).to(DEV)
+    skip = torch.randn(skip_rows, 2 * h, 2 * h, cs, generator=g).to(DEV)
+    raw = torch.randn(rows, 2 * h, 2 * h, C, generator=g).half().to(DEV)
+    part = torch.stack([raw.double().sum((1, 2, 3)), (raw.double() ** 2).sum((1, 2, 3))], -1).float().reshape(rows, 1, 2).contiguous()
+    gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
+    got = torch.empty(rows, 2 * h, 2 * h, C, device=DEV, dtype=dtype)
+    ops.gn_apply_vcat(raw, part, gamma, beta, x, skip, got)
+    cat = torch.empty(rows, 2 * h, 2 * h, C, device=DEV)
+    ops.upsample_cat(x, skip, out_f32=cat)
+    two = torch.empty_like(got)
+    ops.gn_apply(raw, part, gamma, beta, mode=2, residual=cat, out_act=two)
+    torch.cuda.synchronize()
+    assert torch.equal(got, two)
+    up = F.interpolate(nchw(x.cpu()).double(), scale_factor=2, mode="bilinear", align_corners=True)
+    res = nhwc(torch.cat([nchw(skip.cpu().repeat(rows // skip_rows, 1, 1, 1)).double(), up], 1))
+    gn = nhwc(F.group_norm(nchw(raw.cpu().double()), 1, gamma.cpu().double(), beta.cpu().double(), 1e-5))
+    assert O.rel_l2(got.cpu(), F.gelu(gn + res)) < (4e-3 if dtype == torch.bfloat16 else 6e-4)
+
+
 # ------------------------------------------------------------------------------------------ convolutions
 @pytest.mark.parametrize("c_in,S,rows,n_src", [(4, 16, 4, 2), (1, 32, 2, 2), (4, 64, 2, 1), (3, 16, 1, 1)])
 def test_conv_in(ops, c_in, S, rows, n_src):
