@@ -29,7 +29,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert os.path.exists(path)
     lib = _cabi.load()
     declared = _header_symbols()
-    assert len(declared) >= 19
+    assert len(declared) >= 25
     assert sorted(_cabi.PROTOTYPES) == declared, "ctypes prototypes and include/sgb200.h disagree"
     raw = ctypes.CDLL(path)
     for name in declared:
@@ -47,8 +47,9 @@ def test_igemm_args_struct_matches_header_layout():
 
     from spectrogramgenai_b200._cabi import IgemmArgs
 
-    assert ctypes.sizeof(IgemmArgs) == 7 * 8 + 9 * 4 + 4  # 7 pointers, 9 int32, tail padding to 8
-    assert IgemmArgs.rows.offset == 56 and IgemmArgs.act_dtype.offset == 56 + 8 * 4
+    assert ctypes.sizeof(IgemmArgs) == 7 * 8 + 10 * 4  # 7 pointers, 10 int32 (rows .. taps, act, engine, act_dtype, out_dtype)
+    assert IgemmArgs.rows.offset == 56 and IgemmArgs.act.offset == 56 + 6 * 4
+    assert IgemmArgs.act_dtype.offset == 56 + 8 * 4 and IgemmArgs.out_dtype.offset == 56 + 9 * 4
 
 
 def test_state_dict_schema_matches_reference():
