@@ -328,7 +328,7 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
       }
       if (gelu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
       }
       if (stats) {
 #pragma unroll
@@ -391,7 +391,7 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
     }
     if (ep.act == SG_ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+      for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
     }
     if (ep.partials && valid) {
       // same summation order as the packed fast path (even / odd columns in two chains, combined at the end), so that

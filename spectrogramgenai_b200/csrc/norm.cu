@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
       y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
     }
     if (mode >= 1) {
-      y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w);
+      gelu_erf2(y.x, y.y);
+      gelu_erf2(y.z, y.w);
     }
     if (e4 && (!RAW16 || mode >= 1)) {
       y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
         }
         if (MODE >= 1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = gelu_erf(y[j]);
+          for (int j = 0; j < 8; j += 2) gelu_erf2(y[j], y[j + 1]);
           if (e4) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] += ev[j];
@@ -348,7 +349,9 @@ __global__ void __launch_bounds__(256) gn_apply_vcat_kernel(const uint4* __restr
       const float2 a2 = unpack16(hraw.z, SG_F16), a3 = unpack16(hraw.w, SG_F16);
       float y[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = gelu_erf(__fmaf_rn(y[j], sc[half * 8 + j], sf[half * 8 + j]) + r[half * 8 + j]);
+      for (int j = 0; j < 8; ++j) y[j] = __fmaf_rn(y[j], sc[half * 8 + j], sf[half * 8 + j]) + r[half * 8 + j];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) gelu_erf2(y[j], y[j + 1]);
       uint4 wv;
       wv.x = pack16(y[0], y[1], dtype);
       wv.y = pack16(y[2], y[3], dtype);

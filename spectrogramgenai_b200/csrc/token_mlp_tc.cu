@@ -238,10 +238,14 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
         for (int c = 0; c < 4; ++c) {  // 8 channels per 16-byte chunk
           const float4 b0 = *reinterpret_cast<const float4*>(sPar + 3 * TC + h * 32 + c * 8);
           const float4 b1v = *reinterpret_cast<const float4*>(sPar + 3 * TC + h * 32 + c * 8 + 4);
-          const float g0 = gelu_erf(__uint_as_float(v[c * 8 + 0]) + b0.x), g1 = gelu_erf(__uint_as_float(v[c * 8 + 1]) + b0.y);
-          const float g2 = gelu_erf(__uint_as_float(v[c * 8 + 2]) + b0.z), g3 = gelu_erf(__uint_as_float(v[c * 8 + 3]) + b0.w);
-          const float g4 = gelu_erf(__uint_as_float(v[c * 8 + 4]) + b1v.x), g5 = gelu_erf(__uint_as_float(v[c * 8 + 5]) + b1v.y);
-          const float g6 = gelu_erf(__uint_as_float(v[c * 8 + 6]) + b1v.z), g7 = gelu_erf(__uint_as_float(v[c * 8 + 7]) + b1v.w);
+          float g0 = __uint_as_float(v[c * 8 + 0]) + b0.x, g1 = __uint_as_float(v[c * 8 + 1]) + b0.y;
+          float g2 = __uint_as_float(v[c * 8 + 2]) + b0.z, g3 = __uint_as_float(v[c * 8 + 3]) + b0.w;
+          float g4 = __uint_as_float(v[c * 8 + 4]) + b1v.x, g5 = __uint_as_float(v[c * 8 + 5]) + b1v.y;
+          float g6 = __uint_as_float(v[c * 8 + 6]) + b1v.z, g7 = __uint_as_float(v[c * 8 + 7]) + b1v.w;
+          gelu_erf2(g0, g1);
+          gelu_erf2(g2, g3);
+          gelu_erf2(g4, g5);
+          gelu_erf2(g6, g7);
           sts128u(row + ((((uint32_t)(h * 4 + c)) ^ ((uint32_t)r & 7u)) << 4), pack2<DT>(g0, g1), pack2<DT>(g2, g3),
                   pack2<DT>(g4, g5), pack2<DT>(g6, g7));
         }
