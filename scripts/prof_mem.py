@@ -31,7 +31,7 @@ def timeit(name, fn, nbytes, reps=5):
 
 
 for (H, C) in ((64, 64), (32, 128), (64, 128)):
-    raw = torch.randn(rows, H, H, C, device=dev, generator=g)
+    raw = torch.randn(rows, H, H, C, device=dev, generator=g).half()  # fp16 raw conv output (tensor-core modes)
     res = torch.randn(rows, H, H, C, device=dev, generator=g)
     P = H * H // 128
     part = torch.rand(rows, P, 2, device=dev, generator=g) * 1000 + 1000
@@ -40,11 +40,11 @@ for (H, C) in ((64, 64), (32, 128), (64, 128)):
     o32 = torch.empty(rows, H, H, C, device=dev)
     emb = torch.randn(rows, C, device=dev, generator=g)
     n = raw.numel()
-    timeit(f"gn_apply {H}x{H}x{C} mode1 (GELU) -> bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=1, out_act=o16), n * 6)
-    timeit(f"gn_apply {H}x{H}x{C} mode0 -> bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=0, out_act=o16), n * 6)
-    timeit(f"gn_apply {H}x{H}x{C} mode0 +emb -> f32", lambda: ops.gn_apply(raw, part, gam, bet, mode=0, emb=emb, out_f32=o32), n * 8)
-    timeit(f"gn_apply {H}x{H}x{C} mode2 (res+GELU) -> bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=2, residual=res, out_act=o16), n * 10)
-    timeit(f"gn_apply {H}x{H}x{C} mode0 -> f32+bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=0, out_f32=o32, out_act=o16), n * 10)
+    timeit(f"gn_apply {H}x{H}x{C} mode1 (GELU) -> bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=1, out_act=o16), n * 4)
+    timeit(f"gn_apply {H}x{H}x{C} mode0 -> bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=0, out_act=o16), n * 4)
+    timeit(f"gn_apply {H}x{H}x{C} mode0 +emb -> f32", lambda: ops.gn_apply(raw, part, gam, bet, mode=0, emb=emb, out_f32=o32), n * 6)
+    timeit(f"gn_apply {H}x{H}x{C} mode2 (res+GELU) -> bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=2, residual=res, out_act=o16), n * 8)
+    timeit(f"gn_apply {H}x{H}x{C} mode0 -> f32+bf16", lambda: ops.gn_apply(raw, part, gam, bet, mode=0, out_f32=o32, out_act=o16), n * 8)
     del raw, res, o16, o32
 for (L, C) in ((4096, 64), (1024, 128), (1024, 64)):
     M = rows * L
