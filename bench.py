@@ -233,7 +233,7 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args, n, engine):
@@ -248,7 +248,27 @@ def workload_config(args, n, engine):
     }
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner to stdout
+    when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the whole process and
+    the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -439,7 +459,7 @@ def main():
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cb,
         "activation_bytes_allocated": plan.nbytes,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
