@@ -146,7 +146,7 @@ int sg_upsample_cat(const float* x, const float* skip, int rows, int skip_rows, 
 int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t M, int C, void* out_act,
                  int act_dtype, sg_stream_t stream);
 
-/* ---- SelfAttention head, fused (tcgen05 engine, C = 64): qkv = LayerNorm(x) Win^T + bin ----
+/* ---- SelfAttention head, fused (tcgen05 engine, C = 64 or 128): qkv = LayerNorm(x) Win^T + bin ----
  * replaces self.ln (:57,:67) + the in_proj of nn.MultiheadAttention (:56,:69).
  * x fp32 [M,C] (the residual stream, tokens row-major) -> qkv act [M,3C].  w_in act [3C,C] (torch layout),
  * b_in fp32 [3C].  One pass over x, one over qkv; the LayerNorm of a token is register math of the thread that
@@ -155,7 +155,7 @@ int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t
 int sg_ln_inproj(const float* x, const float* ln_g, const float* ln_b, const void* w_in, const float* b_in, int64_t M,
                  int C, void* qkv, int act_dtype, sg_stream_t stream);
 
-/* ---- SelfAttention tail, fused (tcgen05 engine, C = 64) ----
+/* ---- SelfAttention tail, fused (tcgen05 engine, C = 64 or 128) ----
  * replaces out_proj + residual (:69-70), ff_self = LayerNorm -> Linear -> GELU -> Linear (:58-63) and the second
  * residual (:71):   a = att Wo^T + bo + x;   out = GELU(LayerNorm(a) W1^T + b1) W2^T + b2 + a.
  * att act [M,C] (attention core output), x fp32 [M,C], wo/w1/w2 act [C,C] (torch layout: [out, in]),

@@ -1,31 +1,47 @@
 // Fused per-token halves of SelfAttention (/root/reference/src/diff_modules.py:52-72) around the attention core,
-// tcgen05 engine, C = 64 (sa5 / sa6 at 64x64 latents: 80 % of all attention tokens):
+// tcgen05 engine, C = 64 (sa5 / sa6 at 64x64 latents: 80 % of all attention tokens) and C = 128 (sa1 / sa4):
 //
 //   sg_ln_inproj :  qkv = LayerNorm(x) Win^T + bin                                         (:67 self.ln, :69 in_proj)
 //   sg_attn_tail :  a = att Wo^T + bo + x;  h = GELU(LayerNorm(a) W1^T + b1);  out = h W2^T + b2 + a   (:69-71)
 //
 // Unfused, the tail is four launches (out_proj, LayerNorm, FFN1, FFN2) that move the [M, C] activation eleven times
-// (9.7 GB at sa6, n = 512) and the head two launches (2.7 GB + 1.6 GB written); fused they read att (bf16) and x
+// (9.7 GB at sa6, n = 512) and the head two launches (2.7 GB + 1.6 GB written); fused they read att (16 bit) and x
 // (fp32) once and write out once (2.7 GB), resp. read x and write qkv (2.7 GB).
 //
 // One CTA owns a tile of 128 tokens at a time (persistent over tiles).  Thread r of the four warps IS token r: it is
 // TMEM lane r, so bias / residual / LayerNorm / GELU of a token are pure register math (LayerNorm needs no
-// shuffles).  All global traffic is TMA: the fp32 tiles are loaded / stored as two SWIZZLE_128B boxes of 32 floats
-// so that a thread walking its own 256-byte row is bank-conflict free, the 16-bit tiles are SWIZZLE_128B K-major
-// UMMA operands.  The A operand of every GEMM after the first is written by the row threads straight into the
-// operand tile (same swizzle the TMA would have produced).  Weights (3 x 8 KB) stay in shared memory for the
-// lifetime of the CTA.  A tile is a serial chain (load -> GEMM -> epilogue -> GEMM -> ...); three (tail) / two
-// (in_proj) CTAs per SM overlap each other's chains.
+// shuffles).  All global traffic is TMA: the fp32 tiles are loaded / stored as C/32 SWIZZLE_128B boxes of 32 floats
+// so that a thread walking its own row is bank-conflict free, the 16-bit tiles are SWIZZLE_128B K-major UMMA operands
+// (C/64 atom columns of 64 channels).  The A operand of every GEMM after the first is written by the row threads
+// straight into the operand tile (same swizzle the TMA would have produced).  Weights stay in shared memory for the
+// lifetime of the CTA (24 KB at C = 64, 96 KB at C = 128).  A tile is a serial chain (load -> GEMM -> epilogue ->
+// GEMM -> ...); at C = 64 three (tail) / two (in_proj) CTAs per SM overlap each other's chains, at C = 128 the
+// weights leave room for one.
 #include "tc_common.cuh"
 
 namespace sg {
 namespace tc {
 
-constexpr int TM = 128;          // tokens per tile
-constexpr int TC = 64;           // channels
-constexpr int A_TILE = TM * TC * 2;       // 16 KB: [128 x 64] 16-bit, one SWIZZLE_128B atom column
-constexpr int X_TILE = TM * TC * 4;       // 32 KB: [128 x 64] fp32 as two [128 x 32] SWIZZLE_128B boxes
-constexpr int W_TILE = TC * TC * 2;       // 8 KB : [64 x 64] 16-bit weights (rows = output features, K-major)
+constexpr int TM = 128;  // tokens per tile
+
+template <int C>
+struct Tok {
+  static constexpr int KB = C / 64;             // 64-channel k-blocks = SWIZZLE_128B atom columns of a 16-bit tile
+  static constexpr int A_ATOM = TM * 128;       // 16 KB: [128 x 64] 16-bit
+  static constexpr int A_TILE = KB * A_ATOM;    // [128 x C] 16-bit
+  static constexpr int XB = C / 32;             // fp32 boxes of 32 floats
+  static constexpr int X_TILE = XB * TM * 128;  // [128 x C] fp32
+  static constexpr int W_KB = C * 128;          // one k-block of a [C x C] weight: C rows x 128 bytes
+  static constexpr int W_TILE = KB * W_KB;      // [C x C] 16-bit
+  static constexpr int WIN_KB = 3 * C * 128;    // one k-block of Win [3C x C]
+  static constexpr int WIN_TILE = KB * WIN_KB;
+  static constexpr int TAIL_SMEM = 1024 + 3 * W_TILE + A_TILE + X_TILE + 5 * C * 4 + 128;
+  static constexpr int INPROJ_SMEM = 1024 + WIN_TILE + X_TILE + A_TILE + 5 * C * 4 + 128;
+  static constexpr int TAIL_TMEM = 2 * C;               // two accumulators [128 x C]: 128 / 256 columns
+  static constexpr int INPROJ_TMEM = C == 64 ? 256 : 512;  // one accumulator [128 x 3C]
+  static constexpr int TAIL_CTAS = C == 64 ? 3 : 1;
+  static constexpr int INPROJ_CTAS = C == 64 ? 2 : 1;
+};
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -45,9 +61,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return w;
 }
 
-// this thread's fp32 row (64 floats) of a [128 x 64] tile stored as two SWIZZLE_128B [128 x 32] boxes
-__device__ __forceinline__ uint32_t xrow_chunk_addr(uint32_t tile, int r, int c /*16-byte chunk 0..15*/) {
+// 16-byte chunk c (4 floats) of this thread's fp32 row in a [128 x C] tile stored as C/32 SWIZZLE_128B [128 x 32] boxes
+__device__ __forceinline__ uint32_t xrow_chunk_addr(uint32_t tile, int r, int c) {
   return tile + (uint32_t)(c >> 3) * (TM * 128) + (uint32_t)r * 128u + ((((uint32_t)c & 7u) ^ ((uint32_t)r & 7u)) << 4);
+}
+// 16-byte chunk c (8 x 16 bit) of this thread's row in a [128 x C] K-major operand tile (C/64 atom columns)
+__device__ __forceinline__ uint32_t arow_chunk_addr(uint32_t tile, int r, int c) {
+  return tile + (uint32_t)(c >> 3) * (TM * 128) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+         ((((uint32_t)c & 7u) ^ ((uint32_t)r & 7u)) << 4);
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -61,41 +82,46 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// LayerNorm of the 64 values a thread holds (two-pass like torch, eps 1e-5), packed to 16 bit and written as row r
+// LayerNorm of the C values a thread holds (two-pass like torch, eps 1e-5), packed to 16 bit and written as row r
 // of a SWIZZLE_128B K-major operand tile.
-template <int DT>
-__device__ __forceinline__ void ln_row_to_operand(const float (&a)[TC], const float* __restrict__ s_gamma,
+template <int C, int DT>
+__device__ __forceinline__ void ln_row_to_operand(const float (&a)[C], const float* __restrict__ s_gamma,
                                                   const float* __restrict__ s_beta, uint32_t tile, int r) {
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < TC; ++j) s += a[j];
-  const float mean = s * (1.0f / TC);
+  for (int j = 0; j < C; ++j) s += a[j];
+  const float mean = s * (1.0f / C);
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < TC; ++j) {
+  for (int j = 0; j < C; ++j) {
     const float d = a[j] - mean;
     q = fmaf(d, d, q);
   }
-  const float rstd = rsqrtf(q * (1.0f / TC) + 1e-5f);
-  const uint32_t row = tile + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+  const float rstd = rsqrtf(q * (1.0f / C) + 1e-5f);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {  // 8 channels = one 16-byte chunk
+  for (int c = 0; c < C / 8; ++c) {  // 8 channels = one 16-byte chunk
     const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + c * 8), g1 = *reinterpret_cast<const float4*>(s_gamma + c * 8 + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(s_beta + c * 8), b1 = *reinterpret_cast<const float4*>(s_beta + c * 8 + 4);
     const float y0 = fmaf((a[c * 8 + 0] - mean) * rstd, g0.x, b0.x), y1 = fmaf((a[c * 8 + 1] - mean) * rstd, g0.y, b0.y);
     const float y2 = fmaf((a[c * 8 + 2] - mean) * rstd, g0.z, b0.z), y3 = fmaf((a[c * 8 + 3] - mean) * rstd, g0.w, b0.w);
     const float y4 = fmaf((a[c * 8 + 4] - mean) * rstd, g1.x, b1.x), y5 = fmaf((a[c * 8 + 5] - mean) * rstd, g1.y, b1.y);
     const float y6 = fmaf((a[c * 8 + 6] - mean) * rstd, g1.z, b1.z), y7 = fmaf((a[c * 8 + 7] - mean) * rstd, g1.w, b1.w);
-    sts128u(row + ((((uint32_t)c) ^ ((uint32_t)r & 7u)) << 4), pack2<DT>(y0, y1), pack2<DT>(y2, y3), pack2<DT>(y4, y5),
-            pack2<DT>(y6, y7));
+    sts128u(arow_chunk_addr(tile, r, c), pack2<DT>(y0, y1), pack2<DT>(y2, y3), pack2<DT>(y4, y5), pack2<DT>(y6, y7));
   }
 }
 
-// D[tmem, 128 x N] = A[smem 128 x 64, SW128 K-major] * B[smem N x 64, SW128 K-major]^T : four K = 16 steps
-__device__ __forceinline__ void gemm_k64(uint32_t tmem_d, uint32_t a_tile, uint32_t b_tile, uint32_t idesc) {
-  const uint64_t ad = make_desc_k128(a_tile), bd = make_desc_k128(b_tile);
+// D[tmem, 128 x N] (+)= A[smem 128 x C, SW128 K-major] * B[smem rows [row0, row0 + N) of a [ROWS x C] weight]^T.
+// The weight is stored as C/64 k-blocks of ROWS x 128 bytes; called by one elected lane.
+template <int C>
+__device__ __forceinline__ void gemm_kc(uint32_t tmem_d, uint32_t a_tile, uint32_t b_tile, int b_kb_bytes, int row0,
+                                        uint32_t idesc) {
 #pragma unroll
-  for (int k = 0; k < TC / 16; ++k) umma_ss(tmem_d, ad + 2 * k, bd + 2 * k, idesc, k != 0);
+  for (int kb = 0; kb < C / 64; ++kb) {
+    const uint64_t ad = make_desc_k128(a_tile + kb * (TM * 128));
+    const uint64_t bd = make_desc_k128(b_tile + kb * b_kb_bytes + row0 * 128);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_ss(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+  }
 }
 
 struct TailParams {
@@ -112,30 +138,28 @@ struct TailParams {
 // ------------------------------------------------------------------------------------------------------------------
 // sg_attn_tail
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int TAIL_SMEM = 1024 + 3 * W_TILE + A_TILE + X_TILE + 5 * TC * 4 + 128;
-
-template <int DT>
-__global__ void __launch_bounds__(128, 3)
+template <int C, int DT>
+__global__ void __launch_bounds__(128, Tok<C>::TAIL_CTAS)
 attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant__ CUtensorMap tm_x,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_wo,
                  const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
                  const TailParams p) {
+  using T = Tok<C>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sW = smem;                    // Wo | W1 | W2
-  uint8_t* sA = sW + 3 * W_TILE;         // operand tile: att, then LN(a), then GELU(.)
-  uint8_t* sX = sA + A_TILE;             // x tile (fp32), later the output tile
-  float* sPar = reinterpret_cast<float*>(sX + X_TILE);  // bo | ln_g | ln_b | b1 | b2
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 5 * TC);
+  uint8_t* sW = smem;                  // Wo | W1 | W2
+  uint8_t* sA = sW + 3 * T::W_TILE;    // operand tile: att, then LN(a), then GELU(.)
+  uint8_t* sX = sA + T::A_TILE;        // x tile (fp32), later the output tile
+  float* sPar = reinterpret_cast<float*>(sX + T::X_TILE);  // bo | ln_g | ln_b | b1 | b2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 5 * C);
   uint64_t* w_full = bars;
   uint64_t* in_full = bars + 1;
   uint64_t* mma_done = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool leader = tid == 0;
-  if (leader) {
+  if (tid == 0) {
     prefetch_tensormap(&tm_att);
     prefetch_tensormap(&tm_x);
     prefetch_tensormap(&tm_out);
@@ -144,13 +168,13 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     mbar_init(mma_done, 1);
     fence_barrier_init();
   }
-  for (int i = tid; i < 5 * TC; i += 128) {
-    const float* src = i < TC ? p.bo : (i < 2 * TC ? p.ln_g : (i < 3 * TC ? p.ln_b : (i < 4 * TC ? p.b1 : p.b2)));
-    sPar[i] = src[i & (TC - 1)];
+  for (int i = tid; i < 5 * C; i += 128) {
+    const float* src = i < C ? p.bo : (i < 2 * C ? p.ln_g : (i < 3 * C ? p.ln_b : (i < 4 * C ? p.b1 : p.b2)));
+    sPar[i] = src[i & (C - 1)];
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc<128>(tmem_slot);
+    tmem_alloc<T::TAIL_TMEM>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -162,10 +186,13 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
 
   // TMA / MMA instructions are issued by one elected lane of the CONVERGENT warp 0 (descriptors stay in uniform registers)
   if (warp == 0 && elect_one()) {
-    mbar_arrive_expect_tx(w_full, 3 * W_TILE);
-    tma_load_2d(sW, &tm_wo, w_full, 0, 0);
-    tma_load_2d(sW + W_TILE, &tm_w1, w_full, 0, 0);
-    tma_load_2d(sW + 2 * W_TILE, &tm_w2, w_full, 0, 0);
+    mbar_arrive_expect_tx(w_full, 3 * T::W_TILE);
+#pragma unroll
+    for (int kb = 0; kb < T::KB; ++kb) {
+      tma_load_2d(sW + kb * T::W_KB, &tm_wo, w_full, kb * 64, 0);
+      tma_load_2d(sW + T::W_TILE + kb * T::W_KB, &tm_w1, w_full, kb * 64, 0);
+      tma_load_2d(sW + 2 * T::W_TILE + kb * T::W_KB, &tm_w2, w_full, kb * 64, 0);
+    }
   }
   uint32_t in_ph = 0, mma_ph = 0;
   bool first = true;
@@ -174,16 +201,17 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     if (warp == 0) {
       if (elect_one()) {
         tma_store_wait_read();  // the previous tile's output (staged in sX) has left shared memory
-        mbar_arrive_expect_tx(in_full, A_TILE + X_TILE);
-        tma_load_2d(sA, &tm_att, in_full, 0, m0);
-        tma_load_2d(sX, &tm_x, in_full, 0, m0);
-        tma_load_2d(sX + TM * 128, &tm_x, in_full, 32, m0);
+        mbar_arrive_expect_tx(in_full, T::A_TILE + T::X_TILE);
+#pragma unroll
+        for (int kb = 0; kb < T::KB; ++kb) tma_load_2d(sA + kb * T::A_ATOM, &tm_att, in_full, kb * 64, m0);
+#pragma unroll
+        for (int j = 0; j < T::XB; ++j) tma_load_2d(sX + j * (TM * 128), &tm_x, in_full, j * 32, m0);
       }
       if (first) mbar_wait_spin(w_full, 0);
       mbar_wait_spin(in_full, in_ph);
       tc_fence_after();
       if (elect_one()) {
-        gemm_k64(tmem_base, aA, aW, p.idesc);  // att Wo^T
+        gemm_kc<C>(tmem_base, aA, aW, T::W_KB, 0, p.idesc);  // att Wo^T
         umma_commit(mma_done);
       }
       __syncwarp();
@@ -195,9 +223,9 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     tc_fence_after();
     mbar_wait(in_full, in_ph);  // the x tile is visible to this thread (acquire on the TMA barrier)
     in_ph ^= 1u;
-    float a[TC];
+    float a[C];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < C / 32; ++h) {
       uint32_t v[32];
       tmem_ld32(t_row + h * 32, v);
       tmem_ld_wait();
@@ -211,14 +239,14 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
         a[h * 32 + c * 4 + 3] = __uint_as_float(v[c * 4 + 3]) + bv.w + xv.w;
       }
     }
-    ln_row_to_operand<DT>(a, sPar + TC, sPar + 2 * TC, aA, r);  // the GEMM that read sA has completed (mma_done)
+    ln_row_to_operand<C, DT>(a, sPar + C, sPar + 2 * C, aA, r);  // the GEMM that read sA has completed (mma_done)
     tc_fence_before();
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        gemm_k64(tmem_base + 64, aA, aW + W_TILE, p.idesc);  // LN(a) W1^T
+        gemm_kc<C>(tmem_base + C, aA, aW + T::W_TILE, T::W_KB, 0, p.idesc);  // LN(a) W1^T
         umma_commit(mma_done);
       }
       __syncwarp();
@@ -227,28 +255,24 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
     tc_fence_after();
-    {
-      const uint32_t row = aA + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld32(t_row + 64 + h * 32, v);
-        tmem_ld_wait();
+    for (int h = 0; h < C / 32; ++h) {
+      uint32_t v[32];
+      tmem_ld32(t_row + C + h * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {  // 8 channels per 16-byte chunk
-          const float4 b0 = *reinterpret_cast<const float4*>(sPar + 3 * TC + h * 32 + c * 8);
-          const float4 b1v = *reinterpret_cast<const float4*>(sPar + 3 * TC + h * 32 + c * 8 + 4);
-          float g0 = __uint_as_float(v[c * 8 + 0]) + b0.x, g1 = __uint_as_float(v[c * 8 + 1]) + b0.y;
-          float g2 = __uint_as_float(v[c * 8 + 2]) + b0.z, g3 = __uint_as_float(v[c * 8 + 3]) + b0.w;
-          float g4 = __uint_as_float(v[c * 8 + 4]) + b1v.x, g5 = __uint_as_float(v[c * 8 + 5]) + b1v.y;
-          float g6 = __uint_as_float(v[c * 8 + 6]) + b1v.z, g7 = __uint_as_float(v[c * 8 + 7]) + b1v.w;
-          gelu_erf2(g0, g1);
-          gelu_erf2(g2, g3);
-          gelu_erf2(g4, g5);
-          gelu_erf2(g6, g7);
-          sts128u(row + ((((uint32_t)(h * 4 + c)) ^ ((uint32_t)r & 7u)) << 4), pack2<DT>(g0, g1), pack2<DT>(g2, g3),
-                  pack2<DT>(g4, g5), pack2<DT>(g6, g7));
-        }
+      for (int c = 0; c < 4; ++c) {  // 8 channels per 16-byte chunk
+        const float4 b0 = *reinterpret_cast<const float4*>(sPar + 3 * C + h * 32 + c * 8);
+        const float4 b1v = *reinterpret_cast<const float4*>(sPar + 3 * C + h * 32 + c * 8 + 4);
+        float g0 = __uint_as_float(v[c * 8 + 0]) + b0.x, g1 = __uint_as_float(v[c * 8 + 1]) + b0.y;
+        float g2 = __uint_as_float(v[c * 8 + 2]) + b0.z, g3 = __uint_as_float(v[c * 8 + 3]) + b0.w;
+        float g4 = __uint_as_float(v[c * 8 + 4]) + b1v.x, g5 = __uint_as_float(v[c * 8 + 5]) + b1v.y;
+        float g6 = __uint_as_float(v[c * 8 + 6]) + b1v.z, g7 = __uint_as_float(v[c * 8 + 7]) + b1v.w;
+        gelu_erf2(g0, g1);
+        gelu_erf2(g2, g3);
+        gelu_erf2(g4, g5);
+        gelu_erf2(g6, g7);
+        sts128u(arow_chunk_addr(aA, r, h * 4 + c), pack2<DT>(g0, g1), pack2<DT>(g2, g3), pack2<DT>(g4, g5), pack2<DT>(g6, g7));
       }
     }
     tc_fence_before();
@@ -257,7 +281,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        gemm_k64(tmem_base, aA, aW + 2 * W_TILE, p.idesc);  // h W2^T
+        gemm_kc<C>(tmem_base, aA, aW + 2 * T::W_TILE, T::W_KB, 0, p.idesc);  // h W2^T
         umma_commit(mma_done);
       }
       __syncwarp();
@@ -267,13 +291,13 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     mma_ph ^= 1u;
     tc_fence_after();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < C / 32; ++h) {
       uint32_t v[32];
       tmem_ld32(t_row + h * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float4 bv = *reinterpret_cast<const float4*>(sPar + 4 * TC + h * 32 + c * 4);
+        const float4 bv = *reinterpret_cast<const float4*>(sPar + 4 * C + h * 32 + c * 4);
         float4 o;
         o.x = __uint_as_float(v[c * 4 + 0]) + bv.x + a[h * 32 + c * 4 + 0];
         o.y = __uint_as_float(v[c * 4 + 1]) + bv.y + a[h * 32 + c * 4 + 1];
@@ -286,8 +310,8 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     fence_proxy_async();
     __syncthreads();
     if (warp == 0 && elect_one()) {
-      tma_store_2d(&tm_out, sX, 0, m0);
-      tma_store_2d(&tm_out, sX + TM * 128, 32, m0);
+#pragma unroll
+      for (int j = 0; j < T::XB; ++j) tma_store_2d(&tm_out, sX + j * (TM * 128), j * 32, m0);
       tma_store_commit();
     }
   }
@@ -296,43 +320,46 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<T::TAIL_TMEM>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// sg_ln_inproj : qkv[M, 192] = LayerNorm(x) Win^T + bin
+// sg_ln_inproj : qkv[M, 3C] = LayerNorm(x) Win^T + bin
 // ------------------------------------------------------------------------------------------------------------------
 struct InprojParams {
   const float* ln_g;
   const float* ln_b;
-  const float* bias;  // [192]
+  const float* bias;  // [3C]
   int64_t M;
   int ntiles;
-  uint32_t idesc;     // M128 x N192
+  uint32_t idesc_a, idesc_b;  // M128 x N(first MMA) and, at C = 128, M128 x N128 for rows [256, 384) of Win
 };
-constexpr int INPROJ_SMEM = 1024 + 3 * W_TILE + X_TILE + A_TILE + 5 * TC * 4 + 128;
 
-template <int DT>
-__global__ void __launch_bounds__(128, 2)
+template <int C, int DT>
+__global__ void __launch_bounds__(128, Tok<C>::INPROJ_CTAS)
 ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                 const __grid_constant__ CUtensorMap tm_qkv, const InprojParams p) {
+                 const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_qkv,
+                 const InprojParams p) {
+  using T = Tok<C>;
+  constexpr int N = 3 * C;
+  constexpr int NA = N <= 256 ? N : 256;  // columns of the first MMA (an MMA is at most 256 wide)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sW = smem;             // Win: [192 x 64] 16-bit, SWIZZLE_128B (24 KB)
-  uint8_t* sX = sW + 3 * W_TILE;  // x tile (fp32, 32 KB); with sA the 48 KB staging of the three 16-bit output boxes
-  uint8_t* sA = sX + X_TILE;      // LN(x) operand tile (16 KB)
-  float* sPar = reinterpret_cast<float*>(sA + A_TILE);  // ln_g | ln_b | bias[192]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 5 * TC);
+  uint8_t* sW = smem;                // Win: C/64 k-blocks of [3C x 64] 16-bit, SWIZZLE_128B
+  uint8_t* sX = sW + T::WIN_TILE;    // x tile (fp32); with sA the staging of the 3C/64 16-bit output boxes
+  uint8_t* sA = sX + T::X_TILE;      // LN(x) operand tile
+  float* sPar = reinterpret_cast<float*>(sA + T::A_TILE);  // ln_g | ln_b | bias[3C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 5 * C);
   uint64_t* w_full = bars;
   uint64_t* in_full = bars + 1;
   uint64_t* mma_done = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  static_assert(T::X_TILE + T::A_TILE == (N / 64) * T::A_ATOM, "output staging = x tile + operand tile");
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool leader = tid == 0;
-  if (leader) {
+  if (tid == 0) {
     prefetch_tensormap(&tm_x);
     prefetch_tensormap(&tm_qkv);
     mbar_init(w_full, 1);
@@ -340,10 +367,10 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     mbar_init(mma_done, 1);
     fence_barrier_init();
   }
-  for (int i = tid; i < 5 * TC; i += 128) sPar[i] = i < TC ? p.ln_g[i] : (i < 2 * TC ? p.ln_b[i - TC] : p.bias[i - 2 * TC]);
+  for (int i = tid; i < 5 * C; i += 128) sPar[i] = i < C ? p.ln_g[i] : (i < 2 * C ? p.ln_b[i - C] : p.bias[i - 2 * C]);
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc<256>(tmem_slot);
+    tmem_alloc<T::INPROJ_TMEM>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -354,8 +381,12 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const int r = tid;
 
   if (warp == 0 && elect_one()) {
-    mbar_arrive_expect_tx(w_full, 3 * W_TILE);
-    tma_load_2d(sW, &tm_w, w_full, 0, 0);
+    mbar_arrive_expect_tx(w_full, T::WIN_TILE);
+#pragma unroll
+    for (int kb = 0; kb < T::KB; ++kb) {
+      tma_load_2d(sW + kb * T::WIN_KB, &tm_w, w_full, kb * 64, 0);                         // rows [0, NA)
+      if (N > NA) tma_load_2d(sW + kb * T::WIN_KB + NA * 128, &tm_w2, w_full, kb * 64, NA);  // rows [NA, N)
+    }
   }
   uint32_t in_ph = 0, mma_ph = 0;
   bool first = true;
@@ -363,30 +394,33 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int m0 = tile * TM;
     if (warp == 0 && elect_one()) {
       tma_store_wait_read();  // the previous tile's qkv boxes (staged in sX | sA) have left shared memory
-      mbar_arrive_expect_tx(in_full, X_TILE);
-      tma_load_2d(sX, &tm_x, in_full, 0, m0);
-      tma_load_2d(sX + TM * 128, &tm_x, in_full, 32, m0);
+      mbar_arrive_expect_tx(in_full, T::X_TILE);
+#pragma unroll
+      for (int j = 0; j < T::XB; ++j) tma_load_2d(sX + j * (TM * 128), &tm_x, in_full, j * 32, m0);
     }
     __syncthreads();  // nobody writes sA (LN output) before the previous stores have drained
     mbar_wait(in_full, in_ph);
     in_ph ^= 1u;
-    float a[TC];
+    {
+      float a[C];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float4 xv = lds128(xrow_chunk_addr(aX, r, c));
-      a[c * 4 + 0] = xv.x;
-      a[c * 4 + 1] = xv.y;
-      a[c * 4 + 2] = xv.z;
-      a[c * 4 + 3] = xv.w;
+      for (int c = 0; c < C / 4; ++c) {
+        const float4 xv = lds128(xrow_chunk_addr(aX, r, c));
+        a[c * 4 + 0] = xv.x;
+        a[c * 4 + 1] = xv.y;
+        a[c * 4 + 2] = xv.z;
+        a[c * 4 + 3] = xv.w;
+      }
+      ln_row_to_operand<C, DT>(a, sPar, sPar + C, aA, r);
     }
-    ln_row_to_operand<DT>(a, sPar, sPar + TC, aA, r);
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {
       if (first) mbar_wait_spin(w_full, 0);
       tc_fence_after();
       if (elect_one()) {
-        gemm_k64(tmem_base, aA, aW, p.idesc);  // one M128 x N192 accumulator
+        gemm_kc<C>(tmem_base, aA, aW, T::WIN_KB, 0, p.idesc_a);                   // columns [0, NA)
+        if (N > NA) gemm_kc<C>(tmem_base + NA, aA, aW, T::WIN_KB, NA, p.idesc_b);  // columns [NA, N)
         umma_commit(mma_done);
       }
       __syncwarp();
@@ -395,10 +429,10 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
     tc_fence_after();
-    // qkv rows -> three [128 x 64] 16-bit SWIZZLE_128B boxes at sX, sX + 16 KB, sX + 32 KB (= sA: its GEMM is complete)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const uint32_t row = aX + (uint32_t)b * A_TILE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+    // qkv rows -> 3C/64 [128 x 64] 16-bit SWIZZLE_128B boxes at sX + b * 16 KB (the tail of them = sA: its GEMM is complete)
+#pragma unroll 1
+    for (int b = 0; b < N / 64; ++b) {
+      const uint32_t box = aX + (uint32_t)b * T::A_ATOM;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
@@ -406,9 +440,9 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 b0 = *reinterpret_cast<const float4*>(sPar + 2 * TC + b * 64 + h * 32 + c * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(sPar + 2 * TC + b * 64 + h * 32 + c * 8 + 4);
-          sts128u(row + ((((uint32_t)(h * 4 + c)) ^ ((uint32_t)r & 7u)) << 4),
+          const float4 b0 = *reinterpret_cast<const float4*>(sPar + 2 * C + b * 64 + h * 32 + c * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(sPar + 2 * C + b * 64 + h * 32 + c * 8 + 4);
+          sts128u(arow_chunk_addr(box, r, h * 4 + c),
                   pack2<DT>(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y),
                   pack2<DT>(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w),
                   pack2<DT>(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y),
@@ -420,9 +454,8 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     fence_proxy_async();
     __syncthreads();
     if (warp == 0 && elect_one()) {
-      tma_store_2d(&tm_qkv, sX, 0, m0);
-      tma_store_2d(&tm_qkv, sX + A_TILE, 64, m0);
-      tma_store_2d(&tm_qkv, sX + 2 * A_TILE, 128, m0);
+#pragma unroll
+      for (int b = 0; b < N / 64; ++b) tma_store_2d(&tm_qkv, sX + b * T::A_ATOM, b * 64, m0);
       tma_store_commit();
     }
   }
@@ -431,7 +464,7 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<T::INPROJ_TMEM>(tmem_base);
   }
 }
 
@@ -454,6 +487,53 @@ static int set_smem(K kernel, int bytes, const char* what) {
   return SG_OK;
 }
 
+template <int C, int DT>
+static int launch_tail(const void* att, const float* x, const void* wo, const void* w1, const void* w2, float* out,
+                       TailParams p, int act_dtype, cudaStream_t s) {
+  using T = Tok<C>;
+  CUtensorMap tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2;
+  int rc;
+  if ((rc = tmap2d(&tm_att, act_dtype, att, C, (uint64_t)p.M, 64, TM))) return rc;
+  if ((rc = tmap2d(&tm_x, SG_F32, x, C, (uint64_t)p.M, 32, TM))) return rc;
+  if ((rc = tmap2d(&tm_out, SG_F32, out, C, (uint64_t)p.M, 32, TM))) return rc;
+  if ((rc = tmap2d(&tm_wo, act_dtype, wo, C, C, 64, C))) return rc;
+  if ((rc = tmap2d(&tm_w1, act_dtype, w1, C, C, 64, C))) return rc;
+  if ((rc = tmap2d(&tm_w2, act_dtype, w2, C, C, 64, C))) return rc;
+  p.idesc = make_idesc(act_dtype, 128, C, 0, 0);
+  const int per_sm = T::TAIL_CTAS * num_sms();
+  const int grid = p.ntiles < per_sm ? p.ntiles : per_sm;
+  static bool cfg = false;
+  if (!cfg) {
+    if ((rc = set_smem(attn_tail_kernel<C, DT>, T::TAIL_SMEM, "sg_attn_tail"))) return rc;
+    cfg = true;
+  }
+  attn_tail_kernel<C, DT><<<grid, 128, T::TAIL_SMEM, s>>>(tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
+  return launch_status("sg_attn_tail");
+}
+
+template <int C, int DT>
+static int launch_inproj(const float* x, const void* w_in, void* qkv, InprojParams p, int act_dtype, cudaStream_t s) {
+  using T = Tok<C>;
+  constexpr int N = 3 * C, NA = N <= 256 ? N : 256;
+  CUtensorMap tm_x, tm_w, tm_w2, tm_qkv;
+  int rc;
+  if ((rc = tmap2d(&tm_x, SG_F32, x, C, (uint64_t)p.M, 32, TM))) return rc;
+  if ((rc = tmap2d(&tm_w, act_dtype, w_in, C, N, 64, NA))) return rc;
+  if ((rc = tmap2d(&tm_w2, act_dtype, w_in, C, N, 64, N > NA ? N - NA : NA))) return rc;
+  if ((rc = tmap2d(&tm_qkv, act_dtype, qkv, N, (uint64_t)p.M, 64, TM))) return rc;
+  p.idesc_a = make_idesc(act_dtype, 128, NA, 0, 0);
+  p.idesc_b = make_idesc(act_dtype, 128, N > NA ? N - NA : NA, 0, 0);
+  const int per_sm = T::INPROJ_CTAS * num_sms();
+  const int grid = p.ntiles < per_sm ? p.ntiles : per_sm;
+  static bool cfg = false;
+  if (!cfg) {
+    if ((rc = set_smem(ln_inproj_kernel<C, DT>, T::INPROJ_SMEM, "sg_ln_inproj"))) return rc;
+    cfg = true;
+  }
+  ln_inproj_kernel<C, DT><<<grid, 128, T::INPROJ_SMEM, s>>>(tm_x, tm_w, tm_w2, tm_qkv, p);
+  return launch_status("sg_ln_inproj");
+}
+
 }  // namespace tc
 }  // namespace sg
 
@@ -466,76 +546,41 @@ int sg_attn_tail(const void* att, const float* x, const void* wo, const float* b
                  const void* w1, const float* b1, const void* w2, const float* b2, int64_t M, int C, float* out,
                  int act_dtype, sg_stream_t stream) {
   SG_REQUIRE(att && x && wo && bo && ln_g && ln_b && w1 && b1 && w2 && b2 && out, "sg_attn_tail: null pointer");
-  SG_REQUIRE(C == TC, "sg_attn_tail: C=%d (the fused kernel is built for C = 64; use the unfused launches otherwise)", C);
+  SG_REQUIRE(C == 64 || C == 128, "sg_attn_tail: C=%d (the fused kernel is built for C = 64 and 128; use the unfused launches otherwise)", C);
   SG_REQUIRE(act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_attn_tail: act_dtype must be SG_BF16 or SG_F16");
   SG_REQUIRE(M > 0 && M < (1ll << 31) - TM, "sg_attn_tail: M=%lld", (long long)M);
-  CUtensorMap tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2;
-  int rc;
-  if ((rc = tmap2d(&tm_att, act_dtype, att, TC, (uint64_t)M, TC, TM))) return rc;
-  if ((rc = tmap2d(&tm_x, SG_F32, x, TC, (uint64_t)M, 32, TM))) return rc;
-  if ((rc = tmap2d(&tm_out, SG_F32, out, TC, (uint64_t)M, 32, TM))) return rc;
-  if ((rc = tmap2d(&tm_wo, act_dtype, wo, TC, TC, TC, TC))) return rc;
-  if ((rc = tmap2d(&tm_w1, act_dtype, w1, TC, TC, TC, TC))) return rc;
-  if ((rc = tmap2d(&tm_w2, act_dtype, w2, TC, TC, TC, TC))) return rc;
   TailParams p;
   p.bo = bo; p.ln_g = ln_g; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2;
   p.M = M;
   p.ntiles = (int)cdiv(M, TM);
-  p.idesc = make_idesc(act_dtype, 128, TC, 0, 0);
-  const int grid = p.ntiles < 3 * num_sms() ? p.ntiles : 3 * num_sms();
+  p.idesc = 0;
   cudaStream_t s = as_stream(stream);
-  if (act_dtype == SG_BF16) {
-    static bool cfg = false;
-    if (!cfg) {
-      if ((rc = set_smem(attn_tail_kernel<SG_BF16>, TAIL_SMEM, "sg_attn_tail"))) return rc;
-      cfg = true;
-    }
-    attn_tail_kernel<SG_BF16><<<grid, 128, TAIL_SMEM, s>>>(tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
-  } else {
-    static bool cfg = false;
-    if (!cfg) {
-      if ((rc = set_smem(attn_tail_kernel<SG_F16>, TAIL_SMEM, "sg_attn_tail"))) return rc;
-      cfg = true;
-    }
-    attn_tail_kernel<SG_F16><<<grid, 128, TAIL_SMEM, s>>>(tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
+  if (C == 64) {
+    if (act_dtype == SG_BF16) return launch_tail<64, SG_BF16>(att, x, wo, w1, w2, out, p, act_dtype, s);
+    return launch_tail<64, SG_F16>(att, x, wo, w1, w2, out, p, act_dtype, s);
   }
-  return launch_status("sg_attn_tail");
+  if (act_dtype == SG_BF16) return launch_tail<128, SG_BF16>(att, x, wo, w1, w2, out, p, act_dtype, s);
+  return launch_tail<128, SG_F16>(att, x, wo, w1, w2, out, p, act_dtype, s);
 }
 
 int sg_ln_inproj(const float* x, const float* ln_g, const float* ln_b, const void* w_in, const float* b_in, int64_t M,
                  int C, void* qkv, int act_dtype, sg_stream_t stream) {
   SG_REQUIRE(x && ln_g && ln_b && w_in && b_in && qkv, "sg_ln_inproj: null pointer");
-  SG_REQUIRE(C == TC, "sg_ln_inproj: C=%d (the fused kernel is built for C = 64; use the unfused launches otherwise)", C);
+  SG_REQUIRE(C == 64 || C == 128, "sg_ln_inproj: C=%d (the fused kernel is built for C = 64 and 128; use the unfused launches otherwise)", C);
   SG_REQUIRE(act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_ln_inproj: act_dtype must be SG_BF16 or SG_F16");
   SG_REQUIRE(M > 0 && M < (1ll << 31) - TM, "sg_ln_inproj: M=%lld", (long long)M);
-  CUtensorMap tm_x, tm_w, tm_qkv;
-  int rc;
-  if ((rc = tmap2d(&tm_x, SG_F32, x, TC, (uint64_t)M, 32, TM))) return rc;
-  if ((rc = tmap2d(&tm_w, act_dtype, w_in, TC, 3 * TC, TC, 3 * TC))) return rc;
-  if ((rc = tmap2d(&tm_qkv, act_dtype, qkv, 3 * TC, (uint64_t)M, TC, TM))) return rc;
   InprojParams p;
   p.ln_g = ln_g; p.ln_b = ln_b; p.bias = b_in;
   p.M = M;
   p.ntiles = (int)cdiv(M, TM);
-  p.idesc = make_idesc(act_dtype, 128, 3 * TC, 0, 0);
-  const int grid = p.ntiles < 2 * num_sms() ? p.ntiles : 2 * num_sms();
+  p.idesc_a = p.idesc_b = 0;
   cudaStream_t s = as_stream(stream);
-  if (act_dtype == SG_BF16) {
-    static bool cfg = false;
-    if (!cfg) {
-      if ((rc = set_smem(ln_inproj_kernel<SG_BF16>, INPROJ_SMEM, "sg_ln_inproj"))) return rc;
-      cfg = true;
-    }
-    ln_inproj_kernel<SG_BF16><<<grid, 128, INPROJ_SMEM, s>>>(tm_x, tm_w, tm_qkv, p);
-  } else {
-    static bool cfg = false;
-    if (!cfg) {
-      if ((rc = set_smem(ln_inproj_kernel<SG_F16>, INPROJ_SMEM, "sg_ln_inproj"))) return rc;
-      cfg = true;
-    }
-    ln_inproj_kernel<SG_F16><<<grid, 128, INPROJ_SMEM, s>>>(tm_x, tm_w, tm_qkv, p);
+  if (C == 64) {
+    if (act_dtype == SG_BF16) return launch_inproj<64, SG_BF16>(x, w_in, qkv, p, act_dtype, s);
+    return launch_inproj<64, SG_F16>(x, w_in, qkv, p, act_dtype, s);
   }
-  return launch_status("sg_ln_inproj");
+  if (act_dtype == SG_BF16) return launch_inproj<128, SG_BF16>(x, w_in, qkv, p, act_dtype, s);
+  return launch_inproj<128, SG_F16>(x, w_in, qkv, p, act_dtype, s);
 }
 
 }  // extern "C"

@@ -6,6 +6,8 @@ computes on the host and nothing falls back to PyTorch ops.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _cabi
@@ -177,7 +179,7 @@ def tconv2_u8(t, w2, b2, *, n, S, out_u8=None, out_f32=None):
                               ptr(out_f32), stream_ptr()), "sg_tconv2_u8")
 
 
-FUSED_TOKEN_C = (64,)  # channel counts the fused SelfAttention head / tail kernels are built for
+FUSED_TOKEN_C = tuple(int(c) for c in os.environ.get("SGB200_FUSED_C", "64,128").split(",") if c)  # channel counts of the fused SelfAttention head / tail kernels
 
 
 def ln_inproj(x, ln_g, ln_b, w_in, b_in, qkv):

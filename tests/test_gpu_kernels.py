@@ -403,11 +403,11 @@ def _sa_weights(C, g):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C", [64, 128])
 @pytest.mark.parametrize("M", [128, 4096 + 128, 200, 100000])
-def test_ln_inproj_fused(ops, M, dtype):
+def test_ln_inproj_fused(ops, M, C, dtype):
     """Fused LayerNorm + in_proj vs fp64 torch on the same 16-bit weights.  Rounding added by the kernel: LN output
     and qkv to 16 bit (what the unfused path does too).  M = 200 exercises the TMA-clipped last tile."""
-    C = 64
     g = gen(21)
     W = _sa_weights(C, g)
     x = torch.randn(M, C, generator=g) * 2 + 0.5
@@ -418,16 +418,16 @@ def test_ln_inproj_fused(ops, M, dtype):
     ops.ln_inproj(x.to(DEV), W["ln_g"].to(DEV), W["ln_b"].to(DEV), w16.to(DEV), W["b_in"].to(DEV), qkv[:M])
     torch.cuda.synchronize()
     err = O.rel_l2(qkv[:M].cpu(), ref)
-    print(f"ln_inproj M={M} {dtype}: rel-L2 {err:.3e}")
+    print(f"ln_inproj M={M} C={C} {dtype}: rel-L2 {err:.3e}")
     assert err < (6e-3 if dtype == torch.bfloat16 else 8e-4)
     assert torch.isnan(qkv[M:].float()).all()
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C", [64, 128])
 @pytest.mark.parametrize("M", [128, 4096 + 128, 200, 100000])
-def test_attn_tail_fused(ops, M, dtype):
+def test_attn_tail_fused(ops, M, C, dtype):
     """Fused out_proj + residual + LayerNorm + FFN + residual vs fp64 torch on the same 16-bit att / weights."""
-    C = 64
     g = gen(22)
     W = _sa_weights(C, g)
     x = torch.randn(M, C, generator=g) * 2
@@ -442,7 +442,7 @@ def test_attn_tail_fused(ops, M, dtype):
                   out[:M])
     torch.cuda.synchronize()
     err = O.rel_l2(out[:M].cpu(), ref)
-    print(f"attn_tail M={M} {dtype}: rel-L2 {err:.3e}")
+    print(f"attn_tail M={M} C={C} {dtype}: rel-L2 {err:.3e}")
     assert err < (3e-3 if dtype == torch.bfloat16 else 4e-4)
     assert torch.isnan(out[M:]).all()
 
