@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 8
+#define SG_ABI_VERSION 9
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -199,6 +199,11 @@ int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base,
 
 /* ---- K8: (clamp(x,-1,1)+1)/2*255 -> truncating uint8 cast (:440-441) ---- */
 int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream);
+
+/* ---- un-clamped image cast of the denoise-trajectory dumps (DiffusionVAE.sample :672-675) ----
+ * out = uint8((x + 1) / 2 * 255) with torch's cast semantics for values outside [0, 255]: truncate to int32, keep the
+ * low 8 bits. */
+int sg_to_uint8_wrap(const float* x, int64_t count, uint8_t* out, sg_stream_t stream);
 
 /* ---- DiffusionVAE decode tail (:702-706) ----
  * sg_vq_quantize: [clamp(-1,1) +] VQEmbeddingEMA.forward in eval mode (:290-318) over `count` fp32 values taken in

@@ -77,16 +77,25 @@ __device__ __forceinline__ uint32_t quant_u8(float v) {
   v = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
   return (uint32_t)(int)v;  // v in [0,255]; NaN -> 0 like the CPU cast of clamp(NaN)... (NaN never occurs in parity runs)
 }
+// the un-clamped form the denoise-trajectory dumps use (:672-675): (x+1)/2*255 truncated to an integer and reduced mod 256
+// (what the CPU / CUDA float -> uint8 cast of torch does for values that fit an int32)
+__device__ __forceinline__ uint32_t wrap_u8(float v) {
+  v = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), 255.0f);
+  return (uint32_t)__float2int_rz(v) & 255u;
+}
+template <bool WRAP> __device__ __forceinline__ uint32_t to_u8(float v) { return WRAP ? wrap_u8(v) : quant_u8(v); }
+template <bool WRAP>
 __global__ void __launch_bounds__(256) to_uint8_kernel(const float* __restrict__ x, int64_t count4,
                                                        uint32_t* __restrict__ out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count4) return;
   const float4 v = reinterpret_cast<const float4*>(x)[idx];
-  out[idx] = quant_u8(v.x) | (quant_u8(v.y) << 8) | (quant_u8(v.z) << 16) | (quant_u8(v.w) << 24);
+  out[idx] = to_u8<WRAP>(v.x) | (to_u8<WRAP>(v.y) << 8) | (to_u8<WRAP>(v.z) << 16) | (to_u8<WRAP>(v.w) << 24);
 }
+template <bool WRAP>
 __global__ void to_uint8_tail_kernel(const float* __restrict__ x, int64_t begin, int64_t count, uint8_t* out) {
   const int64_t idx = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < count) out[idx] = (uint8_t)quant_u8(x[idx]);
+  if (idx < count) out[idx] = (uint8_t)to_u8<WRAP>(x[idx]);
 }
 
 // K3a  MaxPool2d(2)  (:100).  NHWC, one thread = 4 channels of one output pixel.
@@ -188,6 +197,16 @@ static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 using namespace sg;
 
+template <bool WRAP>
+static int to_uint8_launch(const float* x, int64_t count, uint8_t* out, sg_stream_t stream, const char* what) {
+  if (count == 0) return SG_OK;
+  const int64_t c4 = count / 4;
+  if (c4 > 0)
+    to_uint8_kernel<WRAP><<<cdiv(c4, 256), 256, 0, as_stream(stream)>>>(x, c4, reinterpret_cast<uint32_t*>(out));
+  if (count % 4) to_uint8_tail_kernel<WRAP><<<1, 32, 0, as_stream(stream)>>>(x, c4 * 4, count, out);
+  return launch_status(what);
+}
+
 extern "C" {
 
 int sg_cfg_update(float* x, const float* eps, int n, int E, float cfg_scale, const float* coef, int T,
@@ -215,12 +234,12 @@ int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base,
 
 int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream) {
   SG_REQUIRE(x && out && count >= 0, "sg_to_uint8: bad arguments");
-  if (count == 0) return SG_OK;
-  const int64_t c4 = count / 4;
-  if (c4 > 0)
-    to_uint8_kernel<<<cdiv(c4, 256), 256, 0, as_stream(stream)>>>(x, c4, reinterpret_cast<uint32_t*>(out));
-  if (count % 4) to_uint8_tail_kernel<<<1, 32, 0, as_stream(stream)>>>(x, c4 * 4, count, out);
-  return launch_status("sg_to_uint8");
+  return to_uint8_launch<false>(x, count, out, stream, "sg_to_uint8");
+}
+
+int sg_to_uint8_wrap(const float* x, int64_t count, uint8_t* out, sg_stream_t stream) {
+  SG_REQUIRE(x && out && count >= 0, "sg_to_uint8_wrap: bad arguments");
+  return to_uint8_launch<true>(x, count, out, stream, "sg_to_uint8_wrap");
 }
 
 int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, void* out_act, int act_dtype,

@@ -194,6 +194,16 @@ class EMA:
         ema_model.load_state_dict(model.state_dict())
 
 
+def _viridis():
+    """matplotlib.cm.viridis, imported lazily (the reference imports matplotlib at module top)."""
+    try:
+        from matplotlib import cm
+    except ImportError as e:  # pragma: no cover - depends on the environment
+        raise ImportError("the PNG writers colour with matplotlib.cm.viridis (as the reference does); install "
+                          "matplotlib or pass colormap=") from e
+    return cm.viridis
+
+
 class Diffusion:
     """Linear-β DDPM with classifier-free-guidance ancestral sampling (reference :370-442)."""
 
@@ -258,12 +268,7 @@ class Diffusion:
         from PIL import Image
 
         if colormap is None:
-            try:
-                from matplotlib import cm
-            except ImportError as e:  # pragma: no cover - depends on the environment
-                raise ImportError("gen_images colours with matplotlib.cm.viridis (as the reference does); install "
-                                  "matplotlib or pass colormap=") from e
-            colormap = cm.viridis
+            colormap = getattr(self, "colormap", None) or _viridis()
         class_names = getattr(self, "class_names", None) or [str(k) for k in range(self.num_classes or 0)]
         if labels is None:
             labels = torch.arange(self.num_classes).long().to(self.device)
@@ -280,7 +285,7 @@ class Diffusion:
     # ------------------------------------------------------------------ sampling (:411-442)
     @torch.no_grad()
     def sample(self, use_ema, labels, cfg_scale=3, *legacy, noise=None, seed=0, sample_base=0, micro_batch=512,
-               return_float=False, use_graph=True, max_steps=None):
+               return_float=False, use_graph=True, max_steps=None, step_hook=None):
         """Reference form: sample(use_ema, labels, cfg_scale=3) -> uint8 [n, c_in, S, S].
         Upstream alias: sample(model, n, labels, cfg_scale=3).
 
@@ -291,6 +296,9 @@ class Diffusion:
           micro_batch  samples per captured loop (n is processed in chunks of this size)
           return_float return the fp32 state before the uint8 quantisation
           max_steps    run only the first k loop iterations (benchmarking a bounded number of timesteps)
+          step_hook    callable(i, x, labels) run on the host after the update of loop index i (T-1 ... 1) with the
+                       chunk's fp32 state x (read-only) -- the captured step is replayed once per timestep, so the hook
+                       sits between two replays and costs nothing when absent
         """
         if isinstance(use_ema, nn.Module):  # upstream (model, n, labels, cfg_scale)
             model, n_expected = use_ema, labels
@@ -320,10 +328,10 @@ class Diffusion:
             hi = min(n, lo + micro_batch)
             nz = None if noise is None else noise[:, lo:hi].contiguous()
             self._sample_chunk(model, labels[lo:hi], float(cfg_scale), nz, seed, sample_base + lo, out[lo:hi],
-                               use_graph, max_steps)
+                               use_graph, max_steps, step_hook)
         return out
 
-    def _sample_chunk(self, model, labels, cfg, noise, seed, sample_base, out, use_graph, max_steps):
+    def _sample_chunk(self, model, labels, cfg, noise, seed, sample_base, out, use_graph, max_steps, step_hook=None):
         n = len(labels)
         T = self.noise_steps
         rows = 2 * n if cfg > 0 else n
@@ -358,11 +366,15 @@ class Diffusion:
             with torch.cuda.graph(g):
                 one_step()
             # capture does not execute: state is still (x_T, T-1)
-            for _ in range(iters):
+            for k in range(iters):
                 g.replay()
+                if step_hook is not None:
+                    step_hook(T - 1 - k, x, labels)
         else:
-            for _ in range(iters):
+            for k in range(iters):
                 one_step()
+                if step_hook is not None:
+                    step_hook(T - 1 - k, x, labels)
         self.gpu_launches += iters * launches_per_step
         if out.dtype == torch.uint8:
             ops.to_uint8(x, out)
@@ -375,13 +387,15 @@ class DiffusionVAE(Diffusion):
     """Latent-space variant (reference :578-706): the UNet denoises [n, 4, S/4, S/4] latents and the VQAE codebook +
     decoder turn them into [n, 1, S, S] spectrograms.  Same constructor as the reference; `vqae_path` is loaded with
     torch.load(weights_only=True) unless `vqae_state_dict` (ours, keyword-only) is given.  Only the decode side of
-    the VQAE is on the sampling path; `sav_denoise_path` (per-50-step PNG dumps, :661-700) is not implemented."""
+    the VQAE is on the sampling path.  `sav_denoise_path` (:661-700) writes, at loop indices i % 50 == 0, i == 1 and
+    i == T-1, `{class}_noise_{i}_latent.png` (the quantised latent's four channels as a 2x2 grid) and
+    `{class}_noise_{i}_decode.png` (the decoded spectrogram) per sample, both viridis RGBA like the reference;
+    `colormap` (ours, keyword-only) replaces matplotlib.cm.viridis (callable: uint8 or float-in-[0,1] array -> RGBA
+    floats)."""
 
     def __init__(self, noise_steps=1000, beta_start=1e-4, beta_end=0.02, img_size=256, num_classes=10, c_in=1, c_out=1,
                  device="cuda", vqae_path="models/VQAE/ckpt.pt", sav_denoise_path=None, class_names=(), *,
-                 vqae_state_dict=None, **kwargs):
-        if sav_denoise_path:
-            raise NotImplementedError("sav_denoise_path (denoise-trajectory PNG dumps) is outside the B200 sampling path")
+                 vqae_state_dict=None, colormap=None, **kwargs):
         latent_dim = 4  # (:611); the reference builds UNet_conditional(latent_dim, latent_dim) at img_size // 4 (:624-627)
         super().__init__(noise_steps, beta_start, beta_end, img_size // 4, num_classes, latent_dim, latent_dim, device,
                          **kwargs)
@@ -389,14 +403,46 @@ class DiffusionVAE(Diffusion):
             vqae_state_dict = torch.load(vqae_path, map_location="cpu", weights_only=True)
         self.vqae = VqaeDecoder(vqae_state_dict, self.device, self.model.compute_dtype)
         self.class_names = list(class_names)
+        self.sav_denoise_path = sav_denoise_path
+        self.colormap = colormap
+        self.dump_launches = 0  # kernels launched by the trajectory dumps of the last sample() call
+
+    def dump_steps(self):
+        """Loop indices at which the reference dumps the trajectory (:662)."""
+        T = self.noise_steps
+        return [i for i in range(T - 1, 0, -1) if i % 50 == 0 or i == 1 or i == T - 1]
+
+    def _dump_denoise(self, i, x, labels):
+        """The body of `if self.sav_denoise_path:` (:661-700) for the chunk state x [n, 4, S, S]."""
+        if not (i % 50 == 0 or i == 1 or i == self.noise_steps - 1):
+            return
+        import numpy as np
+        from PIL import Image
+
+        cmap = self.colormap if self.colormap is not None else _viridis()
+        print(f"saving denoise at step {i}...")
+        up, q = self.vqae.decode(x, return_quantized=True)
+        lat = ops.to_uint8_wrap(q)
+        self.dump_launches += self.vqae.gpu_launches + 1
+        lat, up = lat.cpu().numpy(), up.cpu().numpy()
+        for img, img_up, lab in zip(lat, up, labels.tolist()):
+            grid = np.concatenate([np.concatenate([img[0], img[1]], axis=1),
+                                   np.concatenate([img[2], img[3]], axis=1)], axis=0)
+            rgba = (np.asarray(cmap(grid / 255.0)) * 255).astype(np.uint8)  # float input, as the reference passes it
+            Image.fromarray(rgba).save(f"{self.sav_denoise_path}/{self.class_names[lab]}_noise_{i}_latent.png")
+            rgba = (np.asarray(cmap(img_up[0])) * 255).astype(np.uint8)     # uint8 input: a direct LUT index
+            Image.fromarray(rgba).save(f"{self.sav_denoise_path}/{self.class_names[lab]}_noise_{i}_decode.png")
 
     @torch.no_grad()
     def sample(self, use_ema, labels, cfg_scale=3, *legacy, decode_micro_batch=64, **kw):
         """sample(use_ema, labels, cfg_scale=3) -> uint8 [n, 1, 4*img_size, 4*img_size] (:630-706)."""
         if kw.pop("return_float", False):
             raise TypeError("DiffusionVAE.sample returns the decoded uint8 image; use Diffusion.sample for latents")
+        self.dump_launches = 0
+        if self.sav_denoise_path and kw.get("step_hook") is None:
+            kw["step_hook"] = self._dump_denoise
         x = super().sample(use_ema, labels, cfg_scale, *legacy, return_float=True, **kw)
-        launches = self.gpu_launches
+        launches = self.gpu_launches + self.dump_launches
         out = self.vqae.decode(x, micro_batch=decode_micro_batch)
         self.gpu_launches = launches + self.vqae.gpu_launches
         return out

@@ -243,3 +243,13 @@ def philox_normal(x, *, seed, sample_base, step_tag):
 
 def to_uint8(x, out):
     check(_lib().sg_to_uint8(ptr(_f32(x, "x")), x.numel(), ptr(out), stream_ptr()), "sg_to_uint8")
+
+
+def to_uint8_wrap(x, out=None):
+    """uint8((x + 1) / 2 * 255) without a clamp (the cast of the reference's trajectory dumps, :672-675)."""
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    if out.dtype != torch.uint8 or not out.is_contiguous() or out.numel() != x.numel():
+        raise ValueError("to_uint8_wrap: out must be a contiguous uint8 tensor of x's size")
+    check(_lib().sg_to_uint8_wrap(ptr(_f32(x, "x")), x.numel(), ptr(out), stream_ptr()), "sg_to_uint8_wrap")
+    return out

@@ -84,14 +84,17 @@ class VqaeDecoder:
         return b
 
     @torch.no_grad()
-    def decode(self, x, *, micro_batch=64, return_float=False, return_indices=False):
-        """x: fp32 [n, 4, S, S] sampler state -> uint8 [n, 1, 4S, 4S] (or the fp32 decoder output)."""
+    def decode(self, x, *, micro_batch=64, return_float=False, return_indices=False, return_quantized=False):
+        """x: fp32 [n, 4, S, S] sampler state -> uint8 [n, 1, 4S, 4S] (or the fp32 decoder output).  x is not modified.
+        return_indices / return_quantized append the codeword indices / the quantised fp32 latents [n, 4, S, S] (the
+        `x + (q - x)` value of :313) to the result."""
         if x.device != self.device or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != LATENT:
             raise ValueError("decode: x must be an fp32 [n, 4, S, S] tensor on the decoder's device")
         n, _, S, _ = x.shape
         x = x.contiguous()
         out = torch.empty((n, 1, 4 * S, 4 * S), dtype=torch.float32 if return_float else torch.uint8, device=self.device)
         all_idx = torch.empty((n * LATENT * S * S // 4,), dtype=torch.int32, device=self.device) if return_indices else None
+        all_q = torch.empty((n, LATENT, S, S), dtype=torch.float32, device=self.device) if return_quantized else None
         self.gpu_launches = 0
         for lo in range(0, n, micro_batch):
             hi = min(n, lo + micro_batch)
@@ -114,6 +117,7 @@ class VqaeDecoder:
             if return_indices:
                 g = nb * LATENT * S * S // 4
                 all_idx[lo * LATENT * S * S // 4: lo * LATENT * S * S // 4 + g].copy_(b["idx"][:g])
-        if return_indices:
-            return out, all_idx
-        return out
+            if return_quantized:
+                all_q[lo:hi].copy_(b["q"])
+        res = (out,) + ((all_idx,) if return_indices else ()) + ((all_q,) if return_quantized else ())
+        return res if len(res) > 1 else out

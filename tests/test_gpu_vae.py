@@ -110,8 +110,6 @@ def test_diffusion_vae_sample_end_to_end(mode):
     else:
         assert float(diff.float().mean()) < 6.0
     assert d.gpu_launches > 0
-    with pytest.raises(NotImplementedError):
-        DiffusionVAE(noise_steps=T, img_size=64, device=DEV, vqae_state_dict=vsd, sav_denoise_path="/tmp/x")
 
 
 def test_gen_images_writes_reference_named_pngs(tmp_path):
@@ -146,3 +144,79 @@ def test_gen_images_writes_reference_named_pngs(tmp_path):
     with pytest.raises(FileNotFoundError):
         d.load_model(types.SimpleNamespace(load_model=True, run_name="does_not_exist"))
     d.load_model(types.SimpleNamespace(load_model=False, run_name="x"))
+
+
+def test_to_uint8_wrap_matches_torch_cast():
+    """sg_to_uint8_wrap = the un-clamped `((x + 1) / 2 * 255).type(torch.uint8)` of the trajectory dumps (:672-675),
+    including values that leave [0, 255] (torch's CPU cast is the checker) and a ragged count."""
+    from spectrogramgenai_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(4 * 1031 + 3, generator=g) * 8 - 4)  # (x+1)/2*255 in [-382, 637]
+    x[:8] = torch.tensor([-1.0, 1.0, 0.0, -1.0000001, 1.0000001, 3.0, -3.0, 0.999999])
+    got = ops.to_uint8_wrap(x.to(DEV)).cpu()
+    want = V.image_to_uint8(x)
+    assert torch.equal(got, want)
+
+
+def test_denoise_trajectory_dumps(tmp_path):
+    """sav_denoise_path (:661-700): at i % 50 == 0, i == 1 and i == T-1 one `_latent.png` (2x2 grid of
+    the quantised latent channels, float colormap input) and one `_decode.png` (uint8 colormap input) per sample, named
+    by class and step; pixels are checked against the oracle's decode of the very state the hook saw (fp32 engine), and
+    the final image is unchanged by dumping."""
+    import numpy as np
+    from PIL import Image
+
+    from oracle.weights import make_state_dict
+    from spectrogramgenai_b200.diff_modules import DiffusionVAE
+
+    T, S = 103, 16
+    names = ["a", "b", "c"]
+    vsd = V.make_vqae_state_dict(VAE_SEED)
+    lut = np.stack([np.linspace(0, 1, 256), np.linspace(1, 0, 256), np.full(256, 0.25), np.ones(256)], 1)
+
+    def cmap(a):  # matplotlib semantics: integer arrays index the LUT, floats in [0, 1] map to int(x * 256) clipped
+        a = np.asarray(a)
+        if a.dtype.kind in "ui":
+            return lut[a]
+        return lut[np.clip((a * 256).astype(np.int64), 0, 255)]
+
+    d = DiffusionVAE(noise_steps=T, img_size=4 * S, num_classes=27, device=DEV, class_names=names, vqae_state_dict=vsd,
+                     sav_denoise_path=str(tmp_path), colormap=cmap, compute_dtype="fp32")
+    d.model.load_state_dict(make_state_dict(1234, 4, 4, 27))
+    assert d.dump_steps() == [102, 100, 50, 1]
+    labels = torch.tensor([2, 0])
+    seen = {}
+
+    def hook(i, x, lab):
+        if i in (102, 100, 50, 1):
+            seen[i] = x.clone()
+        d._dump_denoise(i, x, lab)
+
+    got = d.sample(False, labels, seed=3, step_hook=hook)
+    plain = DiffusionVAE(noise_steps=T, img_size=4 * S, num_classes=27, device=DEV, class_names=names,
+                         vqae_state_dict=vsd, compute_dtype="fp32")
+    plain.model.load_state_dict(make_state_dict(1234, 4, 4, 27))
+    assert torch.equal(got, plain.sample(False, labels, seed=3))
+    files = sorted(os.listdir(tmp_path))
+    assert files == sorted(f"{names[l]}_noise_{i}_{k}.png" for l in (2, 0) for i in (102, 100, 50, 1)
+                           for k in ("latent", "decode"))
+    assert d.dump_launches == 4 * 8 and d.gpu_launches > d.dump_launches
+    for i, x in seen.items():
+        u8, y, q, _ = V.decode_tail(x.cpu(), vsd, return_all=True)
+        lat = V.image_to_uint8(q).numpy()
+        for k, lab in enumerate((2, 0)):
+            im = Image.open(tmp_path / f"{names[lab]}_noise_{i}_latent.png")
+            assert im.mode == "RGBA" and im.size == (2 * S, 2 * S)
+            grid = np.concatenate([np.concatenate([lat[k, 0], lat[k, 1]], 1), np.concatenate([lat[k, 2], lat[k, 3]], 1)], 0)
+            want = (cmap(grid / 255.0) * 255).astype(np.uint8)
+            assert (np.asarray(im) == want).mean() > 0.995  # quantised latents are codewords: identical up to near-ties
+            im = Image.open(tmp_path / f"{names[lab]}_noise_{i}_decode.png")
+            assert im.mode == "RGBA" and im.size == (4 * S, 4 * S)
+            want = (cmap(u8[k, 0].numpy()) * 255).astype(np.uint8)
+            assert (np.asarray(im) == want).mean() > 0.98
+    # a second run without the custom hook uses the built-in one (same files again)
+    for f in files:
+        os.remove(tmp_path / f)
+    d.sample(False, labels, seed=3)
+    assert sorted(os.listdir(tmp_path)) == files
