@@ -179,7 +179,14 @@ def classify(fn, a, kw):
     if name == "attn_tail":  # att 16-bit + x fp32 in, out fp32; three [M,C] x [C,C] GEMMs
         att, x, out = a[0], a[1], a[10]
         Cc = x.shape[-1]
-        return "sa_tail_fused", 3 * 2.0 * x.numel() * Cc, att.numel() * att.element_size() + x.numel() * 4 + out.numel() * 4
+        fl, by = 3 * 2.0 * x.numel() * Cc, att.numel() * att.element_size() + x.numel() * 4
+        if out is not None:
+            by += out.numel() * 4
+        if kw.get("outc") is not None:  # fused 1x1 output conv: eps NCHW written instead of (or besides) the block output
+            eps = kw["outc"][2]
+            fl += 2.0 * eps.numel() * Cc
+            by += eps.numel() * 4
+        return "sa_tail_fused", fl, by
     if name == "conv_in":
         x, w, raw, part = a
         return "conv_in", 2.0 * raw.numel() * x.shape[1] * 9, raw.shape[0] * x[0].numel() * 4 + raw.numel() * 4

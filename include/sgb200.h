@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 9
+#define SG_ABI_VERSION 11
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -166,6 +166,17 @@ int sg_attn_tail(const void* att, const float* x, const void* wo, const float* b
                  const void* w1, const float* b1, const void* w2, const float* b2, int64_t M, int C, float* out,
                  int act_dtype, sg_stream_t stream);
 
+/* sg_attn_tail with the model's output conv fused behind it (outc, :166,:195: 1x1 conv C -> c_out + bias on the last
+ * SelfAttention block's output): eps fp32 NCHW [M/HW, c_out, HW] = outc_b + out . outc_w^T, computed from the fp32
+ * `out` row each thread already holds, so the [M,C] fp32 tensor is neither written nor re-read (sa6 at n = 512: 2.1 GB).
+ * outc_w fp32 [c_out, C], outc_b fp32 [c_out], c_out in 1..4, C = 64, HW = tokens per sample (power of two >= 128).
+ * out may be NULL (only eps is produced) or a fp32 [M,C] buffer that also receives the block output.
+ */
+int sg_attn_tail_outc(const void* att, const float* x, const void* wo, const float* bo, const float* ln_g,
+                      const float* ln_b, const void* w1, const float* b1, const void* w2, const float* b2, int64_t M,
+                      int C, float* out, const float* outc_w, const float* outc_b, int c_out, int HW, float* eps,
+                      int act_dtype, sg_stream_t stream);
+
 /* ---- K4: multi-head self-attention core, never materialising the L x L matrix ----
  * replaces the scaled-dot-product inside nn.MultiheadAttention (:56,:69): per row and head,
  * softmax(q k^T / sqrt(d)) v.  qkv act [rows*L, 3C] = in_proj output (q | k | v, head h at
@@ -199,6 +210,13 @@ int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base,
 
 /* ---- K8: (clamp(x,-1,1)+1)/2*255 -> truncating uint8 cast (:440-441) ---- */
 int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream);
+
+/* ---- weight repack, once per load_state_dict (UNet_conditional.load_state_dict / Diffusion.load :509-510) ----
+ * w: a Conv2d / Linear weight of the reference state_dict, fp32 [Cout, Cin, taps] (taps = kh*kw: 9 for the 3x3 convs,
+ * 1 for Linear / 1x1) -> out [taps, Cout, Cin] in out_dtype (SG_F32 / SG_BF16 / SG_F16, round to nearest even): the
+ * `w` operand of sg_igemm.  Kernel-owned scratch does not exist: the only sizes a host must ask for are the GroupNorm
+ * partial counts (sg_igemm_partials, sg_conv_in_partials); every other buffer has the shape its entry point states. */
+int sg_pack_weights(const float* w, int Cout, int Cin, int taps, void* out, int out_dtype, sg_stream_t stream);
 
 /* ---- un-clamped image cast of the denoise-trajectory dumps (DiffusionVAE.sample :672-675) ----
  * out = uint8((x + 1) / 2 * 255) with torch's cast semantics for values outside [0, 255]: truncate to int32, keep the

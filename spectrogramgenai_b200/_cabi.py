@@ -14,7 +14,7 @@ from . import build as _build
 
 SG_F32, SG_BF16, SG_F16 = 0, 1, 2
 SG_ENGINE_SIMT, SG_ENGINE_TC = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 11
 SG_ACT_NONE, SG_ACT_GELU, SG_ACT_RELU_POST = 0, 1, 2
 
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
@@ -50,6 +50,8 @@ PROTOTYPES = {
     "sg_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
     "sg_ln_inproj": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
     "sg_attn_tail": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
+    "sg_attn_tail_outc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp,
+                               _i, _vp]),
     "sg_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sg_conv_out": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "sg_cfg_update": (_i, [_vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp, _u64, _i64, _vp]),
@@ -57,6 +59,7 @@ PROTOTYPES = {
     "sg_philox_normal": (_i, [_vp, _i, _i, _u64, _i64, _i, _vp]),
     "sg_to_uint8": (_i, [_vp, _i64, _vp, _vp]),
     "sg_to_uint8_wrap": (_i, [_vp, _i64, _vp, _vp]),
+    "sg_pack_weights": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "sg_vq_quantize": (_i, [_vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "sg_dec_in_proj": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sg_tconv2_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

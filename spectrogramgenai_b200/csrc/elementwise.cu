@@ -193,6 +193,26 @@ __global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restri
 
 static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// Weight repack (once per load_state_dict): Conv2d / Linear fp32 [Cout][Cin][taps] -> [taps][Cout][Cin] in the operand
+// dtype, K (= Cin) contiguous -- the B-operand layout of sg_igemm.  One thread per output element; rounding is
+// round-to-nearest-even (what torch's .to(bfloat16 / float16) does), fp16 overflow goes to inf (no saturation).
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int taps,
+                                                           void* __restrict__ out, int dtype) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_tap = (int64_t)Cout * Cin;
+  if (idx >= per_tap * taps) return;
+  const int tap = (int)(idx / per_tap);
+  const int64_t oc = idx - (int64_t)tap * per_tap;  // co * Cin + ci
+  const float v = w[oc * taps + tap];
+  if (dtype == SG_F32) {
+    reinterpret_cast<float*>(out)[idx] = v;
+  } else if (dtype == SG_BF16) {
+    reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
+  } else {
+    reinterpret_cast<__half*>(out)[idx] = __float2half_rn(v);
+  }
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -235,6 +255,15 @@ int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base,
 int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream) {
   SG_REQUIRE(x && out && count >= 0, "sg_to_uint8: bad arguments");
   return to_uint8_launch<false>(x, count, out, stream, "sg_to_uint8");
+}
+
+int sg_pack_weights(const float* w, int Cout, int Cin, int taps, void* out, int out_dtype, sg_stream_t stream) {
+  SG_REQUIRE(w && out, "sg_pack_weights: null pointer");
+  SG_REQUIRE(Cout > 0 && Cin > 0 && taps > 0, "sg_pack_weights: bad shape Cout=%d Cin=%d taps=%d", Cout, Cin, taps);
+  SG_REQUIRE(out_dtype == SG_F32 || out_dtype == SG_BF16 || out_dtype == SG_F16, "sg_pack_weights: bad dtype %d", out_dtype);
+  const int64_t total = (int64_t)Cout * Cin * taps;
+  pack_weights_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, Cout, Cin, taps, out, out_dtype);
+  return launch_status("sg_pack_weights");
 }
 
 int sg_to_uint8_wrap(const float* x, int64_t count, uint8_t* out, sg_stream_t stream) {

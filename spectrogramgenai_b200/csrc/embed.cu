@@ -5,7 +5,8 @@
 
 namespace sg {
 
-constexpr int TE_ROWS = 8;  // batch rows per block: the 896 x 256 projection matrix is read once per 8 rows
+constexpr int TE_ROWS = 8;    // batch rows per block: a slice of the 896 x 256 projection matrix is read once per 8 rows
+constexpr int TE_SLICES = 4;  // blockIdx.y: interleaved slices of the output channels (more CTAs than SMs at n = 512)
 
 __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict__ t, const int32_t* __restrict__ step,
                                                          const int64_t* __restrict__ y,
@@ -29,26 +30,49 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
         const int64_t cls = y[row];
         if (cls >= 0 && cls < num_classes) v += label[cls * 256 + tid];
       }
-      temb[(int64_t)row * 256 + tid] = v;
+      if (blockIdx.y == 0) temb[(int64_t)row * 256 + tid] = v;
       v = v / (1.0f + expf(-v));  // SiLU
     }
     act[rr][tid] = v;
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  for (int j = warp; j < emb_total; j += 8) {
+  // lane -> the row whose total it ends up with after the transposing reduction below
+  const int my_rr = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  for (int j = blockIdx.y * 8 + warp; j < emb_total; j += 8 * TE_SLICES) {
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_emb + (int64_t)j * 256) + lane);
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_emb + (int64_t)j * 256) + 32 + lane);
     const float bj = __ldg(b_emb + j);
+    float s[TE_ROWS];
 #pragma unroll
     for (int rr = 0; rr < TE_ROWS; ++rr) {
       const float4 a0 = reinterpret_cast<const float4*>(&act[rr][0])[lane];
       const float4 a1 = reinterpret_cast<const float4*>(&act[rr][0])[32 + lane];
-      float s = a0.x * w0.x + a0.y * w0.y + a0.z * w0.z + a0.w * w0.w + a1.x * w1.x + a1.y * w1.y + a1.z * w1.z +
-                a1.w * w1.w;
-      s = warp_sum(s);
-      if (lane == 0 && r0 + rr < rows) emb[(int64_t)(r0 + rr) * emb_total + j] = s + bj;
+      s[rr] = a0.x * w0.x + a0.y * w0.y + a0.z * w0.z + a0.w * w0.w + a1.x * w1.x + a1.y * w1.y + a1.z * w1.z +
+              a1.w * w1.w;
     }
+    // 8 row sums over 32 lanes in 9 shuffles: each step halves the values a lane carries (the same pairing tree for
+    // every row, so a row's result does not depend on its position in the block)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool hi = lane & 16;
+      const float send = hi ? s[i] : s[i + 4], keep = hi ? s[i + 4] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool hi = lane & 8;
+      const float send = hi ? s[i] : s[i + 2], keep = hi ? s[i + 2] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+      const bool hi = lane & 4;
+      const float send = hi ? s[0] : s[1], keep = hi ? s[1] : s[0];
+      s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+    if ((lane & 3) == 0 && r0 + my_rr < rows) emb[(int64_t)(r0 + my_rr) * emb_total + j] = s[0] + bj;
   }
 }
 
@@ -62,7 +86,7 @@ extern "C" int sg_time_embed(const float* t, const int32_t* step, const int64_t*
   SG_REQUIRE((t || step) && inv_freq && w_emb && b_emb && temb && emb, "sg_time_embed: null pointer");
   SG_REQUIRE(!y || label, "sg_time_embed: labels given without a label table");
   SG_REQUIRE(rows > 0 && emb_total > 0, "sg_time_embed: bad shape");
-  time_embed_kernel<<<cdiv(rows, TE_ROWS), 256, 0, as_stream(stream)>>>(t, step, y, inv_freq, label, num_classes, w_emb,
+  time_embed_kernel<<<dim3((unsigned)cdiv(rows, TE_ROWS), TE_SLICES), 256, 0, as_stream(stream)>>>(t, step, y, inv_freq, label, num_classes, w_emb,
                                                                         b_emb, emb_total, rows, temb, emb);
   return launch_status("sg_time_embed");
 }

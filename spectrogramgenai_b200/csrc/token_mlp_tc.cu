@@ -133,12 +133,37 @@ struct TailParams {
   int64_t M;
   int ntiles;
   uint32_t idesc;
+  // fused outc (sg_attn_tail_outc): eps[row, k, pix] = outc_b[k] + sum_c out[token, c] * outc_w[k, c]
+  float* eps;     // NCHW [rows, c_out, HW]
+  int c_out;      // 1..4
+  int log_hw;     // HW is a power of two
+  int write_out;  // also write the fp32 token tensor (debug taps)
 };
+
+// 1x1 output conv weights [4][C] (rows >= c_out zero) followed by the 4 biases: every thread reads the same word at the
+// same time, so they are FFMA constant-bank operands (no load instructions); rewritten through the bank's global
+// address by a one-block kernel ahead of each launch (stream order makes it visible)
+constexpr int OUTC_MAXC = 128;
+__constant__ __align__(16) float c_outc[4 * OUTC_MAXC + 4];
+
+__global__ void outc_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ dst,
+                                 int c_out, int C) {
+  for (int i = threadIdx.x; i < 4 * OUTC_MAXC + 4; i += blockDim.x) {
+    float v = 0.f;
+    if (i < 4 * OUTC_MAXC) {
+      const int k = i / OUTC_MAXC, c = i % OUTC_MAXC;
+      if (k < c_out && c < C) v = w[k * C + c];
+    } else if (i - 4 * OUTC_MAXC < c_out) {
+      v = b[i - 4 * OUTC_MAXC];
+    }
+    dst[i] = v;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // sg_attn_tail
 // ------------------------------------------------------------------------------------------------------------------
-template <int C, int DT>
+template <int C, int DT, bool OUTC>
 __global__ void __launch_bounds__(128, Tok<C>::TAIL_CTAS)
 attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant__ CUtensorMap tm_x,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_wo,
@@ -286,10 +311,18 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
       }
       __syncwarp();
     }
-    // ---- out = . + b2 + a -> fp32 tile (over this thread's own x row) -> TMA store ----
+    // ---- out = . + b2 + a -> fp32 tile (over this thread's own x row) -> TMA store [and / or the fused outc] ----
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
     tc_fence_after();
+    const bool stage = !OUTC || p.write_out;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+    if constexpr (OUTC) {
+      e0 = c_outc[4 * OUTC_MAXC + 0];
+      e1 = c_outc[4 * OUTC_MAXC + 1];
+      e2 = c_outc[4 * OUTC_MAXC + 2];
+      e3 = c_outc[4 * OUTC_MAXC + 3];
+    }
 #pragma unroll
     for (int h = 0; h < C / 32; ++h) {
       uint32_t v[32];
@@ -303,13 +336,37 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
         o.y = __uint_as_float(v[c * 4 + 1]) + bv.y + a[h * 32 + c * 4 + 1];
         o.z = __uint_as_float(v[c * 4 + 2]) + bv.z + a[h * 32 + c * 4 + 2];
         o.w = __uint_as_float(v[c * 4 + 3]) + bv.w + a[h * 32 + c * 4 + 3];
-        sts128(xrow_chunk_addr(aX, r, h * 8 + c), o);
+        if constexpr (OUTC) {
+          const int ch = h * 32 + c * 4;
+          const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            e0 = fmaf(ov[u], c_outc[0 * OUTC_MAXC + ch + u], e0);
+            e1 = fmaf(ov[u], c_outc[1 * OUTC_MAXC + ch + u], e1);
+            e2 = fmaf(ov[u], c_outc[2 * OUTC_MAXC + ch + u], e2);
+            e3 = fmaf(ov[u], c_outc[3 * OUTC_MAXC + ch + u], e3);
+          }
+        }
+        if (stage) sts128(xrow_chunk_addr(aX, r, h * 8 + c), o);
       }
     }
-    tc_fence_before();
-    fence_proxy_async();
+    if constexpr (OUTC) {
+      const int64_t m = (int64_t)m0 + r;
+      if (m < p.M) {  // consecutive threads = consecutive pixels of one sample: 128-byte stores per output channel
+        const int64_t row = m >> p.log_hw;
+        const int64_t pix = m - (row << p.log_hw);
+        float* dst = p.eps + ((row * p.c_out) << p.log_hw) + pix;
+        const int64_t hw = (int64_t)1 << p.log_hw;
+        dst[0] = e0;
+        if (p.c_out > 1) dst[hw] = e1;
+        if (p.c_out > 2) dst[2 * hw] = e2;
+        if (p.c_out > 3) dst[3 * hw] = e3;
+      }
+    }
+    tc_fence_before();  // every thread's tcgen05.ld of this accumulator precedes the next tile's first GEMM
+    if (stage) fence_proxy_async();
     __syncthreads();
-    if (warp == 0 && elect_one()) {
+    if (stage && warp == 0 && elect_one()) {
 #pragma unroll
       for (int j = 0; j < T::XB; ++j) tma_store_2d(&tm_out, sX + j * (TM * 128), j * 32, m0);
       tma_store_commit();
@@ -487,7 +544,7 @@ static int set_smem(K kernel, int bytes, const char* what) {
   return SG_OK;
 }
 
-template <int C, int DT>
+template <int C, int DT, bool OUTC>
 static int launch_tail(const void* att, const float* x, const void* wo, const void* w1, const void* w2, float* out,
                        TailParams p, int act_dtype, cudaStream_t s) {
   using T = Tok<C>;
@@ -495,7 +552,7 @@ static int launch_tail(const void* att, const float* x, const void* wo, const vo
   int rc;
   if ((rc = tmap2d(&tm_att, act_dtype, att, C, (uint64_t)p.M, 64, TM))) return rc;
   if ((rc = tmap2d(&tm_x, SG_F32, x, C, (uint64_t)p.M, 32, TM))) return rc;
-  if ((rc = tmap2d(&tm_out, SG_F32, out, C, (uint64_t)p.M, 32, TM))) return rc;
+  if ((rc = tmap2d(&tm_out, SG_F32, out ? out : x, C, (uint64_t)p.M, 32, TM))) return rc;  // unused when out is NULL
   if ((rc = tmap2d(&tm_wo, act_dtype, wo, C, C, 64, C))) return rc;
   if ((rc = tmap2d(&tm_w1, act_dtype, w1, C, C, 64, C))) return rc;
   if ((rc = tmap2d(&tm_w2, act_dtype, w2, C, C, 64, C))) return rc;
@@ -504,10 +561,10 @@ static int launch_tail(const void* att, const float* x, const void* wo, const vo
   const int grid = p.ntiles < per_sm ? p.ntiles : per_sm;
   static bool cfg = false;
   if (!cfg) {
-    if ((rc = set_smem(attn_tail_kernel<C, DT>, T::TAIL_SMEM, "sg_attn_tail"))) return rc;
+    if ((rc = set_smem(attn_tail_kernel<C, DT, OUTC>, T::TAIL_SMEM, "sg_attn_tail"))) return rc;
     cfg = true;
   }
-  attn_tail_kernel<C, DT><<<grid, 128, T::TAIL_SMEM, s>>>(tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
+  attn_tail_kernel<C, DT, OUTC><<<grid, 128, T::TAIL_SMEM, s>>>(tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
   return launch_status("sg_attn_tail");
 }
 
@@ -542,25 +599,61 @@ using namespace sg::tc;
 
 extern "C" {
 
-int sg_attn_tail(const void* att, const float* x, const void* wo, const float* bo, const float* ln_g, const float* ln_b,
-                 const void* w1, const float* b1, const void* w2, const float* b2, int64_t M, int C, float* out,
-                 int act_dtype, sg_stream_t stream) {
-  SG_REQUIRE(att && x && wo && bo && ln_g && ln_b && w1 && b1 && w2 && b2 && out, "sg_attn_tail: null pointer");
-  SG_REQUIRE(C == 64 || C == 128, "sg_attn_tail: C=%d (the fused kernel is built for C = 64 and 128; use the unfused launches otherwise)", C);
-  SG_REQUIRE(act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_attn_tail: act_dtype must be SG_BF16 or SG_F16");
-  SG_REQUIRE(M > 0 && M < (1ll << 31) - TM, "sg_attn_tail: M=%lld", (long long)M);
+static int attn_tail_impl(const void* att, const float* x, const void* wo, const float* bo, const float* ln_g,
+                          const float* ln_b, const void* w1, const float* b1, const void* w2, const float* b2, int64_t M,
+                          int C, float* out, const float* outc_w, const float* outc_b, int c_out, int HW, float* eps,
+                          int act_dtype, sg_stream_t stream, const char* what) {
+  SG_REQUIRE(att && x && wo && bo && ln_g && ln_b && w1 && b1 && w2 && b2, "%s: null pointer", what);
+  SG_REQUIRE(act_dtype == SG_BF16 || act_dtype == SG_F16, "%s: act_dtype must be SG_BF16 or SG_F16", what);
+  SG_REQUIRE(M > 0 && M < (1ll << 31) - TM, "%s: M=%lld", what, (long long)M);
   TailParams p;
   p.bo = bo; p.ln_g = ln_g; p.ln_b = ln_b; p.b1 = b1; p.b2 = b2;
   p.M = M;
   p.ntiles = (int)cdiv(M, TM);
   p.idesc = 0;
+  p.eps = eps; p.c_out = c_out; p.log_hw = 0; p.write_out = out != nullptr;
   cudaStream_t s = as_stream(stream);
-  if (C == 64) {
-    if (act_dtype == SG_BF16) return launch_tail<64, SG_BF16>(att, x, wo, w1, w2, out, p, act_dtype, s);
-    return launch_tail<64, SG_F16>(att, x, wo, w1, w2, out, p, act_dtype, s);
+  if (eps) {
+    SG_REQUIRE(C == 64, "%s: C=%d (the fused output conv follows the C = 64 block sa6)", what, C);
+    SG_REQUIRE(outc_w && outc_b && c_out >= 1 && c_out <= 4, "%s: c_out=%d not in 1..4 or null weights", what, c_out);
+    SG_REQUIRE(HW > 0 && (HW & (HW - 1)) == 0 && HW >= TM && M % HW == 0, "%s: HW=%d must be a power of two >= %d dividing M", what, HW, TM);
+    while ((1 << p.log_hw) < HW) ++p.log_hw;
+    static float* bank = nullptr;  // global address of the constant bank
+    if (!bank) {
+      cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&bank), c_outc);
+      if (e != cudaSuccess) {
+        set_error("%s: cudaGetSymbolAddress: %s", what, cudaGetErrorString(e));
+        return SG_ERR_LAUNCH;
+      }
+    }
+    outc_pack_kernel<<<1, 256, 0, s>>>(outc_w, outc_b, bank, c_out, C);
+    if (act_dtype == SG_BF16) return launch_tail<64, SG_BF16, true>(att, x, wo, w1, w2, out, p, act_dtype, s);
+    return launch_tail<64, SG_F16, true>(att, x, wo, w1, w2, out, p, act_dtype, s);
   }
-  if (act_dtype == SG_BF16) return launch_tail<128, SG_BF16>(att, x, wo, w1, w2, out, p, act_dtype, s);
-  return launch_tail<128, SG_F16>(att, x, wo, w1, w2, out, p, act_dtype, s);
+  SG_REQUIRE(out, "%s: null output", what);
+  SG_REQUIRE(C == 64 || C == 128, "%s: C=%d (the fused kernel is built for C = 64 and 128; use the unfused launches otherwise)", what, C);
+  if (C == 64) {
+    if (act_dtype == SG_BF16) return launch_tail<64, SG_BF16, false>(att, x, wo, w1, w2, out, p, act_dtype, s);
+    return launch_tail<64, SG_F16, false>(att, x, wo, w1, w2, out, p, act_dtype, s);
+  }
+  if (act_dtype == SG_BF16) return launch_tail<128, SG_BF16, false>(att, x, wo, w1, w2, out, p, act_dtype, s);
+  return launch_tail<128, SG_F16, false>(att, x, wo, w1, w2, out, p, act_dtype, s);
+}
+
+int sg_attn_tail(const void* att, const float* x, const void* wo, const float* bo, const float* ln_g, const float* ln_b,
+                 const void* w1, const float* b1, const void* w2, const float* b2, int64_t M, int C, float* out,
+                 int act_dtype, sg_stream_t stream) {
+  return attn_tail_impl(att, x, wo, bo, ln_g, ln_b, w1, b1, w2, b2, M, C, out, nullptr, nullptr, 0, 0, nullptr, act_dtype,
+                        stream, "sg_attn_tail");
+}
+
+int sg_attn_tail_outc(const void* att, const float* x, const void* wo, const float* bo, const float* ln_g,
+                      const float* ln_b, const void* w1, const float* b1, const void* w2, const float* b2, int64_t M,
+                      int C, float* out, const float* outc_w, const float* outc_b, int c_out, int HW, float* eps,
+                      int act_dtype, sg_stream_t stream) {
+  SG_REQUIRE(eps, "sg_attn_tail_outc: null eps");
+  return attn_tail_impl(att, x, wo, bo, ln_g, ln_b, w1, b1, w2, b2, M, C, out, outc_w, outc_b, c_out, HW, eps, act_dtype,
+                        stream, "sg_attn_tail_outc");
 }
 
 int sg_ln_inproj(const float* x, const float* ln_g, const float* ln_b, const void* w_in, const float* b_in, int64_t M,

@@ -285,7 +285,7 @@ class Diffusion:
     # ------------------------------------------------------------------ sampling (:411-442)
     @torch.no_grad()
     def sample(self, use_ema, labels, cfg_scale=3, *legacy, noise=None, seed=0, sample_base=0, micro_batch=512,
-               return_float=False, use_graph=True, max_steps=None, step_hook=None):
+               return_float=False, use_graph=True, max_steps=None, step_hook=None, return_trajectory=False):
         """Reference form: sample(use_ema, labels, cfg_scale=3) -> uint8 [n, c_in, S, S].
         Upstream alias: sample(model, n, labels, cfg_scale=3).
 
@@ -296,6 +296,8 @@ class Diffusion:
           micro_batch  samples per captured loop (n is processed in chunks of this size)
           return_float return the fp32 state before the uint8 quantisation
           max_steps    run only the first k loop iterations (benchmarking a bounded number of timesteps)
+          return_trajectory  also return the fp32 states [K+1, n, c, S, S]: x_T, then x after each of the K executed
+                       loop iterations (K = T-1 unless max_steps) -> (out, trajectory)
           step_hook    callable(i, x, labels) run on the host after the update of loop index i (T-1 ... 1) with the
                        chunk's fp32 state x (read-only) -- the captured step is replayed once per timestep, so the hook
                        sits between two replays and costs nothing when absent
@@ -324,14 +326,19 @@ class Diffusion:
         out_dtype = torch.float32 if return_float else torch.uint8
         out = torch.empty((n, c, S, S), dtype=out_dtype, device=self.device)
         self.gpu_launches = 0
+        traj = None
+        if return_trajectory:
+            iters = T - 1 if max_steps is None else min(T - 1, max_steps)
+            traj = torch.empty((iters + 1, n, c, S, S), dtype=torch.float32, device=self.device)
         for lo in range(0, n, micro_batch):
             hi = min(n, lo + micro_batch)
             nz = None if noise is None else noise[:, lo:hi].contiguous()
             self._sample_chunk(model, labels[lo:hi], float(cfg_scale), nz, seed, sample_base + lo, out[lo:hi],
-                               use_graph, max_steps, step_hook)
-        return out
+                               use_graph, max_steps, step_hook, None if traj is None else traj[:, lo:hi])
+        return (out, traj) if return_trajectory else out
 
-    def _sample_chunk(self, model, labels, cfg, noise, seed, sample_base, out, use_graph, max_steps, step_hook=None):
+    def _sample_chunk(self, model, labels, cfg, noise, seed, sample_base, out, use_graph, max_steps, step_hook=None,
+                      traj=None):
         n = len(labels)
         T = self.noise_steps
         rows = 2 * n if cfg > 0 else n
@@ -361,20 +368,22 @@ class Diffusion:
             self.gpu_launches += 1
         plan.step.fill_(T - 1)
         iters = T - 1 if max_steps is None else min(T - 1, max_steps)
+        if traj is not None:
+            traj[0].copy_(x)
         if use_graph and iters > 0:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 one_step()
             # capture does not execute: state is still (x_T, T-1)
-            for k in range(iters):
-                g.replay()
-                if step_hook is not None:
-                    step_hook(T - 1 - k, x, labels)
+            step = g.replay
         else:
-            for k in range(iters):
-                one_step()
-                if step_hook is not None:
-                    step_hook(T - 1 - k, x, labels)
+            step = one_step
+        for k in range(iters):
+            step()
+            if traj is not None:
+                traj[k + 1].copy_(x)
+            if step_hook is not None:
+                step_hook(T - 1 - k, x, labels)
         self.gpu_launches += iters * launches_per_step
         if out.dtype == torch.uint8:
             ops.to_uint8(x, out)
@@ -442,6 +451,9 @@ class DiffusionVAE(Diffusion):
         if self.sav_denoise_path and kw.get("step_hook") is None:
             kw["step_hook"] = self._dump_denoise
         x = super().sample(use_ema, labels, cfg_scale, *legacy, return_float=True, **kw)
+        traj = None
+        if kw.get("return_trajectory"):
+            x, traj = x  # latent trajectory [K+1, n, 4, S/4, S/4]
         launches = self.gpu_launches + self.dump_launches
         out = self.vqae.decode(x, micro_batch=decode_micro_batch)
         self.gpu_launches = launches + self.vqae.gpu_launches

@@ -26,12 +26,11 @@ TIME_DIM = 256
 
 def _pack_conv(w: torch.Tensor, dtype, device):
     """[Cout, Cin, 3, 3] -> [9 taps (dy, dx), Cout, Cin], K (= Cin) contiguous."""
-    co, ci, kh, kw = w.shape
-    return w.detach().to(device=device, dtype=torch.float32).permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous().to(dtype)
+    return ops.pack_weights(w.detach().to(device=device, dtype=torch.float32).contiguous(), dtype)
 
 
 def _pack_linear(w: torch.Tensor, dtype, device):
-    return w.detach().to(device=device, dtype=torch.float32).reshape(1, *w.shape).contiguous().to(dtype)
+    return ops.pack_weights(w.detach().to(device=device, dtype=torch.float32).contiguous(), dtype)
 
 
 class PackedWeights:
@@ -210,8 +209,10 @@ class UNetPlan:
         off, n = self.W.emb_off[block]
         return self.emb[:, off:off + n]
 
-    def _self_attention(self, p, x, rows, H, W, C, *, want_act):
-        """SelfAttention (:52-72) on the fp32 residual stream x [rows, H, W, C] (tokens are already row-major)."""
+    def _self_attention(self, p, x, rows, H, W, C, *, want_act, outc=None):
+        """SelfAttention (:52-72) on the fp32 residual stream x [rows, H, W, C] (tokens are already row-major).
+        outc = (w, b, eps): the block is the last one and the fused tail applies the 1x1 output conv itself; returns
+        None when it did (eps is written, the block output is only materialised in debug mode)."""
         W_ = self.W
         L = H * W
         M = rows * L
@@ -236,11 +237,17 @@ class UNetPlan:
         self._free(qkv)
         if fused and not want_act:
             # out_proj + residual + LayerNorm + FFN + residual in one pass (sg_attn_tail)
-            out = self._pair((rows, H, W, C), True, False)
+            fuse_outc = outc is not None and C == 64 and os.environ.get("SGB200_FUSED_OUTC", "1") != "0"
+            out = self._pair((rows, H, W, C), True, False) if (not fuse_outc or self.debug) else (None, None)
             self._op(ops.attn_tail, att, x, W_[f"{p}.mha.out_proj.weight"], W_[f"{p}.mha.out_proj.bias"],
                      W_[f"{p}.ff_self.0.weight"], W_[f"{p}.ff_self.0.bias"], W_[f"{p}.ff_self.1.weight"],
-                     W_[f"{p}.ff_self.1.bias"], W_[f"{p}.ff_self.3.weight"], W_[f"{p}.ff_self.3.bias"], out[0])
+                     W_[f"{p}.ff_self.1.bias"], W_[f"{p}.ff_self.3.weight"], W_[f"{p}.ff_self.3.bias"], out[0],
+                     **({"outc": outc} if fuse_outc else {}))
             self._free(att)
+            if fuse_outc:
+                if self.debug:
+                    self.taps_last = out[0]
+                return None
             return out
         a = self._alloc((rows, H, W, C), f32)
         self._op(ops.igemm_launch, ops.make_igemm_args(att, W_[f"{p}.mha.out_proj.weight"], rows=rows, H=H, W=W,
@@ -342,11 +349,16 @@ class UNetPlan:
         self._free_pair(a)
         self._free_pair(x1)
         keep["up3"] = u[0]
-        a = self._self_attention("sa6", u[0], rows, S, S, 64, want_act=False)
+        a = self._self_attention("sa6", u[0], rows, S, S, 64, want_act=False,
+                                 outc=(W_["outc.weight"], W_["outc.bias"], self.eps))
         self._free_pair(u)
-        keep["sa6"] = a[0]
-        self._op(ops.conv_out, a[0].view(rows, S * S, 64), W_["outc.weight"], W_["outc.bias"], self.eps)
-        self._free_pair(a)
+        if a is None:  # the fused tail applied outc itself
+            if self.debug:
+                keep["sa6"] = self.taps_last
+        else:
+            keep["sa6"] = a[0]
+            self._op(ops.conv_out, a[0].view(rows, S * S, 64), W_["outc.weight"], W_["outc.bias"], self.eps)
+            self._free_pair(a)
         self._pool.clear()
 
     def run(self):

@@ -190,10 +190,22 @@ def ln_inproj(x, ln_g, ln_b, w_in, b_in, qkv):
                               dtype_code(qkv.dtype), stream_ptr()), "sg_ln_inproj")
 
 
-def attn_tail(att, x, wo, bo, ln_g, ln_b, w1, b1, w2, b2, out):
-    """Fused out_proj + residual + LayerNorm + FFN + residual (tcgen05).  att 16-bit [M, C]; x, out fp32 [M, C]."""
+def attn_tail(att, x, wo, bo, ln_g, ln_b, w1, b1, w2, b2, out, *, outc=None):
+    """Fused out_proj + residual + LayerNorm + FFN + residual (tcgen05).  att 16-bit [M, C]; x, out fp32 [M, C].
+    outc = (w fp32 [c_out, C], b fp32 [c_out], eps fp32 NCHW [rows, c_out, S, S]) also applies the model's 1x1 output
+    conv to the block output (sg_attn_tail_outc); `out` may then be None."""
     Cc = x.shape[-1]
     M = x.numel() // Cc
+    if outc is not None:
+        w, b, eps = outc
+        c_out, HW = eps.shape[1], eps.shape[2] * eps.shape[3]
+        if eps.numel() != (M // HW) * c_out * HW or M % HW:
+            raise ValueError("attn_tail: eps does not match the token count")
+        check(_lib().sg_attn_tail_outc(ptr(att), ptr(_f32(x, "x")), ptr(wo), ptr(bo), ptr(ln_g), ptr(ln_b), ptr(w1),
+                                       ptr(b1), ptr(w2), ptr(b2), M, Cc, ptr(_f32(out, "out")), ptr(_f32(w, "outc_w")),
+                                       ptr(_f32(b, "outc_b")), c_out, HW, ptr(_f32(eps, "eps")), dtype_code(att.dtype),
+                                       stream_ptr()), "sg_attn_tail_outc")
+        return
     check(_lib().sg_attn_tail(ptr(att), ptr(_f32(x, "x")), ptr(wo), ptr(bo), ptr(ln_g), ptr(ln_b), ptr(w1), ptr(b1),
                               ptr(w2), ptr(b2), M, Cc, ptr(_f32(out, "out")), dtype_code(att.dtype), stream_ptr()),
           "sg_attn_tail")
@@ -243,6 +255,16 @@ def philox_normal(x, *, seed, sample_base, step_tag):
 
 def to_uint8(x, out):
     check(_lib().sg_to_uint8(ptr(_f32(x, "x")), x.numel(), ptr(out), stream_ptr()), "sg_to_uint8")
+
+
+def pack_weights(w, dtype):
+    """fp32 device weight [Cout, Cin, *kernel] -> [taps, Cout, Cin] of `dtype` (the B operand of sg_igemm)."""
+    w = _f32(w, "w")
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w.numel() // (cout * cin)
+    out = torch.empty((taps, cout, cin), dtype=dtype, device=w.device)
+    check(_lib().sg_pack_weights(ptr(w), cout, cin, taps, ptr(out), dtype_code(dtype), stream_ptr()), "sg_pack_weights")
+    return out
 
 
 def to_uint8_wrap(x, out=None):

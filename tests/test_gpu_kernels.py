@@ -447,6 +447,41 @@ def test_attn_tail_fused(ops, M, C, dtype):
     assert torch.isnan(out[M:]).all()
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,HW,c_out", [(3, 256, 4), (2, 1024, 1), (5, 128, 3), (1100, 256, 4)])
+def test_attn_tail_with_fused_output_conv(ops, rows, HW, c_out, dtype):
+    """sg_attn_tail_outc: eps NCHW = outc(block output), computed from the fp32 rows the tail holds.  The block output
+    it optionally also writes is bit-identical to sg_attn_tail's, eps is the same with and without that write, and
+    eps matches the 1x1 conv of that output (fp64) to fp32 rounding."""
+    C, M = 64, rows * HW
+    g = gen(23)
+    W = _sa_weights(C, g)
+    x = torch.randn(M, C, generator=g) * 2
+    att = torch.randn(M, C, generator=g).to(dtype)
+    wc = torch.randn(c_out, C, generator=g) * 0.2
+    bc = torch.randn(c_out, generator=g)
+    d = lambda t: t.to(DEV)  # noqa: E731
+    args = [d(att), d(x)] + [d(t) for t in (W["wo"].to(dtype), W["bo"], W["ln2_g"], W["ln2_b"], W["w1"].to(dtype), W["b1"],
+                                            W["w2"].to(dtype), W["b2"])]
+    plain = torch.empty(M, C, device=DEV)
+    ops.attn_tail(*args, plain)
+    both = torch.empty(M, C, device=DEV)
+    eps1 = torch.full((rows + 1, c_out, HW // 16, 16), float("nan"), device=DEV)
+    ops.attn_tail(*args, both, outc=(d(wc), d(bc), eps1[:rows]))
+    eps2 = torch.empty((rows, c_out, HW // 16, 16), device=DEV)
+    ops.attn_tail(*args, None, outc=(d(wc), d(bc), eps2))
+    torch.cuda.synchronize()
+    assert torch.equal(plain, both)
+    assert torch.equal(eps1[:rows], eps2) and torch.isnan(eps1[rows:]).all()
+    ref = (plain.cpu().double() @ wc.double().T + bc.double()).reshape(rows, HW, c_out).permute(0, 2, 1)
+    err = O.rel_l2(eps2.cpu().reshape(rows, c_out, HW), ref)
+    print(f"attn_tail+outc rows={rows} HW={HW} c_out={c_out} {dtype}: rel-L2 {err:.3e}")
+    assert err < 2e-6
+    with pytest.raises(Exception):  # C = 128 has no fused output conv
+        ops.attn_tail(d(att.reshape(-1, 128)), d(x.reshape(-1, 128)), *args[2:], None,
+                      outc=(d(wc), d(bc), eps2))
+
+
 def _attention_ref(qkv, rows, L, C):
     d = C // 4
     q, k, v = qkv.double().reshape(rows, L, 3 * C).split(C, -1)
@@ -521,3 +556,18 @@ def test_error_reporting(ops):
                     torch.zeros(2, 9, 2, device=DEV))
     with pytest.raises(SgError, match="head dim"):
         ops.attention(torch.zeros(4, 3 * 32, device=DEV), torch.zeros(4, 32, device=DEV), rows=1, L=4, C=32)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(64, 4, 3, 3), (128, 64, 3, 3), (192, 64), (3, 5, 1, 1), (512, 512, 3, 3)])
+def test_pack_weights_is_permute_and_rne_cast(ops, shape, dtype):
+    """sg_pack_weights: state_dict weight [Cout, Cin, kh, kw] -> [taps, Cout, Cin] in the operand dtype, bit-identical
+    to torch's permute + .to(dtype) (round to nearest even), incl. values that overflow fp16."""
+    w = torch.randn(shape, generator=gen(31), dtype=torch.float32)
+    w.view(-1)[:4] = torch.tensor([70000.0, -70000.0, 1e-8, 65519.9])
+    got = ops.pack_weights(w.to(DEV), dtype)
+    cout, cin = shape[:2]
+    want = w.reshape(cout, cin, -1).permute(2, 0, 1).contiguous().to(dtype)
+    assert got.shape == want.shape and got.dtype == dtype
+    assert torch.equal(got.cpu().view(torch.int16 if dtype != torch.float32 else torch.int32),
+                       want.view(torch.int16 if dtype != torch.float32 else torch.int32))

@@ -222,3 +222,23 @@ def test_shared_prefix_is_bit_identical(monkeypatch, mode):
     m.release_plans()
     assert torch.equal(eps["1"], eps["0"])
     assert not torch.equal(eps["1"][:n], eps["1"][n:])
+
+
+def test_return_trajectory_matches_oracle_step_by_step():
+    """return_trajectory: [K+1, n, c, S, S] = x_T and the state after every loop iteration, against the CPU oracle's
+    trajectory with the same injected noise (fp32 engine, T = 12 at R16), also through micro-batches and max_steps."""
+    T, s, c, n = 12, 16, 4, 3
+    d = _diffusion("fp32", s, T, c)
+    _, y = golden_inputs(s, c, n)
+    noise = O.draw_reference_noise(7, n, c, s, T)
+    ref = []
+    O.sample(make_state_dict(WEIGHT_SEED, c, c, NUM_CLASSES), y, noise, noise_steps=T, trajectory=ref)
+    u8, traj = d.sample(False, y, cfg_scale=3, noise=noise, return_trajectory=True)
+    assert traj.shape == (T, n, c, s, s) and traj.dtype == torch.float32
+    assert torch.equal(traj[0].cpu(), noise[0])
+    for k, (i, _, x_ref) in enumerate(ref):
+        assert i == T - 1 - k
+        assert float((traj[k + 1].cpu() - x_ref).abs().max()) < 1e-3
+    assert torch.equal(u8.cpu(), O.to_uint8(traj[-1].cpu()))
+    u8b, trajb = d.sample(False, y, cfg_scale=3, noise=noise, return_trajectory=True, micro_batch=2, max_steps=5)
+    assert trajb.shape == (6, n, c, s, s) and torch.equal(trajb, traj[:6])
