@@ -193,6 +193,58 @@ __global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restri
 
 static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// Cx == Cs, multiples of 8: one thread = one output pixel x (8 skip channels k, 8 upsampled channels k), so no warp mixes
+// "copy" lanes with "gather" lanes (the generic kernel runs both branches in every warp with half the lanes idle).
+__global__ void __launch_bounds__(256) upsample_cat_paired_kernel(const float* __restrict__ x, const float* __restrict__ skip,
+                                                                  unsigned per_row, int skip_rows, int h, int w, int C8,
+                                                                  float sh, float sw, float* __restrict__ o32,
+                                                                  void* __restrict__ o16, int dtype) {
+  // per_row = pixels * C8 thread-units; C8 = Cs / 8 = Cx / 8
+  const unsigned row = blockIdx.y;
+  const unsigned W = 2 * w, HW = 4u * h * w;
+  const float4* xrow = reinterpret_cast<const float4*>(x) + (size_t)row * h * w * (C8 * 2);
+  const float4* srow = reinterpret_cast<const float4*>(skip) + (size_t)(row % (unsigned)skip_rows) * HW * (C8 * 2);
+  const size_t obase = (size_t)row * HW * (C8 * 16);  // elements
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+    const unsigned p = i / (unsigned)C8, k = i - p * (unsigned)C8;
+    const unsigned ho = p / W, wo = p - ho * W;
+    const float4* src = srow + ((size_t)p * C8 + k) * 2;
+    const float4 s0 = __ldcs(src), s1 = __ldcs(src + 1);
+    const float fy = sh * (float)ho, fx = sw * (float)wo;  // align_corners=True: src = dst * (in-1)/(out-1)
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    const float4* base = xrow + k * 2;
+    float4 v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float4 a = __ldg(base + (size_t)(y0 * w + x0) * (C8 * 2) + u), b = __ldg(base + (size_t)(y0 * w + x1) * (C8 * 2) + u);
+      const float4 c = __ldg(base + (size_t)(y1 * w + x0) * (C8 * 2) + u), d = __ldg(base + (size_t)(y1 * w + x1) * (C8 * 2) + u);
+      v[u].x = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
+      v[u].y = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
+      v[u].z = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
+      v[u].w = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
+    }
+    const size_t off_s = obase + ((size_t)p * (2 * C8) + k) * 8, off_x = off_s + (size_t)C8 * 8;
+    if (o32) {
+      __stcs(reinterpret_cast<float4*>(o32 + off_s), s0);
+      __stcs(reinterpret_cast<float4*>(o32 + off_s + 4), s1);
+      __stcs(reinterpret_cast<float4*>(o32 + off_x), v[0]);
+      __stcs(reinterpret_cast<float4*>(o32 + off_x + 4), v[1]);
+    }
+    if (o16) {
+      uint4 ws, wx;
+      ws.x = pack16(s0.x, s0.y, dtype); ws.y = pack16(s0.z, s0.w, dtype);
+      ws.z = pack16(s1.x, s1.y, dtype); ws.w = pack16(s1.z, s1.w, dtype);
+      wx.x = pack16(v[0].x, v[0].y, dtype); wx.y = pack16(v[0].z, v[0].w, dtype);
+      wx.z = pack16(v[1].x, v[1].y, dtype); wx.w = pack16(v[1].z, v[1].w, dtype);
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(o16) + off_s) = ws;
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(o16) + off_x) = wx;
+    }
+  }
+}
+
 // Weight repack (once per load_state_dict): Conv2d / Linear fp32 [Cout][Cin][taps] -> [taps][Cout][Cin] in the operand
 // dtype, K (= Cin) contiguous -- the B-operand layout of sg_igemm.  One thread per output element; rounding is
 // round-to-nearest-even (what torch's .to(bfloat16 / float16) does), fp16 overflow goes to inf (no saturation).
@@ -299,7 +351,13 @@ int sg_upsample_cat(const float* x, const float* skip, int rows, int skip_rows, 
   const int want = (int)cdiv(148 * 8, rows);
   if (chunks > want) chunks = want > 1 ? want : 1;
   dim3 grid((unsigned)chunks, (unsigned)rows);
-  if (v == 2)
+  if (v == 2 && Cx == Cs) {
+    const int64_t units = (int64_t)(2 * h) * (2 * w) * (Cs / 8);
+    int ch = (int)cdiv(units, 256 * 2);
+    if (ch > want) ch = want > 1 ? want : 1;
+    upsample_cat_paired_kernel<<<dim3((unsigned)ch, (unsigned)rows), 256, 0, as_stream(stream)>>>(
+        x, skip, (unsigned)units, skip_rows, h, w, Cs / 8, sh, sw, out_f32, out_act, act_dtype);
+  } else if (v == 2)
     upsample_cat_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, skip, (unsigned)per_row, skip_rows, h, w, Cx / 4, Cs / 4, sh,
                                                                 sw, out_f32, out_act, act_dtype);
   else

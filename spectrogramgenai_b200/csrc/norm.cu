@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
 // 2.1 GB read here at up3 (n = 512); the sources are 0.8 GB and mostly L2-resident.  Same bilinear expression as
 // upsample_cat_kernel (align_corners=True).  One thread = 8 channels of one pixel; fp16 raw only (tensor-core modes).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_apply_vcat_kernel(const uint4* __restrict__ raw8, const float* __restrict__ partials,
+constexpr int VCAT_MAXC = 512;  // channels of the concatenated tensor (up1: 256 + 256)
+
+__global__ void __launch_bounds__(256, 4) gn_apply_vcat_kernel(const uint4* __restrict__ raw8, const float* __restrict__ partials,
                                                             int P, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int HW, int W2, int C8,
                                                             int Cs8, const float* __restrict__ x,
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(256) gn_apply_vcat_kernel(const uint4* __restr
                                                             float sh, float sw, void* __restrict__ o16, int dtype) {
   __shared__ double red[2][8];
   __shared__ float stat[2];
+  __shared__ __align__(16) float s_sc[VCAT_MAXC], s_sf[VCAT_MAXC];
   const int row = blockIdx.y;
   const int64_t per_row8 = (int64_t)HW * C8;
   {
@@ -289,75 +292,76 @@ __global__ void __launch_bounds__(256) gn_apply_vcat_kernel(const uint4* __restr
   }
   const float mean = stat[0], rstd = stat[1];
   const int Cx8 = C8 - Cs8;
+  // folded scale / shift of every channel (same rounding as gn_apply_kernel) in shared memory: a thread re-reads its
+  // 16 channels each iteration (8 LDS.128) instead of holding 32 registers, which doubles the resident warps
+  for (int c = threadIdx.x; c < C8 * 8; c += blockDim.x) {
+    const float scv = __fmul_rn(rstd, __ldg(gamma + c));
+    s_sc[c] = scv;
+    s_sf[c] = __fmaf_rn(-mean, scv, __ldg(beta + c));
+  }
+  __syncthreads();
   const uint4* rrow = raw8 + (int64_t)row * per_row8;
   uint4* orow = reinterpret_cast<uint4*>(o16) + (int64_t)row * per_row8;
   const float4* skip4 = reinterpret_cast<const float4*>(skip) + (int64_t)(row % skip_rows) * HW * (Cs8 * 2);
   const float4* x4 = reinterpret_cast<const float4*>(x) + (int64_t)row * h * w * (Cx8 * 2);
-  // One thread = one pixel x (8 skip channels k, 8 upsampled channels Cs8 + k): every lane runs both the skip load and
-  // the bilinear gather (a warp that mixed "skip lanes" and "x lanes" executed both branches with half its lanes idle).
-  // 32-bit index arithmetic; the launcher makes the grid stride a multiple of Cs8 (= Cx8, checked there), so a
-  // thread keeps its channels and the folded scale / shift of its 16 channels live in registers.
+  // One thread = one pixel x (8 skip channels k, then the 8 upsampled channels Cs8 + k): every lane runs both the skip
+  // load and the bilinear gather (a warp that mixed "skip lanes" and "x lanes" executed both branches with half its
+  // lanes idle).  32-bit index arithmetic; the launcher makes the grid stride a multiple of Cs8 (= Cx8, checked
+  // there), so a thread keeps its channels.
   const unsigned nu = (unsigned)HW * (unsigned)Cs8, stride = gridDim.x * blockDim.x;
   const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned k = first % (unsigned)Cs8;
-  float sc[16], sf[16];
+  // y = GELU(GN(raw) + r) for 8 channels starting at channel c0 -> one 16-byte store
+  auto finish = [&](const uint4 hraw, const float (&r)[8], unsigned c0, size_t e) {
+    const float2 a0 = unpack16(hraw.x, SG_F16), a1 = unpack16(hraw.y, SG_F16);
+    const float2 a2 = unpack16(hraw.z, SG_F16), a3 = unpack16(hraw.w, SG_F16);
+    float y[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+    const float4 c0v = *reinterpret_cast<const float4*>(s_sc + c0), c1v = *reinterpret_cast<const float4*>(s_sc + c0 + 4);
+    const float4 f0v = *reinterpret_cast<const float4*>(s_sf + c0), f1v = *reinterpret_cast<const float4*>(s_sf + c0 + 4);
+    const float sc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+    const float sf[8] = {f0v.x, f0v.y, f0v.z, f0v.w, f1v.x, f1v.y, f1v.z, f1v.w};
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const unsigned c4 = (u < 2 ? k * 2 + u : ((unsigned)Cs8 + k) * 2 + (u - 2));
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+    for (int j = 0; j < 8; ++j) y[j] = __fmaf_rn(y[j], sc[j], sf[j]) + r[j];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      sc[u * 4 + j] = __fmul_rn(rstd, gg[j]);
-      sf[u * 4 + j] = __fmaf_rn(-mean, sc[u * 4 + j], bb[j]);  // same rounding as gn_apply_kernel
-    }
-  }
+    for (int j = 0; j < 8; j += 2) gelu_erf2(y[j], y[j + 1]);
+    uint4 wv;
+    wv.x = pack16(y[0], y[1], dtype);
+    wv.y = pack16(y[2], y[3], dtype);
+    wv.z = pack16(y[4], y[5], dtype);
+    wv.w = pack16(y[6], y[7], dtype);
+    orow[e] = wv;
+  };
   unsigned p = first / (unsigned)Cs8;
   const unsigned dp = stride / (unsigned)Cs8;
   for (unsigned i = first; i < nu; i += stride, p += dp) {
     const size_t e_s = (size_t)p * C8 + k, e_x = e_s + Cs8;  // units of 8 channels inside the row
     const uint4 h_s = __ldcs(rrow + e_s), h_x = __ldcs(rrow + e_x);
-    float r[16];
+    const unsigned ho = p / (unsigned)W2, wo = p - ho * (unsigned)W2;
+    const float fy = sh * (float)ho, fx = sw * (float)wo;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    const float4* xa = x4 + (size_t)(y0 * w + x0) * (Cx8 * 2) + k * 2;
+    const float4* xb = x4 + (size_t)(y0 * w + x1) * (Cx8 * 2) + k * 2;
+    const float4* xc = x4 + (size_t)(y1 * w + x0) * (Cx8 * 2) + k * 2;
+    const float4* xd = x4 + (size_t)(y1 * w + x1) * (Cx8 * 2) + k * 2;
     {
       const float4 a = __ldg(skip4 + ((size_t)p * Cs8 + k) * 2), b = __ldg(skip4 + ((size_t)p * Cs8 + k) * 2 + 1);
-      r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+      const float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      finish(h_s, r, k * 8, e_s);
     }
     {
-      const unsigned ho = p / (unsigned)W2, wo = p - ho * (unsigned)W2;
-      const float fy = sh * (float)ho, fx = sw * (float)wo;
-      const int y0 = (int)fy, x0 = (int)fx;
-      const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-      const float ly = fy - (float)y0, lx = fx - (float)x0;
-      const float hy = 1.0f - ly, hx = 1.0f - lx;
+      float r[8];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const float4 a = __ldg(x4 + (size_t)(y0 * w + x0) * (Cx8 * 2) + k * 2 + u);
-        const float4 b = __ldg(x4 + (size_t)(y0 * w + x1) * (Cx8 * 2) + k * 2 + u);
-        const float4 c = __ldg(x4 + (size_t)(y1 * w + x0) * (Cx8 * 2) + k * 2 + u);
-        const float4 d = __ldg(x4 + (size_t)(y1 * w + x1) * (Cx8 * 2) + k * 2 + u);
-        r[8 + u * 4 + 0] = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
-        r[8 + u * 4 + 1] = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
-        r[8 + u * 4 + 2] = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
-        r[8 + u * 4 + 3] = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
+        const float4 a = __ldg(xa + u), b = __ldg(xb + u), c = __ldg(xc + u), d = __ldg(xd + u);
+        r[u * 4 + 0] = hy * (hx * a.x + lx * b.x) + ly * (hx * c.x + lx * d.x);
+        r[u * 4 + 1] = hy * (hx * a.y + lx * b.y) + ly * (hx * c.y + lx * d.y);
+        r[u * 4 + 2] = hy * (hx * a.z + lx * b.z) + ly * (hx * c.z + lx * d.z);
+        r[u * 4 + 3] = hy * (hx * a.w + lx * b.w) + ly * (hx * c.w + lx * d.w);
       }
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const uint4 hraw = half ? h_x : h_s;
-      const float2 a0 = unpack16(hraw.x, SG_F16), a1 = unpack16(hraw.y, SG_F16);
-      const float2 a2 = unpack16(hraw.z, SG_F16), a3 = unpack16(hraw.w, SG_F16);
-      float y[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = __fmaf_rn(y[j], sc[half * 8 + j], sf[half * 8 + j]) + r[half * 8 + j];
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) gelu_erf2(y[j], y[j + 1]);
-      uint4 wv;
-      wv.x = pack16(y[0], y[1], dtype);
-      wv.y = pack16(y[2], y[3], dtype);
-      wv.z = pack16(y[4], y[5], dtype);
-      wv.w = pack16(y[6], y[7], dtype);
-      orow[half ? e_x : e_s] = wv;
+      finish(h_x, r, (Cs8 + k) * 8, e_x);
     }
   }
 }
@@ -483,6 +487,7 @@ int sg_gn_apply_vcat(const void* raw, const float* partials, int P, const float*
   const int want = cdiv(148 * 8, rows);
   if (chunks > want) chunks = want > 1 ? want : 1;
   if (chunks < 1) chunks = 1;
+  SG_REQUIRE(C <= VCAT_MAXC, "sg_gn_apply_vcat: %d channels > %d", C, VCAT_MAXC);
   SG_REQUIRE(Cx == Cs, "sg_gn_apply_vcat: Cx=%d != Cs=%d (a thread pairs skip channel k with upsampled channel k)", Cx, Cs);
   // the kernel keeps a thread on the same channels: the grid stride (chunks * 256 threads) must be a multiple of Cs/8
   while (((int64_t)chunks * 256) % (Cs / 8) != 0) ++chunks;

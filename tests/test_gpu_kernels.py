@@ -118,7 +118,7 @@ def test_maxpool2(ops, shape):
     assert torch.equal(o16.cpu(), ref.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("h,cx,cs", [(2, 256, 256), (8, 128, 128), (32, 64, 64), (1, 64, 64)])
+@pytest.mark.parametrize("h,cx,cs", [(2, 256, 256), (8, 128, 128), (32, 64, 64), (1, 64, 64), (4, 64, 128), (4, 12, 4), (16, 8, 8)])
 def test_upsample_cat(ops, h, cx, cs):
     rows = 2
     x = torch.randn(rows, h, h, cx, generator=gen(2))
