@@ -244,9 +244,15 @@ def run_reference(args):
 
 
 def workload_config(args, n, engine):
+    if (args.size, args.channels) == (64, 4):
+        which = "BASELINE configs[2]"  # the configuration the metric is quoted on
+    elif (args.size, args.channels) == (256, 1):
+        which = "BASELINE configs[4] (pixel-space 256x256, attention-dominated)"
+    else:
+        which = "non-baseline geometry"
     return {
-        "workload": "BASELINE configs[2]: full CFG-DDPM sampling loop, cond+uncond batched 2x, cfg_scale=3, "
-                    f"noise_steps={T_STEPS}, latent [{args.channels},{args.size},{args.size}], {NUM_CLASSES} classes",
+        "workload": f"{which}: full CFG-DDPM sampling loop, cond+uncond batched 2x, cfg_scale=3, "
+                    f"noise_steps={T_STEPS}, UNet input [{args.channels},{args.size},{args.size}], {NUM_CLASSES} classes",
         "batch_per_gpu": n, "engine": engine,
         "step": "one denoising timestep over the batch (2n UNet rows + CFG lerp + posterior update + noise)",
         "timesteps_per_spectrogram": T_STEPS - 1,
