@@ -801,7 +801,18 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
     const uint32_t ph = (uint32_t)j & 1u;
     mbar_wait(s_full, ph);
     tc_fence_after();
-    if (j == 0) m_ref = tile_max();
+    if (j == 0) {
+      // initial reference: the maximum of the row's first 16 scores only (1/8 of the full-tile pre-pass).  Any reference
+      // within 2^redo_log2 of the true maximum is exact enough -- P keeps its relative precision in bf16 / fp16 and the
+      // row sum is fp32 -- and one that is too low is caught by the overflow guard below like on any later tile.
+      uint32_t v[16];
+      tmem_ld16(t_row, v);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+      m_ref = mx;
+    }
     // The reference m_ref is NOT tracked per tile (that costs an FMNMX per pair): p = exp2((s - m_ref) c) may exceed 1.
     // Overflow guard: the tile's row sum (MUFU lanes saturate to +inf) and the maximum over the polynomial lanes only
     // (their exponent arithmetic wraps instead of saturating).  If either exceeds 2^redo_log2 the reference is raised

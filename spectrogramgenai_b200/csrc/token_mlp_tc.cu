@@ -36,7 +36,8 @@ struct Tok {
   static constexpr int WIN_KB = 3 * C * 128;    // one k-block of Win [3C x C]
   static constexpr int WIN_TILE = KB * WIN_KB;
   static constexpr int TAIL_SMEM = 1024 + 3 * W_TILE + A_TILE + X_TILE + 5 * C * 4 + 128;
-  static constexpr int INPROJ_SMEM = 1024 + WIN_TILE + X_TILE + A_TILE + 5 * C * 4 + 128;
+  static constexpr int INPROJ_XBUF = C == 64 ? 2 : 1;  // x tiles in flight (C = 64: the next tile's x is prefetched)
+  static constexpr int INPROJ_SMEM = 1024 + WIN_TILE + INPROJ_XBUF * X_TILE + A_TILE + 5 * C * 4 + 128;
   static constexpr int TAIL_TMEM = 2 * C;               // two accumulators [128 x C]: 128 / 256 columns
   static constexpr int INPROJ_TMEM = C == 64 ? 256 : 512;  // one accumulator [128 x 3C]
   static constexpr int TAIL_CTAS = C == 64 ? 3 : 1;
@@ -405,22 +406,25 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sW = smem;                // Win: C/64 k-blocks of [3C x 64] 16-bit, SWIZZLE_128B
-  uint8_t* sX = sW + T::WIN_TILE;    // x tile (fp32); with sA the staging of the 3C/64 16-bit output boxes
-  uint8_t* sA = sX + T::X_TILE;      // LN(x) operand tile
+  constexpr int NBUF = T::INPROJ_XBUF;
+  uint8_t* sX = sW + T::WIN_TILE;    // x tile(s) (fp32); the consumed tile + sA stage the 3C/64 16-bit output boxes
+  uint8_t* sA = sX + NBUF * T::X_TILE;  // LN(x) operand tile
   float* sPar = reinterpret_cast<float*>(sA + T::A_TILE);  // ln_g | ln_b | bias[3C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 5 * C);
   uint64_t* w_full = bars;
-  uint64_t* in_full = bars + 1;
-  uint64_t* mma_done = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* in_full = bars + 1;  // [NBUF]
+  uint64_t* mma_done = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   static_assert(T::X_TILE + T::A_TILE == (N / 64) * T::A_ATOM, "output staging = x tile + operand tile");
+  constexpr int XBOXES = T::X_TILE / T::A_ATOM;  // output boxes staged in the x tile; the rest go to sA
 
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     prefetch_tensormap(&tm_x);
     prefetch_tensormap(&tm_qkv);
     mbar_init(w_full, 1);
-    mbar_init(in_full, 1);
+    mbar_init(&in_full[0], 1);
+    mbar_init(&in_full[1], 1);
     mbar_init(mma_done, 1);
     fence_barrier_init();
   }
@@ -434,8 +438,13 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t aA = smem_u32(sA), aX = smem_u32(sX), aW = smem_u32(sW);
+  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
   const int r = tid;
+  auto load_x = [&](int tile, int buf) {  // one elected lane
+    mbar_arrive_expect_tx(&in_full[buf], T::X_TILE);
+#pragma unroll
+    for (int j = 0; j < T::XB; ++j) tma_load_2d(sX + buf * T::X_TILE + j * (TM * 128), &tm_x, &in_full[buf], j * 32, tile * TM);
+  };
 
   if (warp == 0 && elect_one()) {
     mbar_arrive_expect_tx(w_full, T::WIN_TILE);
@@ -445,19 +454,25 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       if (N > NA) tma_load_2d(sW + kb * T::WIN_KB + NA * 128, &tm_w2, w_full, kb * 64, NA);  // rows [NA, N)
     }
   }
-  uint32_t in_ph = 0, mma_ph = 0;
+  uint32_t mma_ph = 0;
   bool first = true;
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+  if (NBUF == 2 && warp == 0 && elect_one() && (int)blockIdx.x < p.ntiles) load_x(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int m0 = tile * TM;
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    const uint32_t aX = smem_u32(sX + buf * T::X_TILE);
     if (warp == 0 && elect_one()) {
-      tma_store_wait_read();  // the previous tile's qkv boxes (staged in sX | sA) have left shared memory
-      mbar_arrive_expect_tx(in_full, T::X_TILE);
-#pragma unroll
-      for (int j = 0; j < T::XB; ++j) tma_load_2d(sX + j * (TM * 128), &tm_x, in_full, j * 32, m0);
+      tma_store_wait_read();  // the previous tile's qkv boxes (staged in its x tile | sA) have left shared memory
+      if (NBUF == 2) {
+        // prefetch: the other buffer staged the previous tile's output and is free now; the load overlaps this tile
+        if (tile + (int)gridDim.x < p.ntiles) load_x(tile + gridDim.x, buf ^ 1);
+      } else {
+        load_x(tile, 0);
+      }
     }
     __syncthreads();  // nobody writes sA (LN output) before the previous stores have drained
-    mbar_wait(in_full, in_ph);
-    in_ph ^= 1u;
+    mbar_wait(&in_full[buf], NBUF == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u));
     {
       float a[C];
 #pragma unroll
@@ -486,10 +501,10 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
     tc_fence_after();
-    // qkv rows -> 3C/64 [128 x 64] 16-bit SWIZZLE_128B boxes at sX + b * 16 KB (the tail of them = sA: its GEMM is complete)
+    // qkv rows -> 3C/64 [128 x 64] 16-bit SWIZZLE_128B boxes in the consumed x tile, the last ones in sA (its GEMM is complete)
 #pragma unroll 1
     for (int b = 0; b < N / 64; ++b) {
-      const uint32_t box = aX + (uint32_t)b * T::A_ATOM;
+      const uint32_t box = b < XBOXES ? aX + (uint32_t)b * T::A_ATOM : aA + (uint32_t)(b - XBOXES) * T::A_ATOM;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
@@ -512,7 +527,8 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     __syncthreads();
     if (warp == 0 && elect_one()) {
 #pragma unroll
-      for (int b = 0; b < N / 64; ++b) tma_store_2d(&tm_qkv, sX + b * T::A_ATOM, b * 64, m0);
+      for (int b = 0; b < N / 64; ++b)
+        tma_store_2d(&tm_qkv, b < XBOXES ? sX + buf * T::X_TILE + b * T::A_ATOM : sA + (b - XBOXES) * T::A_ATOM, b * 64, m0);
       tma_store_commit();
     }
   }
