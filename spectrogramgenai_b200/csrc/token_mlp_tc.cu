@@ -180,9 +180,10 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
   float* sPar = reinterpret_cast<float*>(sX + T::X_TILE);  // bo | ln_g | ln_b | b1 | b2
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 5 * C);
   uint64_t* w_full = bars;
-  uint64_t* in_full = bars + 1;
+  uint64_t* att_full = bars + 1;
   uint64_t* mma_done = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* x_full = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
@@ -190,7 +191,8 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     prefetch_tensormap(&tm_x);
     prefetch_tensormap(&tm_out);
     mbar_init(w_full, 1);
-    mbar_init(in_full, 1);
+    mbar_init(att_full, 1);
+    mbar_init(x_full, 1);
     mbar_init(mma_done, 1);
     fence_barrier_init();
   }
@@ -220,21 +222,39 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
       tma_load_2d(sW + 2 * T::W_TILE + kb * T::W_KB, &tm_w2, w_full, kb * 64, 0);
     }
   }
+  auto load_att = [&](int tile) {  // one elected lane
+    mbar_arrive_expect_tx(att_full, T::A_TILE);
+#pragma unroll
+    for (int kb = 0; kb < T::KB; ++kb) tma_load_2d(sA + kb * T::A_ATOM, &tm_att, att_full, kb * 64, tile * TM);
+  };
+  auto load_x = [&](int tile) {
+    mbar_arrive_expect_tx(x_full, T::X_TILE);
+#pragma unroll
+    for (int j = 0; j < T::XB; ++j) tma_load_2d(sX + j * (TM * 128), &tm_x, x_full, j * 32, tile * TM);
+  };
+  // When the block output is not written (fused outc), sX is never an output staging buffer: the next tile's x is
+  // fetched as soon as this tile's x has been read, and its att as soon as the last GEMM has released sA.
+  const bool prefetch = OUTC && !p.write_out;
   uint32_t in_ph = 0, mma_ph = 0;
   bool first = true;
+  if (prefetch && warp == 0 && (int)blockIdx.x < p.ntiles) {
+    if (elect_one()) {
+      load_att(blockIdx.x);
+      load_x(blockIdx.x);
+    }
+    __syncwarp();
+  }
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int m0 = tile * TM;
+    const int next = tile + (int)gridDim.x;
     if (warp == 0) {
-      if (elect_one()) {
+      if (!prefetch && elect_one()) {
         tma_store_wait_read();  // the previous tile's output (staged in sX) has left shared memory
-        mbar_arrive_expect_tx(in_full, T::A_TILE + T::X_TILE);
-#pragma unroll
-        for (int kb = 0; kb < T::KB; ++kb) tma_load_2d(sA + kb * T::A_ATOM, &tm_att, in_full, kb * 64, m0);
-#pragma unroll
-        for (int j = 0; j < T::XB; ++j) tma_load_2d(sX + j * (TM * 128), &tm_x, in_full, j * 32, m0);
+        load_att(tile);
+        load_x(tile);
       }
       if (first) mbar_wait_spin(w_full, 0);
-      mbar_wait_spin(in_full, in_ph);
+      mbar_wait_spin(att_full, in_ph);
       tc_fence_after();
       if (elect_one()) {
         gemm_kc<C>(tmem_base, aA, aW, T::W_KB, 0, p.idesc);  // att Wo^T
@@ -247,7 +267,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
     tc_fence_after();
-    mbar_wait(in_full, in_ph);  // the x tile is visible to this thread (acquire on the TMA barrier)
+    mbar_wait(x_full, in_ph);  // the x tile is visible to this thread (acquire on the TMA barrier)
     in_ph ^= 1u;
     float a[C];
 #pragma unroll
@@ -274,6 +294,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
       if (elect_one()) {
         gemm_kc<C>(tmem_base + C, aA, aW + T::W_TILE, T::W_KB, 0, p.idesc);  // LN(a) W1^T
         umma_commit(mma_done);
+        if (prefetch && next < p.ntiles) load_x(next);  // every thread has read its x row (barrier above)
       }
       __syncwarp();
     }
@@ -316,6 +337,10 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
     tc_fence_after();
+    if (prefetch && next < p.ntiles && warp == 0) {
+      if (elect_one()) load_att(next);  // the last GEMM has completed: sA is free
+      __syncwarp();
+    }
     const bool stage = !OUTC || p.write_out;
     float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
     if constexpr (OUTC) {
