@@ -143,7 +143,8 @@ class UNetPlan:
 
     def _op(self, fn, *a, **kw):
         self.ops.append((fn, a, kw))
-        self.n_launches += 1
+        # kernels per entry point: sg_conv_in and sg_attn_tail_outc first rewrite their constant weight bank (one block)
+        self.n_launches += 2 if (fn is ops.conv_in or kw.get("outc") is not None) else 1
 
     def _pair(self, shape, want_f32=True, want_act=True):
         """(fp32 buffer, GEMM-operand buffer) for one logical tensor; in fp32 mode they are the same buffer."""
