@@ -9,6 +9,9 @@
 //                                V = 5  packed body without the row sum (tensor-core row sums)
 //                                V = 6  packed body, no exponential at all (p = x): the cost of everything else
 //                                V = 7  packed body, MUFU, but no 16-bit pack (stores raw words): is F2FP the limiter?
+//                                V = 8 / 9 / 10  lazy reference (max only on polynomial lanes), no row sum (tensor-core row sums),
+//                                                1/4 / 3/8 / 1/2 polynomial pairs
+//                                V = 11 / 12     lazy reference, row sum in the body, 1/4 (= the attention kernel today) / 3/8 polynomial
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/mufu_bench scripts/mufu_bench.cu
 #include <cstdint>
 #include <cstdio>
@@ -53,9 +56,9 @@ __global__ void __launch_bounds__(512) k_ex2(float* out, int iters) {
 }
 
 template <int V> __device__ __forceinline__ bool use_poly(int pair) {
-  if (V == 2) return (pair & 3) == 3;
-  if (V == 3) return (pair & 7) == 2 || (pair & 7) == 5 || (pair & 7) == 7;
-  if (V == 4) return (pair & 1) == 1;
+  if (V == 2 || V == 8 || V == 11) return (pair & 3) == 3;
+  if (V == 3 || V == 9 || V == 12) return (pair & 7) == 2 || (pair & 7) == 5 || (pair & 7) == 7;
+  if (V == 4 || V == 10) return (pair & 1) == 1;
   return false;
 }
 
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_softmax(float* out, int iters, f
       const uint64_t nmc2 = pk2(-mc, -mc);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        tmax = max3(tmax, v[i], v[i + 1]);
+        if (V < 8 || use_poly<V>(i >> 1)) tmax = max3(tmax, v[i], v[i + 1]);  // V >= 8: lazy reference, guard on polynomial lanes only
         const uint64_t x2 = fma2(pk2(v[i], v[i + 1]), c2, nmc2);
         float p0, p1;
         if (use_poly<V>(i >> 1)) {
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_softmax(float* out, int iters, f
           p1 = ex2(x1);
         }
         pk[i >> 1] = V == 7 ? (__float_as_uint(p0) ^ __float_as_uint(p1)) : pack(p0, p1);
-        if (V != 5) psum2 = add2(psum2, pk2(p0, p1));
+        if (V != 5 && (V < 8 || V > 10)) psum2 = add2(psum2, pk2(p0, p1));
       }
     }
 #pragma unroll
@@ -158,6 +161,7 @@ int main() {
   run<4, 5>(2); run<4, 5>(4); run<8, 5>(4);
   run<4, 6>(4); run<8, 6>(4);
   run<4, 7>(4); run<8, 7>(4);
+  run<4, 11>(4); run<4, 12>(4); run<4, 8>(4); run<4, 9>(4); run<4, 10>(4); run<8, 11>(4); run<8, 8>(4); run<8, 9>(4); run<8, 10>(4);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

@@ -23,6 +23,8 @@
 // is in attention_version() below and in profiles/README.md.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace sg {
@@ -31,6 +33,7 @@ namespace tc {
 constexpr int ATT_BM = 128;   // queries per CTA
 constexpr int ATT_BN = 128;   // keys per tile
 constexpr int P_BYTES = ATT_BM * ATT_BN * 2;  // 32 KB: two SWIZZLE_128B atoms of 64 keys
+constexpr int ATT11_ONES = 2048;               // v11: [16 keys x d] 16-bit tile of ones (d <= 64)
 
 // generic K-/MN-major descriptor for tiles whose rows are one swizzle span of `row_bytes` (32 / 64 / 128)
 __device__ __forceinline__ uint64_t make_desc_rows(uint32_t saddr, int row_bytes) {
@@ -78,9 +81,10 @@ struct AttGeom {
   int nkv;            // key tiles per query tile
   float c;            // softmax scale * log2(e)
   uint32_t tile_bytes;  // bytes of one TMA box (d*2 * min(128, M))
-  uint32_t idesc_s, idesc_o, idesc_1;
+  uint32_t idesc_s, idesc_o, idesc_1, idesc_ol;  // idesc_ol: v11, N = d + 16 (O partial | row sums)
   int act_dtype;
   float redo_log2;  // largest tolerated (tile max - reference max) * c before the tile is recomputed
+  float l_max;      // v11: largest tolerated row sum of one key tile in the fast pass
 };
 
 constexpr int ONES_BYTES = 2048;  // a [16 x 64] 16-bit K-major tile of 1.0: B operand of the row-sum MMA
@@ -949,6 +953,309 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   }
 }
 
+// v11 = v8 with the row sums taken from the tensor core and a two-pass overflow scheme.
+//  * l = sum_j p_ij comes from eight extra M128 x N16 x K16 MMAs per key tile (A = the P tile the PV MMAs read, B = a
+//    512-byte tile of ones), accumulated next to the O partial in the dead S columns: the sweep loses its FADD2 per pair,
+//    which moves the balance point between the MUFU and the FMA pipe from 1/4 to 3/8 polynomial pairs
+//    (scripts/mufu_bench.cu: +9 % on the isolated body; in the kernel 4.11 -> 3.86 ms at sa6, rows = 256).
+//  * pass 0 (fast) never looks for the maximum: the reference is the maximum of the row's first 16 scores and a tile
+//    whose row sum (from the tensor core: +inf / NaN if a p overflowed) or polynomial-lane exponent leaves the safe
+//    range only raises a flag.  If any row of the CTA raised it, the whole query tile is recomputed in pass 1 (safe):
+//    the classical online softmax with a full-tile maximum before every sweep, where p <= 1 always.
+template <int D, int DT, int POLY, int NACC>
+__global__ void __launch_bounds__(128, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
+attention_tc11_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
+  constexpr int ROWB = D * 2;
+  constexpr int TILE = ATT_BN * ROWB;
+  // TMEM columns of accumulator a (NACC independent accumulation chains over the 8 k-steps of a key tile):
+  // O partial [a W, a W + D), row-sum partial [a W + D, a W + D + 16) (16 identical columns), W = D + 16
+  constexpr int W = D + 16;
+  static_assert(NACC * W <= 128 && (ATT_BN / 16) % NACC == 0, "accumulators must fit the dead S columns");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE;      // [2 stages]
+  uint8_t* sV = sK + 2 * TILE;  // [2 stages]
+  uint8_t* sP = sV + 2 * TILE;
+  uint8_t* sOnes = sP + P_BYTES;  // [16 keys x D] 16-bit ones in V's layout: the second N atom of the PV MMAs' B operand
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ATT11_ONES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;  // [2]
+  uint64_t* s_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // heads are the FASTEST grid dimension: the head slices of a token (d * 2 = 32..128 bytes) share 128-byte lines, so
+  // the heads of one query tile must run together to be served from L2 (with heads slowest, ncu showed 4x the
+  // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
+  const int head = blockIdx.x;
+  const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
+  const int64_t kv0 = (m0 >> g.logL) << g.logL;
+  const int nkv = g.L / ATT_BN;
+  const bool leader = threadIdx.x == 0;
+
+  if (leader) {
+    prefetch_tensormap(&tm);
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  {
+    const uint32_t one2 = DT == SG_BF16 ? 0x3F803F80u : 0x3C003C00u;  // two 1.0 values
+    for (int i = threadIdx.x; i < 16 * ROWB / 4; i += 128) reinterpret_cast<uint32_t*>(sOnes)[i] = one2;
+    fence_proxy_async();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc<128>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Issue helpers: called by ALL lanes of warp 0 (convergent); one elected lane executes the TMA / MMA instructions.
+  const uint64_t q_desc = make_desc_rows(smem_u32(sQ), ROWB);
+  const uint64_t p_desc = make_desc_k128(smem_u32(sP));
+  // barrier parities continue across the two passes: pass 1 starts after nkv completions of s_full / o_full and
+  // ceil / floor (nkv / 2) completions of kv_full[0] / kv_full[1]
+  int so_off = 0, kv_off0 = 0, kv_off1 = 0;
+  const uint32_t ones_addr = smem_u32(sOnes);
+  auto load_tile = [&](int t) {
+    const int s = t & 1;
+    const int tok = (int)(kv0 + (int64_t)t * ATT_BN);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
+      tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
+      tma_load_2d(sV + s * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
+    }
+  };
+  auto issue_s = [&](int t) {  // S = Q K_t^T
+    mbar_wait_spin(&kv_full[t & 1], (uint32_t)((t >> 1) + ((t & 1) ? kv_off1 : kv_off0)) & 1u);
+    tc_fence_after();
+    const uint64_t kd = make_desc_rows(smem_u32(sK + (t & 1) * TILE), ROWB);
+    if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base, q_desc + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
+      umma_commit(s_full);
+    }
+  };
+  auto issue_pv = [&](int t) {  // O_t = P V_t : A = P (K-major, two SWIZZLE_128B atoms of 64 keys), B = V MN-major
+    tc_fence_after();
+    const uint64_t vd = make_desc_rows(smem_u32(sV + (t & 1) * TILE), ROWB);
+    if (elect_one()) {
+      // B = [V slab | ones slab]: N = D + 16 columns of an MN-major operand are two swizzle atoms along N, and the
+      // descriptor's leading-dimension offset is the distance between them -- the second atom is the tile of ones, so
+      // the same MMA (one read of P) yields the O partial in columns [0, D) and the row sums in [D, D + 16)
+      const uint32_t v0 = smem_u32(sV + (t & 1) * TILE);
+#pragma unroll
+      for (int k = 0; k < ATT_BN / 16; ++k) {
+        const uint64_t pd = p_desc + (uint64_t)((k >> 2) * (ATT_BM * 128 / 16) + (k & 3) * 2);
+        const uint32_t slab = v0 + (uint32_t)(k * 16 * ROWB);
+        const uint64_t bd = (make_desc_rows(slab, ROWB) & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((ones_addr - slab) >> 4) << 16);
+        umma_ss(tmem_base + (uint32_t)((k % NACC) * W), pd, bd, g.idesc_ol, k >= NACC);
+      }
+      umma_commit(o_full);
+    }
+  };
+  const int r = warp * 32 + lane;
+  const int64_t tok = m0 + r;
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+  const uint32_t rx = (uint32_t)(r & 7);
+  uint64_t o2[D / 2];
+  float m_ref = 0.f, l = 0.f;
+  const uint64_t c2 = pk2(g.c, g.c);
+  // row maximum of the current S tile (safe pass only)
+  auto tile_max = [&]() {
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t v[16];
+      tmem_ld16(t_row + ch * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+    }
+    return mx;
+  };
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, g.tile_bytes);
+      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
+    }
+    __syncwarp();
+  }
+  // one pass over the key tiles; `safe` is a compile-time tag so that the fast pass carries none of the safe pass's code
+  auto run_pass = [&](auto safe_tag) -> bool {
+    constexpr bool safe = decltype(safe_tag)::value;
+    if (warp == 0) {
+      load_tile(0);
+      if (nkv > 1) load_tile(1);
+      if (!safe) mbar_wait_spin(q_full, 0);
+      issue_s(0);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < D / 2; ++i) o2[i] = 0ull;  // two +0.0f
+    l = 0.f;
+    m_ref = -INFINITY;
+    bool bad = false;
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t ph = (uint32_t)(j + so_off) & 1u;
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      if constexpr (safe) {
+        const float tmax = tile_max();
+        if (tmax > m_ref) {  // exact rescale of the running numerator / denominator (a0 = 0 on the first tile)
+          const float a0 = ex2((m_ref - tmax) * g.c);
+          l *= a0;
+          const uint64_t a2 = pk2(a0, a0);
+#pragma unroll
+          for (int i = 0; i < D / 2; ++i) o2[i] = mul2(o2[i], a2);
+          m_ref = tmax;
+        }
+      } else if (j == 0) {
+        // fast pass: the reference is the maximum of the row's first 16 scores.  Any reference within the dynamic
+        // range of the 16-bit P / fp32 sums is exact enough, and it is never searched for again.
+        uint32_t v[16];
+        tmem_ld16(t_row, v);
+        tmem_ld_wait();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        m_ref = mx;
+      }
+      const float nmc = -m_ref * g.c;
+      const uint64_t nmc2 = pk2(nmc, nmc);
+      float xmax = -INFINITY;  // largest exponent seen by a polynomial lane (its exponent arithmetic wraps, no +inf)
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld16(t_row, va);
+        tmem_ld_wait();
+        auto chunk = [&](const uint32_t(&v)[16], int ch) {  // 16 columns: 8 pairs -> two 16-byte stores of the P row
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const uint64_t x2 = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nmc2);
+            float p0, p1, x0, x1;
+            un2(x2, x0, x1);
+            if (pair_is_poly<POLY>(i >> 1)) {
+              xmax = max3(xmax, x0, x1);
+              ex2_poly2(x2, p0, p1);
+            } else {
+              p0 = ex2(x0);
+              p1 = ex2(x1);
+            }
+            pk[i >> 1] = pack_pair<DT>(p0, p1);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int jj = ch * 2 + u;
+            const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + ((((uint32_t)jj & 7u) ^ rx) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
+                         "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
+                         : "memory");
+          }
+        };
+#pragma unroll
+        for (int ch = 0; ch < 8; ch += 2) {
+          tmem_ld16(t_row + (ch + 1) * 16, vb);  // in flight while chunk ch is processed
+          chunk(va, ch);
+          tmem_ld_wait();
+          if (ch + 2 < 8) tmem_ld16(t_row + (ch + 2) * 16, va);
+          chunk(vb, ch + 1);
+          if (ch + 2 < 8) tmem_ld_wait();
+        }
+      }
+      tc_fence_before();    // our tcgen05.ld of S precede the MMA that overwrites those columns
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      if (warp == 0) {
+        named_bar_sync<1, 128>();
+        issue_pv(j);
+        __syncwarp();
+      } else {
+        named_bar_arrive<1, 128>();
+      }
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      float l_part = 0.f;
+#pragma unroll
+      for (int acc = 0; acc < NACC; ++acc) {
+        if constexpr (D == 16) {
+          uint32_t v[32];
+          tmem_ld32(t_row + acc * W, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) o2[i >> 1] = add2(o2[i >> 1], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          l_part += __uint_as_float(v[16]);
+        } else {
+#pragma unroll
+          for (int cch = 0; cch < D / 32; ++cch) {
+            uint32_t v[32];
+            tmem_ld32(t_row + acc * W + cch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2)
+              o2[cch * 16 + (i >> 1)] = add2(o2[cch * 16 + (i >> 1)], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          }
+          uint32_t v[16];
+          tmem_ld16(t_row + acc * W + D, v);
+          tmem_ld_wait();
+          l_part += __uint_as_float(v[0]);
+        }
+      }
+      l += l_part;
+      bad |= !(l_part <= g.l_max) || xmax > g.redo_log2;  // NaN-safe
+      tc_fence_before();
+      if (j + 1 < nkv) {
+        if (warp == 0) {
+          named_bar_sync<2, 128>();
+          // o_full(j) has been observed: every MMA that read K/V stage j&1 is complete -> it can be refilled with tile j+2
+          issue_s(j + 1);
+          if (j + 2 < nkv) load_tile(j + 2);
+          __syncwarp();
+        } else {
+          named_bar_arrive<2, 128>();
+        }
+      }
+    }
+    return bad;
+  };
+  // every row of the CTA takes the same decision: the MMAs are issued for the whole query tile
+  if (__syncthreads_or(run_pass(std::false_type{}))) {
+    so_off = nkv;
+    kv_off0 = (nkv + 1) >> 1;
+    kv_off1 = nkv >> 1;
+    run_pass(std::true_type{});
+  }
+  const float inv = 1.0f / l;
+  uint16_t* dst = out + tok * g.C + head * D;
+#pragma unroll
+  for (int i = 0; i < D; i += 8) {
+    float f[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) un2(o2[(i >> 1) + u], f[2 * u], f[2 * u + 1]);
+    uint4 w;
+    w.x = pack_pair<DT>(f[0] * inv, f[1] * inv);
+    w.y = pack_pair<DT>(f[2] * inv, f[3] * inv);
+    w.z = pack_pair<DT>(f[4] * inv, f[5] * inv);
+    w.w = pack_pair<DT>(f[6] * inv, f[7] * inv);
+    *reinterpret_cast<uint4*>(dst + i) = w;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
 template <int D, int DT, int POLY, int NACC>
 static int launch_att8(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
   constexpr int smem = att4_smem_bytes<D>();
@@ -974,6 +1281,36 @@ static int dispatch_att8(const CUtensorMap& tm, const AttGeom& g, uint16_t* out,
   return launch_att8<D, DT, 2, 2>(tm, g, out, grid, stream);
 }
 
+template <int D, int DT, int POLY, int NACC>
+static int launch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = att4_smem_bytes<D>() + ATT11_ONES;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc11_kernel<D, DT, POLY, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("sg_attention(tc11): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
+      return SG_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  attention_tc11_kernel<D, DT, POLY, NACC><<<grid, 128, smem, stream>>>(tm, g, out);
+  return launch_status("sg_attention(tc11)");
+}
+
+template <int D, int DT>
+static int dispatch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
+  static const int poly = env_int("SGB200_ATTN_POLY11", 3);  // eighths of the pairs evaluated by the polynomial
+  static const int nacc = env_int("SGB200_ATTN_NACC11", 2);
+  constexpr int NA = D == 64 ? 1 : 2;
+  if (nacc == 1) {
+    if (poly == 2) return launch_att11<D, DT, 2, 1>(tm, g, out, grid, stream);
+    return launch_att11<D, DT, 3, 1>(tm, g, out, grid, stream);
+  }
+  if (poly == 2) return launch_att11<D, DT, 2, NA>(tm, g, out, grid, stream);
+  if (poly == 4) return launch_att11<D, DT, 4, NA>(tm, g, out, grid, stream);
+  return launch_att11<D, DT, 3, NA>(tm, g, out, grid, stream);
+}
+
 // fraction of exponentials evaluated by the FMA-pipe polynomial: SGB200_ATTN_POLY = 0 (none), 4 (1/4), 2 (1/2)
 static int attention_poly() {
   static int v = -1;
@@ -988,16 +1325,16 @@ static int attention_poly() {
 static int attention_version() {
   static int v = -1;
   if (v < 0) {
-    // SGB200_ATTN: 0 = auto (default): v8 for L >= 128, v1 below (block-diagonal tile over 128/L batch rows);
-    // 1 = v1 everywhere, 3 = v3 (TMEM-resident O, 128-d key tiles) for L >= 256, 8 = v8.
+    // SGB200_ATTN: 0 = auto (default): L >= 128: v11 for d = 16, v8 otherwise; v1 below (block-diagonal tile over 128/L
+    // batch rows); 1 = v1 everywhere, 3 = v3 (TMEM-resident O, 128-d key tiles) for L >= 256, 8 = v8, 11 = v11.
     // Measured on B200 (rows=128, bf16, ms); v2/v4/v5/v7/v9/v10 were experiments, removed (see profiles/README.md):
-    //                           v1     v2    v3     v4     v5     v7     v8     v9     v10
+    //                           v1     v2    v3     v4     v5     v7     v8     v9     v10    v11 (rows=256: v8 4.11 / v11 3.98)
     //   d=16 L=4096 (sa6)       3.07   3.57  3.12   2.82   2.43   3.41   2.12   2.48   2.25
     //   d=32 L=1024 (sa1)       0.347  -     0.267  0.234  0.227  0.348  0.188  0.220  0.184
     //   d=16 L=1024 (sa5)       0.226  -     -      0.200  0.183  0.237  0.152  0.175  0.158
     const char* e = getenv("SGB200_ATTN");
     v = e ? atoi(e) : 0;
-    if (v != 1 && v != 3 && v != 8) v = 0;
+    if (v != 1 && v != 3 && v != 8 && v != 11) v = 0;
   }
   return v;
 }
@@ -1027,7 +1364,9 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
   g.idesc_s = make_idesc(act_dtype, 128, ATT_BN, 0, 0);
   g.idesc_o = make_idesc(act_dtype, 128, d, 0, 1);  // B = V is MN-major
   g.idesc_1 = make_idesc(act_dtype, 128, 16, 0, 0);
+  g.idesc_ol = make_idesc(act_dtype, 128, d + 16, 0, 1);
   g.redo_log2 = act_dtype == SG_BF16 ? 60.0f : 13.0f;  // p <= 2^60 (bf16/fp32 range) / 2^13 (fp16 max 65504)
+  g.l_max = act_dtype == SG_BF16 ? 1.152921504606847e18f : 16777216.0f;  // 2^60 / 2^24 (an overflowed fp16 p is +inf)
   g.act_dtype = act_dtype;
   CUtensorMap tm;
   const uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)g.M};
@@ -1041,6 +1380,17 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
   SG_REQUIRE(tiles <= 32768 || tiles % 32768 == 0, "sg_attention(tc): %lld query tiles (must be <= 32768 or a multiple of it)", (long long)tiles);
   dim3 grid((unsigned)heads, (unsigned)(tiles < 32768 ? tiles : 32768), (unsigned)cdiv(tiles, 32768));
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  // auto: v11 for d = 16 (sa5 / sa6: measured 3.2 % / 2.4 % faster than v8); its N = d + 16 PV MMA is slower than v8's at d = 32
+  if (L >= ATT_BN && (attention_version() == 11 || (attention_version() == 0 && d == 16))) {
+    if (act_dtype == SG_BF16) {
+      if (d == 16) return dispatch_att11<16, SG_BF16>(tm, g, o, grid, stream);
+      if (d == 32) return dispatch_att11<32, SG_BF16>(tm, g, o, grid, stream);
+      return dispatch_att11<64, SG_BF16>(tm, g, o, grid, stream);
+    }
+    if (d == 16) return dispatch_att11<16, SG_F16>(tm, g, o, grid, stream);
+    if (d == 32) return dispatch_att11<32, SG_F16>(tm, g, o, grid, stream);
+    return dispatch_att11<64, SG_F16>(tm, g, o, grid, stream);
+  }
   if (L >= ATT_BN && (attention_version() == 8 || attention_version() == 0)) {
     if (act_dtype == SG_BF16) {
       if (d == 16) return dispatch_att8<16, SG_BF16>(tm, g, o, grid, stream);

@@ -546,6 +546,30 @@ def test_attention_tensor_core_growing_scores(ops, rows, L, C, dtype):
     assert err < (8e-3 if dtype == torch.bfloat16 else 1.5e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,L,C", [(2, 512, 64), (1, 4096, 64), (1, 256, 128)])
+def test_attention_tensor_core_reference_overflow(ops, rows, L, C, dtype):
+    """Scores whose spread exceeds the dynamic range of the fast pass (the d = 16 kernel takes the maximum of a row's
+    first 16 scores as the softmax reference and never searches for it again): later keys beat that reference by far
+    more than 2^60, the tile row sums overflow, and the query tile must be recomputed by the safe pass (full-tile
+    maximum before every sweep).  Rows are nearly one-hot, so the result is essentially one V row."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    qkv = torch.randn(rows * L, 3 * C, generator=gen(14))
+    ramp = (0.05 + 60.0 * (torch.arange(L) / L) ** 2).repeat(rows)[:, None]  # tiny first keys, huge last ones
+    qkv[:, C:2 * C] *= ramp
+    qkv[:, :C] *= 3.0
+    qkv = qkv.to(dtype)
+    ref = _attention_ref(qkv.float(), rows, L, C)
+    out = torch.full((rows * L, C), float("nan"), device=DEV, dtype=dtype)
+    ops.attention(qkv.to(DEV), out, rows=rows, L=L, C=C, engine=SG_ENGINE_TC)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    err = O.rel_l2(out.cpu(), ref)
+    print(f"attention tc (reference overflow) rows={rows} L={L} C={C} {dtype}: rel-L2 {err:.3e}")
+    assert err < (8e-3 if dtype == torch.bfloat16 else 1.5e-3)
+
+
 def test_error_reporting(ops):
     """Bad arguments come back as a status + message (no exception crosses the C ABI, no crash)."""
     from spectrogramgenai_b200._cabi import SgError
