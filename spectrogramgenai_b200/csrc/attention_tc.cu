@@ -1300,7 +1300,7 @@ static int launch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, 
 template <int D, int DT>
 static int dispatch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
   static const int poly = env_int("SGB200_ATTN_POLY11", 3);  // eighths of the pairs evaluated by the polynomial
-  static const int nacc = env_int("SGB200_ATTN_NACC11", 2);
+  static const int nacc = env_int("SGB200_ATTN_NACC11", 1);
   constexpr int NA = D == 64 ? 1 : 2;
   if (nacc == 1) {
     if (poly == 2) return launch_att11<D, DT, 2, 1>(tm, g, out, grid, stream);
