@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 11
+#define SG_ABI_VERSION 12
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -210,6 +210,22 @@ int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base,
 
 /* ---- K8: (clamp(x,-1,1)+1)/2*255 -> truncating uint8 cast (:440-441) ---- */
 int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream);
+
+/* ---- forward-only training helpers (no backward pass) ----
+ * sg_noise_images: Diffusion.noise_images (:404-409).  x fp32 [n,E], t int64 [n] (index into alpha_hat fp32 [T]):
+ *   x_t = sqrt(alpha_hat[t]) * x + sqrt(1 - alpha_hat[t]) * eps, un-fused products / sum like the reference, so equal
+ *   eps gives bit-identical x_t.  eps_in fp32 [n,E], or NULL to draw N(0,1) from the Philox stream keyed by
+ *   (seed, sample_base + sample); eps_out (may be NULL) receives the eps used -- the method returns it.
+ * sg_ema_update: EMA.update_average (:37-40) in place: ma = ma * beta + one_minus_beta * cur (the reference passes the
+ *   Python float 1 - beta; both scalars are applied in fp32).
+ * sg_mse: nn.MSELoss() (:478) of two fp32 buffers -> *out (fp32 scalar); scratch = sg_mse_scratch_doubles() doubles;
+ *   deterministic (fixed partition, double partial sums).
+ */
+int sg_noise_images(const float* x, const int64_t* t, const float* alpha_hat, int T, int n, int E, const float* eps_in,
+                    uint64_t seed, int64_t sample_base, float* x_t, float* eps_out, sg_stream_t stream);
+int sg_ema_update(float* ma, const float* cur, int64_t n, float beta, float one_minus_beta, sg_stream_t stream);
+int sg_mse_scratch_doubles(void);
+int sg_mse(const float* a, const float* b, int64_t n, double* scratch, float* out, sg_stream_t stream);
 
 /* ---- weight repack, once per load_state_dict (UNet_conditional.load_state_dict / Diffusion.load :509-510) ----
  * w: a Conv2d / Linear weight of the reference state_dict, fp32 [Cout, Cin, taps] (taps = kh*kw: 9 for the 3x3 convs,

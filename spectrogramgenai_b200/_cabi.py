@@ -14,7 +14,7 @@ from . import build as _build
 
 SG_F32, SG_BF16, SG_F16 = 0, 1, 2
 SG_ENGINE_SIMT, SG_ENGINE_TC = 0, 1
-ABI_VERSION = 11
+ABI_VERSION = 12
 SG_ACT_NONE, SG_ACT_GELU, SG_ACT_RELU_POST = 0, 1, 2
 
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
@@ -60,6 +60,10 @@ PROTOTYPES = {
     "sg_to_uint8": (_i, [_vp, _i64, _vp, _vp]),
     "sg_to_uint8_wrap": (_i, [_vp, _i64, _vp, _vp]),
     "sg_pack_weights": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
+    "sg_noise_images": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _u64, _i64, _vp, _vp, _vp]),
+    "sg_ema_update": (_i, [_vp, _vp, _i64, _f, _f, _vp]),
+    "sg_mse_scratch_doubles": (_i, []),
+    "sg_mse": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "sg_vq_quantize": (_i, [_vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "sg_dec_in_proj": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sg_tconv2_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

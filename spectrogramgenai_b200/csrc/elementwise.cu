@@ -245,6 +245,78 @@ __global__ void __launch_bounds__(256) upsample_cat_paired_kernel(const float* _
   }
 }
 
+// ---- forward-only training helpers (the backward pass is not built) ----
+// Diffusion.noise_images (:404-409): x_t = sqrt(ah[t]) * x + sqrt(1 - ah[t]) * eps, un-fused like the reference's
+// two multiplies and one add; eps injected or drawn from the Philox stream (and written back, the method returns it)
+constexpr int NOISE_TAG = 1 << 20;  // Philox step tag of the training-noise stream (sampling uses 1..T)
+__global__ void __launch_bounds__(256) noise_images_kernel(const float* __restrict__ x, const int64_t* __restrict__ t,
+                                                           const float* __restrict__ alpha_hat, int T, int n, int E4,
+                                                           const float* __restrict__ eps_in, uint64_t seed,
+                                                           int64_t sample_base, float* __restrict__ x_t,
+                                                           float* __restrict__ eps_out) {
+  const int64_t total = (int64_t)n * E4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t sample = idx / E4;
+  int64_t ti = t[sample];
+  ti = ti < 0 ? ti + T : ti;  // python-style negative index, as alpha_hat[t] would take it
+  const float ah = alpha_hat[ti];
+  const float sa = __fsqrt_rn(ah), sb = __fsqrt_rn(__fsub_rn(1.0f, ah));
+  const float4 xv = reinterpret_cast<const float4*>(x)[idx];
+  float4 e;
+  if (eps_in) e = reinterpret_cast<const float4*>(eps_in)[idx];
+  else e = philox_normal4(seed, (uint64_t)(sample_base + sample), (uint32_t)NOISE_TAG, (uint32_t)(idx - sample * E4));
+  float4 o;
+  o.x = __fadd_rn(__fmul_rn(sa, xv.x), __fmul_rn(sb, e.x));
+  o.y = __fadd_rn(__fmul_rn(sa, xv.y), __fmul_rn(sb, e.y));
+  o.z = __fadd_rn(__fmul_rn(sa, xv.z), __fmul_rn(sb, e.z));
+  o.w = __fadd_rn(__fmul_rn(sa, xv.w), __fmul_rn(sb, e.w));
+  reinterpret_cast<float4*>(x_t)[idx] = o;
+  if (eps_out) reinterpret_cast<float4*>(eps_out)[idx] = e;
+}
+
+// EMA.update_average (:37-40): ma = ma * beta + (1 - beta) * cur, two rounded products and a rounded sum
+__global__ void __launch_bounds__(256) ema_update_kernel(float* __restrict__ ma, const float* __restrict__ cur, int64_t n,
+                                                         float beta, float one_minus_beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ma[i] = __fadd_rn(__fmul_rn(ma[i], beta), __fmul_rn(one_minus_beta, cur[i]));
+}
+
+// nn.MSELoss (:478), deterministic: MSE_BLOCKS partial sums in double (fixed assignment of elements to blocks), then a
+// fixed-order final sum by one block
+constexpr int MSE_BLOCKS = 1024;
+__global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          int64_t n, double* __restrict__ partial) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = __fsub_rn(a[i], b[i]);
+    s += (double)d * (double)d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tsum = 0.0;
+    for (int i = 0; i < 8; ++i) tsum += red[i];
+    partial[blockIdx.x] = tsum;
+  }
+}
+__global__ void __launch_bounds__(256) mse_final_kernel(const double* __restrict__ partial, int blocks, int64_t n,
+                                                        float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < blocks; i += 256) s += partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)(red[0] / (double)n);
+}
+
 // Weight repack (once per load_state_dict): Conv2d / Linear fp32 [Cout][Cin][taps] -> [taps][Cout][Cin] in the operand
 // dtype, K (= Cin) contiguous -- the B-operand layout of sg_igemm.  One thread per output element; rounding is
 // round-to-nearest-even (what torch's .to(bfloat16 / float16) does), fp16 overflow goes to inf (no saturation).
@@ -307,6 +379,33 @@ int sg_philox_normal(float* x, int n, int E, uint64_t seed, int64_t sample_base,
 int sg_to_uint8(const float* x, int64_t count, uint8_t* out, sg_stream_t stream) {
   SG_REQUIRE(x && out && count >= 0, "sg_to_uint8: bad arguments");
   return to_uint8_launch<false>(x, count, out, stream, "sg_to_uint8");
+}
+
+int sg_noise_images(const float* x, const int64_t* t, const float* alpha_hat, int T, int n, int E, const float* eps_in,
+                    uint64_t seed, int64_t sample_base, float* x_t, float* eps_out, sg_stream_t stream) {
+  SG_REQUIRE(x && t && alpha_hat && x_t, "sg_noise_images: null pointer");
+  SG_REQUIRE(n > 0 && E > 0 && E % 4 == 0 && T > 0, "sg_noise_images: bad shape n=%d E=%d T=%d", n, E, T);
+  const int64_t total = (int64_t)n * (E / 4);
+  noise_images_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(x, t, alpha_hat, T, n, E / 4, eps_in, seed,
+                                                                       sample_base, x_t, eps_out);
+  return launch_status("sg_noise_images");
+}
+
+int sg_ema_update(float* ma, const float* cur, int64_t n, float beta, float one_minus_beta, sg_stream_t stream) {
+  SG_REQUIRE(ma && cur && n >= 0, "sg_ema_update: bad arguments");
+  if (n == 0) return SG_OK;
+  ema_update_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(ma, cur, n, beta, one_minus_beta);
+  return launch_status("sg_ema_update");
+}
+
+int sg_mse_scratch_doubles(void) { return MSE_BLOCKS; }
+
+int sg_mse(const float* a, const float* b, int64_t n, double* scratch, float* out, sg_stream_t stream) {
+  SG_REQUIRE(a && b && scratch && out && n > 0, "sg_mse: bad arguments");
+  int blocks = (int)(cdiv(n, 256) < MSE_BLOCKS ? cdiv(n, 256) : MSE_BLOCKS);
+  mse_partial_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, b, n, scratch);
+  mse_final_kernel<<<1, 256, 0, as_stream(stream)>>>(scratch, blocks, n, out);
+  return launch_status("sg_mse");
 }
 
 int sg_pack_weights(const float* w, int Cout, int Cin, int taps, void* out, int out_dtype, sg_stream_t stream) {

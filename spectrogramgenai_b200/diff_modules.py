@@ -184,11 +184,29 @@ class UNet_conditional(nn.Module):
 
 
 class EMA:
-    """Load side of the reference's EMA helper (:24-49)."""
+    """The reference's EMA helper (:24-49); the average itself is one kernel launch per parameter tensor."""
 
     def __init__(self, beta=0.995):
         self.beta = beta
         self.step = 0
+
+    def update_model_average(self, ma_model, current_model):
+        for current_params, ma_params in zip(current_model.parameters(), ma_model.parameters()):
+            ma_params.data = self.update_average(ma_params.data, current_params.data)
+
+    def update_average(self, old, new):
+        """old * beta + (1 - beta) * new (:37-40), in place on `old` (the reference rebinds .data to a new tensor)."""
+        if old is None:
+            return new
+        return ops.ema_update(old, new.to(old.device), self.beta)
+
+    def step_ema(self, ema_model, model, step_start_ema=2000):
+        if self.step < step_start_ema:
+            self.reset_parameters(ema_model, model)
+            self.step += 1
+            return
+        self.update_model_average(ema_model, model)
+        self.step += 1
 
     def reset_parameters(self, ema_model, model):
         ema_model.load_state_dict(model.state_dict())
@@ -231,6 +249,34 @@ class Diffusion:
 
     def prepare_noise_schedule(self):
         return torch.linspace(self.beta_start, self.beta_end, self.noise_steps)
+
+    # ------------------------------------------------------------------ forward-only training helpers (:401-409, :474-478)
+    def sample_timesteps(self, n):
+        return torch.randint(low=1, high=self.noise_steps, size=(n,))
+
+    def noise_images(self, x, t, *, noise=None, seed=0, sample_base=0):
+        """Reference `noise_images(x, t)` -> (x_t, eps): x_t = sqrt(alpha_hat[t]) x + sqrt(1 - alpha_hat[t]) eps.
+        `noise` (ours) injects eps (then x_t is bit-identical to the reference's expression); otherwise eps comes from
+        the Philox stream keyed by (seed, sample_base + sample index)."""
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        t = torch.as_tensor(t).reshape(-1).to(device=self.device, dtype=torch.int64)
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
+        return ops.noise_images(x, t, self.alpha_hat, eps=noise, seed=seed, sample_base=sample_base)
+
+    def mse(self, noise, pred):
+        """The reference's `self.mse = nn.MSELoss()` (:392, used at :478)."""
+        return ops.mse(noise.to(self.device, torch.float32).contiguous(), pred.to(self.device, torch.float32).contiguous())
+
+    @torch.no_grad()
+    def eval_loss(self, images, labels=None, *, t=None, noise=None, seed=0):
+        """The body of `one_epoch(train=False)` for one batch (:474-478): t ~ sample_timesteps, noise_images, model
+        forward (labels=None is the unconditional pass the training loop takes 10 % of the time), MSE(noise, pred)."""
+        n = images.shape[0]
+        t = self.sample_timesteps(n) if t is None else t
+        x_t, eps = self.noise_images(images, t, noise=noise, seed=seed)
+        pred = self.model(x_t, torch.as_tensor(t).to(self.device), labels)
+        return self.mse(eps, pred)
 
     # ------------------------------------------------------------------ checkpoints (:509-510)
     def load(self, model_cpkt_path, model_ckpt="ckpt.pt", ema_model_ckpt="ema_ckpt.pt"):

@@ -267,6 +267,42 @@ def pack_weights(w, dtype):
     return out
 
 
+def noise_images(x, t, alpha_hat, *, eps=None, seed=0, sample_base=0):
+    """Diffusion.noise_images (:404-409): returns (x_t, eps).  x fp32 [n, ...]; t int64 [n]; alpha_hat fp32 [T]."""
+    x = _f32(x, "x")
+    n = x.shape[0]
+    E = x.numel() // max(n, 1)
+    if t.dtype != torch.int64 or not t.is_cuda or t.numel() != n:
+        raise ValueError("noise_images: t must be a CUDA int64 tensor with one timestep per sample")
+    if eps is not None and (eps.shape != x.shape):
+        raise ValueError("noise_images: eps must have x's shape")
+    x_t = torch.empty_like(x)
+    eps_out = torch.empty_like(x) if eps is None else None
+    check(_lib().sg_noise_images(ptr(x), ptr(t.contiguous()), ptr(_f32(alpha_hat, "alpha_hat")), alpha_hat.numel(), n, E,
+                                 ptr(_f32(eps, "eps")), seed, sample_base, ptr(x_t), ptr(eps_out), stream_ptr()),
+          "sg_noise_images")
+    return x_t, (eps if eps is not None else eps_out)
+
+
+def ema_update(ma, cur, beta):
+    """EMA.update_average (:37-40) in place on ma: ma * beta + (1 - beta) * cur."""
+    if ma.shape != cur.shape:
+        raise ValueError("ema_update: shape mismatch")
+    check(_lib().sg_ema_update(ptr(_f32(ma, "ma")), ptr(_f32(cur, "cur")), ma.numel(), float(beta), float(1 - beta),
+                               stream_ptr()), "sg_ema_update")
+    return ma
+
+
+def mse(a, b):
+    """nn.MSELoss() (:478): 0-dim fp32 tensor."""
+    if a.shape != b.shape or a.numel() == 0:
+        raise ValueError("mse: shape mismatch / empty input")
+    scratch = torch.empty(_lib().sg_mse_scratch_doubles(), dtype=torch.float64, device=a.device)
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    check(_lib().sg_mse(ptr(_f32(a, "a")), ptr(_f32(b, "b")), a.numel(), ptr(scratch), ptr(out), stream_ptr()), "sg_mse")
+    return out
+
+
 def to_uint8_wrap(x, out=None):
     """uint8((x + 1) / 2 * 255) without a clamp (the cast of the reference's trajectory dumps, :672-675)."""
     if out is None:
