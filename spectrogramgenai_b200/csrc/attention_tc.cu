@@ -1047,7 +1047,6 @@ attention_tc11_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, u
   };
   auto issue_pv = [&](int t) {  // O_t = P V_t : A = P (K-major, two SWIZZLE_128B atoms of 64 keys), B = V MN-major
     tc_fence_after();
-    const uint64_t vd = make_desc_rows(smem_u32(sV + (t & 1) * TILE), ROWB);
     if (elect_one()) {
       // B = [V slab | ones slab]: N = D + 16 columns of an MN-major operand are two swizzle atoms along N, and the
       // descriptor's leading-dimension offset is the distance between them -- the second atom is the tile of ones, so

@@ -191,8 +191,6 @@ __global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restri
   }
 }
 
-static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-
 // Cx == Cs, multiples of 8: one thread = one output pixel x (8 skip channels k, 8 upsampled channels k), so no warp mixes
 // "copy" lanes with "gather" lanes (the generic kernel runs both branches in every warp with half the lanes idle).
 __global__ void __launch_bounds__(256) upsample_cat_paired_kernel(const float* __restrict__ x, const float* __restrict__ skip,
