@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sg {
@@ -22,6 +24,25 @@ int launch_status(const char* what) {
     return SG_ERR_LAUNCH;
   }
   return SG_OK;
+}
+
+int pdl_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SGB200_PDL");
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 2) v = 2;
+  }
+  return v;
+}
+
+int pdl_max_ctas() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SGB200_PDL_MAX_CTAS");
+    v = e ? atoi(e) : 4 * num_sms();  // measured: larger grids gain nothing from the early launch and the programmatic edge costs ~5 us
+  }
+  return v;
 }
 
 int num_sms() {

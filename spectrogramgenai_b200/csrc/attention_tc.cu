@@ -153,6 +153,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // every activation access (TMA loads included) follows this point; parameters read above are immutable weights
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -342,7 +344,7 @@ static int launch_att(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, di
     }
     configured = true;
   }
-  attention_tc_kernel<D, DT, POLY><<<grid, 192, smem, stream>>>(tm, g, out);
+  launch_k(attention_tc_kernel<D, DT, POLY>, grid, dim3(192), smem, stream, tm, g, out);
   return launch_status("sg_attention(tc)");
 }
 
@@ -416,6 +418,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // every activation access (TMA loads included) follows this point; parameters read above are immutable weights
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -731,6 +735,8 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // every activation access (TMA loads included) follows this point; parameters read above are immutable weights
+  pdl_launch_dependents();
 
   // Issue helpers: called by ALL lanes of warp 0 (convergent); one elected lane executes the TMA / MMA instructions.
   const uint64_t q_desc = make_desc_rows(smem_u32(sQ), ROWB);
@@ -1018,6 +1024,8 @@ attention_tc11_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, u
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // every activation access (TMA loads included) follows this point; parameters read above are immutable weights
+  pdl_launch_dependents();
 
   // Issue helpers: called by ALL lanes of warp 0 (convergent); one elected lane executes the TMA / MMA instructions.
   const uint64_t q_desc = make_desc_rows(smem_u32(sQ), ROWB);
@@ -1267,7 +1275,7 @@ static int launch_att8(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, d
     }
     configured = true;
   }
-  attention_tc8_kernel<D, DT, POLY, NACC><<<grid, 128, smem, stream>>>(tm, g, out);
+  launch_k(attention_tc8_kernel<D, DT, POLY, NACC>, grid, dim3(128), smem, stream, tm, g, out);
   return launch_status("sg_attention(tc8)");
 }
 
@@ -1292,7 +1300,7 @@ static int launch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, 
     }
     configured = true;
   }
-  attention_tc11_kernel<D, DT, POLY, NACC><<<grid, 128, smem, stream>>>(tm, g, out);
+  launch_k(attention_tc11_kernel<D, DT, POLY, NACC>, grid, dim3(128), smem, stream, tm, g, out);
   return launch_status("sg_attention(tc11)");
 }
 

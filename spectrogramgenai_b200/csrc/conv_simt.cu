@@ -20,6 +20,8 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream);  // igemm_tc.cu
 __constant__ __align__(16) float c_conv_in_w[36 * 64];
 
 __global__ void conv_in_pack_kernel(const float* __restrict__ w, float* __restrict__ dst, int K) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) dst[(i % K) * 64 + i / K] = w[i];  // w is [co][ci][3][3]
 }
 
@@ -28,6 +30,10 @@ __global__ void __launch_bounds__(128, 4) conv_in_kernel(const float* __restrict
                                                          void* __restrict__ raw_v, float* __restrict__ partials) {
   constexpr int K = CIN * 9;
   __shared__ float red[2][4];
+  // launched fully serialised behind conv_in_pack_kernel (constant-cache coherence), so the wait is a no-op; the
+  // trigger lets the next kernel start early
+  pdl_wait();
+  pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int HW = S * S;
   const int blocks_per_row = HW / 128;
@@ -310,7 +316,7 @@ int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w, int r
       return SG_ERR_LAUNCH;
     }
   }
-  conv_in_pack_kernel<<<1, 256, 0, s>>>(w, bank, 9 * c_in);
+  launch_k(conv_in_pack_kernel, dim3(1), dim3(256), 0, s, w, bank, 9 * c_in);
   const int blocks = (int)ntiles;
 #define SG_CONV_IN(CI)                                                                              \
   do {                                                                                              \

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256) cfg_update_kernel(float* __restrict__ x, 
                                                          const int32_t* __restrict__ step,
                                                          const float* __restrict__ noise, uint64_t seed,
                                                          int64_t sample_base) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t total = (int64_t)n * E4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -59,7 +61,11 @@ __global__ void __launch_bounds__(256) cfg_update_kernel(float* __restrict__ x, 
   reinterpret_cast<float4*>(x)[idx] = xv;
 }
 
-__global__ void step_advance_kernel(int32_t* step) { *step -= 1; }
+__global__ void step_advance_kernel(int32_t* step) {
+  pdl_wait();
+  pdl_launch_dependents();
+  *step -= 1;
+}
 
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ x, int n, int E4, uint64_t seed,
                                                             int64_t sample_base, int step_tag) {
@@ -102,6 +108,8 @@ __global__ void to_uint8_tail_kernel(const float* __restrict__ x, int64_t begin,
 __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ in, int64_t total4, int Ho, int Wo,
                                                        int C4, float* __restrict__ o32, void* __restrict__ o16,
                                                        int dtype) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total4) return;
   const int c4 = (int)(idx % C4);
@@ -131,6 +139,8 @@ __global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restri
                                                            void* __restrict__ o16, int dtype) {
   // grid = (chunks, rows): 32-bit index arithmetic inside a row (the 64-bit div / mod chain of the flat version cost
   // more than the loads); per_row counts units of V float4's
+  pdl_wait();
+  pdl_launch_dependents();
   const unsigned row = blockIdx.y;
   const unsigned Ct = (unsigned)(Cx4 + Cs4) / V;
   const unsigned H = 2 * h, W = 2 * w;
@@ -198,6 +208,8 @@ __global__ void __launch_bounds__(256) upsample_cat_paired_kernel(const float* _
                                                                   float sh, float sw, float* __restrict__ o32,
                                                                   void* __restrict__ o16, int dtype) {
   // per_row = pixels * C8 thread-units; C8 = Cs / 8 = Cx / 8
+  pdl_wait();
+  pdl_launch_dependents();
   const unsigned row = blockIdx.y;
   const unsigned W = 2 * w, HW = 4u * h * w;
   const float4* xrow = reinterpret_cast<const float4*>(x) + (size_t)row * h * w * (C8 * 2);
@@ -356,14 +368,14 @@ int sg_cfg_update(float* x, const float* eps, int n, int E, float cfg_scale, con
   SG_REQUIRE(x && eps && coef && step, "sg_cfg_update: null pointer");
   SG_REQUIRE(n > 0 && E > 0 && E % 4 == 0 && T > 1, "sg_cfg_update: bad shape n=%d E=%d T=%d", n, E, T);
   const int64_t total = (int64_t)n * (E / 4);
-  cfg_update_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(x, eps, n, E / 4, cfg_scale, coef, T, step, noise,
-                                                                     seed, sample_base);
+  launch_k(cfg_update_kernel, dim3(cdiv(total, 256)), dim3(256), 0, as_stream(stream), x, eps, n, E / 4, cfg_scale, coef, T, step,
+           noise, seed, sample_base);
   return launch_status("sg_cfg_update");
 }
 
 int sg_step_advance(int32_t* step, sg_stream_t stream) {
   SG_REQUIRE(step, "sg_step_advance: null pointer");
-  step_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(step);
+  launch_k(step_advance_kernel, dim3(1), dim3(1), 0, as_stream(stream), step);
   return launch_status("sg_step_advance");
 }
 
@@ -426,8 +438,8 @@ int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, 
   SG_REQUIRE(rows > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "sg_maxpool2: bad shape");
   SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_maxpool2: out_act needs a 16-bit dtype");
   const int64_t total4 = (int64_t)rows * (H / 2) * (W / 2) * (C / 4);
-  maxpool2_kernel<<<cdiv(total4, 256), 256, 0, as_stream(stream)>>>(in, total4, H / 2, W / 2, C / 4, out_f32, out_act,
-                                                                    act_dtype);
+  launch_k(maxpool2_kernel, dim3(cdiv(total4, 256)), dim3(256), 0, as_stream(stream), in, total4, H / 2, W / 2, C / 4, out_f32,
+           out_act, act_dtype);
   return launch_status("sg_maxpool2");
 }
 
@@ -452,14 +464,14 @@ int sg_upsample_cat(const float* x, const float* skip, int rows, int skip_rows, 
     const int64_t units = (int64_t)(2 * h) * (2 * w) * (Cs / 8);
     int ch = (int)cdiv(units, 256 * 2);
     if (ch > want) ch = want > 1 ? want : 1;
-    upsample_cat_paired_kernel<<<dim3((unsigned)ch, (unsigned)rows), 256, 0, as_stream(stream)>>>(
-        x, skip, (unsigned)units, skip_rows, h, w, Cs / 8, sh, sw, out_f32, out_act, act_dtype);
+    launch_k(upsample_cat_paired_kernel, dim3((unsigned)ch, (unsigned)rows), dim3(256), 0, as_stream(stream), x, skip,
+             (unsigned)units, skip_rows, h, w, Cs / 8, sh, sw, out_f32, out_act, act_dtype);
   } else if (v == 2)
-    upsample_cat_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, skip, (unsigned)per_row, skip_rows, h, w, Cx / 4, Cs / 4, sh,
-                                                                sw, out_f32, out_act, act_dtype);
+    launch_k(upsample_cat_kernel<2>, grid, dim3(256), 0, as_stream(stream), x, skip, (unsigned)per_row, skip_rows, h, w, Cx / 4,
+             Cs / 4, sh, sw, out_f32, out_act, act_dtype);
   else
-    upsample_cat_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, skip, (unsigned)per_row, skip_rows, h, w, Cx / 4, Cs / 4, sh,
-                                                                sw, out_f32, out_act, act_dtype);
+    launch_k(upsample_cat_kernel<1>, grid, dim3(256), 0, as_stream(stream), x, skip, (unsigned)per_row, skip_rows, h, w, Cx / 4,
+             Cs / 4, sh, sw, out_f32, out_act, act_dtype);
   return launch_status("sg_upsample_cat");
 }
 

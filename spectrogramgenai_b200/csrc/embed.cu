@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) time_embed_kernel(const float* __restrict
                                                          const float* __restrict__ b_emb, int emb_total, int rows,
                                                          float* __restrict__ temb, float* __restrict__ emb) {
   __shared__ __align__(16) float act[TE_ROWS][256];  // SiLU(temb)
+  pdl_wait();
+  pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * TE_ROWS;
   for (int rr = 0; rr < TE_ROWS; ++rr) {
@@ -86,7 +88,7 @@ extern "C" int sg_time_embed(const float* t, const int32_t* step, const int64_t*
   SG_REQUIRE((t || step) && inv_freq && w_emb && b_emb && temb && emb, "sg_time_embed: null pointer");
   SG_REQUIRE(!y || label, "sg_time_embed: labels given without a label table");
   SG_REQUIRE(rows > 0 && emb_total > 0, "sg_time_embed: bad shape");
-  time_embed_kernel<<<dim3((unsigned)cdiv(rows, TE_ROWS), TE_SLICES), 256, 0, as_stream(stream)>>>(t, step, y, inv_freq, label, num_classes, w_emb,
+  launch_k(time_embed_kernel, dim3((unsigned)cdiv(rows, TE_ROWS), TE_SLICES), dim3(256), 0, as_stream(stream), t, step, y, inv_freq, label, num_classes, w_emb,
                                                                         b_emb, emb_total, rows, temb, emb);
   return launch_status("sg_time_embed");
 }

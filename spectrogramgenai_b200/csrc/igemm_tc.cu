@@ -549,6 +549,8 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // (the bias above is an immutable weight; every activation access follows this point)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== TMA producer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
@@ -652,7 +654,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGe
     return SG_ERR_ARG;
   }
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  igemm_tc2_kernel<BN><<<grid, V2<BN>::THREADS, smem, stream>>>(tmA, tmB, g, ep, (int)tiles);
+  launch_k(igemm_tc2_kernel<BN>, dim3(grid), dim3(V2<BN>::THREADS), smem, stream, tmA, tmB, g, ep, (int)tiles);
   return launch_status("sg_igemm(tc2)");
 }
 

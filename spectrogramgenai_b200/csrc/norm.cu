@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
                                                        float* __restrict__ o32, void* __restrict__ o16, int dtype) {
   __shared__ double red[2][8];
   __shared__ float stat[2];
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.y;
   const int rrow = row % raw_rows;  // raw / partials row (the label-independent prefix is stored once for both halves)
   const int mode = MODE >= 0 ? MODE : mode_rt;
@@ -255,6 +257,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_vcat_kernel(const uint4* __re
   __shared__ double red[2][8];
   __shared__ float stat[2];
   __shared__ __align__(16) float s_sc[VCAT_MAXC], s_sf[VCAT_MAXC];
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.y;
   const int64_t per_row8 = (int64_t)HW * C8;
   {
@@ -380,6 +384,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   constexpr int NV = C / (4 * LPT);             // float4's per lane: 1, 1, 2
   constexpr int TPW = 32 / LPT;                 // tokens per warp pass: 2, 1, 1
   constexpr int U = 4;                          // passes in flight
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPT, tsel = lane / LPT;
   const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -456,8 +462,8 @@ int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, co
   dim3 grid(chunks, rows);
   cudaStream_t st = as_stream(stream);
 #define SG_GN_LAUNCH(R16, MD)                                                                                          \
-  gn_apply_kernel<R16, MD><<<grid, 256, 0, st>>>(raw, partials, P, gamma, beta, per_row4, C / 4, raw_rows, mode, residual, emb, \
-                                                 emb_stride, out_f32, out_act, act_dtype)
+  launch_k(gn_apply_kernel<R16, MD>, grid, dim3(256), 0, st, raw, partials, P, gamma, beta, per_row4, C / 4, raw_rows, mode, \
+           residual, emb, emb_stride, out_f32, out_act, act_dtype)
   if (raw_dtype == SG_F16) {
     // fixed-channel fast path: every thread of the grid-stride loop must land on the same 8 channels each pass
     const bool fixed = ((int64_t)chunks * 256 * 8) % C == 0;
@@ -494,9 +500,8 @@ int sg_gn_apply_vcat(const void* raw, const float* partials, int P, const float*
   // torch: scale = (in - 1) / (out - 1) in fp32 (area_pixel_compute_scale, align_corners=True), as sg_upsample_cat
   const float sh = (H2 > 1) ? (float)(h - 1) / (float)(H2 - 1) : 0.f;
   const float sw = (W2 > 1) ? (float)(w - 1) / (float)(W2 - 1) : 0.f;
-  gn_apply_vcat_kernel<<<dim3(chunks, rows), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const uint4*>(raw), partials, P, gamma, beta, H2 * W2, W2, C / 8, Cs / 8, x, skip, skip_rows, h, w,
-      sh, sw, out_act, act_dtype);
+  launch_k(gn_apply_vcat_kernel, dim3(chunks, rows), dim3(256), 0, as_stream(stream), reinterpret_cast<const uint4*>(raw),
+           partials, P, gamma, beta, H2 * W2, W2, C / 8, Cs / 8, x, skip, skip_rows, h, w, sh, sw, out_act, act_dtype);
   return launch_status("sg_gn_apply_vcat");
 }
 
@@ -510,9 +515,9 @@ int sg_layernorm(const float* in, const float* gamma, const float* beta, int64_t
   const int blocks = cdiv(M, tok_per_block);
   cudaStream_t s = as_stream(stream);
   switch (C) {
-    case 64: layernorm_kernel<64><<<blocks, 256, 0, s>>>(in, gamma, beta, M, o32, o16, act_dtype); break;
-    case 128: layernorm_kernel<128><<<blocks, 256, 0, s>>>(in, gamma, beta, M, o32, o16, act_dtype); break;
-    case 256: layernorm_kernel<256><<<blocks, 256, 0, s>>>(in, gamma, beta, M, o32, o16, act_dtype); break;
+    case 64: launch_k(layernorm_kernel<64>, dim3(blocks), dim3(256), 0, s, in, gamma, beta, M, o32, o16, act_dtype); break;
+    case 128: launch_k(layernorm_kernel<128>, dim3(blocks), dim3(256), 0, s, in, gamma, beta, M, o32, o16, act_dtype); break;
+    case 256: launch_k(layernorm_kernel<256>, dim3(blocks), dim3(256), 0, s, in, gamma, beta, M, o32, o16, act_dtype); break;
     default: SG_REQUIRE(false, "sg_layernorm: C=%d not in {64,128,256}", C);
   }
   return launch_status("sg_layernorm");

@@ -149,6 +149,8 @@ __constant__ __align__(16) float c_outc[4 * OUTC_MAXC + 4];
 
 __global__ void outc_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ dst,
                                  int c_out, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 4 * OUTC_MAXC + 4; i += blockDim.x) {
     float v = 0.f;
     if (i < 4 * OUTC_MAXC) {
@@ -208,6 +210,8 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // every activation access (TMA loads included) follows this point; parameters read above are immutable weights
+  pdl_launch_dependents();
   const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
   const uint32_t aA = smem_u32(sA), aX = smem_u32(sX), aW = smem_u32(sW);
   const int r = tid;
@@ -462,6 +466,8 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // every activation access (TMA loads included) follows this point; parameters read above are immutable weights
+  pdl_launch_dependents();
   const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
   const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
   const int r = tid;
@@ -605,7 +611,10 @@ static int launch_tail(const void* att, const float* x, const void* wo, const vo
     if ((rc = set_smem(attn_tail_kernel<C, DT, OUTC>, T::TAIL_SMEM, "sg_attn_tail"))) return rc;
     cfg = true;
   }
-  attn_tail_kernel<C, DT, OUTC><<<grid, 128, T::TAIL_SMEM, s>>>(tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
+  if (OUTC)  // fully serialised behind outc_pack_kernel (constant-cache coherence of the bank it rewrites)
+    attn_tail_kernel<C, DT, OUTC><<<grid, 128, T::TAIL_SMEM, s>>>(tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
+  else
+    launch_k(attn_tail_kernel<C, DT, OUTC>, dim3(grid), dim3(128), T::TAIL_SMEM, s, tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
   return launch_status("sg_attn_tail");
 }
 
@@ -628,7 +637,7 @@ static int launch_inproj(const float* x, const void* w_in, void* qkv, InprojPara
     if ((rc = set_smem(ln_inproj_kernel<C, DT>, T::INPROJ_SMEM, "sg_ln_inproj"))) return rc;
     cfg = true;
   }
-  ln_inproj_kernel<C, DT><<<grid, 128, T::INPROJ_SMEM, s>>>(tm_x, tm_w, tm_w2, tm_qkv, p);
+  launch_k(ln_inproj_kernel<C, DT>, dim3(grid), dim3(128), T::INPROJ_SMEM, s, tm_x, tm_w, tm_w2, tm_qkv, p);
   return launch_status("sg_ln_inproj");
 }
 
@@ -667,7 +676,7 @@ static int attn_tail_impl(const void* att, const float* x, const void* wo, const
         return SG_ERR_LAUNCH;
       }
     }
-    outc_pack_kernel<<<1, 256, 0, s>>>(outc_w, outc_b, bank, c_out, C);
+    launch_k(outc_pack_kernel, dim3(1), dim3(256), 0, s, outc_w, outc_b, bank, c_out, C);
     if (act_dtype == SG_BF16) return launch_tail<64, SG_BF16, true>(att, x, wo, w1, w2, out, p, act_dtype, s);
     return launch_tail<64, SG_F16, true>(att, x, wo, w1, w2, out, p, act_dtype, s);
   }
