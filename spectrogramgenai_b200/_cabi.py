@@ -14,7 +14,7 @@ from . import build as _build
 
 SG_F32, SG_BF16, SG_F16 = 0, 1, 2
 SG_ENGINE_SIMT, SG_ENGINE_TC = 0, 1
-ABI_VERSION = 12
+ABI_VERSION = 13
 SG_ACT_NONE, SG_ACT_GELU, SG_ACT_RELU_POST = 0, 1, 2
 
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
@@ -38,6 +38,7 @@ PROTOTYPES = {
     "sg_last_error": (C.c_char_p, []),
     "sg_device_check": (_i, [_i]),
     "sg_set_device": (_i, [_i]),
+    "sg_set_pdl": (_i, [_i]),
     "sg_time_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sg_conv_in_partials": (_i, [_i]),
     "sg_conv_in": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),

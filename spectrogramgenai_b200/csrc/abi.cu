@@ -26,14 +26,17 @@ int launch_status(const char* what) {
   return SG_OK;
 }
 
+static int g_pdl_mode = -1;     // -1: not initialised
+static bool g_pdl_env = false;  // SGB200_PDL was given: sg_set_pdl does not override it
+
 int pdl_mode() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_pdl_mode < 0) {
     const char* e = getenv("SGB200_PDL");
-    v = e ? atoi(e) : 2;
-    if (v < 0 || v > 2) v = 2;
+    g_pdl_env = e != nullptr;
+    g_pdl_mode = e ? atoi(e) : 2;
+    if (g_pdl_mode < 0 || g_pdl_mode > 2) g_pdl_mode = 2;
   }
-  return v;
+  return g_pdl_mode;
 }
 
 int pdl_max_ctas() {
@@ -61,6 +64,13 @@ int num_sms() {
 extern "C" {
 
 int sg_abi_version(void) { return SG_ABI_VERSION; }
+
+int sg_set_pdl(int mode) {
+  SG_REQUIRE(mode >= 0 && mode <= 2, "sg_set_pdl: mode %d not in 0..2", mode);
+  (void)sg::pdl_mode();  // reads the environment once
+  if (!sg::g_pdl_env) sg::g_pdl_mode = mode;
+  return SG_OK;
+}
 
 const char* sg_last_error(void) { return sg::g_err; }
 

@@ -24,6 +24,9 @@ EMB_BLOCKS = ("down1", "down2", "down3", "up1", "up2", "up3")  # order of the co
 TIME_DIM = 256
 
 
+PDL_MAX_ROWS = 128  # UNet rows (2 x batch under CFG) up to which the step kernels are launched with PDL
+
+
 def _pack_conv(w: torch.Tensor, dtype, device):
     """[Cout, Cin, 3, 3] -> [9 taps (dy, dx), Cout, Cin], K (= Cin) contiguous."""
     return ops.pack_weights(w.detach().to(device=device, dtype=torch.float32).contiguous(), dtype)
@@ -364,5 +367,7 @@ class UNetPlan:
 
     def run(self):
         """Issue the whole forward on torch's current stream (graph-capturable)."""
+        # programmatic dependent launch pays off while the step is launch-latency bound (measured break-even: batch 64)
+        ops.set_pdl(2 if self.rows <= PDL_MAX_ROWS else 0)
         for fn, a, kw in self.ops:
             fn(*a, **kw)

@@ -257,6 +257,11 @@ def to_uint8(x, out):
     check(_lib().sg_to_uint8(ptr(_f32(x, "x")), x.numel(), ptr(out), stream_ptr()), "sg_to_uint8")
 
 
+def set_pdl(mode: int):
+    """Programmatic dependent launch mode of the following launches (0 off, 1 all, 2 small grids); SGB200_PDL wins."""
+    check(_lib().sg_set_pdl(int(mode)), "sg_set_pdl")
+
+
 def pack_weights(w, dtype):
     """fp32 device weight [Cout, Cin, *kernel] -> [taps, Cout, Cin] of `dtype` (the B operand of sg_igemm)."""
     w = _f32(w, "w")
