@@ -35,9 +35,13 @@ struct Tok {
   static constexpr int W_TILE = KB * W_KB;      // [C x C] 16-bit
   static constexpr int WIN_KB = 3 * C * 128;    // one k-block of Win [3C x C]
   static constexpr int WIN_TILE = KB * WIN_KB;
-  static constexpr int TAIL_SMEM = 1024 + 3 * W_TILE + A_TILE + X_TILE + 5 * C * 4 + 128;
+  static constexpr bool TAIL_DIRECT = C == 128;  // block output stored through per-warp transposition scratch, no TMA staging
+  static constexpr int TAIL_SCR = TAIL_DIRECT ? 4 * 4096 : 0;  // 4 warps x [32 rows x 32 floats]
+  static constexpr int TAIL_SMEM = 1024 + 3 * W_TILE + A_TILE + X_TILE + TAIL_SCR + 5 * C * 4 + 128;
   static constexpr int INPROJ_XBUF = C == 64 ? 2 : 1;  // x tiles in flight (C = 64: the next tile's x is prefetched)
-  static constexpr int INPROJ_SMEM = 1024 + WIN_TILE + INPROJ_XBUF * X_TILE + A_TILE + 5 * C * 4 + 128;
+  static constexpr bool INPROJ_DIRECT = C == 128;  // epilogue stores qkv through per-warp transposition scratch, no TMA staging
+  static constexpr int INPROJ_SCR = INPROJ_DIRECT ? 4 * 4096 : 0;  // 4 warps x [32 rows x 64 cols] 16 bit
+  static constexpr int INPROJ_SMEM = 1024 + WIN_TILE + INPROJ_XBUF * X_TILE + A_TILE + INPROJ_SCR + 5 * C * 4 + 128;
   static constexpr int TAIL_TMEM = 2 * C;               // two accumulators [128 x C]: 128 / 256 columns
   static constexpr int INPROJ_TMEM = C == 64 ? 256 : 512;  // one accumulator [128 x 3C]
   static constexpr int TAIL_CTAS = C == 64 ? 3 : 1;
@@ -135,6 +139,7 @@ struct TailParams {
   int ntiles;
   uint32_t idesc;
   // fused outc (sg_attn_tail_outc): eps[row, k, pix] = outc_b[k] + sum_c out[token, c] * outc_w[k, c]
+  float* out;     // direct-store epilogue (C = 128): fp32 [M, C]
   float* eps;     // NCHW [rows, c_out, HW]
   int c_out;      // 1..4
   int log_hw;     // HW is a power of two
@@ -179,7 +184,9 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
   uint8_t* sW = smem;                  // Wo | W1 | W2
   uint8_t* sA = sW + 3 * T::W_TILE;    // operand tile: att, then LN(a), then GELU(.)
   uint8_t* sX = sA + T::A_TILE;        // x tile (fp32), later the output tile
-  float* sPar = reinterpret_cast<float*>(sX + T::X_TILE);  // bo | ln_g | ln_b | b1 | b2
+  uint8_t* sScr = sX + T::X_TILE;      // C = 128: per-warp transposition scratch of the direct-store epilogue
+  float* sPar = reinterpret_cast<float*>(sScr + T::TAIL_SCR);  // bo | ln_g | ln_b | b1 | b2
+  constexpr bool DIRECT = T::TAIL_DIRECT && !OUTC;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 5 * C);
   uint64_t* w_full = bars;
   uint64_t* att_full = bars + 1;
@@ -238,7 +245,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
   };
   // When the block output is not written (fused outc), sX is never an output staging buffer: the next tile's x is
   // fetched as soon as this tile's x has been read, and its att as soon as the last GEMM has released sA.
-  const bool prefetch = OUTC && !p.write_out;
+  const bool prefetch = DIRECT || (OUTC && !p.write_out);
   uint32_t in_ph = 0, mma_ph = 0;
   bool first = true;
   if (prefetch && warp == 0 && (int)blockIdx.x < p.ntiles) {
@@ -345,7 +352,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
       if (elect_one()) load_att(next);  // the last GEMM has completed: sA is free
       __syncwarp();
     }
-    const bool stage = !OUTC || p.write_out;
+    const bool stage = !DIRECT && (!OUTC || p.write_out);
     float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
     if constexpr (OUTC) {
       e0 = c_outc[4 * OUTC_MAXC + 0];
@@ -378,6 +385,23 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
           }
         }
         if (stage) sts128(xrow_chunk_addr(aX, r, h * 8 + c), o);
+        if constexpr (DIRECT) {  // this warp's [32 rows x 128 B] scratch, 16-byte chunks XOR-swizzled by the row
+          const uint32_t scr = smem_u32(sScr) + (uint32_t)warp * 4096u;
+          sts128(scr + (uint32_t)(tid & 31) * 128u + ((((uint32_t)c) ^ ((uint32_t)tid & 7u)) << 4), o);
+        }
+      }
+      if constexpr (DIRECT) {  // 32 channels of 32 tokens -> global, four complete 128-byte lines per store instruction
+        const uint32_t scr = smem_u32(sScr) + (uint32_t)warp * 4096u;
+        const int lane = tid & 31, rrow = lane >> 3, rchunk = lane & 7;
+        __syncwarp();
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) {
+          const int row = i2 * 4 + rrow;
+          const float4 w4 = lds128(scr + (uint32_t)row * 128u + (((uint32_t)rchunk ^ ((uint32_t)row & 7u)) << 4));
+          const int64_t m = (int64_t)m0 + warp * 32 + row;
+          if (m < p.M) *reinterpret_cast<float4*>(p.out + m * C + h * 32 + rchunk * 4) = w4;
+        }
+        __syncwarp();
       }
     }
     if constexpr (OUTC) {
@@ -418,6 +442,7 @@ struct InprojParams {
   const float* ln_g;
   const float* ln_b;
   const float* bias;  // [3C]
+  uint16_t* qkv;      // direct-store epilogue (C = 128)
   int64_t M;
   int ntiles;
   uint32_t idesc_a, idesc_b;  // M128 x N(first MMA) and, at C = 128, M128 x N128 for rows [256, 384) of Win
@@ -438,7 +463,9 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   constexpr int NBUF = T::INPROJ_XBUF;
   uint8_t* sX = sW + T::WIN_TILE;    // x tile(s) (fp32); the consumed tile + sA stage the 3C/64 16-bit output boxes
   uint8_t* sA = sX + NBUF * T::X_TILE;  // LN(x) operand tile
-  float* sPar = reinterpret_cast<float*>(sA + T::A_TILE);  // ln_g | ln_b | bias[3C]
+  uint8_t* sScr = sA + T::A_TILE;    // C = 128: per-warp transposition scratch of the direct-store epilogue
+  float* sPar = reinterpret_cast<float*>(sScr + T::INPROJ_SCR);  // ln_g | ln_b | bias[3C]
+  constexpr bool DIRECT = T::INPROJ_DIRECT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 5 * C);
   uint64_t* w_full = bars;
   uint64_t* in_full = bars + 1;  // [NBUF]
@@ -487,13 +514,13 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   }
   uint32_t mma_ph = 0;
   bool first = true;
-  if (NBUF == 2 && warp == 0 && elect_one() && (int)blockIdx.x < p.ntiles) load_x(blockIdx.x, 0);
+  if ((NBUF == 2 || DIRECT) && warp == 0 && elect_one() && (int)blockIdx.x < p.ntiles) load_x(blockIdx.x, 0);
   int it = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int m0 = tile * TM;
     const int buf = NBUF == 2 ? (it & 1) : 0;
     const uint32_t aX = smem_u32(sX + buf * T::X_TILE);
-    if (warp == 0 && elect_one()) {
+    if (!DIRECT && warp == 0 && elect_one()) {
       tma_store_wait_read();  // the previous tile's qkv boxes (staged in its x tile | sA) have left shared memory
       if (NBUF == 2) {
         // prefetch: the other buffer staged the previous tile's output and is free now; the load overlaps this tile
@@ -502,7 +529,7 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         load_x(tile, 0);
       }
     }
-    __syncthreads();  // nobody writes sA (LN output) before the previous stores have drained
+    if (!DIRECT) __syncthreads();  // nobody writes sA (LN output) before the previous stores have drained
     mbar_wait(&in_full[buf], NBUF == 2 ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u));
     {
       float a[C];
@@ -525,6 +552,8 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         gemm_kc<C>(tmem_base, aA, aW, T::WIN_KB, 0, p.idesc_a);                   // columns [0, NA)
         if (N > NA) gemm_kc<C>(tmem_base + NA, aA, aW, T::WIN_KB, NA, p.idesc_b);  // columns [NA, N)
         umma_commit(mma_done);
+        // DIRECT: every thread has read its x row (barrier above) and nothing is staged in sX: fetch the next tile now
+        if (DIRECT && tile + (int)gridDim.x < p.ntiles) load_x(tile + gridDim.x, 0);
       }
       __syncwarp();
     }
@@ -532,35 +561,78 @@ ln_inproj_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     mbar_wait(mma_done, mma_ph);
     mma_ph ^= 1u;
     tc_fence_after();
-    // qkv rows -> 3C/64 [128 x 64] 16-bit SWIZZLE_128B boxes in the consumed x tile, the last ones in sA (its GEMM is complete)
+    if constexpr (DIRECT) {
+      // qkv rows -> global, 64 columns at a time through this warp's [32 rows x 128 B] scratch (16-byte chunks XOR-swizzled
+      // by the row so that both the row-per-thread writes and the 4-rows-per-instruction reads are conflict free): every
+      // global store instruction writes four complete 128-byte lines
+      const uint32_t scr = smem_u32(sScr) + (uint32_t)warp * 4096u;
+      const int lane = tid & 31;
+      const int rrow = lane >> 3, rchunk = lane & 7;  // read side: 4 rows x 8 chunks per instruction
 #pragma unroll 1
-    for (int b = 0; b < N / 64; ++b) {
-      const uint32_t box = b < XBOXES ? aX + (uint32_t)b * T::A_ATOM : aA + (uint32_t)(b - XBOXES) * T::A_ATOM;
+      for (int b = 0; b < N / 64; ++b) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld32(t_row + b * 64 + h * 32, v);
-        tmem_ld_wait();
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(t_row + b * 64 + h * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 b0 = *reinterpret_cast<const float4*>(sPar + 2 * C + b * 64 + h * 32 + c * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(sPar + 2 * C + b * 64 + h * 32 + c * 8 + 4);
-          sts128u(arow_chunk_addr(box, r, h * 4 + c),
-                  pack2<DT>(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y),
-                  pack2<DT>(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w),
-                  pack2<DT>(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y),
-                  pack2<DT>(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w));
+          for (int c = 0; c < 4; ++c) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sPar + 2 * C + b * 64 + h * 32 + c * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sPar + 2 * C + b * 64 + h * 32 + c * 8 + 4);
+            const uint32_t chunk = (uint32_t)(h * 4 + c);
+            sts128u(scr + (uint32_t)lane * 128u + ((chunk ^ ((uint32_t)lane & 7u)) << 4),
+                    pack2<DT>(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y),
+                    pack2<DT>(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w),
+                    pack2<DT>(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y),
+                    pack2<DT>(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w));
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i2 = 0; i2 < 8; ++i2) {
+          const int row = i2 * 4 + rrow;
+          uint4 w4;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w4.x), "=r"(w4.y), "=r"(w4.z), "=r"(w4.w)
+                       : "r"(scr + (uint32_t)row * 128u + (((uint32_t)rchunk ^ ((uint32_t)row & 7u)) << 4)));
+          const int64_t m = (int64_t)m0 + warp * 32 + row;
+          if (m < p.M) *reinterpret_cast<uint4*>(p.qkv + m * N + b * 64 + rchunk * 8) = w4;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();  // the accumulator reads above precede the next tile's MMAs
+      __syncthreads();    // ... and every warp is done with sA / the accumulator before warp 0 moves on
+    } else {
+      // qkv rows -> 3C/64 [128 x 64] 16-bit SWIZZLE_128B boxes in the consumed x tile, the last ones in sA (its GEMM is complete)
+  #pragma unroll 1
+      for (int b = 0; b < N / 64; ++b) {
+        const uint32_t box = b < XBOXES ? aX + (uint32_t)b * T::A_ATOM : aA + (uint32_t)(b - XBOXES) * T::A_ATOM;
+  #pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(t_row + b * 64 + h * 32, v);
+          tmem_ld_wait();
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sPar + 2 * C + b * 64 + h * 32 + c * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sPar + 2 * C + b * 64 + h * 32 + c * 8 + 4);
+            sts128u(arow_chunk_addr(box, r, h * 4 + c),
+                    pack2<DT>(__uint_as_float(v[c * 8 + 0]) + b0.x, __uint_as_float(v[c * 8 + 1]) + b0.y),
+                    pack2<DT>(__uint_as_float(v[c * 8 + 2]) + b0.z, __uint_as_float(v[c * 8 + 3]) + b0.w),
+                    pack2<DT>(__uint_as_float(v[c * 8 + 4]) + b1.x, __uint_as_float(v[c * 8 + 5]) + b1.y),
+                    pack2<DT>(__uint_as_float(v[c * 8 + 6]) + b1.z, __uint_as_float(v[c * 8 + 7]) + b1.w));
+          }
         }
       }
-    }
-    tc_fence_before();
-    fence_proxy_async();
-    __syncthreads();
-    if (warp == 0 && elect_one()) {
-#pragma unroll
-      for (int b = 0; b < N / 64; ++b)
-        tma_store_2d(&tm_qkv, b < XBOXES ? sX + buf * T::X_TILE + b * T::A_ATOM : sA + (b - XBOXES) * T::A_ATOM, b * 64, m0);
-      tma_store_commit();
+      tc_fence_before();
+      fence_proxy_async();
+      __syncthreads();
+      if (warp == 0 && elect_one()) {
+  #pragma unroll
+        for (int b = 0; b < N / 64; ++b)
+          tma_store_2d(&tm_qkv, b < XBOXES ? sX + buf * T::X_TILE + b * T::A_ATOM : sA + (b - XBOXES) * T::A_ATOM, b * 64, m0);
+        tma_store_commit();
+      }
     }
   }
   if (warp == 0 && elect_one()) tma_store_wait_all();
@@ -661,7 +733,7 @@ static int attn_tail_impl(const void* att, const float* x, const void* wo, const
   p.M = M;
   p.ntiles = (int)cdiv(M, TM);
   p.idesc = 0;
-  p.eps = eps; p.c_out = c_out; p.log_hw = 0; p.write_out = out != nullptr;
+  p.out = out; p.eps = eps; p.c_out = c_out; p.log_hw = 0; p.write_out = out != nullptr;
   cudaStream_t s = as_stream(stream);
   if (eps) {
     SG_REQUIRE(C == 64, "%s: C=%d (the fused output conv follows the C = 64 block sa6)", what, C);
@@ -714,6 +786,7 @@ int sg_ln_inproj(const float* x, const float* ln_g, const float* ln_b, const voi
   SG_REQUIRE(M > 0 && M < (1ll << 31) - TM, "sg_ln_inproj: M=%lld", (long long)M);
   InprojParams p;
   p.ln_g = ln_g; p.ln_b = ln_b; p.bias = b_in;
+  p.qkv = reinterpret_cast<uint16_t*>(qkv);
   p.M = M;
   p.ntiles = (int)cdiv(M, TM);
   p.idesc_a = p.idesc_b = 0;
