@@ -52,7 +52,7 @@ def load_peaks():
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,enforced.power.limit")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
@@ -74,7 +74,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw, plim = [], None, set(), [], None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [s.strip() for s in ln.split(",")]
@@ -88,9 +88,15 @@ class ClockSampler:
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+            try:  # board power during the timed region next to the enforced limit: the sustained loop is power-bound
+                pw.append(float(f[2]))
+                plim = float(f[7]) if len(f) > 7 else plim
+            except ValueError:
+                pass
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": plim}
 
 
 # ----------------------------------------------------------------------------------------------------
