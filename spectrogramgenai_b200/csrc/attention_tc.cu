@@ -1310,6 +1310,8 @@ static int dispatch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out
   static const int nacc = env_int("SGB200_ATTN_NACC11", 1);
   constexpr int NA = D == 64 ? 1 : 2;
   if (nacc == 1) {
+    if (poly == 0) return launch_att11<D, DT, 0, 1>(tm, g, out, grid, stream);
+    if (poly == 1) return launch_att11<D, DT, 1, 1>(tm, g, out, grid, stream);
     if (poly == 2) return launch_att11<D, DT, 2, 1>(tm, g, out, grid, stream);
     return launch_att11<D, DT, 3, 1>(tm, g, out, grid, stream);
   }
