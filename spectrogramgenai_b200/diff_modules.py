@@ -310,6 +310,13 @@ class Diffusion:
         written as RGBA PNG `{class_name}_gen_imgs_{i}_{samp_i}.png` (the name format src/helpers.py:602-610 parses).
         `colormap` (ours): callable uint8 [H, W] -> float RGBA [H, W, 4]; default matplotlib.cm.viridis, imported
         lazily (the reference imports matplotlib at module top).  Returns the list of files written."""
+        return self.gen_images_many(img_folder, [samp_i], labels, colormap=colormap, **sample_kw)
+
+    def gen_images_many(self, img_folder, samp_is, labels=None, *, colormap=None, **sample_kw):
+        """`gen_images` for several `samp_i` in ONE sampling call (ours): the label set is tiled len(samp_is) times so
+        that the batch fills the GPU (27 labels alone run at ~75 % of the throughput of a 512-sample batch).  Files and
+        pixels are those of the per-`samp_i` calls when the caller passes `sample_base = samp_is[0] * len(labels)`
+        and consecutive `samp_is` (the Philox stream is keyed by the global sample index)."""
         import numpy as np
         from PIL import Image
 
@@ -318,14 +325,19 @@ class Diffusion:
         class_names = getattr(self, "class_names", None) or [str(k) for k in range(self.num_classes or 0)]
         if labels is None:
             labels = torch.arange(self.num_classes).long().to(self.device)
-        sampled_images = self.sample(False, labels, **sample_kw)
+        labels = torch.as_tensor(labels).reshape(-1)
+        samp_is = list(samp_is)
+        sampled_images = self.sample(False, labels.repeat(len(samp_is)), **sample_kw)
+        lab_list = labels.tolist()
         paths = []
-        for i, (lab, img) in enumerate(zip(torch.as_tensor(labels).reshape(-1).tolist(), sampled_images)):
-            rgba = colormap(img.permute(1, 2, 0).cpu().numpy().squeeze())
-            rgba = (np.asarray(rgba) * 255).astype(np.uint8)
-            path = f"{img_folder}/{class_names[lab]}_gen_imgs_{i}_{samp_i}.png"
-            Image.fromarray(rgba).save(path)
-            paths.append(path)
+        for g, samp_i in enumerate(samp_is):
+            for i, lab in enumerate(lab_list):
+                img = sampled_images[g * len(lab_list) + i]
+                rgba = colormap(img.permute(1, 2, 0).cpu().numpy().squeeze())
+                rgba = (np.asarray(rgba) * 255).astype(np.uint8)
+                path = f"{img_folder}/{class_names[lab]}_gen_imgs_{i}_{samp_i}.png"
+                Image.fromarray(rgba).save(path)
+                paths.append(path)
         return paths
 
     # ------------------------------------------------------------------ sampling (:411-442)

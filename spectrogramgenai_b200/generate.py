@@ -36,6 +36,8 @@ def parse_args(argv=None):
     p.add_argument("--sav_denoise_path", type=str, default=c.sav_denoise_path)
     p.add_argument("--vqae_path", type=str, default="models/VQAE/ckpt.pt")
     p.add_argument("--compute_dtype", type=str, default="bf16", choices=["bf16", "f16", "fp32"])
+    p.add_argument("--batch_samples", type=int, default=512,
+                   help="spectrograms per sampling call (several samp_i are generated together; images do not depend on it)")
     a = p.parse_args(argv)
     for k, v in vars(a).items():
         setattr(c, k, v)
@@ -54,9 +56,16 @@ def main(argv=None):
                             device=f"cuda:{local}", vqae_path=config.vqae_path, sav_denoise_path=config.sav_denoise_path,
                             class_names=class_names, compute_dtype=config.compute_dtype)
     diffuser.load_model(config)
-    for samp_i in range(config.start_idx + rank, config.start_idx + config.num_samples, world):
-        # the Philox stream is keyed by (seed, global sample index): every samp_i gets its own noise on any rank count
-        diffuser.gen_images(config.img_folder, samp_i, seed=config.seed, sample_base=samp_i * config.num_classes)
+    # each rank takes a contiguous block of samp_i and samples several of them per call so that the batch fills the GPU;
+    # the Philox stream is keyed by (seed, global sample index = samp_i * num_classes + class): every image is the same
+    # on any rank count and for any grouping
+    from .sharding import shard_bounds
+
+    lo, hi = shard_bounds(config.num_samples, world, rank)
+    group = max(1, config.batch_samples // config.num_classes)
+    for first in range(config.start_idx + lo, config.start_idx + hi, group):
+        samp_is = list(range(first, min(first + group, config.start_idx + hi)))
+        diffuser.gen_images_many(config.img_folder, samp_is, seed=config.seed, sample_base=first * config.num_classes)
     print("done!")
 
 

@@ -146,6 +146,32 @@ def test_gen_images_writes_reference_named_pngs(tmp_path):
     d.load_model(types.SimpleNamespace(load_model=False, run_name="x"))
 
 
+def test_gen_images_many_equals_per_samp_i_calls(tmp_path):
+    """The generation driver samples several samp_i per call (the 27-label batch alone under-fills the GPU): files and
+    pixels must be those of the reference-style one-call-per-samp_i loop (Philox keyed by the global sample index)."""
+    import numpy as np
+    from PIL import Image
+
+    from oracle.weights import make_state_dict
+    from spectrogramgenai_b200.diff_modules import DiffusionVAE
+
+    T, S, names = 4, 16, ["a", "b", "c"]
+    d = DiffusionVAE(noise_steps=T, img_size=4 * S, num_classes=3, device=DEV, class_names=names,
+                     vqae_state_dict=V.make_vqae_state_dict(VAE_SEED), compute_dtype="bf16")
+    d.model.load_state_dict(make_state_dict(1234, 4, 4, 3))
+    lut = np.stack([np.linspace(0, 1, 256), np.linspace(1, 0, 256), np.full(256, 0.5), np.ones(256)], 1)
+    cm = lambda a: lut[a]  # noqa: E731
+    one, many = tmp_path / "one", tmp_path / "many"
+    one.mkdir()
+    many.mkdir()
+    for samp_i in (5, 6, 7):
+        d.gen_images(str(one), samp_i, colormap=cm, seed=3, sample_base=samp_i * 3)
+    paths = d.gen_images_many(str(many), [5, 6, 7], colormap=cm, seed=3, sample_base=5 * 3)
+    assert len(paths) == 9 and sorted(os.listdir(one)) == sorted(os.listdir(many))
+    for f in os.listdir(one):
+        assert np.array_equal(np.asarray(Image.open(one / f)), np.asarray(Image.open(many / f))), f
+
+
 def test_to_uint8_wrap_matches_torch_cast():
     """sg_to_uint8_wrap = the un-clamped `((x + 1) / 2 * 255).type(torch.uint8)` of the trajectory dumps (:672-675),
     including values that leave [0, 255] (torch's CPU cast is the checker) and a ragged count."""
