@@ -317,23 +317,29 @@ class Diffusion:
         that the batch fills the GPU (27 labels alone run at ~75 % of the throughput of a 512-sample batch).  Files and
         pixels are those of the per-`samp_i` calls when the caller passes `sample_base = samp_is[0] * len(labels)`
         and consecutive `samp_is` (the Philox stream is keyed by the global sample index)."""
+        if labels is None:
+            labels = torch.arange(self.num_classes).long().to(self.device)
+        labels = torch.as_tensor(labels).reshape(-1)
+        samp_is = list(samp_is)
+        sampled_images = self.sample(False, labels.repeat(len(samp_is)), **sample_kw)
+        return self.write_images(img_folder, samp_is, labels, sampled_images, colormap=colormap)
+
+    def write_images(self, img_folder, samp_is, labels, sampled_images, *, colormap=None):
+        """Host half of gen_images (:766-775): colour map + PNG files for images [len(samp_is) * len(labels), 1, H, W]
+        (device or host tensor; the copy to the host happens here, so a caller may run this on a worker thread while the
+        next batch is being sampled)."""
         import numpy as np
         from PIL import Image
 
         if colormap is None:
             colormap = getattr(self, "colormap", None) or _viridis()
         class_names = getattr(self, "class_names", None) or [str(k) for k in range(self.num_classes or 0)]
-        if labels is None:
-            labels = torch.arange(self.num_classes).long().to(self.device)
-        labels = torch.as_tensor(labels).reshape(-1)
-        samp_is = list(samp_is)
-        sampled_images = self.sample(False, labels.repeat(len(samp_is)), **sample_kw)
-        lab_list = labels.tolist()
+        lab_list = torch.as_tensor(labels).reshape(-1).tolist()
+        host = sampled_images.cpu().numpy()
         paths = []
         for g, samp_i in enumerate(samp_is):
             for i, lab in enumerate(lab_list):
-                img = sampled_images[g * len(lab_list) + i]
-                rgba = colormap(img.permute(1, 2, 0).cpu().numpy().squeeze())
+                rgba = colormap(host[g * len(lab_list) + i].transpose(1, 2, 0).squeeze())
                 rgba = (np.asarray(rgba) * 255).astype(np.uint8)
                 path = f"{img_folder}/{class_names[lab]}_gen_imgs_{i}_{samp_i}.png"
                 Image.fromarray(rgba).save(path)

@@ -63,9 +63,20 @@ def main(argv=None):
 
     lo, hi = shard_bounds(config.num_samples, world, rank)
     group = max(1, config.batch_samples // config.num_classes)
-    for first in range(config.start_idx + lo, config.start_idx + hi, group):
-        samp_is = list(range(first, min(first + group, config.start_idx + hi)))
-        diffuser.gen_images_many(config.img_folder, samp_is, seed=config.seed, sample_base=first * config.num_classes)
+    labels = torch.arange(config.num_classes).long()
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=1) as writer:  # colour map + PNG encoding of batch k overlap the sampling of k+1
+        pending = None
+        for first in range(config.start_idx + lo, config.start_idx + hi, group):
+            samp_is = list(range(first, min(first + group, config.start_idx + hi)))
+            images = diffuser.sample(False, labels.repeat(len(samp_is)), seed=config.seed,
+                                     sample_base=first * config.num_classes)
+            if pending is not None:
+                pending.result()
+            pending = writer.submit(diffuser.write_images, config.img_folder, samp_is, labels, images)
+        if pending is not None:
+            pending.result()
     print("done!")
 
 

@@ -172,6 +172,41 @@ def test_gen_images_many_equals_per_samp_i_calls(tmp_path):
         assert np.array_equal(np.asarray(Image.open(one / f)), np.asarray(Image.open(many / f))), f
 
 
+def test_generation_driver_cli(tmp_path, monkeypatch):
+    """python -m spectrogramgenai_b200.generate (the drop-in for src/ddpm_conditional_generate.py): class names from
+    <dataset>/train, weights from models/<run_name>/ckpt.pt + the VQAE checkpoint, num_samples x num_classes PNGs named
+    as the downstream parser expects -- identical for any --batch_samples grouping."""
+    import numpy as np
+    from PIL import Image
+
+    from oracle.weights import make_state_dict
+    from spectrogramgenai_b200 import diff_modules, generate
+
+    names = ["blackbird", "robin", "wren"]
+    for nm in names:
+        (tmp_path / "data" / "train" / nm).mkdir(parents=True)
+    (tmp_path / "models" / "run").mkdir(parents=True)
+    torch.save(make_state_dict(1234, 4, 4, 3), tmp_path / "models" / "run" / "ckpt.pt")
+    torch.save({}, tmp_path / "models" / "run" / "optim.pt")
+    torch.save(V.make_vqae_state_dict(VAE_SEED), tmp_path / "vqae.pt")
+    lut = np.stack([np.linspace(0, 1, 256), np.linspace(1, 0, 256), np.full(256, 0.5), np.ones(256)], 1)
+    monkeypatch.setattr(diff_modules, "_viridis", lambda: (lambda a: lut[a]))  # matplotlib is absent from the image
+    monkeypatch.chdir(tmp_path)
+    outs = {}
+    for tag, bs in (("grouped", 6), ("single", 3)):
+        argv = ["--num_classes", "3", "--noise_steps", "4", "--img_size", "64", "--img_folder", str(tmp_path / tag),
+                "--num_samples", "5", "--run_name", "run", "--dataset_path", str(tmp_path / "data"),
+                "--vqae_path", str(tmp_path / "vqae.pt"), "--batch_samples", str(bs), "--start_idx", "2"]
+        generate.main(argv)
+        outs[tag] = sorted(os.listdir(tmp_path / tag))
+    want = sorted(f"{names[c]}_gen_imgs_{c}_{k}.png" for c in range(3) for k in range(2, 7))
+    assert outs["grouped"] == want and outs["single"] == want
+    for f in want:
+        a, b = Image.open(tmp_path / "grouped" / f), Image.open(tmp_path / "single" / f)
+        assert a.mode == "RGBA" and a.size == (64, 64)
+        assert np.array_equal(np.asarray(a), np.asarray(b)), f
+
+
 def test_to_uint8_wrap_matches_torch_cast():
     """sg_to_uint8_wrap = the un-clamped `((x + 1) / 2 * 255).type(torch.uint8)` of the trajectory dumps (:672-675),
     including values that leave [0, 255] (torch's CPU cast is the checker) and a ragged count."""
