@@ -286,6 +286,14 @@ class Diffusion:
             self.ema_model = copy.deepcopy(self.model).eval().requires_grad_(False)
             self.ema_model.load_state_dict(torch.load(ema_path, weights_only=True))
 
+    def prepare(self, args):
+        """Reference `prepare(args)` (:548-560) as far as sampling needs it: the run folders of `mk_folders`
+        (models/<run_name>, results/<run_name>) and the EMA helper.  The data loaders, AdamW, OneCycleLR and GradScaler
+        the reference also builds here belong to training (no backward pass in this package)."""
+        os.makedirs(os.path.join("models", args.run_name), exist_ok=True)
+        os.makedirs(os.path.join("results", args.run_name), exist_ok=True)
+        self.ema = EMA(0.995)
+
     def load_model(self, args):
         """Reference `load_model(args)` (:525-546): loads models/<run_name>/ckpt.pt when args.load_model is set and
         raises FileNotFoundError when a checkpoint is missing.  The reference also restores optim.pt into its AdamW

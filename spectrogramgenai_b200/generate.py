@@ -26,6 +26,8 @@ def parse_args(argv=None):
     p.add_argument("--seed", type=int, default=c.seed)
     p.add_argument("--img_size", type=int, default=c.img_size)
     p.add_argument("--num_classes", type=int, default=c.num_classes)
+    p.add_argument("--device", type=str, default="cuda", help="accepted for compatibility; sampling runs on the rank's B200")
+    p.add_argument("--slice_size", type=int, default=1, help="accepted for compatibility (training-data option, unused)")
     p.add_argument("--noise_steps", type=int, default=c.noise_steps)
     p.add_argument("--load_model", type=bool, default=True)
     p.add_argument("--img_folder", type=str, default=c.img_folder)
@@ -50,11 +52,16 @@ def main(argv=None):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     set_seed(config.seed)
+    if not str(config.device).startswith("cuda"):
+        raise SystemExit(f"--device {config.device}: this generator runs on B200 (CUDA) devices only")
     os.makedirs(config.img_folder, exist_ok=True)
+    if config.sav_denoise_path is not None:
+        os.makedirs(config.sav_denoise_path, exist_ok=True)
     class_names = sorted(os.listdir(os.path.join(config.dataset_path, config.train_folder)))
     diffuser = DiffusionVAE(config.noise_steps, img_size=config.img_size, num_classes=config.num_classes,
                             device=f"cuda:{local}", vqae_path=config.vqae_path, sav_denoise_path=config.sav_denoise_path,
                             class_names=class_names, compute_dtype=config.compute_dtype)
+    diffuser.prepare(config)
     diffuser.load_model(config)
     # each rank takes a contiguous block of samp_i and samples several of them per call so that the batch fills the GPU;
     # the Philox stream is keyed by (seed, global sample index = samp_i * num_classes + class): every image is the same

@@ -196,7 +196,8 @@ def test_generation_driver_cli(tmp_path, monkeypatch):
     for tag, bs in (("grouped", 6), ("single", 3)):
         argv = ["--num_classes", "3", "--noise_steps", "4", "--img_size", "64", "--img_folder", str(tmp_path / tag),
                 "--num_samples", "5", "--run_name", "run", "--dataset_path", str(tmp_path / "data"),
-                "--vqae_path", str(tmp_path / "vqae.pt"), "--batch_samples", str(bs), "--start_idx", "2"]
+                "--vqae_path", str(tmp_path / "vqae.pt"), "--batch_samples", str(bs), "--start_idx", "2", "--device", "cuda",
+                "--slice_size", "1"]
         generate.main(argv)
         outs[tag] = sorted(os.listdir(tmp_path / tag))
     want = sorted(f"{names[c]}_gen_imgs_{c}_{k}.png" for c in range(3) for k in range(2, 7))
