@@ -570,6 +570,26 @@ def test_attention_tensor_core_reference_overflow(ops, rows, L, C, dtype):
     assert err < (8e-3 if dtype == torch.bfloat16 else 1.5e-3)
 
 
+def test_attention_grid_split_beyond_32768_query_tiles(ops):
+    """More than 32768 query tiles per head (n > 512 at [4, 64, 64]) spill into the grid's z dimension.  Property check at
+    rows = 2048, L = 4096, d = 16 (65536 tiles): every row equals what it gets when its half is run alone."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    rows, L, C = 2048, 4096, 64
+    g = torch.Generator(device=DEV).manual_seed(3)
+    qkv = torch.empty(rows * L, 3 * C, device=DEV, dtype=torch.bfloat16)
+    for r0 in range(0, rows, 256):  # generated in slices: no full-size fp32 temporary
+        qkv[r0 * L:(r0 + 256) * L] = torch.randn(256 * L, 3 * C, device=DEV, generator=g).to(torch.bfloat16)
+    out = torch.empty(rows * L, C, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, rows=rows, L=L, C=C, engine=SG_ENGINE_TC)
+    half = rows // 2
+    for h in (0, 1):
+        o = torch.empty(half * L, C, device=DEV, dtype=torch.bfloat16)
+        ops.attention(qkv[h * half * L:(h + 1) * half * L], o, rows=half, L=L, C=C, engine=SG_ENGINE_TC)
+        assert torch.equal(o, out[h * half * L:(h + 1) * half * L]), h
+    assert torch.isfinite(out.float()).all()
+
+
 def test_error_reporting(ops):
     """Bad arguments come back as a status + message (no exception crosses the C ABI, no crash)."""
     from spectrogramgenai_b200._cabi import SgError

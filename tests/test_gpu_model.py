@@ -242,3 +242,43 @@ def test_return_trajectory_matches_oracle_step_by_step():
     assert torch.equal(u8.cpu(), O.to_uint8(traj[-1].cpu()))
     u8b, trajb = d.sample(False, y, cfg_scale=3, noise=noise, return_trajectory=True, micro_batch=2, max_steps=5)
     assert trajb.shape == (6, n, c, s, s) and torch.equal(trajb, traj[:6])
+
+
+def test_full_bench_batch_is_batch_invariant():
+    """BASELINE configs[2] geometry at full size: one CFG step of n = 512 spectrograms at [4, 64, 64] (1024 UNet rows:
+    32768 query tiles per attention head, persistent GEMM / fused-kernel loops tens of tiles deep, the shared
+    label-independent prefix).  The oracle cannot run this size in seconds, so the check is the size-independent
+    property: a sample's conditional and unconditional predictions are bit-identical to those it gets in a batch of 2
+    (which the small-batch tests pin to the reference)."""
+    from spectrogramgenai_b200.diff_modules import UNet_conditional
+
+    m = UNet_conditional(4, 4, num_classes=NUM_CLASSES, compute_dtype="bf16")
+    m.load_state_dict(make_state_dict(WEIGHT_SEED, 4, 4, NUM_CLASSES))
+    m = m.to(DEV)
+    n, S = 512, 64
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(n, 4, S, S, generator=g).to(DEV)
+    y = (torch.arange(n) % NUM_CLASSES).to(DEV)
+    plan = m.plan(n_src=n, rows=2 * n, S=S)
+    plan.x_in.copy_(x)
+    plan.t.fill_(437.0)
+    plan.y.fill_(-1)
+    plan.y[:n].copy_(y)
+    plan.run()
+    torch.cuda.synchronize()
+    big = plan.eps.clone()
+    assert torch.isfinite(big).all()
+    m.release_plans()
+    pick = [0, 255, 511]
+    for i in pick:
+        small = m.plan(n_src=2, rows=4, S=S)
+        j = (i + 7) % n
+        small.x_in.copy_(x[[i, j]])
+        small.t.fill_(437.0)
+        small.y.fill_(-1)
+        small.y[:2].copy_(y[[i, j]])
+        small.run()
+        torch.cuda.synchronize()
+        assert torch.equal(small.eps[0], big[i]) and torch.equal(small.eps[2], big[n + i]), i
+        assert torch.equal(small.eps[1], big[j]) and torch.equal(small.eps[3], big[n + j]), j
+    m.release_plans()
