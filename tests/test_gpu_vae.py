@@ -172,6 +172,19 @@ def test_gen_images_many_equals_per_samp_i_calls(tmp_path):
         assert np.array_equal(np.asarray(Image.open(one / f)), np.asarray(Image.open(many / f))), f
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_decode_is_micro_batch_invariant(mode):
+    """The decode tail at the generator's geometry ([n, 4, 64, 64] -> [n, 1, 256, 256]) for n = 130: the images do not
+    depend on how the samples are chunked (64 + 64 + 2, one chunk of 130, chunks of 7)."""
+    dec = _decoder(mode)
+    x = golden_latents(64, 130, 21).to(DEV)
+    a = dec.decode(x, micro_batch=64)
+    b = dec.decode(x, micro_batch=130)
+    c = dec.decode(x, micro_batch=7)
+    assert a.shape == (130, 1, 256, 256) and a.dtype == torch.uint8
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
 def test_generation_driver_cli(tmp_path, monkeypatch):
     """python -m spectrogramgenai_b200.generate (the drop-in for src/ddpm_conditional_generate.py): class names from
     <dataset>/train, weights from models/<run_name>/ckpt.pt + the VQAE checkpoint, num_samples x num_classes PNGs named
