@@ -100,41 +100,119 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference path on the host cores (bounded sample)
+# CPU baseline: the UNMODIFIED reference on the host cores (bounded sample); the oracle port only as a fallback
 # ----------------------------------------------------------------------------------------------------
-def cpu_baseline(S, c, n_cpu, steps, warmup=1):
-    from oracle import ddpm_oracle as O
-    from oracle.weights import make_state_dict
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")  # staged by __graft_entry__.build() from /root/reference/src (git-ignored)
 
+
+def import_reference():
+    """The reference's own modules (src/diff_modules.py + src/diff_utils.py, unmodified, staged under baseline/_ref/).
+    They import matplotlib at module top only for plotting and it is absent from this image, so two empty modules are
+    registered first.  Returns the diff_modules module or None."""
+    if not os.path.exists(os.path.join(REF_DIR, "diff_modules.py")):
+        return None
+    import types
+
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    if "matplotlib" not in sys.modules:
+        try:
+            import matplotlib  # noqa: F401
+            import matplotlib.pyplot  # noqa: F401
+        except ImportError:
+            plt = types.ModuleType("matplotlib.pyplot")
+            mpl = types.ModuleType("matplotlib")
+            mpl.pyplot = plt
+            sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import diff_modules  # the reference's module (bare name, as its own scripts import it)
+    except Exception as e:  # pragma: no cover - depends on the box
+        sys.stderr.write(f"bench: reference import failed ({type(e).__name__}: {e}); falling back to the oracle port\n")
+        return None
+    diff_modules.progress_bar = lambda it, **kw: it  # silence tqdm; the loop body is untouched
+    return diff_modules
+
+
+def cpu_baseline(S, c, n_cpu, steps, warmup=1):
+    """The reference's CPU sampling path, timed on the host cores on a bounded sample: `steps` loop iterations of
+    Diffusion.sample (2 UNet forwards + lerp + posterior update + randn each) at batch n_cpu, extrapolated to the T-1 = 999
+    iterations of a full run.  kind "reference": the reference's own Diffusion / UNet_conditional classes through their
+    public API -- sample() runs noise_steps-1 iterations, so a Diffusion(noise_steps=steps+1) call is exactly `steps`
+    iterations of the stock loop (same per-iteration work, shorter schedule).  kind "port": the oracle restatement."""
     torch.set_num_threads(os.cpu_count())
-    sd = make_state_dict(1234, c, c, NUM_CLASSES)
     y = torch.arange(n_cpu) % NUM_CLASSES
-    g = torch.Generator().manual_seed(0)
-    noise = torch.randn((warmup + steps + 1, n_cpu, c, S, S), generator=g)
-    ts = []
-    beta, alpha, ah = O.noise_schedule(T_STEPS)
-    c1, c2, c3 = O.posterior_coefficients(beta, alpha, ah)
-    x = noise[0]
-    for k in range(warmup + steps):
-        i = T_STEPS - 1 - k
-        t0 = time.perf_counter()
-        t = (torch.ones(n_cpu) * i).long()
-        e_c = O.unet_forward(sd, x, t, y)
-        e_u = O.unet_forward(sd, x, t, None)
-        eps = O.cfg_combine(e_c, e_u, 3)
-        x = O.posterior_update(x, eps, c1[i], c2[i], c3[i], noise[k + 1])
-        ts.append(time.perf_counter() - t0)
-    sec = sum(ts[warmup:]) / steps
+    dm = import_reference()
+    if dm is not None:
+        torch.manual_seed(0)
+
+        def run(k):
+            d = dm.Diffusion(noise_steps=k + 1, img_size=S, num_classes=NUM_CLASSES, c_in=c, c_out=c, device="cpu")
+            t0 = time.perf_counter()
+            out = d.sample(False, y, cfg_scale=3)
+            dt = time.perf_counter() - t0
+            assert tuple(out.shape) == (n_cpu, c, S, S) and out.dtype == torch.uint8
+            return dt
+
+        run(max(1, warmup))
+        sec = run(steps) / steps
+        kind = "reference"
+        what = ("the unmodified reference (baseline/_ref: src/diff_modules.py Diffusion.sample, nn.MultiheadAttention incl. "
+                "its discarded head-averaged weights)")
+    else:
+        from oracle import ddpm_oracle as O
+        from oracle.weights import make_state_dict
+
+        sd = make_state_dict(1234, c, c, NUM_CLASSES)
+        g = torch.Generator().manual_seed(0)
+        noise = torch.randn((warmup + steps + 1, n_cpu, c, S, S), generator=g)
+        ts = []
+        beta, alpha, ah = O.noise_schedule(T_STEPS)
+        c1, c2, c3 = O.posterior_coefficients(beta, alpha, ah)
+        x = noise[0]
+        for k in range(warmup + steps):
+            i = T_STEPS - 1 - k
+            t0 = time.perf_counter()
+            t = (torch.ones(n_cpu) * i).long()
+            e_c = O.unet_forward(sd, x, t, y)
+            e_u = O.unet_forward(sd, x, t, None)
+            eps = O.cfg_combine(e_c, e_u, 3)
+            x = O.posterior_update(x, eps, c1[i], c2[i], c3[i], noise[k + 1])
+            ts.append(time.perf_counter() - t0)
+        sec = sum(ts[warmup:]) / steps
+        kind = "port"
+        what = "oracle port of the reference (same ATen CPU kernels, attention without the discarded head-averaged weights)"
     return {
         "value": n_cpu / (sec * (T_STEPS - 1)),
         "unit": UNIT,
         "cores": torch.get_num_threads(),
-        "kind": "port",
+        "kind": kind,
         "sample": f"{steps} CFG timesteps (2 UNet fwd + update each) of n={n_cpu} at [{c},{S},{S}] fp32 on the host, "
-                  f"{sec:.3f} s/step, extrapolated x{T_STEPS - 1} timesteps; oracle port of the reference "
-                  "(same ATen CPU kernels, attention without the discarded head-averaged weights)",
+                  f"{sec:.3f} s/step, extrapolated x{T_STEPS - 1} timesteps; {what}",
         "sec_per_step": sec,
     }
+
+
+def flops_per_forward(s, c_in=4, c_out=4):
+    """Algorithmic FLOPs (2 * MAC) of one UNet_conditional forward for one sample at S x S:
+    conv 2*Cin*Cout*9*h*w, Linear 2*Cin*Cout per token, SelfAttention block 12*L*C^2 + 4*L^2*C, emb_layer 2*256*Cout."""
+    def dc(cin, cout, hw, mid=None):
+        mid = mid or cout
+        return 2.0 * 9 * hw * (cin * mid + mid * cout)
+
+    def sa(ch, L):
+        return 12.0 * L * ch * ch + 4.0 * L * L * ch
+
+    s1, s2, s4, s8 = s * s, (s // 2) ** 2, (s // 4) ** 2, (s // 8) ** 2
+    f = dc(c_in, 64, s1)
+    f += dc(64, 64, s2) + dc(64, 128, s2) + 512.0 * 128 + sa(128, s2)
+    f += dc(128, 128, s4) + dc(128, 256, s4) + 512.0 * 256 + sa(256, s4)
+    f += dc(256, 256, s8) + dc(256, 256, s8) + 512.0 * 256 + sa(256, s8)
+    f += dc(256, 512, s8) + dc(512, 512, s8) + dc(512, 256, s8)
+    f += dc(512, 512, s4) + dc(512, 128, s4, 256) + 512.0 * 128 + sa(128, s4)
+    f += dc(256, 256, s2) + dc(256, 64, s2, 128) + 512.0 * 64 + sa(64, s2)
+    f += dc(128, 128, s1) + dc(128, 64, s1, 64) + 512.0 * 64 + sa(64, s1)
+    return f + 2.0 * 64 * c_out * s1
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -150,13 +228,18 @@ def classify(fn, a, kw):
         M = g.rows * g.H * g.W
         fl = 2.0 * M * g.Cin * g.Cout * g.taps
         esz = 4 if g.act_dtype == 0 else 2
-        by = M * g.Cin * esz + g.taps * g.Cin * g.Cout * esz + M * g.Cout * (4 if g.out_f32 else 0) \
+        esz_in = esz * (2 if g.a_lo else 1)  # split-tf32 engine: hi and lo parts are both read
+        by = M * g.Cin * esz_in + g.taps * g.Cin * g.Cout * esz_in + M * g.Cout * (4 if g.out_f32 else 0) \
             + M * g.Cout * ((2 if g.out_dtype else esz) if g.out_act else 0) + (M * g.Cout * 4 if g.residual else 0)
-        eng = "tc" if g.engine == 1 else "simt"
+        eng = ("tf32x3" if g.a_lo else "tc") if g.engine == 1 else "simt"
         return (f"igemm_{eng}_conv3x3" if g.taps == 9 else f"igemm_{eng}_linear"), fl, by
     if name == "attention":
         rows, L, C = kw["rows"], kw["L"], kw["C"]
-        return "attention", 4.0 * rows * L * L * C, rows * L * C * (3 * a[0].element_size() + a[1].element_size())
+        q = a[0][0] if isinstance(a[0], tuple) else a[0]
+        qb = q.element_size() * (2 if isinstance(a[0], tuple) else 1)
+        return "attention", 4.0 * rows * L * L * C, rows * L * C * (3 * qb + a[1].element_size())
+    if name == "split_tf32":
+        return "split_tf32", 0.0, a[0].numel() * 12
     if name == "gn_apply":
         raw = a[0]
         by = raw.numel() * raw.element_size()
@@ -208,6 +291,7 @@ def per_launch_profile(plan, extra_ops, reps=2):
     """Eager pass with a CUDA event pair around every launch on the launching (current) stream."""
     ops_list = list(plan.ops) + extra_ops
     acc = {}
+    per_op = [0.0] * len(ops_list)
     for rep in range(reps + 1):
         evs = []
         torch.cuda.synchronize()
@@ -220,14 +304,15 @@ def per_launch_profile(plan, extra_ops, reps=2):
         torch.cuda.synchronize()
         if rep == 0:
             continue  # warm-up
-        for (fn, a, kw), (e0, e1) in zip(ops_list, evs):
+        for i, ((fn, a, kw), (e0, e1)) in enumerate(zip(ops_list, evs)):
             fam, fl, by = classify(fn, a, kw)
             d = acc.setdefault(fam, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            per_op[i] += e0.elapsed_time(e1) / reps
             d["ms"] += e0.elapsed_time(e1) / reps
             d["flops"] += fl / reps
             d["bytes"] += by / reps
             d["launches"] += 1.0 / reps
-    return acc
+    return acc, [(classify(fn, a, kw), (fn, a, kw), ms) for (fn, a, kw), ms in zip(ops_list, per_op)]
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -241,7 +326,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.cpu_batch, "fp32 CPU"),
+        "config": workload_config(args, args.cpu_batch, "fp32 CPU (reference Diffusion.sample on the host cores)",
+                                  loop="the reference's Python loop, bounded to --steps iterations"),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -249,7 +335,7 @@ def run_reference(args):
     emit(out)
 
 
-def workload_config(args, n, engine):
+def workload_config(args, n, engine, loop="CUDA graph replay per timestep"):
     if (args.size, args.channels) == (64, 4):
         which = "BASELINE configs[2]"  # the configuration the metric is quoted on
     elif (args.size, args.channels) == (256, 1):
@@ -263,7 +349,7 @@ def workload_config(args, n, engine):
         "step": "one denoising timestep over the batch (2n UNet rows + CFG lerp + posterior update + noise)",
         "timesteps_per_spectrogram": T_STEPS - 1,
         "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush",
-        "loop": "CUDA graph replay per timestep",
+        "loop": loop,
     }
 
 
@@ -296,7 +382,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="spectrograms per GPU")
     ap.add_argument("--size", type=int, default=64, help="UNet input size (reference generation config: 256/4 = 64)")
     ap.add_argument("--channels", type=int, default=4)
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "f16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "f16", "fp32", "fp32_simt"])
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--cpu-steps", type=int, default=10, help="CPU-baseline sample: timesteps of n = cpu-batch (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -381,14 +467,15 @@ def main():
 
     # ---- e2e: public API, pinned host labels in, uint8 host images out, the one NCCL gather included ----
     labels_host = labels.clone().pin_memory()
-    out_host = torch.empty((world * n if rank == 0 or world > 1 else n, c, S, S), dtype=torch.uint8).pin_memory()
+    out_host = torch.empty((world * n, c, S, S), dtype=torch.uint8).pin_memory() if rank == 0 else None
     d.sample(False, labels_host, 3, seed=seed, sample_base=base, micro_batch=n, max_steps=1)  # warm the API path
     sync_all()
     t0 = time.perf_counter()
     u8 = d.sample(False, labels_host, 3, seed=seed, sample_base=base, micro_batch=n, max_steps=K)
     if world > 1:
-        u8 = gather_shards(u8, world * n)
-    out_host[: u8.shape[0]].copy_(u8, non_blocking=True)
+        u8 = gather_shards(u8, world * n, dst=0)  # ONE NCCL gather to rank 0; the other ranks send and are done
+    if rank == 0:
+        out_host.copy_(u8, non_blocking=True)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -402,12 +489,12 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- per-launch profile (eager, CUDA events on the launching stream) -> roofline of the dominant family ----
+    # ---- per-launch profile (eager, CUDA events on the launching stream) -> roofline of the dominant KERNEL ----
     kernels, roofline = {}, None
     if not args.no_profile:
         extra = [(ops.cfg_update, (x, plan.eps, d._coef, plan.step), dict(cfg_scale=3.0, seed=seed, sample_base=base))]
         plan.step.fill_(T_STEPS - 1)
-        acc = per_launch_profile(plan, extra)
+        acc, per_op = per_launch_profile(plan, extra)
         tot = sum(v["ms"] for v in acc.values())
         for fam, v in sorted(acc.items(), key=lambda kv: -kv[1]["ms"]):
             tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0
@@ -415,63 +502,91 @@ def main():
             kernels[fam] = {"ms": round(v["ms"], 4), "share": round(v["ms"] / tot, 4), "launches": round(v["launches"]),
                             "tflops": round(tf, 2), "gbs": round(gb, 1)}
         kernels["_eager_step_ms"] = round(tot, 3)
-        dom = max((f for f in acc if not f.startswith("_")), key=lambda f: acc[f]["ms"])
-        v = acc[dom]
-        tensor_bound = v["flops"] / max(v["bytes"], 1.0) > peaks["tensor"] * 1e12 / (peaks["hbm"] * 1e9)
+        # the dominant kernel = the single launch that takes the largest part of the step (sa6's attention core at the
+        # baseline geometry); its algorithmic FLOPs / bytes over its own CUDA-event duration
+        (fam, fl, by), (fn, a_, kw_), ms_op = max(per_op, key=lambda r: r[2])
+        tensor_bound = fl / max(by, 1.0) > peaks["tensor"] * 1e12 / (peaks["hbm"] * 1e9)
         if tensor_bound:
-            ach = v["flops"] / (v["ms"] * 1e-3) / 1e12
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tensor"],
+            ach = fl / (ms_op * 1e-3) / 1e12
+            roofline = {"kernel": fam, "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tensor"],
                         "unit": "TFLOP/s", "frac": round(ach / peaks["tensor"], 4), "traffic": None}
         else:
-            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"],
+            ach = by / (ms_op * 1e-3) / 1e9
+            roofline = {"kernel": fam, "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"],
                         "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "traffic": None}
-        # DRAM traffic per launch of the dominant family from the committed `ncu --set full` capture of this command
-        try:
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic_r1.json")) as f:
-                tr = json.load(f).get(dom)
-            if tr and int(tr.get("batch_per_gpu", -1)) == n and tr.get("mode") == args.mode:
-                roofline["traffic"] = tr["dram_bytes_per_launch"]
-                roofline["traffic_source"] = tr["source"]
-        except (OSError, ValueError):
-            pass
-        if dom == "attention":
-            # d = 16 heads: a score tile is 0.5 M tensor MACs but 16 K exponentials, so the binding unit is the MUFU
-            # pipe (16 ex2/clk/SM, measured 15.8), not the tensor pipe: report that roofline beside the tensor one
-            exps = sum(float(kw["rows"]) * 4 * kw["L"] * kw["L"] for fn, a, kw in plan.ops if fn.__name__ == "attention")
+        roofline["launch"] = {k: kw_[k] for k in ("rows", "L", "C") if k in kw_} or None
+        roofline["launch_ms"] = round(ms_op, 4)
+        roofline["share_of_step"] = round(ms_op / tot, 4)
+        roofline["algorithmic_flops_per_launch"] = fl
+        roofline["algorithmic_bytes_per_launch"] = by
+        famv = acc[fam]
+        roofline["family"] = {"launches_per_step": round(famv["launches"]), "ms": round(famv["ms"], 4),
+                              "tflops": round(famv["flops"] / (famv["ms"] * 1e-3) / 1e12, 2),
+                              "frac_of_tensor_peak": round(famv["flops"] / (famv["ms"] * 1e-3) / 1e12 / peaks["tensor"], 4)}
+        # DRAM traffic of that launch from the committed `ncu --set full` capture of this command
+        for name in ("ncu_traffic_r2.json", "ncu_traffic_r1.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    tr = json.load(f).get(fam)
+                if tr and int(tr.get("batch_per_gpu", -1)) == n and tr.get("mode") == args.mode:
+                    roofline["traffic"] = tr.get("dram_bytes_dominant_launch", tr.get("dram_bytes_per_launch"))
+                    roofline["traffic_source"] = tr["source"]
+                    break
+            except (OSError, ValueError):
+                pass
+        if fam == "attention":
+            # d = 16 heads: a 128 x 128 score tile is 0.5 M tensor MACs but 16 K exponentials, so what binds the kernel is
+            # the exponential rate, not the tensor pipe.  Exponentials are produced by two units: MUFU (16 ex2/clk/SM)
+            # and, for POLY/8 of the pairs, a degree-3 polynomial on the FMA pipe (measured cost: 3 FMA-pipe instructions
+            # per element beyond the scale FMA every element needs).  Report true utilisations at the sampled SM clock.
+            L_, C_, rows_ = kw_["L"], kw_["C"], kw_["rows"]
+            dh = C_ // 4
+            exps = float(rows_) * 4 * L_ * L_
+            poly = (3.0 / 8 if dh == 16 else 1.0 / 4) if L_ >= 128 else 0.0
             sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-            mufu_peak = 16.0 * 148 * sm_mhz * 1e6
+            clk_s = 148 * sm_mhz * 1e6 * (ms_op * 1e-3)  # SM-clocks spent by the launch
+            xu_util = exps * (1 - poly) / (16.0 * clk_s)
+            # FMA-pipe thread-instructions per element: 0.5 (packed scale FMA) + poly * 5 * 0.5 (packed Cody-Waite +
+            # Horner) + 0.5 (packed F2FP runs on the FMA-heavy half pipe, pipe_bench: 62/clk); 64 packed issues/clk/SM
+            fma_util = exps * (0.5 + poly * 2.5 + 0.5) / (64.0 * clk_s)
+            t_mufu = exps * (1 - poly) / 16.0
+            t_fma = exps * (1.0 + poly * 2.5) / 64.0
             roofline["binding_unit"] = {
-                "unit": "MUFU ex2 (16/clk/SM at the sampled SM clock); 1/4 of the exponentials run on the FMA pipe",
-                "exp_per_s": round(exps / (v["ms"] * 1e-3), 1), "mufu_peak_exp_per_s": mufu_peak,
-                "frac_all_on_mufu": round(exps / (v["ms"] * 1e-3) / mufu_peak, 4)}
+                "unit": "exponential throughput: MUFU ex2 (16/clk/SM) + FMA-pipe polynomial for %.3f of the pairs" % poly,
+                "exp_per_s": round(exps / (ms_op * 1e-3), 1), "sm_mhz": sm_mhz,
+                "xu_pipe_util": round(xu_util, 4), "fma_pipe_util_model": round(fma_util, 4),
+                "joint_bound_ms": round(max(t_mufu, t_fma) / (148 * sm_mhz * 1e6) * 1e3, 3),
+                "frac_of_joint_bound": round(max(t_mufu, t_fma) / clk_s, 4),
+                "note": "xu_pipe_util = MUFU-evaluated exponentials / (16 per clk per SM x SM-clocks of the launch): a "
+                        "utilisation, comparable with ncu's sm__inst_executed_pipe_xu; joint bound = the slower of the two "
+                        "pipes if they overlapped perfectly"}
         roofline["peak_source"] = peaks["source"]
-        roofline["launches_per_step"] = round(v["launches"])
-        roofline["avg_launch_ms"] = round(v["ms"] / max(v["launches"], 1), 4)
 
     cb = None
     if not args.no_cpu_baseline:
         cb = cpu_baseline(S, c, args.cpu_batch, args.cpu_steps)
         cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    from oracle.ddpm_oracle import flops_per_forward
-
     flops_step = 2.0 * n * flops_per_forward(S, c, c)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.mode, "data": "synthetic (random-init weights seed 42, Philox x_T and noise)",
-        "config": workload_config(args, n, f"{args.mode} operands, fp32 accumulate (tcgen05)" if args.mode != "fp32" else "fp32 SIMT"),
+        "config": workload_config(args, n, {
+            "bf16": "bf16 operands, fp32 accumulate (tcgen05 kind::f16)", "f16": "fp16 operands, fp32 accumulate (tcgen05 kind::f16)",
+            "fp32": "fp32 operands split hi + lo, 3 x tcgen05 kind::tf32 per product, fp32 accumulate",
+            "fp32_simt": "fp32 CUDA-core kernels (comparator)"}[args.mode]),
         "unet_fwd_ms_per_step": ms_per_step,
         "model_tflops": round(world * flops_step / (ms_per_step * 1e-3) / 1e12, 2),
         "model_tflops_frac_of_peak": round(flops_step / (ms_per_step * 1e-3) / 1e12 / peaks["tensor"], 4),
         "finite": finite,
+        "fp16_range_guard_tripped": plan.range_overflow(),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": labels_host.numel() * 8 / K,
-                "d2h_bytes_per_step": n * c * S * S / K,
+                "d2h_bytes_per_step": world * n * c * S * S / K,
                 "note": f"Diffusion.sample(labels on pinned host, max_steps={K}) -> uint8 on pinned host; one call "
-                        "includes x_T Philox init, graph capture, K timesteps, uint8 tail"
-                        + (", NCCL all_gather of the uint8 output" if world > 1 else "")
+                        "includes x_T Philox init, K replays of the step graph cached with the plan, uint8 tail"
+                        + (", one NCCL gather of the uint8 output to rank 0" if world > 1 else "")
                         + "; per-call copies are amortised over K (a real run amortises them over 999)"},
         "gpu_launches": world * K * launches_per_step,
         "launches_per_step": launches_per_step,

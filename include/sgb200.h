@@ -7,13 +7,18 @@
  * the ctypes stub a maintainer of the reference would add.
  *
  * Conventions
- *   - every pointer is a DEVICE pointer owned by the caller (PyTorch owns all memory);
- *     kernels never allocate, free or synchronise;
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch owns all memory), with two documented exceptions
+ *     (the <= 9 KB weights of sg_conv_in and of the fused output conv are HOST pointers: they travel BY VALUE as kernel
+ *     launch parameters); kernels never allocate, free or synchronise;
+ *   - the library keeps no mutable device state: every launch carries its own operands, so calls on different streams,
+ *     for different models (model and ema_model) or on different devices of one process are independent.  Host-side
+ *     caches are read-only after first use and keyed by device (function attributes, SM count);
  *   - activations are channels-last: [rows, H, W, C] ("NHWC"), rows = batch rows
  *     (2n when the conditional and unconditional passes are batched).  H and W are powers
  *     of two;
- *   - "act" tensors are SG_F32 (fp32-accurate SIMT engine) or SG_BF16 / SG_F16 (tcgen05
- *     engine: 16-bit operands, fp32 accumulation in TMEM);
+ *   - "act" tensors are SG_BF16 / SG_F16 (tcgen05 engine: 16-bit operands, fp32 accumulation in TMEM) or SG_F32:
+ *     with SG_ENGINE_TC the fp32-accurate tensor-core engine (split-TF32 operands x = hi + lo, three kind::tf32 MMAs per
+ *     product into one fp32 TMEM accumulator), with SG_ENGINE_SIMT the CUDA-core comparator kernels;
  *   - every function returns 0 on success, non-zero on error; sg_last_error() returns a
  *     thread-local human-readable reason.  No exceptions, no CPU fallback: a non-sm_100
  *     device is an error (SG_ERR_ARCH);
@@ -28,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 13
+#define SG_ABI_VERSION 14
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -46,13 +51,13 @@ enum {
 typedef void* sg_stream_t;
 
 int sg_abi_version(void);
-/* Programmatic dependent launch of the step kernels: 0 = off (every launch fully serialised), 1 = every launch,
- * 2 = only grids of at most 4 x #SM CTAs.  Process-wide tuning knob (it affects launch overlap only, never results); the
- * SGB200_PDL environment variable, when set, wins.  Measured: mode 2 lowers the latency of a CFG step by 5 % at batch 1-8
- * and costs 0.6 % at batch 512, so the Python plan selects 2 for small batches and 0 for large ones. */
+/* Programmatic dependent launch of the step kernels issued by the CALLING THREAD from now on: 0 = off (every launch fully
+ * serialised), 1 = every launch, 2 (default) = only grids of at most 4 x #SM CTAs.  Thread-local launch policy, like the
+ * current device; it affects launch overlap only, never results.  Measured: mode 2 lowers the latency of a CFG step by
+ * 5 % at batch 1-8 and costs 0.6 % at batch 512, so the Python plan selects 2 for small batches and 0 for large ones. */
 int sg_set_pdl(int mode);
 const char* sg_last_error(void);
-/* 0 iff `device` is a compute-capability 10.x device with the sm_100a image loadable. */
+/* 0 iff `device` is a compute-capability 10.0 device (B200: the library ships an sm_100a image only). */
 int sg_device_check(int device);
 /* Make `device` current for this library's CUDA runtime on the calling thread (one rank = one GPU). */
 int sg_set_device(int device);
@@ -77,9 +82,11 @@ int sg_time_embed(const float* t, const int32_t* step, const int64_t* y, const f
  * replaces nn.Conv2d(c_in, 64, 3, padding=1, bias=False) (:82 via :144).  Row r reads sample
  * r % n_src of x (the cond/uncond halves share x).  Also emits GroupNorm partial sums:
  * partials fp32 [rows, P, 2] (sum, sum of squares), P = sg_conv_in_partials(S).
+ * `w` is a HOST pointer: the 64 x c_in x 9 weights (<= 9216 B) are passed by value as a kernel parameter, so every FMA
+ * reads its weight as a constant-bank operand and each launch owns its copy (no global bank, no repack launch).
  */
 int sg_conv_in_partials(int S);
-int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w /*[64,c_in,3,3]*/, int rows,
+int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w /* HOST [64,c_in,3,3] */, int rows,
                void* raw, int raw_dtype /* SG_F32 or SG_F16 (saturating) */, float* partials, sg_stream_t stream);
 
 /* ---- K1: implicit-GEMM 3x3 (taps=9, pad 1) or 1x1 (taps=1; Linear) over NHWC activations ----
@@ -88,8 +95,10 @@ int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w /*[64,
  * out[m, co] = sum_{tap, ci} a[pixel(m) + tap offset, ci] * w[tap, co, ci]; epilogue, in order:
  * + bias[co]; GELU(erf) if gelu; + residual[m, co].  M = rows*H*W.
  * SG_ENGINE_SIMT: fp32 CUDA-core kernel (act_dtype = SG_F32).  SG_ENGINE_TC: tcgen05/TMEM kernel
- * fed by TMA (act_dtype = SG_BF16 or SG_F16, fp32 accumulate).
- * Requires Cin % 64 == 0 (TC) / % 16 (SIMT), Cout % 64 == 0.
+ * fed by TMA: act_dtype = SG_BF16 or SG_F16 (fp32 accumulate), or act_dtype = SG_F32 = the fp32-accurate engine on
+ * split-TF32 operands: a / w hold the hi parts, a_lo / w_lo the lo parts (sg_split_tf32), and the kernel accumulates
+ * a_hi w_hi + a_hi w_lo + a_lo w_hi in one fp32 TMEM tile (eps rel-L2 ~1e-6 of the fp32 reference; plain TF32: ~1e-3).
+ * Requires Cin % 64 == 0 (TC 16-bit) / % 32 (TC fp32) / % 16 (SIMT), Cout % 64 == 0.
  */
 typedef struct {
   const void* a;         /* act  [rows, H, W, Cin]                              */
@@ -99,6 +108,8 @@ typedef struct {
   float* out_f32;        /* fp32 [M, Cout] or NULL                              */
   void* out_act;         /* act  [M, Cout] or NULL                              */
   float* partials;       /* fp32 [rows, P, 2] GroupNorm partial sums or NULL    */
+  const void* a_lo;      /* fp32 engine on tensor cores: lo part of a (same shape), else NULL */
+  const void* w_lo;      /* fp32 engine on tensor cores: lo part of w (same shape), else NULL */
   int32_t rows, H, W, Cin, Cout, taps;
   int32_t act;           /* sg_act: applied as described below                  */
   int32_t engine;        /* sg_engine                                           */
@@ -120,10 +131,14 @@ int sg_igemm(const sg_igemm_args* args, sg_stream_t stream);
  * inc and down1's convolutions see no embedding, :187-188, :110-113).
  * raw is fp32 (raw_dtype SG_F32) or fp16 (SG_F16, written by sg_igemm with out_dtype = SG_F16); the statistics in
  * `partials` always come from the fp32 accumulators.
+ * range_flag (device int32, may be NULL): GroupNorm is scale invariant, fp16 is not.  With an fp16 raw tensor the kernel
+ * sets *range_flag = 1 when the row's mean square (known exactly from the fp32 statistics) lies outside [2^-20, 2^20],
+ * i.e. when values could have saturated at 65504 or lost precision to fp16 subnormals; the caller then re-runs with
+ * fp32 raw tensors.  Never cleared by the library.
  */
 int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, const float* gamma, const float* beta,
                 int rows, int raw_rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride,
-                float* out_f32, void* out_act, int act_dtype, sg_stream_t stream);
+                float* out_f32, void* out_act, int act_dtype, int32_t* range_flag, sg_stream_t stream);
 
 /* ---- K2 + K3b: GELU(GroupNorm(raw) + cat([skip, upsample2x(x)])) -> act, residual recomputed from its sources ----
  * The first DoubleConv of Up is residual (:88-91 with :132-134): its input -- the concatenation of the skip and the
@@ -134,7 +149,7 @@ int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, co
  */
 int sg_gn_apply_vcat(const void* raw, const float* partials, int P, const float* gamma, const float* beta, int rows,
                      const float* x, const float* skip, int skip_rows, int h, int w, int Cx, int Cs, void* out_act,
-                     int act_dtype, sg_stream_t stream);
+                     int act_dtype, int32_t* range_flag /* as sg_gn_apply */, sg_stream_t stream);
 
 /* ---- K3a: MaxPool2d(2) (:100).  in fp32 [rows,H,W,C] -> fp32 and/or act [rows,H/2,W/2,C] ---- */
 int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, void* out_act, int act_dtype,
@@ -174,7 +189,8 @@ int sg_attn_tail(const void* att, const float* x, const void* wo, const float* b
 /* sg_attn_tail with the model's output conv fused behind it (outc, :166,:195: 1x1 conv C -> c_out + bias on the last
  * SelfAttention block's output): eps fp32 NCHW [M/HW, c_out, HW] = outc_b + out . outc_w^T, computed from the fp32
  * `out` row each thread already holds, so the [M,C] fp32 tensor is neither written nor re-read (sa6 at n = 512: 2.1 GB).
- * outc_w fp32 [c_out, C], outc_b fp32 [c_out], c_out in 1..4, C = 64, HW = tokens per sample (power of two >= 128).
+ * outc_w fp32 [c_out, C], outc_b fp32 [c_out] are HOST pointers (1 KB, passed by value as kernel parameters: constant-bank
+ * FMA operands owned by the launch), c_out in 1..4, C = 64, HW = tokens per sample (power of two >= 128).
  * out may be NULL (only eps is produced) or a fp32 [M,C] buffer that also receives the block output.
  */
 int sg_attn_tail_outc(const void* att, const float* x, const void* wo, const float* bo, const float* ln_g,
@@ -191,6 +207,14 @@ int sg_attn_tail_outc(const void* att, const float* x, const void* wo, const flo
  */
 int sg_attention(const void* qkv, void* out, int rows, int L, int C, int heads, int engine, int act_dtype,
                  sg_stream_t stream);
+/* K4 of the fp32-accurate tensor-core engine: the same product with split-TF32 operands.  qkv_hi / qkv_lo fp32
+ * [rows*L, 3C] (sg_split_tf32 of the in_proj output), out fp32 [rows*L, C]; S = Q K^T and O = P V are each three
+ * kind::tf32 MMAs (hi hi + hi lo + lo hi) into one fp32 TMEM accumulator, the probabilities are split in the kernel. */
+int sg_attention_tf32(const float* qkv_hi, const float* qkv_lo, float* out, int rows, int L, int C, int heads,
+                      sg_stream_t stream);
+/* x fp32 [n] -> hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand form of the fp32-accurate tensor-core
+ * engine (x - hi is exact in fp32; hi + lo keeps ~21 mantissa bits).  n % 4 == 0, buffers 16-byte aligned. */
+int sg_split_tf32(const float* x, float* hi, float* lo, int64_t n, sg_stream_t stream);
 
 /* ---- outc: 1x1 conv 64 -> c_out with bias, NHWC fp32 in, NCHW fp32 out (:166,:195) ---- */
 int sg_conv_out(const float* in, const float* w /*[c_out,64]*/, const float* b, int rows, int HW, int c_out,

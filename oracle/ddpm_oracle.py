@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 NUM_HEADS = 4  # diff_modules.py:56
 EPS = 1e-5  # torch default eps of GroupNorm / LayerNorm
+ATTN_QUERY_CHUNK = 4096  # query rows per materialised block of the attention matrix
 
 
 # --------------------------------------------------------------------------------------
@@ -105,7 +106,14 @@ def _self_attention(sd, p, x):
         return z.reshape(n, -1, NUM_HEADS, d).transpose(1, 2)  # [n, heads, L, d]
 
     q, k, v = heads(q) * (d ** -0.5), heads(k), heads(v)
-    att = torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v  # [n, heads, L, d]
+    L = q.shape[2]
+    if L <= ATTN_QUERY_CHUNK:
+        att = torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v  # [n, heads, L, d]
+    else:
+        # same arithmetic per query row (softmax over ALL keys); only the L x L matrix is built ATTN_QUERY_CHUNK query
+        # rows at a time so that L = 16384 / 65536 (256 x 256 spectrograms, :376-378) fits the host memory
+        att = torch.cat([torch.softmax(q[:, :, i:i + ATTN_QUERY_CHUNK] @ k.transpose(-1, -2), dim=-1) @ v
+                         for i in range(0, L, ATTN_QUERY_CHUNK)], dim=2)
     att = att.transpose(1, 2).reshape(n, -1, c)
     att = F.linear(att, sd[f"{p}.mha.out_proj.weight"], sd[f"{p}.mha.out_proj.bias"])
     a = att + tok  # residual is the pre-LN x (:70)

@@ -14,7 +14,7 @@ from . import build as _build
 
 SG_F32, SG_BF16, SG_F16 = 0, 1, 2
 SG_ENGINE_SIMT, SG_ENGINE_TC = 0, 1
-ABI_VERSION = 13
+ABI_VERSION = 14
 SG_ACT_NONE, SG_ACT_GELU, SG_ACT_RELU_POST = 0, 1, 2
 
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
@@ -25,7 +25,7 @@ class IgemmArgs(C.Structure):
 
     _fields_ = [
         ("a", _vp), ("w", _vp), ("bias", _vp), ("residual", _vp), ("out_f32", _vp), ("out_act", _vp),
-        ("partials", _vp),
+        ("partials", _vp), ("a_lo", _vp), ("w_lo", _vp),
         ("rows", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
         ("taps", C.c_int32), ("act", C.c_int32), ("engine", C.c_int32), ("act_dtype", C.c_int32),
         ("out_dtype", C.c_int32),
@@ -44,8 +44,8 @@ PROTOTYPES = {
     "sg_conv_in": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "sg_igemm_partials": (_i, [_i, _i, _i, _i]),
     "sg_igemm": (_i, [C.POINTER(IgemmArgs), _vp]),
-    "sg_gn_apply": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
-    "sg_gn_apply_vcat": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "sg_gn_apply": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "sg_gn_apply_vcat": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "sg_maxpool2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sg_upsample_cat": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sg_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
@@ -54,6 +54,8 @@ PROTOTYPES = {
     "sg_attn_tail_outc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp,
                                _i, _vp]),
     "sg_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sg_attention_tf32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sg_split_tf32": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "sg_conv_out": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "sg_cfg_update": (_i, [_vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp, _u64, _i64, _vp]),
     "sg_step_advance": (_i, [_vp, _vp]),
@@ -109,14 +111,19 @@ def check(rc: int, what: str = ""):
         raise SgError(f"{what or 'libsgb200'} failed (status {rc}): {msg.decode() if msg else '?'}")
 
 
+_checked_devices = set()
+
+
 def require_b200(device: torch.device):
-    """No fallback: the device must be a CUDA sm_100 part."""
+    """No fallback: the device must be a CUDA sm_100 part.  The check does not change the current device; callers that
+    launch on a non-current device wrap the launches in `torch.cuda.device(device)` (engine.UNetPlan.run does)."""
     if device.type != "cuda":
         raise SgError(f"spectrogramgenai_b200 runs only on a B200 (sm_100a) CUDA device, got device '{device}'")
     lib = load()
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    check(lib.sg_device_check(idx), "sg_device_check")
-    check(lib.sg_set_device(idx), "sg_set_device")
+    if idx not in _checked_devices:
+        check(lib.sg_device_check(idx), "sg_device_check")
+        _checked_devices.add(idx)
 
 
 def ptr(t):

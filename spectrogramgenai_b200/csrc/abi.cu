@@ -26,37 +26,23 @@ int launch_status(const char* what) {
   return SG_OK;
 }
 
-static int g_pdl_mode = -1;     // -1: not initialised
-static bool g_pdl_env = false;  // SGB200_PDL was given: sg_set_pdl does not override it
+// launch policy of the calling thread (like the current device, it is per-thread state of the caller, not of the library's
+// kernels): 2 = programmatic dependent launch for grids of at most pdl_max_ctas() CTAs
+static thread_local int g_pdl_mode = 2;
 
-int pdl_mode() {
-  if (g_pdl_mode < 0) {
-    const char* e = getenv("SGB200_PDL");
-    g_pdl_env = e != nullptr;
-    g_pdl_mode = e ? atoi(e) : 2;
-    if (g_pdl_mode < 0 || g_pdl_mode > 2) g_pdl_mode = 2;
-  }
-  return g_pdl_mode;
-}
+int pdl_mode() { return g_pdl_mode; }
 
-int pdl_max_ctas() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SGB200_PDL_MAX_CTAS");
-    v = e ? atoi(e) : 4 * num_sms();  // measured: larger grids gain nothing from the early launch and the programmatic edge costs ~5 us
-  }
-  return v;
-}
+// measured: grids larger than 4 x #SM CTAs gain nothing from the early launch and the programmatic edge costs ~5 us
+int pdl_max_ctas() { return 4 * num_sms(); }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[SG_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 }  // namespace sg
@@ -67,8 +53,7 @@ int sg_abi_version(void) { return SG_ABI_VERSION; }
 
 int sg_set_pdl(int mode) {
   SG_REQUIRE(mode >= 0 && mode <= 2, "sg_set_pdl: mode %d not in 0..2", mode);
-  (void)sg::pdl_mode();  // reads the environment once
-  if (!sg::g_pdl_env) sg::g_pdl_mode = mode;
+  sg::g_pdl_mode = mode;
   return SG_OK;
 }
 
@@ -81,7 +66,7 @@ int sg_device_check(int device) {
     sg::set_error("cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
     return SG_ERR_LAUNCH;
   }
-  if (p.major != 10) {
+  if (p.major != 10 || p.minor != 0) {
     sg::set_error("device %d is sm_%d%d; libsgb200 ships only an sm_100a image (B200) and has no fallback", device,
                   p.major, p.minor);
     return SG_ERR_ARCH;

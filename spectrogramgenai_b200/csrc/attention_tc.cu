@@ -16,11 +16,11 @@
 //                 o = o*alpha + O_j   running output, max and sum stay in registers (fp32)
 // TMEM use is 128 columns (O_j aliases the dead S columns), so up to four CTAs share an SM and overlap each
 // other's MMA / MUFU / TMA phases; inside a CTA the phases are serial.
-// Three kernels live here: v8 (default for L >= 128; four softmax warps, named-barrier hand-offs, packed fp32 body,
-// part of the exponentials on the FMA pipe), v1 (the first tcgen05 kernel: 192 threads, warp 0 = TMA producer,
-// warp 1 = MMA issuer, warps 2..5 = softmax; still used for L < 128, where a tile holds several batch rows and needs
-// the block-diagonal mask) and v3 (TMEM-resident output, kept selectable).  The measured history of the other variants
-// is in attention_version() below and in profiles/README.md.
+// Three kernels live here: v8 (L >= 128, d = 32 / 64; four softmax warps, named-barrier hand-offs, packed fp32 body,
+// part of the exponentials on the FMA pipe), v11 (L >= 128, d = 16: v8 with tensor-core row sums) and v1 (the first
+// tcgen05 kernel: 192 threads, warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = softmax; used for L < 128, where
+// a tile holds several batch rows and needs the block-diagonal mask).  The measured history of the other variants
+// is in the dispatch comment of attention_tc() below and in profiles/README.md.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -123,6 +123,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
   // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
   const int head = blockIdx.x;
   const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
+  if (m0 >= g.M) return;  // ragged last grid.z slice (more than 32768 query tiles, not a multiple of it); nothing was touched yet
   const int64_t kv0 = g.L >= ATT_BN ? (m0 >> g.logL) << g.logL : m0;  // first key token of this tile's row(s)
 
   if (warp == 0 && lane == 0) {
@@ -335,296 +336,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uin
 template <int D, int DT, int POLY>
 static int launch_att(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
   constexpr int smem = att_smem_bytes<D>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D, DT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
+  if (int rc = set_max_smem<attention_tc_kernel<D, DT, POLY>>(smem, "sg_attention(tc)")) return rc;
   launch_k(attention_tc_kernel<D, DT, POLY>, grid, dim3(192), smem, stream, tm, g, out);
   return launch_status("sg_attention(tc)");
 }
 
-// =====================================================================================================
-// v3 (L >= 256): the occupancy of v1 (128 TMEM columns, four CTAs per SM) with the short hand-off chain of v2.
-// The key tile is BN = 128 - D keys, so S (BN columns) and the running output O (D columns) live side by side in
-// the CTA's 128 TMEM columns:
-//   * O accumulates in TMEM across key tiles (no per-tile O round trip); the exponent reference m_ref is only
-//     raised -- with O rescaled through tcgen05.ld/st and the sweep repeated -- when a tile maximum exceeds it by
-//     more than redo_log2 (always on the first tile, rare afterwards);
-//   * the issuer launches S(j+1) = Q K(j+1)^T the moment the softmax warps have released S(j), BEFORE P(j) V(j),
-//     so the next sweep never waits for the P V phase: one mbarrier wait per key tile per thread;
-//   * one sweep over S per tile: p = exp2(s*c - m_ref*c), row sum, tile max, 16-bit pack, swizzled st.shared.
-// The last key tile of a row may be ragged (L is not a multiple of BN): keys >= L get p = 0.
-// =====================================================================================================
-template <int D>
-struct Att3 {
-  static constexpr int BN = 128 - D;               // keys per tile: 112 / 96 / 64
-  static constexpr int ROWB = D * 2;
-  static constexpr int QT = ATT_BM * ROWB;         // Q tile bytes
-  static constexpr int KVT = ((BN * ROWB + 1023) / 1024) * 1024;  // K / V stage bytes (1024-aligned)
-  static constexpr int SMEM = 1024 + QT + 4 * KVT + P_BYTES + 256;
-};
-
-template <int D, int DT>
-__global__ void __launch_bounds__(192, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
-attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                     const AttGeom g, uint16_t* __restrict__ out) {
-  using A = Att3<D>;
-  constexpr int BN = A::BN, ROWB = A::ROWB;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + A::QT;          // [2 stages]
-  uint8_t* sV = sK + 2 * A::KVT;     // [2 stages]
-  uint8_t* sP = sV + 2 * A::KVT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint64_t* o_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // heads are the FASTEST grid dimension: the head slices of a token (d * 2 = 32..128 bytes) share 128-byte lines, so
-  // the heads of one query tile must run together to be served from L2 (with heads slowest, ncu showed 4x the
-  // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
-  const int head = blockIdx.x;
-  const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
-  const int64_t kv0 = (m0 >> g.logL) << g.logL;
-  const int nkv = (g.L + BN - 1) / BN;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tmQ);
-    prefetch_tensormap(&tmKV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 4);
-    mbar_init(o_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // every activation access (TMA loads included) follows this point; parameters read above are immutable weights
-  pdl_launch_dependents();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      mbar_arrive_expect_tx(q_full, (uint32_t)A::QT);
-      tma_load_2d(sQ, &tmQ, q_full, head * D, (int)m0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait_spin(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[s], 2u * BN * ROWB);
-        const int tok = (int)(kv0 + (int64_t)j * BN);
-        tma_load_2d(sK + s * A::KVT, &tmKV, &kv_full[s], g.C + head * D, tok);
-        tma_load_2d(sV + s * A::KVT, &tmKV, &kv_full[s], 2 * g.C + head * D, tok);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      auto issue_s = [&](int s) {
-        const uint64_t qd = make_desc_rows(smem_u32(sQ), ROWB);
-        const uint64_t kd = make_desc_rows(smem_u32(sK + s * A::KVT), ROWB);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base, qd + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
-        umma_commit(s_full);
-      };
-      mbar_wait_spin(q_full, 0);
-      mbar_wait_spin(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait_spin(p_ready, (uint32_t)j & 1u);  // S(j) released, P(j) written
-        tc_fence_after();
-        if (j + 1 < nkv) {
-          mbar_wait_spin(&kv_full[s ^ 1], (uint32_t)((j + 1) >> 1) & 1u);
-          tc_fence_after();
-          issue_s(s ^ 1);  // next scores first: the softmax warps never wait for the P V phase
-        }
-        const uint32_t pa = smem_u32(sP);
-        const uint32_t va = smem_u32(sV + s * A::KVT);
-#pragma unroll
-        for (int k = 0; k < BN / 16; ++k) {
-          const uint64_t pd = make_desc_k128(pa + (k >> 2) * (ATT_BM * 128) + (k & 3) * 32);
-          const uint64_t vd = make_desc_rows(va + k * 16 * ROWB, ROWB);
-          umma_ss(tmem_base + BN, pd, vd, g.idesc_o, (j | k) != 0);
-        }
-        umma_commit(&kv_empty[s]);
-        umma_commit(o_done);
-      }
-    }
-  } else {
-    // ===== softmax + epilogue =====
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int64_t tok = m0 + r;
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_o = t_row + BN;
-    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    float m_ref = -INFINITY, l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      const int nvalid = g.L - j * BN;  // keys of this tile that belong to the row (>= BN except on the last tile)
-      bool waited_o = (j == 0);
-      float tmax, psum;
-      bool redo;
-      do {
-        const float mc = m_ref * g.c;
-        tmax = -INFINITY;
-        psum = 0.f;
-        // one chunk = NC columns starting at c0: exp, sum, max, pack, store
-        auto chunk = [&](const uint32_t* v, int c0, int nc) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            if (i < nc) {
-              float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-              if (c0 + i >= nvalid) s0 = -INFINITY;
-              if (c0 + i + 1 >= nvalid) s1 = -INFINITY;
-              tmax = fmaxf(tmax, fmaxf(s0, s1));
-              const float p0 = ex2(fmaf(s0, g.c, -mc)), p1 = ex2(fmaf(s1, g.c, -mc));
-              pk[i >> 1] = pack_pair<DT>(p0, p1);
-              psum += p0 + p1;
-            }
-          }
-          if (!waited_o) {  // P(j-1) V(j-1) must have finished reading the P buffer (and O is quiescent)
-            mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
-            tc_fence_after();
-            waited_o = true;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (u * 8 < nc) {
-              const int jj = (c0 >> 3) + u;
-              const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + (uint32_t)(((jj & 7) ^ (r & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                           "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                           : "memory");
-            }
-          }
-        };
-#pragma unroll 1
-        for (int c0 = 0; c0 + 32 <= BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);
-          tmem_ld_wait();
-          chunk(v, c0, 32);
-        }
-        if constexpr (BN % 32 != 0) {
-          uint32_t v16[16];
-          tmem_ld16(t_row + (BN / 32) * 32, v16);
-          tmem_ld_wait();
-          uint32_t v[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = v16[i];
-          chunk(v, (BN / 32) * 32, 16);
-        }
-        const bool over = (tmax - m_ref) * g.c > g.redo_log2;  // also true while m_ref == -inf
-        redo = __any_sync(0xffffffffu, over);
-        if (redo) {
-          const float a0 = over ? ex2((m_ref - tmax) * g.c) : 1.0f;  // 0 on the first tile
-          if (over) m_ref = tmax;
-          l *= a0;
-          if (j > 0) {
-#pragma unroll
-            for (int cch = 0; cch < D / 16; ++cch) {
-              uint32_t ov[16];
-              tmem_ld16(t_o + cch * 16, ov);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * a0);
-              tmem_st16(t_o + cch * 16, ov);
-            }
-            tmem_st_wait();
-          }
-        }
-      } while (redo);
-      l += psum;
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
-    }
-    // ---- epilogue: O / l ----
-    mbar_wait(o_done, (uint32_t)(nkv - 1) & 1u);
-    tc_fence_after();
-    const float inv = 1.0f / l;
-    uint16_t* dst = out + tok * g.C + head * D;
-#pragma unroll
-    for (int cch = 0; cch < D / 16; ++cch) {
-      uint32_t ov[16];
-      tmem_ld16(t_o + cch * 16, ov);
-      tmem_ld_wait();
-      uint4 w0, w1;
-      w0.x = pack_pair<DT>(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv);
-      w0.y = pack_pair<DT>(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv);
-      w0.z = pack_pair<DT>(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv);
-      w0.w = pack_pair<DT>(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv);
-      w1.x = pack_pair<DT>(__uint_as_float(ov[8]) * inv, __uint_as_float(ov[9]) * inv);
-      w1.y = pack_pair<DT>(__uint_as_float(ov[10]) * inv, __uint_as_float(ov[11]) * inv);
-      w1.z = pack_pair<DT>(__uint_as_float(ov[12]) * inv, __uint_as_float(ov[13]) * inv);
-      w1.w = pack_pair<DT>(__uint_as_float(ov[14]) * inv, __uint_as_float(ov[15]) * inv);
-      *reinterpret_cast<uint4*>(dst + cch * 16) = w0;
-      *reinterpret_cast<uint4*>(dst + cch * 16 + 8) = w1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc<128>(tmem_base);
-  }
-}
-
-template <int D, int DT>
-static int launch_att3(const void* qkv, const AttGeom& g0, int act_dtype, uint16_t* out, cudaStream_t stream) {
-  using A = Att3<D>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel<D, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, A::SMEM);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc3): cudaFuncSetAttribute(%d B smem): %s", A::SMEM, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  AttGeom g = g0;
-  g.idesc_s = make_idesc(act_dtype, 128, A::BN, 0, 0);
-  CUtensorMap tmQ, tmKV;
-  const uint64_t dims[2] = {(uint64_t)3 * g.C, (uint64_t)g.M};
-  const uint64_t strides[1] = {(uint64_t)3 * g.C * 2};
-  const uint32_t boxq[2] = {(uint32_t)D, 128u};
-  const uint32_t boxkv[2] = {(uint32_t)D, (uint32_t)A::BN};
-  const CUtensorMapSwizzle sw = D == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (D == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  int rc = make_tmap(&tmQ, act_dtype, 2, qkv, dims, strides, boxq, sw);
-  if (rc) return rc;
-  rc = make_tmap(&tmKV, act_dtype, 2, qkv, dims, strides, boxkv, sw);
-  if (rc) return rc;
-  const int64_t tiles3 = g.M / ATT_BM;
-  dim3 grid((unsigned)g.heads, (unsigned)(tiles3 < 32768 ? tiles3 : 32768), (unsigned)cdiv(tiles3, 32768));
-  attention_tc3_kernel<D, DT><<<grid, 192, A::SMEM, stream>>>(tmQ, tmKV, g, out);
-  return launch_status("sg_attention(tc3)");
-}
-
-// shared-memory footprint of the 128-key-tile kernels: Q + two K/V stages + the 16-bit P tile + barriers
 template <int D>
 constexpr int att4_smem_bytes() {
   return 1024 + ATT_BM * D * 2 /*Q*/ + 2 * 2 * ATT_BN * D * 2 /*K,V x 2 stages*/ + P_BYTES + 256;
@@ -662,11 +378,6 @@ __device__ __forceinline__ constexpr bool pair_is_poly(int pair) {
          : POLY == 2 ? (pair & 3) == 3
          : POLY == 3 ? ((pair & 7) == 2 || (pair & 7) == 5 || (pair & 7) == 7)
                      : (pair & 1) == 1;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
 }
 
 // =====================================================================================================
@@ -714,6 +425,7 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
   const int head = blockIdx.x;
   const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
+  if (m0 >= g.M) return;  // ragged last grid.z slice (more than 32768 query tiles, not a multiple of it); nothing was touched yet
   const int64_t kv0 = (m0 >> g.logL) << g.logL;
   const int nkv = g.L / ATT_BN;
   const bool leader = threadIdx.x == 0;
@@ -998,6 +710,7 @@ attention_tc11_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, u
   // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
   const int head = blockIdx.x;
   const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
+  if (m0 >= g.M) return;  // ragged last grid.z slice (more than 32768 query tiles, not a multiple of it); nothing was touched yet
   const int64_t kv0 = (m0 >> g.logL) << g.logL;
   const int nkv = g.L / ATT_BN;
   const bool leader = threadIdx.x == 0;
@@ -1266,86 +979,17 @@ attention_tc11_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, u
 template <int D, int DT, int POLY, int NACC>
 static int launch_att8(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
   constexpr int smem = att4_smem_bytes<D>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc8_kernel<D, DT, POLY, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc8): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
+  if (int rc = set_max_smem<attention_tc8_kernel<D, DT, POLY, NACC>>(smem, "sg_attention(tc8)")) return rc;
   launch_k(attention_tc8_kernel<D, DT, POLY, NACC>, grid, dim3(128), smem, stream, tm, g, out);
   return launch_status("sg_attention(tc8)");
-}
-
-template <int D, int DT>
-static int dispatch_att8(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
-  static const int poly = env_int("SGB200_ATTN_POLY8", 2);  // eighths of the pairs evaluated by the polynomial
-  if (poly == 0) return launch_att8<D, DT, 0, 2>(tm, g, out, grid, stream);
-  if (poly == 1) return launch_att8<D, DT, 1, 2>(tm, g, out, grid, stream);
-  if (poly == 3) return launch_att8<D, DT, 3, 2>(tm, g, out, grid, stream);
-  return launch_att8<D, DT, 2, 2>(tm, g, out, grid, stream);
 }
 
 template <int D, int DT, int POLY, int NACC>
 static int launch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
   constexpr int smem = att4_smem_bytes<D>() + ATT11_ONES;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc11_kernel<D, DT, POLY, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_attention(tc11): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
+  if (int rc = set_max_smem<attention_tc11_kernel<D, DT, POLY, NACC>>(smem, "sg_attention(tc11)")) return rc;
   launch_k(attention_tc11_kernel<D, DT, POLY, NACC>, grid, dim3(128), smem, stream, tm, g, out);
   return launch_status("sg_attention(tc11)");
-}
-
-template <int D, int DT>
-static int dispatch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
-  static const int poly = env_int("SGB200_ATTN_POLY11", 3);  // eighths of the pairs evaluated by the polynomial
-  static const int nacc = env_int("SGB200_ATTN_NACC11", 1);
-  constexpr int NA = D == 64 ? 1 : 2;
-  if (nacc == 1) {
-    if (poly == 0) return launch_att11<D, DT, 0, 1>(tm, g, out, grid, stream);
-    if (poly == 1) return launch_att11<D, DT, 1, 1>(tm, g, out, grid, stream);
-    if (poly == 2) return launch_att11<D, DT, 2, 1>(tm, g, out, grid, stream);
-    return launch_att11<D, DT, 3, 1>(tm, g, out, grid, stream);
-  }
-  if (poly == 2) return launch_att11<D, DT, 2, NA>(tm, g, out, grid, stream);
-  if (poly == 4) return launch_att11<D, DT, 4, NA>(tm, g, out, grid, stream);
-  return launch_att11<D, DT, 3, NA>(tm, g, out, grid, stream);
-}
-
-// fraction of exponentials evaluated by the FMA-pipe polynomial: SGB200_ATTN_POLY = 0 (none), 4 (1/4), 2 (1/2)
-static int attention_poly() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SGB200_ATTN_POLY");
-    v = e ? atoi(e) : 0;  // measured: no gain on B200 (the kernel is not MUFU-throughput bound), so off by default
-    if (v != 0 && v != 2 && v != 4) v = 0;
-  }
-  return v;
-}
-
-static int attention_version() {
-  static int v = -1;
-  if (v < 0) {
-    // SGB200_ATTN: 0 = auto (default): L >= 128: v11 for d = 16, v8 otherwise; v1 below (block-diagonal tile over 128/L
-    // batch rows); 1 = v1 everywhere, 3 = v3 (TMEM-resident O, 128-d key tiles) for L >= 256, 8 = v8, 11 = v11.
-    // Measured on B200 (rows=128, bf16, ms); v2/v4/v5/v7/v9/v10 were experiments, removed (see profiles/README.md):
-    //                           v1     v2    v3     v4     v5     v7     v8     v9     v10    v11 (rows=256: v8 4.11 / v11 3.98)
-    //   d=16 L=4096 (sa6)       3.07   3.57  3.12   2.82   2.43   3.41   2.12   2.48   2.25
-    //   d=32 L=1024 (sa1)       0.347  -     0.267  0.234  0.227  0.348  0.188  0.220  0.184
-    //   d=16 L=1024 (sa5)       0.226  -     -      0.200  0.183  0.237  0.152  0.175  0.158
-    const char* e = getenv("SGB200_ATTN");
-    v = e ? atoi(e) : 0;
-    if (v != 1 && v != 3 && v != 8 && v != 11) v = 0;
-  }
-  return v;
 }
 
 }  // namespace tc
@@ -1386,56 +1030,28 @@ const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cu
   if (rc) return rc;
   SG_REQUIRE(heads <= 65535, "sg_attention(tc): too many heads");
   const int64_t tiles = cdiv(g.M, ATT_BM);
-  SG_REQUIRE(tiles <= 32768 || tiles % 32768 == 0, "sg_attention(tc): %lld query tiles (must be <= 32768 or a multiple of it)", (long long)tiles);
   dim3 grid((unsigned)heads, (unsigned)(tiles < 32768 ? tiles : 32768), (unsigned)cdiv(tiles, 32768));
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
-  // auto: v11 for d = 16 (sa5 / sa6: measured 3.2 % / 2.4 % faster than v8); its N = d + 16 PV MMA is slower than v8's at d = 32
-  if (L >= ATT_BN && (attention_version() == 11 || (attention_version() == 0 && d == 16))) {
-    if (act_dtype == SG_BF16) {
-      if (d == 16) return dispatch_att11<16, SG_BF16>(tm, g, o, grid, stream);
-      if (d == 32) return dispatch_att11<32, SG_BF16>(tm, g, o, grid, stream);
-      return dispatch_att11<64, SG_BF16>(tm, g, o, grid, stream);
-    }
-    if (d == 16) return dispatch_att11<16, SG_F16>(tm, g, o, grid, stream);
-    if (d == 32) return dispatch_att11<32, SG_F16>(tm, g, o, grid, stream);
-    return dispatch_att11<64, SG_F16>(tm, g, o, grid, stream);
-  }
-  if (L >= ATT_BN && (attention_version() == 8 || attention_version() == 0)) {
-    if (act_dtype == SG_BF16) {
-      if (d == 16) return dispatch_att8<16, SG_BF16>(tm, g, o, grid, stream);
-      if (d == 32) return dispatch_att8<32, SG_BF16>(tm, g, o, grid, stream);
-      return dispatch_att8<64, SG_BF16>(tm, g, o, grid, stream);
-    }
-    if (d == 16) return dispatch_att8<16, SG_F16>(tm, g, o, grid, stream);
-    if (d == 32) return dispatch_att8<32, SG_F16>(tm, g, o, grid, stream);
-    return dispatch_att8<64, SG_F16>(tm, g, o, grid, stream);
-  }
-  if (L >= 2 * ATT_BM && attention_version() == 3) {
-    if (act_dtype == SG_BF16) {
-      if (d == 16) return launch_att3<16, SG_BF16>(qkv, g, act_dtype, o, stream);
-      if (d == 32) return launch_att3<32, SG_BF16>(qkv, g, act_dtype, o, stream);
-      return launch_att3<64, SG_BF16>(qkv, g, act_dtype, o, stream);
-    }
-    if (d == 16) return launch_att3<16, SG_F16>(qkv, g, act_dtype, o, stream);
-    if (d == 32) return launch_att3<32, SG_F16>(qkv, g, act_dtype, o, stream);
-    return launch_att3<64, SG_F16>(qkv, g, act_dtype, o, stream);
-  }
-  const int poly = attention_poly();
-#define SG_ATT_DISPATCH(DD, TT)                                                  \
-  do {                                                                           \
-    if (poly == 2) return launch_att<DD, TT, 2>(tm, g, o, grid, stream);         \
-    if (poly == 4) return launch_att<DD, TT, 4>(tm, g, o, grid, stream);         \
-    return launch_att<DD, TT, 0>(tm, g, o, grid, stream);                        \
+  // Kernel choice (measured on B200, bf16, rows = 128, ms; v2-v7 / v9 / v10 were experiments, see profiles/README.md):
+  //                           v1     v8     v11
+  //   d=16 L=4096 (sa6)       3.07   2.12   2.07      v11 (tensor-core row sums, 3/8 polynomial exp2, one accumulator) for
+  //   d=32 L=1024 (sa1)       0.347  0.188  (slower)  d = 16; v8 (1/4 polynomial exp2, two accumulators) for d = 32 / 64:
+  //   d=16 L=1024 (sa5)       0.226  0.152  0.147     the N = d + 16 PV MMA of v11 is slower than v8's there
+  // L < 128: v1, whose tile holds 128 / L batch rows under a block-diagonal mask.
+#define SG_ATT_BY_DTYPE(CALL_BF16, CALL_F16) \
+  do {                                       \
+    if (act_dtype == SG_BF16) return CALL_BF16; \
+    return CALL_F16;                         \
   } while (0)
-  if (act_dtype == SG_BF16) {
-    if (d == 16) SG_ATT_DISPATCH(16, SG_BF16);
-    if (d == 32) SG_ATT_DISPATCH(32, SG_BF16);
-    SG_ATT_DISPATCH(64, SG_BF16);
+  if (L >= ATT_BN) {
+    if (d == 16) SG_ATT_BY_DTYPE((launch_att11<16, SG_BF16, 3, 1>(tm, g, o, grid, stream)), (launch_att11<16, SG_F16, 3, 1>(tm, g, o, grid, stream)));
+    if (d == 32) SG_ATT_BY_DTYPE((launch_att8<32, SG_BF16, 2, 2>(tm, g, o, grid, stream)), (launch_att8<32, SG_F16, 2, 2>(tm, g, o, grid, stream)));
+    SG_ATT_BY_DTYPE((launch_att8<64, SG_BF16, 2, 2>(tm, g, o, grid, stream)), (launch_att8<64, SG_F16, 2, 2>(tm, g, o, grid, stream)));
   }
-  if (d == 16) SG_ATT_DISPATCH(16, SG_F16);
-  if (d == 32) SG_ATT_DISPATCH(32, SG_F16);
-  SG_ATT_DISPATCH(64, SG_F16);
-#undef SG_ATT_DISPATCH
+  if (d == 16) SG_ATT_BY_DTYPE((launch_att<16, SG_BF16, 0>(tm, g, o, grid, stream)), (launch_att<16, SG_F16, 0>(tm, g, o, grid, stream)));
+  if (d == 32) SG_ATT_BY_DTYPE((launch_att<32, SG_BF16, 0>(tm, g, o, grid, stream)), (launch_att<32, SG_F16, 0>(tm, g, o, grid, stream)));
+  SG_ATT_BY_DTYPE((launch_att<64, SG_BF16, 0>(tm, g, o, grid, stream)), (launch_att<64, SG_F16, 0>(tm, g, o, grid, stream)));
+#undef SG_ATT_BY_DTYPE
 }
 
 }  // namespace sg

@@ -1,0 +1,374 @@
+// K4 (fp32-accurate tensor-core engine): flash-style multi-head self-attention with SPLIT TF32 operands.
+//
+// Replaces the scaled-dot-product inside nn.MultiheadAttention (/root/reference/src/diff_modules.py:56,:69) at the
+// reference's own precision: the reference computes in fp32, and a plain TF32 contraction (10-bit mantissa) misses the
+// 1e-4 parity bar by 10x.  Every fp32 operand x is therefore split into hi = tf32(x) and
+// lo = tf32(x - hi) (sg_split_tf32), and each product is evaluated as three kind::tf32 MMAs into ONE fp32 TMEM accumulator
+//   A B  ~=  A_hi B_hi + A_hi B_lo + A_lo B_hi                       (dropped term lo x lo: 2^-22 relative)
+// so that S = Q K^T and O = P V carry ~21 mantissa bits.  The probabilities are split by the softmax threads themselves.
+//
+// One CTA = 128 consecutive query tokens x one head; key tiles of 64 tokens.  Per key tile:
+//   S   = Q K^T      3 x d/8 tcgen05.mma kind::tf32 (M128 x N64 x K8), K-major operands           -> TMEM cols [0, 64)
+//   P   = exp2(S c - m c)   one query row per thread, fp32; P_hi / P_lo written as swizzled K-major fp32 tiles
+//   O_j = P V        3 x 8 tcgen05.mma (M128 x N=d x K8), V consumed MN-major                     -> TMEM cols [64, 64+d)
+//   o   = o alpha + O_j     running output / maximum / sum in registers
+// Warp roles (192 threads, as the first 16-bit kernel): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax.
+// L < 128: the query tile holds 128 / L whole batch rows and the two key tiles are the same 128 tokens under a
+// block-diagonal mask.  This engine is the accuracy mode (1 CTA per SM, serial phases): ~5x the CUDA-core kernel, not a
+// roofline kernel -- the throughput path is attention_tc.cu.
+#include "tc_common.cuh"
+
+namespace sg {
+namespace tc {
+
+template <int D>
+struct AttF {
+  static constexpr int BM = 128, BN = 64;
+  static constexpr int ROWB = D * 4 < 128 ? D * 4 : 128;  // bytes of one swizzle row of a head slice
+  static constexpr int NATOM = D * 4 / ROWB;              // swizzle atoms along the head dimension (d = 64: 2)
+  static constexpr int AE = ROWB / 4;                     // floats per atom row
+  static constexpr int Q_ATOM = BM * ROWB, KV_ATOM = BN * ROWB;
+  static constexpr int Q_TILE = NATOM * Q_ATOM;           // one of hi / lo
+  static constexpr int KV_TILE = NATOM * KV_ATOM;
+  static constexpr int STAGES = D == 64 ? 1 : 2;
+  static constexpr int KV_STAGE = 4 * KV_TILE;            // K_hi, K_lo, V_hi, V_lo
+  static constexpr int P_ATOM = BM * 128;                 // [128 queries x 32 keys] fp32, SWIZZLE_128B
+  static constexpr int P_TILE = 2 * P_ATOM;               // 64 keys; one of hi / lo
+  static constexpr int SMEM = 1024 + 2 * Q_TILE + STAGES * KV_STAGE + 2 * P_TILE + 256;
+  static_assert(SMEM <= 227 * 1024, "smem budget");
+};
+
+struct AttFGeom {
+  int64_t M;  // rows * L tokens
+  int L, logL, C;
+  int nkv;    // key tiles (64 tokens) per query tile
+  float c;    // softmax scale * log2(e)
+  uint32_t q_bytes, kv_bytes;  // bytes the TMA boxes of Q (hi + lo) / one K,V stage deliver
+  uint32_t idesc_s, idesc_o;
+};
+
+// operand tile whose rows are one swizzle span of `row_bytes` (64 / 128); lbo_bytes = distance to the next atom along
+// the OTHER dimension (MN-major B operand wider than one atom), 0 = single atom
+__device__ __forceinline__ uint64_t make_desc_f(uint32_t saddr, int row_bytes, uint32_t lbo_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes ? (lbo_bytes >> 4) : 1) << 16;
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;  // 8-row groups
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int D>
+__global__ void __launch_bounds__(192, 1)
+attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                      const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                      const AttFGeom g, float* __restrict__ out) {
+  using A = AttF<D>;
+  constexpr int ROWB = A::ROWB, NATOM = A::NATOM, AE = A::AE, STAGES = A::STAGES, BN = A::BN, BM = A::BM;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;                             // [hi | lo] x NATOM atoms
+  uint8_t* sKV = sQ + 2 * A::Q_TILE;              // [STAGES] x [K_hi | K_lo | V_hi | V_lo]
+  uint8_t* sP = sKV + STAGES * A::KV_STAGE;       // [hi | lo] x 2 atoms of 32 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * A::P_TILE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint64_t* o_read = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x;  // heads fastest: the head slices of a token share cache lines
+  const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * BM;
+  if (m0 >= g.M) return;
+  const int64_t kv0 = g.L >= BM ? (m0 >> g.logL) << g.logL : m0;  // first key token of this tile's row(s)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQh);
+    prefetch_tensormap(&tmQl);
+    prefetch_tensormap(&tmKh);
+    prefetch_tensormap(&tmKl);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);  // one elected lane per softmax warp
+    mbar_init(o_full, 1);
+    mbar_init(o_read, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (g.M < BM) {
+    // tiny problems: the TMA boxes are clamped to M rows, so clear the tiles once (0 x stale NaN would poison the MMAs)
+    for (int i = threadIdx.x; i < (2 * A::Q_TILE + STAGES * A::KV_STAGE) / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + BN;
+  pdl_wait();  // every activation access (TMA loads included) follows this point
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: Q (hi, lo) once, then the K / V ring =====
+      mbar_arrive_expect_tx(q_full, g.q_bytes);
+#pragma unroll
+      for (int a = 0; a < NATOM; ++a) {
+        tma_load_2d(sQ + a * A::Q_ATOM, &tmQh, q_full, head * D + a * AE, (int)m0);
+        tma_load_2d(sQ + A::Q_TILE + a * A::Q_ATOM, &tmQl, q_full, head * D + a * AE, (int)m0);
+      }
+      for (int j = 0; j < g.nkv; ++j) {
+        const int s = j % STAGES;
+        mbar_wait_spin(&kv_empty[s], ((uint32_t)(j / STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[s], g.kv_bytes);
+        const int tok = (int)(kv0 + (int64_t)j * BN);
+        uint8_t* st = sKV + s * A::KV_STAGE;
+#pragma unroll
+        for (int a = 0; a < NATOM; ++a) {
+          tma_load_2d(st + 0 * A::KV_TILE + a * A::KV_ATOM, &tmKh, &kv_full[s], g.C + head * D + a * AE, tok);
+          tma_load_2d(st + 1 * A::KV_TILE + a * A::KV_ATOM, &tmKl, &kv_full[s], g.C + head * D + a * AE, tok);
+          tma_load_2d(st + 2 * A::KV_TILE + a * A::KV_ATOM, &tmKh, &kv_full[s], 2 * g.C + head * D + a * AE, tok);
+          tma_load_2d(st + 3 * A::KV_TILE + a * A::KV_ATOM, &tmKl, &kv_full[s], 2 * g.C + head * D + a * AE, tok);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      mbar_wait_spin(q_full, 0);
+      const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
+      for (int j = 0; j < g.nkv; ++j) {
+        const int s = j % STAGES;
+        mbar_wait_spin(&kv_full[s], (uint32_t)(j / STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t st = smem_u32(sKV + s * A::KV_STAGE);
+        // S = Q K^T = Qh Kh + Qh Kl + Ql Kh: K-major A and B, K = d in steps of 8 floats (32 bytes inside the swizzle span).
+        // The S columns are free: p_ready(j-1) was observed before P_{j-1} V was issued.
+        uint32_t acc = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t qt = qa + (t == 2 ? A::Q_TILE : 0);
+          const uint32_t kt = st + (t == 1 ? A::KV_TILE : 0);
+#pragma unroll
+          for (int a = 0; a < NATOM; ++a) {
+            const uint64_t qd = make_desc_f(qt + a * A::Q_ATOM, ROWB, 0);
+            const uint64_t kd = make_desc_f(kt + a * A::KV_ATOM, ROWB, 0);
+#pragma unroll
+            for (int k = 0; k < AE / 8; ++k) {
+              umma_ss_tf32(tmem_base, qd + 2 * k, kd + 2 * k, g.idesc_s, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(s_full);
+        // O_j = P V = Ph Vh + Ph Vl + Pl Vh: A = P (K-major, two 32-key SWIZZLE_128B atoms), B = V consumed MN-major
+        mbar_wait_spin(p_ready, (uint32_t)j & 1u);
+        if (j > 0) mbar_wait_spin(o_read, (uint32_t)(j - 1) & 1u);  // O_{j-1} has been added to the running output
+        tc_fence_after();
+        acc = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t pt = pa + (t == 2 ? A::P_TILE : 0);
+          const uint32_t vt = st + 2 * A::KV_TILE + (t == 1 ? A::KV_TILE : 0);
+#pragma unroll
+          for (int k = 0; k < BN / 8; ++k) {
+            const uint64_t pd = make_desc_k128(pt + (k >> 2) * A::P_ATOM + (k & 3) * 32);
+            const uint64_t vd = make_desc_f(vt + k * 8 * ROWB, ROWB, NATOM > 1 ? A::KV_ATOM : 0);
+            umma_ss_tf32(tmem_o, pd, vd, g.idesc_o, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ===== softmax + epilogue: thread = one query row (TMEM lane quadrant = warp % 4) =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int64_t tok = m0 + r;
+    const bool row_valid = tok < g.M;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool masked = g.L < BM;  // block-diagonal tile (several batch rows) and / or ragged tail
+    const int64_t my_row = tok >> g.logL;
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    float m_ref = -INFINITY, l = 0.f;  // reference maximum of the exponent; running row sum (relative to m_ref)
+    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+    const uint32_t rx = (uint32_t)(r & 7);
+    for (int j = 0; j < g.nkv; ++j) {
+      mbar_wait(s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      const int64_t key0 = kv0 + (int64_t)j * BN;
+      // ONE sweep over S: p = exp2(s c - m_ref c) against the maximum known BEFORE this tile, the tile maximum as a
+      // by-product.  Exact algebra (o, l are rescaled afterwards); the sweep is repeated only when the tile maximum
+      // exceeds the reference by more than 2^60 (always on the first tile, where m_ref = -inf).
+      float tmax, psum;
+      bool redo;
+      do {
+        const float mc = m_ref * g.c;
+        tmax = -INFINITY;
+        psum = 0.f;
+#pragma unroll 1
+        for (int cch = 0; cch < BN / 32; ++cch) {
+          uint32_t v[32];
+          tmem_ld32(t_row + cch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {  // four keys = one 16-byte chunk of the P row
+            float ph[4], pl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float s0 = __uint_as_float(v[i4 * 4 + u]);
+              bool keep = true;
+              if (masked) {
+                const int64_t kt = key0 + cch * 32 + i4 * 4 + u;
+                keep = !(row_valid && (kt >= g.M || (kt >> g.logL) != my_row));
+                if (!keep) s0 = -INFINITY;
+              }
+              tmax = fmaxf(tmax, s0);
+              float p;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s0, g.c, -mc)));
+              if (masked && !keep) p = 0.f;
+              psum += p;
+              ph[u] = tf32_rna(p);
+              pl[u] = tf32_rna(p - ph[u]);
+            }
+            const uint32_t addr = p_row + (uint32_t)cch * A::P_ATOM + ((((uint32_t)i4) ^ rx) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(ph[0]), "f"(ph[1]), "f"(ph[2]),
+                         "f"(ph[3])
+                         : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + (uint32_t)A::P_TILE), "f"(pl[0]),
+                         "f"(pl[1]), "f"(pl[2]), "f"(pl[3])
+                         : "memory");
+          }
+        }
+        const bool over = (tmax - m_ref) * g.c > 60.0f;  // also true while m_ref == -inf
+        redo = __any_sync(0xffffffffu, over);
+        if (over) {
+          float a0;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"((m_ref - tmax) * g.c));  // 0 on the first tile
+          l *= a0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) o[i] *= a0;
+          m_ref = tmax;
+        }
+      } while (redo);
+      tc_fence_before();    // our tcgen05.ld of S precede the next S MMA
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      // ---- O_j and the row sum, both relative to m_ref ----
+      mbar_wait(o_full, (uint32_t)j & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int cch = 0; cch < D / 16; ++cch) {
+        uint32_t v[16];
+        tmem_ld16(t_row + BN + cch * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[cch * 16 + i] += __uint_as_float(v[i]);
+      }
+      l += psum;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_read);
+      // ---- raise the reference to the new running maximum (exact rescale of o, l) ----
+      if (tmax > m_ref) {
+        float a1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"((m_ref - tmax) * g.c));
+        l *= a1;
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] *= a1;
+        m_ref = tmax;
+      }
+    }
+    if (row_valid) {
+      const float inv = 1.0f / l;
+      float* dst = out + tok * g.C + head * D;
+#pragma unroll
+      for (int i = 0; i < D; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+template <int D>
+static int launch_att_tf32(const float* qkv_hi, const float* qkv_lo, float* out, AttFGeom g, cudaStream_t stream) {
+  using A = AttF<D>;
+  const uint32_t q_rows = (uint32_t)(g.M < A::BM ? g.M : A::BM), kv_rows = (uint32_t)(g.M < A::BN ? g.M : A::BN);
+  const CUtensorMapSwizzle sw = A::ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const uint64_t dims[2] = {(uint64_t)3 * g.C, (uint64_t)g.M};
+  const uint64_t strides[1] = {(uint64_t)3 * g.C * 4};
+  const uint32_t qbox[2] = {(uint32_t)A::AE, q_rows}, kbox[2] = {(uint32_t)A::AE, kv_rows};
+  CUtensorMap tmQh, tmQl, tmKh, tmKl;
+  int rc;
+  if ((rc = make_tmap(&tmQh, SG_F32, 2, qkv_hi, dims, strides, qbox, sw))) return rc;
+  if ((rc = make_tmap(&tmQl, SG_F32, 2, qkv_lo, dims, strides, qbox, sw))) return rc;
+  if ((rc = make_tmap(&tmKh, SG_F32, 2, qkv_hi, dims, strides, kbox, sw))) return rc;
+  if ((rc = make_tmap(&tmKl, SG_F32, 2, qkv_lo, dims, strides, kbox, sw))) return rc;
+  g.q_bytes = 2u * A::NATOM * q_rows * (uint32_t)A::ROWB;
+  g.kv_bytes = 4u * A::NATOM * kv_rows * (uint32_t)A::ROWB;
+  g.idesc_s = make_idesc_tf32(128, A::BN, 0);
+  g.idesc_o = make_idesc_tf32(128, D, 1);  // B = V is MN-major
+  if ((rc = set_max_smem<attention_tf32_kernel<D>>(A::SMEM, "sg_attention_tf32"))) return rc;
+  const int64_t tiles = cdiv(g.M, A::BM);
+  dim3 grid((unsigned)(g.C / D), (unsigned)(tiles < 32768 ? tiles : 32768), (unsigned)cdiv(tiles, 32768));
+  launch_k(attention_tf32_kernel<D>, grid, dim3(192), (size_t)A::SMEM, stream, tmQh, tmQl, tmKh, tmKl, g, out);
+  return launch_status("sg_attention_tf32");
+}
+
+}  // namespace tc
+}  // namespace sg
+
+using namespace sg;
+using namespace sg::tc;
+
+extern "C" int sg_attention_tf32(const float* qkv_hi, const float* qkv_lo, float* out, int rows, int L, int C, int heads,
+                                 sg_stream_t stream) {
+  SG_REQUIRE(qkv_hi && qkv_lo && out, "sg_attention_tf32: null pointer");
+  SG_REQUIRE(rows > 0 && L > 0 && (L & (L - 1)) == 0 && heads > 0 && heads <= 65535 && C % heads == 0,
+             "sg_attention_tf32: bad shape rows=%d L=%d C=%d heads=%d (L must be a power of two)", rows, L, C, heads);
+  SG_REQUIRE(((reinterpret_cast<uintptr_t>(qkv_hi) | reinterpret_cast<uintptr_t>(qkv_lo) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             "sg_attention_tf32: operands must be 16-byte aligned");
+  const int d = C / heads;
+  SG_REQUIRE(d == 16 || d == 32 || d == 64, "sg_attention_tf32: head dim %d not in {16,32,64}", d);
+  AttFGeom g;
+  g.M = (int64_t)rows * L;
+  SG_REQUIRE(g.M < (1ll << 31), "sg_attention_tf32: too many tokens");
+  g.L = L;
+  g.logL = 0;
+  while ((1 << g.logL) < L) ++g.logL;
+  g.C = C;
+  g.nkv = (L >= 128 ? L : 128) / 64;
+  g.c = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
+  cudaStream_t s = as_stream(stream);
+  if (d == 16) return launch_att_tf32<16>(qkv_hi, qkv_lo, out, g, s);
+  if (d == 32) return launch_att_tf32<32>(qkv_hi, qkv_lo, out, g, s);
+  return launch_att_tf32<64>(qkv_hi, qkv_lo, out, g, s);
+}

@@ -25,6 +25,30 @@ int num_sms();                        // SM count of the current device (persist
   } while (0)
 
 static inline cudaStream_t as_stream(sg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Per-device caches are indexed by the CUDA ordinal of the calling thread's current device (one rank = one GPU is the
+// normal case, but nothing here is wrong for a process that drives several devices).
+constexpr int SG_MAX_DEVICES = 64;
+static inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < SG_MAX_DEVICES ? dev : 0;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-kernel attribute: set once for each (kernel, device).
+template <auto Kernel>
+static inline int set_max_smem(int bytes, const char* what) {
+  static bool done[SG_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (done[dev]) return SG_OK;
+  cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%d B smem): %s", what, bytes, cudaGetErrorString(e));
+    return SG_ERR_LAUNCH;
+  }
+  done[dev] = true;
+  return SG_OK;
+}
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------------
@@ -37,10 +61,10 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // Measured (B200): 5 % lower latency per CFG step at batch 1-8 (1.06 -> 1.01 ms), break-even around batch 64, and 2-3 %
 // SLOWER at batch 256-512 when every launch carries the attribute -- long kernels gain nothing from the early launch and
 // each programmatic edge costs a few microseconds -- so by default only grids of at most 4 x #SM CTAs are launched that way
-// (SGB200_PDL = 2; 1 = every launch, 0 = none: everything fully serialised and the waits are no-ops).
+// (sg_set_pdl: 2; 1 = every launch, 0 = none: everything fully serialised and the waits are no-ops).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-int pdl_mode();  // abi.cu: SGB200_PDL = 0 off, 1 every launch, 2 (default) only grids of at most pdl_max_ctas() CTAs
+int pdl_mode();  // abi.cu (sg_set_pdl, thread-local): 0 off, 1 every launch, 2 (default) only grids of at most pdl_max_ctas() CTAs
 int pdl_max_ctas();
 
 template <typename... KArgs, typename... Args>

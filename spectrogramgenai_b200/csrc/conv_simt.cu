@@ -11,27 +11,22 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream);  // igemm_tc.cu
 // inc.double_conv.0  (/root/reference/src/diff_modules.py:82 via :144): direct 3x3, NCHW fp32 in,
 // NHWC fp32 out (64 channels) + GroupNorm partials.
 // ------------------------------------------------------------------------------------------------
-// The 64 x c_in x 3 x 3 weights (<= 9216 B) live in constant memory: with one pixel x all 64 output channels per
-// thread every weight index is a compile-time constant, so each FMA takes its weight straight from the constant bank
-// (no shared-memory staging, no load instructions; the first version was bound by LDS.128 wavefronts at 1.4 ms).
-// sg_conv_in refreshes the bank with a stream-ordered repack kernel ([co][k] -> [k][co], so that four weights arrive per
-// LDCU.128), so calls on ONE stream may use different weights; concurrent calls on different streams must use the same
-// weights.
-__constant__ __align__(16) float c_conv_in_w[36 * 64];
-
-__global__ void conv_in_pack_kernel(const float* __restrict__ w, float* __restrict__ dst, int K) {
-  pdl_wait();
-  pdl_launch_dependents();
-  for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) dst[(i % K) * 64 + i / K] = w[i];  // w is [co][ci][3][3]
-}
+// The 64 x c_in x 3 x 3 weights (<= 9216 B) are passed BY VALUE as a __grid_constant__ kernel parameter, i.e. they live in
+// the constant bank of this launch: with one pixel x all 64 output channels per thread every weight index is a
+// compile-time constant, so each FMA takes its weight straight from the constant bank (no shared-memory staging, no load
+// instructions; the first version was bound by LDS.128 wavefronts at 1.4 ms), four at a time by LDCU.128 in the [k][co]
+// order sg_conv_in repacks them to.  A launch carries its own copy: two streams / two models never share state.
+template <int CIN>
+struct ConvInW {
+  float w[CIN * 9 * 64];  // [k = ci*9 + dy*3 + dx][co]
+};
 
 template <int CIN, bool RAW16>
-__global__ void __launch_bounds__(128, 4) conv_in_kernel(const float* __restrict__ x, int n_src, int S,
+__global__ void __launch_bounds__(128, 4) conv_in_kernel(const __grid_constant__ ConvInW<CIN> cw,
+                                                         const float* __restrict__ x, int n_src, int S,
                                                          void* __restrict__ raw_v, float* __restrict__ partials) {
   constexpr int K = CIN * 9;
   __shared__ float red[2][4];
-  // launched fully serialised behind conv_in_pack_kernel (constant-cache coherence), so the wait is a no-op; the
-  // trigger lets the next kernel start early
   pdl_wait();
   pdl_launch_dependents();
   const int tid = threadIdx.x;
@@ -62,7 +57,7 @@ __global__ void __launch_bounds__(128, 4) conv_in_kernel(const float* __restrict
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = fmaf(in[k], c_conv_in_w[k * 64 + c0 + j], acc[j]);
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(in[k], cw.w[k * 64 + c0 + j], acc[j]);
     if constexpr (RAW16) {  // statistics from the fp32 values, storage in (saturating) fp16: 2 x 16 bytes
 #pragma unroll
       for (int j8 = 0; j8 < 2; ++j8) {
@@ -308,20 +303,16 @@ int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w, int r
   const int64_t ntiles = (int64_t)rows * (S * S / 128);
   SG_REQUIRE(ntiles < (1ll << 31), "sg_conv_in: too many tiles");
   cudaStream_t s = as_stream(stream);
-  static float* bank = nullptr;  // global address of the constant bank (constant memory is written through it)
-  if (!bank) {
-    cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&bank), c_conv_in_w);
-    if (e != cudaSuccess) {
-      set_error("sg_conv_in: cudaGetSymbolAddress: %s", cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-  }
-  launch_k(conv_in_pack_kernel, dim3(1), dim3(256), 0, s, w, bank, 9 * c_in);
   const int blocks = (int)ntiles;
-#define SG_CONV_IN(CI)                                                                              \
-  do {                                                                                              \
-    if (raw_dtype == SG_F16) conv_in_kernel<CI, true><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials);  \
-    else conv_in_kernel<CI, false><<<blocks, 128, 0, s>>>(x, n_src, S, raw, partials);              \
+#define SG_CONV_IN(CI)                                                                                                \
+  do {                                                                                                                \
+    ConvInW<CI> cw;                                                                                                   \
+    for (int co = 0; co < 64; ++co)                                                                                   \
+      for (int k = 0; k < CI * 9; ++k) cw.w[k * 64 + co] = w[co * CI * 9 + k]; /* w: HOST pointer, [co][ci][3][3] */  \
+    if (raw_dtype == SG_F16)                                                                                          \
+      launch_k(conv_in_kernel<CI, true>, dim3(blocks), dim3(128), 0, s, cw, x, n_src, S, raw, partials);              \
+    else                                                                                                              \
+      launch_k(conv_in_kernel<CI, false>, dim3(blocks), dim3(128), 0, s, cw, x, n_src, S, raw, partials);             \
   } while (0)
   switch (c_in) {
     case 1: SG_CONV_IN(1); break;

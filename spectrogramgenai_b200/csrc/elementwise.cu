@@ -347,6 +347,27 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   }
 }
 
+// fp32 -> (hi, lo) with hi = tf32(x) (round to nearest, ties away) and lo = tf32(x - hi): x - hi is exact in fp32, so
+// hi + lo carries 21-22 of x's 24 mantissa bits and both parts are exactly representable TF32 operands.
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
+                                                         float4* __restrict__ lo, int64_t n4) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldcs(x + i);
+  float4 h, l;
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+  hi[i] = h;
+  lo[i] = l;
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -425,6 +446,17 @@ int sg_pack_weights(const float* w, int Cout, int Cin, int taps, void* out, int 
   const int64_t total = (int64_t)Cout * Cin * taps;
   pack_weights_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, Cout, Cin, taps, out, out_dtype);
   return launch_status("sg_pack_weights");
+}
+
+int sg_split_tf32(const float* x, float* hi, float* lo, int64_t n, sg_stream_t stream) {
+  SG_REQUIRE(x && hi && lo && n > 0 && n % 4 == 0, "sg_split_tf32: null pointer or n=%lld not a positive multiple of 4", (long long)n);
+  SG_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+             "sg_split_tf32: buffers must be 16-byte aligned");
+  const int64_t n4 = n / 4;
+  SG_REQUIRE(cdiv(n4, 256) < (1ll << 31) - 1, "sg_split_tf32: too many elements");
+  launch_k(split_tf32_kernel, dim3(cdiv(n4, 256)), dim3(256), 0, as_stream(stream), reinterpret_cast<const float4*>(x),
+           reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n4);
+  return launch_status("sg_split_tf32");
 }
 
 int sg_to_uint8_wrap(const float* x, int64_t count, uint8_t* out, sg_stream_t stream) {

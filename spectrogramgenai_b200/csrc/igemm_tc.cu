@@ -69,7 +69,9 @@ constexpr int A_BYTES = BM * BK * 2;
 struct IgemmGeom {
   int64_t M;
   int H, W, HW;
-  int Cout, taps, cblocks;  // cblocks = Cin / 64
+  int Cout, taps, cblocks;  // cblocks = Cin / bke
+  int bke;                  // channels per k-block: one 128-byte swizzle span = 64 (16-bit operands) or 32 (tf32)
+  int passes;               // 1 (16-bit operands) or 3 (split tf32: A_hi B_hi + A_hi B_lo + A_lo B_hi)
   int n_tiles;              // Cout / BN
   int tiles_per_sample;     // HW / 128 when HW >= 128, else 0
   int samples_per_tile;     // 128 / HW when HW < 128, else 0
@@ -84,202 +86,6 @@ struct IgemmEpi {
   float* partials;
   int act, P, act_dtype;  // act: sg_act
 };
-
-// Epilogue of one 128-row x BN accumulator (TMEM columns [tmem_acc, tmem_acc+BN)): executed by the four epilogue
-// warps (threadIdx 64..191).  Thread = one output row (TMEM lane); bias -> GELU -> residual -> stores -> GN partials.
-template <int BN>
-__device__ __forceinline__ void epilogue_128rows(uint32_t tmem_acc, int64_t m0, int n0, int tile_n, int warp, int lane,
-                                                 const IgemmGeom& g, const IgemmEpi& ep, float (*rowstat)[2]) {
-  const int q = warp & 3;
-  const int r = q * 32 + lane;
-  const int64_t m = m0 + r;
-  const bool valid = m < g.M;
-  float s_sum = 0.f, s_sq = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    uint32_t v[32];
-    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-    tmem_ld_wait();
-    const int nb = n0 + c * 32;
-    const int64_t off = m * g.Cout + nb;
-    float f[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = __uint_as_float(v[j]);
-      if (ep.bias) x += __ldg(ep.bias + nb + j);
-      if (ep.act == SG_ACT_GELU) x = gelu_erf(x);
-      f[j] = x;
-    }
-    if (valid) {
-      if (ep.residual) {
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 rr = __ldg(reinterpret_cast<const float4*>(ep.residual + off) + j4);
-          f[j4 * 4 + 0] += rr.x; f[j4 * 4 + 1] += rr.y; f[j4 * 4 + 2] += rr.z; f[j4 * 4 + 3] += rr.w;
-        }
-      }
-      if (ep.act == SG_ACT_RELU_POST) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-      }
-      if (ep.out_f32) {
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          reinterpret_cast<float4*>(ep.out_f32 + off)[j4] =
-              make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
-      }
-      if (ep.out_act) {
-        uint16_t* dst = reinterpret_cast<uint16_t*>(ep.out_act) + off;
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          uint4 w;
-          w.x = pack16(f[j8 * 8 + 0], f[j8 * 8 + 1], ep.act_dtype);
-          w.y = pack16(f[j8 * 8 + 2], f[j8 * 8 + 3], ep.act_dtype);
-          w.z = pack16(f[j8 * 8 + 4], f[j8 * 8 + 5], ep.act_dtype);
-          w.w = pack16(f[j8 * 8 + 6], f[j8 * 8 + 7], ep.act_dtype);
-          reinterpret_cast<uint4*>(dst)[j8] = w;
-        }
-      }
-      if (ep.partials) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          s_sum += f[j];
-          s_sq += f[j] * f[j];
-        }
-      }
-    }
-  }
-  if (ep.partials) {
-    rowstat[r][0] = s_sum;
-    rowstat[r][1] = s_sq;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-    write_tile_partials<BM>(rowstat, (int)threadIdx.x - 64, m0, g.M, g.HW, ep.partials, ep.P, tile_n, g.n_tiles);
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // rowstat may be rewritten by the next accumulator
-  }
-}
-
-template <int BN, int STAGES>
-constexpr int igemm_smem_bytes() {
-  return 1024 /*alignment slack*/ + STAGES * (A_BYTES + BN * BK * 2) + 256 /*barriers*/ + BM * 2 * 4 /*rowstat*/;
-}
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                       const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
-                                                       const IgemmEpi ep) {
-  constexpr int B_BYTES = BN * BK * 2;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + STAGES * (A_BYTES + B_BYTES) + 256);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x % g.n_tiles;
-  const int mt = blockIdx.x / g.n_tiles;
-  const int n0 = tile_n * BN;
-  const int64_t m0 = (int64_t)mt * BM;
-  const int nk = g.taps * g.cblocks;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tmA);
-    prefetch_tensormap(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(tmem_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      int cn, ch, cw;
-      if (g.taps == 1) {
-        cn = 0; ch = 0; cw = (int)m0;  // linear layer: the map is {Cin, M, 1, 1}
-      } else if (g.tiles_per_sample > 0) {
-        cn = mt / g.tiles_per_sample;
-        const int p0 = (mt % g.tiles_per_sample) * BM;
-        ch = p0 / g.W;
-        cw = p0 % g.W;
-      } else {
-        cn = mt * g.samples_per_tile; ch = 0; cw = 0;
-      }
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        const int tap = kb / g.cblocks, c0 = (kb % g.cblocks) * BK;
-        int dy = 0, dx = 0;
-        if (g.taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
-        }
-        mbar_arrive_expect_tx(&full[s], g.tx_bytes);
-        tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, cw + dx, ch + dy, cn);
-        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], c0, tap * g.Cout + n0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint64_t adesc = make_desc_k128(smem_u32(sA + s * A_BYTES));
-        const uint64_t bdesc = make_desc_k128(smem_u32(sB + s * B_BYTES));
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // +32 bytes per K=16 step inside the 128-byte swizzle span: start-address field += 2
-          umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, g.idesc, (kb | k) != 0);
-        }
-        umma_commit(&empty[s]);
-      }
-      umma_commit(tmem_full);
-    }
-  } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    epilogue_128rows<BN>(tmem_base, m0, n0, tile_n, warp, lane, g, ep, rowstat);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc<BN>(tmem_base);
-  }
-}
-
-template <int BN, int STAGES>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const IgemmEpi& ep, int grid,
-                  cudaStream_t stream) {
-  constexpr int smem = igemm_smem_bytes<BN, STAGES>();
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_igemm(tc): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  igemm_tc_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(tmA, tmB, g, ep);
-  return launch_status("sg_igemm(tc)");
-}
 
 // Coalesced epilogue of one 128-row x BN accumulator, executed by ONE group of four warps (TMEM lane quadrant =
 // warp % 4).  Each warp owns a 32-row x 32-column block per step: thread = accumulator row for the TMEM read, bias,
@@ -509,9 +315,17 @@ __device__ __forceinline__ void tile_coords(const IgemmGeom& g, int mt, int& cn,
   }
 }
 
-template <int BN>
+// KIND = 0: kind::f16 (bf16 / fp16 operands), one pass over K.  KIND = 1: the fp32-accurate engine -- kind::tf32 on SPLIT
+// operands (x = hi + lo, both tf32-representable fp32 tensors written by sg_split_tf32): the k-loop runs three times over
+// (tap, channel block) with the operand maps (A_hi, B_hi), (A_hi, B_lo), (A_lo, B_hi), all accumulating into the same
+// fp32 TMEM tile, so the product carries ~21 mantissa bits (the dropped lo x lo term is 2^-22 relative) at 1/6 of the
+// 16-bit rate.  A k-block is the same 128-byte swizzle span either way (64 x 16 bit or 32 x fp32) and one MMA consumes
+// 32 bytes of it (K = 16 or K = 8), so tiles, descriptors and the pipeline are identical.
+template <int BN, int KIND>
 __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmA_lo,
+                                                           const __grid_constant__ CUtensorMap tmB_lo, const IgemmGeom g,
                                                            const IgemmEpi ep, const int num_tiles) {
   using K = V2<BN>;
   constexpr int STAGES = K::STAGES;
@@ -529,11 +343,16 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   for (int i = threadIdx.x; i < g.Cout; i += blockDim.x) s_bias[i] = ep.bias ? __ldg(ep.bias + i) : 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = g.taps * g.cblocks;
+  const int nk1 = g.taps * g.cblocks;  // k-blocks of one pass
+  const int nk = nk1 * g.passes;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
+    if (KIND == 1) {
+      prefetch_tensormap(&tmA_lo);
+      prefetch_tensormap(&tmB_lo);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -563,18 +382,21 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait_spin(&empty[s], ((it / STAGES) & 1u) ^ 1u);
-        const int tap = kb / g.cblocks, c0 = (kb % g.cblocks) * BK;
+        const int pass = KIND == 1 ? kb / nk1 : 0, kk = kb - pass * nk1;
+        const int tap = kk / g.cblocks, c0 = (kk % g.cblocks) * g.bke;
         int dy = 0, dx = 0;
         if (g.taps == 9) {
           dy = tap / 3 - 1;
           dx = tap % 3 - 1;
         }
+        const CUtensorMap* ma = (KIND == 1 && pass == 2) ? &tmA_lo : &tmA;
+        const CUtensorMap* mb = (KIND == 1 && pass == 1) ? &tmB_lo : &tmB;
         uint8_t* st = smem + s * K::STAGE;
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], g.tx_bytes);
-          tma_load_4d(st, &tmA, &full[s], c0, cw0 + dx, ch0 + dy, cn0);
-          tma_load_4d(st + A_BYTES, &tmA, &full[s], c0, cw1 + dx, ch1 + dy, cn1);
-          tma_load_2d(st + 2 * A_BYTES, &tmB, &full[s], c0, tap * g.Cout + n0);
+          tma_load_4d(st, ma, &full[s], c0, cw0 + dx, ch0 + dy, cn0);
+          tma_load_4d(st + A_BYTES, ma, &full[s], c0, cw1 + dx, ch1 + dy, cn1);
+          tma_load_2d(st + 2 * A_BYTES, mb, &full[s], c0, tap * g.Cout + n0);
         }
         __syncwarp();
       }
@@ -596,9 +418,14 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
         const uint64_t bd = make_desc_k128(sa + 2 * A_BYTES);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_ss(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
-            umma_ss(acc1, a1 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte swizzle span
+            if constexpr (KIND == 1) {
+              umma_ss_tf32(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
+              umma_ss_tf32(acc1, a1 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
+            } else {
+              umma_ss(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
+              umma_ss(acc1, a1 + 2 * k, bd + 2 * k, g.idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty[s]);
         }
@@ -634,19 +461,11 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   }
 }
 
-template <int BN>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const IgemmEpi& ep,
-                   cudaStream_t stream) {
+template <int BN, int KIND>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_lo,
+                   const IgemmGeom& g, const IgemmEpi& ep, cudaStream_t stream) {
   constexpr int smem = V2<BN>::SMEM;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_igemm(tc2): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
+  if (int rc = set_max_smem<igemm_tc2_kernel<BN, KIND>>(smem, "sg_igemm(tc2)")) return rc;
   const int64_t mt2 = cdiv(g.M, 2 * BM);
   const int64_t tiles = mt2 * g.n_tiles;
   if (tiles >= (1ll << 31)) {
@@ -654,211 +473,51 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGe
     return SG_ERR_ARG;
   }
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  launch_k(igemm_tc2_kernel<BN>, dim3(grid), dim3(V2<BN>::THREADS), smem, stream, tmA, tmB, g, ep, (int)tiles);
+  launch_k(igemm_tc2_kernel<BN, KIND>, dim3(grid), dim3(V2<BN>::THREADS), smem, stream, tmA, tmB, tmA_lo, tmB_lo, g, ep,
+           (int)tiles);
   return launch_status("sg_igemm(tc2)");
-}
-
-// =====================================================================================================
-// v3 ("halo" mode, 3x3 convs with 16 <= W <= 64 and H*W >= 256): same persistent / double-buffered-TMEM /
-// two-group-epilogue skeleton as v2, but the A operand is loaded ONCE PER COLUMN SHIFT instead of once per tap.
-// A 256-pixel tile is R = 256/W whole image rows; for a fixed dx the three taps (dy = -1, 0, +1) read row-shifted
-// views of the same (R+2)-row halo slab, and because the slab's row pitch is exactly W pixels (the x shift and
-// both paddings are done by TMA coordinates / out-of-bounds fill), every shifted view is a 1024-byte aligned,
-// uniformly strided K-major UMMA tile: descriptor start = slab + (dy + half*R/2) * W * 128 bytes.
-// L2 -> smem A traffic drops from 9 x 256 to 3 x (256 + 2W) pixel rows per channel block (2.2x - 2.6x less), which
-// is what bounds these kernels (measured ~11-13 TB/s operand ceiling).
-// smem: A ring 2 x 48 KB (one slab per (channel block, dx)), B ring 4 x BN*128 B (one weight tile per tap).
-// =====================================================================================================
-template <int BN>
-struct V3 {
-  static constexpr int A_STAGES = 2, B_STAGES = 4;
-  static constexpr int A_SLAB = 48 * 1024;  // (R + 2) * W * 128 B <= 48 KB for W in {16, 32, 64}
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int TMEM_COLS = 4 * BN;
-  static constexpr int THREADS = 320;
-  static constexpr int BAR_OFF = 1024 * 0 + A_STAGES * A_SLAB + B_STAGES * B_BYTES;
-  static constexpr int SMEM = 1024 + BAR_OFF + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES;
-  static_assert(SMEM <= 227 * 1024, "smem budget");
-};
-
-template <int BN>
-__global__ void __launch_bounds__(320, 1) igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
-                                                           const IgemmEpi ep, const int num_tiles) {
-  using K = V3<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + K::A_STAGES * K::A_SLAB;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + K::BAR_OFF);
-  uint64_t* a_empty = a_full + K::A_STAGES;
-  uint64_t* b_full = a_empty + K::A_STAGES;
-  uint64_t* b_empty = b_full + K::B_STAGES;
-  uint64_t* tmem_full = b_empty + K::B_STAGES;  // [2]
-  uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + K::BAR_OFF + 256);
-  float* scratch_all = reinterpret_cast<float*>(smem + K::BAR_OFF + 256 + 2 * BM * 2 * 4);
-  float* s_bias = scratch_all + 8 * (EPI_SCRATCH / 4);
-  for (int i = threadIdx.x; i < g.Cout; i += blockDim.x) s_bias[i] = ep.bias ? __ldg(ep.bias + i) : 0.f;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = 256 / g.W;                        // image rows per tile
-  const int tiles_per_sample = g.HW / 256;
-  const uint32_t row_bytes = (uint32_t)g.W * 128u;
-  const uint32_t slab_bytes = (uint32_t)(R + 2) * row_bytes;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tmA);
-    prefetch_tensormap(&tmB);
-    for (int s = 0; s < K::A_STAGES; ++s) {
-      mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
-    }
-    for (int s = 0; s < K::B_STAGES; ++s) {
-      mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 256);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<K::TMEM_COLS>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t ia = 0, ib = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt2 = tile / g.n_tiles, n0 = (tile % g.n_tiles) * BN;
-        const int cn = mt2 / tiles_per_sample, h0 = (mt2 % tiles_per_sample) * R;
-        for (int cb = 0; cb < g.cblocks; ++cb) {
-          for (int dx = 0; dx < 3; ++dx, ++ia) {
-            const int as = ia % K::A_STAGES;
-            mbar_wait_spin(&a_empty[as], ((ia / K::A_STAGES) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&a_full[as], slab_bytes);
-            tma_load_4d(sA + as * K::A_SLAB, &tmA, &a_full[as], cb * BK, dx - 1, h0 - 1, cn);
-            for (int dy = 0; dy < 3; ++dy, ++ib) {
-              const int bs = ib % K::B_STAGES;
-              mbar_wait_spin(&b_empty[bs], ((ib / K::B_STAGES) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)K::B_BYTES);
-              tma_load_2d(sB + bs * K::B_BYTES, &tmB, &b_full[bs], cb * BK, (dy * 3 + dx) * g.Cout + n0);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      uint32_t ia = 0, ib = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1u;
-        mbar_wait_spin(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * (2 * BN), acc1 = acc0 + BN;
-        uint32_t first = 1;
-        for (int cb = 0; cb < g.cblocks; ++cb) {
-          for (int dx = 0; dx < 3; ++dx, ++ia) {
-            const int as = ia % K::A_STAGES;
-            mbar_wait_spin(&a_full[as], (ia / K::A_STAGES) & 1u);
-            tc_fence_after();
-            const uint32_t slab = smem_u32(sA + as * K::A_SLAB);
-            for (int dy = 0; dy < 3; ++dy, ++ib) {
-              const int bs = ib % K::B_STAGES;
-              mbar_wait_spin(&b_full[bs], (ib / K::B_STAGES) & 1u);
-              tc_fence_after();
-              const uint64_t a0 = make_desc_k128(slab + (uint32_t)dy * row_bytes);
-              const uint64_t a1 = make_desc_k128(slab + (uint32_t)(dy + R / 2) * row_bytes);
-              const uint64_t bd = make_desc_k128(smem_u32(sB + bs * K::B_BYTES));
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                umma_ss(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, accum);
-                umma_ss(acc1, a1 + 2 * k, bd + 2 * k, g.idesc, accum);
-              }
-              first = 0;
-              umma_commit(&b_empty[bs]);
-            }
-            umma_commit(&a_empty[as]);
-          }
-        }
-        umma_commit(&tmem_full[buf]);
-      }
-    }
-  } else {
-    // ===== epilogue (identical to v2) =====
-    const int grp = (warp - 2) >> 2;
-    const int group_tid = (int)threadIdx.x - 64 - grp * 128;
-    float* scratch = scratch_all + (warp - 2) * (EPI_SCRATCH / 4);
-    uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const uint32_t buf = lt & 1u;
-      const int mt2 = tile / g.n_tiles, tile_n = tile % g.n_tiles;
-      mbar_wait_spin(&tmem_full[buf], (lt >> 1) & 1u);
-      tc_fence_after();
-      const int64_t m0 = (int64_t)(2 * mt2 + grp) * BM;
-      if (m0 < g.M)
-        epilogue_coalesced<BN>(tmem_base + buf * (2 * BN) + grp * BN, m0, tile_n * BN, tile_n, warp, lane, group_tid,
-                               1 + grp, g, ep, rowstat + grp * BM, scratch, s_bias);
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[buf]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tmem_dealloc<K::TMEM_COLS>(tmem_base);
-  }
-}
-
-template <int BN>
-static int launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const IgemmEpi& ep,
-                   cudaStream_t stream) {
-  constexpr int smem = V3<BN>::SMEM;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_error("sg_igemm(tc3): cudaFuncSetAttribute(%d B smem): %s", smem, cudaGetErrorString(e));
-      return SG_ERR_LAUNCH;
-    }
-    configured = true;
-  }
-  const int64_t tiles = (g.M / 256) * g.n_tiles;
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  igemm_tc3_kernel<BN><<<grid, V3<BN>::THREADS, smem, stream>>>(tmA, tmB, g, ep, (int)tiles);
-  return launch_status("sg_igemm(tc3)");
-}
-
-static int igemm_version() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("SGB200_IGEMM");
-    // 1 = one tile per CTA, 2 = persistent 256 x BN (default), 3 = v2 + halo-slab A reuse for 3x3 convs.
-    // Measured on B200: v3 moves 2.3x fewer bytes L2 -> smem yet is not faster (128->128 @64x64: 777 vs 906 TFLOP/s),
-    // i.e. these kernels are bound by the shared-memory port (SS-mode MMA operand reads + TMA writes), not by L2.
-    v = e ? atoi(e) : 2;
-    if (v < 1 || v > 3) v = 2;
-  }
-  return v;
 }
 
 }  // namespace tc
 
+// A operand maps of one activation tensor (hi or lo part): NHWC rank-4 {C, W, H, rows} for the 3x3 convs, {Cin, M, 1, 1}
+// for Linear layers; box = one 128-byte channel span x 128 pixels.
+static int make_a_map(CUtensorMap* tm, const sg_igemm_args* a, const void* base, int dtype, int esz, int bke, int64_t M,
+                      uint32_t* box_rows) {
+  using tc::make_tmap;
+  const uint64_t cb = (uint64_t)a->Cin * esz;
+  if (a->taps == 1) {
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)M, 1, 1};
+    const uint64_t strides[3] = {cb, cb * M, cb * M};
+    const uint32_t box[4] = {(uint32_t)bke, (uint32_t)(M < 128 ? M : 128), 1, 1};
+    *box_rows = box[1];
+    return make_tmap(tm, dtype, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  const uint32_t bw = a->W < 128 ? a->W : 128;
+  const uint32_t bh = (uint32_t)a->H < 128 / bw ? a->H : 128 / bw;
+  uint32_t bn = 128 / (bw * bh);
+  if (bn > (uint32_t)a->rows) bn = a->rows;
+  const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->rows};
+  const uint64_t strides[3] = {cb, cb * a->W, cb * a->W * a->H};
+  const uint32_t box[4] = {(uint32_t)bke, bw, bh, bn};
+  *box_rows = bw * bh * bn;
+  return make_tmap(tm, dtype, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
   using namespace tc;
-  SG_REQUIRE(a->act_dtype == SG_BF16 || a->act_dtype == SG_F16, "sg_igemm(tc): act_dtype must be SG_BF16 or SG_F16");
-  SG_REQUIRE(a->out_dtype == 0 || a->out_dtype == SG_BF16 || a->out_dtype == SG_F16, "sg_igemm(tc): out_dtype %d", a->out_dtype);
-  SG_REQUIRE(a->Cin % 64 == 0, "sg_igemm(tc): Cin=%d %% 64 != 0", a->Cin);
+  const bool tf32 = a->act_dtype == SG_F32;
+  SG_REQUIRE(tf32 || a->act_dtype == SG_BF16 || a->act_dtype == SG_F16, "sg_igemm(tc): act_dtype %d", a->act_dtype);
+  const int esz = tf32 ? 4 : 2, bke = 128 / esz;  // one k-block = one 128-byte swizzle span of channels
+  if (tf32) {
+    SG_REQUIRE(a->a_lo && a->w_lo, "sg_igemm(tc, fp32): the split-tf32 engine needs a_lo and w_lo (sg_split_tf32)");
+    SG_REQUIRE(a->out_dtype == 0, "sg_igemm(tc, fp32): outputs are fp32");
+    SG_REQUIRE(((reinterpret_cast<uintptr_t>(a->a_lo) | reinterpret_cast<uintptr_t>(a->w_lo)) & 15) == 0,
+               "sg_igemm(tc): operands must be 16-byte aligned");
+  } else {
+    SG_REQUIRE(a->out_dtype == 0 || a->out_dtype == SG_BF16 || a->out_dtype == SG_F16, "sg_igemm(tc): out_dtype %d", a->out_dtype);
+  }
+  SG_REQUIRE(a->Cin % bke == 0, "sg_igemm(tc): Cin=%d %% %d != 0", a->Cin, bke);
   SG_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
              "sg_igemm(tc): operands must be 16-byte aligned");
   const int BN = (a->Cout % 128 == 0) ? 128 : 64;
@@ -866,65 +525,43 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
   IgemmGeom g;
   g.M = (int64_t)a->rows * HW;
   g.H = a->H; g.W = a->W; g.HW = HW;
-  g.Cout = a->Cout; g.taps = a->taps; g.cblocks = a->Cin / 64;
+  g.Cout = a->Cout; g.taps = a->taps; g.cblocks = a->Cin / bke;
+  g.bke = bke;
+  g.passes = tf32 ? 3 : 1;
   g.n_tiles = a->Cout / BN;
   g.tiles_per_sample = HW >= 128 ? HW / 128 : 0;
   g.samples_per_tile = HW >= 128 ? 0 : 128 / HW;
-  g.idesc = make_idesc(a->act_dtype, 128, BN, 0, 0);
+  g.idesc = tf32 ? make_idesc_tf32(128, BN, 0) : make_idesc(a->act_dtype, 128, BN, 0, 0);
   SG_REQUIRE(g.M < (1ll << 31), "sg_igemm(tc): M too large");
   SG_REQUIRE(a->Cout <= MAX_COUT, "sg_igemm(tc): Cout=%d > %d", a->Cout, MAX_COUT);
 
-  CUtensorMap tmA, tmB;
-  uint32_t box_rows;
-  const uint64_t cb = (uint64_t)a->Cin * 2;
-  if (a->taps == 1) {
-    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)g.M, 1, 1};
-    const uint64_t strides[3] = {cb, cb * g.M, cb * g.M};
-    const uint32_t box[4] = {64, (uint32_t)(g.M < 128 ? g.M : 128), 1, 1};
-    box_rows = box[1];
-    int rc = make_tmap(&tmA, a->act_dtype, 4, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+  CUtensorMap tmA, tmB, tmA_lo, tmB_lo;
+  uint32_t box_rows = 0;
+  int rc;
+  if ((rc = make_a_map(&tmA, a, a->a, a->act_dtype, esz, bke, g.M, &box_rows))) return rc;
+  const uint64_t wdims[2] = {(uint64_t)a->Cin, (uint64_t)a->taps * a->Cout};
+  const uint64_t wstrides[1] = {(uint64_t)a->Cin * esz};
+  const uint32_t wbox[2] = {(uint32_t)bke, (uint32_t)BN};
+  if ((rc = make_tmap(&tmB, a->act_dtype, 2, a->w, wdims, wstrides, wbox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if (tf32) {
+    if ((rc = make_a_map(&tmA_lo, a, a->a_lo, a->act_dtype, esz, bke, g.M, &box_rows))) return rc;
+    if ((rc = make_tmap(&tmB_lo, a->act_dtype, 2, a->w_lo, wdims, wstrides, wbox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   } else {
-    const uint32_t bw = a->W < 128 ? a->W : 128;
-    const uint32_t bh = (uint32_t)a->H < 128 / bw ? a->H : 128 / bw;
-    uint32_t bn = 128 / (bw * bh);
-    if (bn > (uint32_t)a->rows) bn = a->rows;
-    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->rows};
-    const uint64_t strides[3] = {cb, cb * a->W, cb * a->W * a->H};
-    const uint32_t box[4] = {64, bw, bh, bn};
-    box_rows = bw * bh * bn;
-    int rc = make_tmap(&tmA, a->act_dtype, 4, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+    tmA_lo = tmA;
+    tmB_lo = tmB;
   }
-  {
-    const uint64_t dims[2] = {(uint64_t)a->Cin, (uint64_t)a->taps * a->Cout};
-    const uint64_t strides[1] = {cb};
-    const uint32_t box[2] = {64, (uint32_t)BN};
-    int rc = make_tmap(&tmB, a->act_dtype, 2, a->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-  }
-  const bool halo = igemm_version() == 3 && a->taps == 9 && a->W >= 16 && a->W <= 64 && HW >= 256;
-  const bool v2 = igemm_version() >= 2;
-  g.tx_bytes = (v2 ? 2u : 1u) * box_rows * 128u + (uint32_t)BN * 128u;
+  g.tx_bytes = 2u * box_rows * 128u + (uint32_t)BN * 128u;
 
   IgemmEpi ep;
   ep.bias = a->bias; ep.residual = a->residual; ep.out_f32 = a->out_f32; ep.out_act = a->out_act;
   ep.partials = a->partials; ep.act = a->act; ep.act_dtype = a->out_dtype ? a->out_dtype : a->act_dtype;
-  ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
-  if (halo) {
-    // A map with the slab box {64, W, 256/W + 2, 1}; x shift and zero padding come from the TMA coordinates
-    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->rows};
-    const uint64_t strides[3] = {cb, cb * a->W, cb * a->W * a->H};
-    const uint32_t box[4] = {64, (uint32_t)a->W, (uint32_t)(256 / a->W + 2), 1};
-    int rc = make_tmap(&tmA, a->act_dtype, 4, a->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    return BN == 128 ? launch3<128>(tmA, tmB, g, ep, stream) : launch3<64>(tmA, tmB, g, ep, stream);
+  if (tf32) {  // fp32 engine: a single fp32 output (callers may pass it in either slot, like the SIMT engine)
+    if (!ep.out_f32) ep.out_f32 = reinterpret_cast<float*>(a->out_act);
+    ep.out_act = nullptr;
   }
-  if (v2) return BN == 128 ? launch2<128>(tmA, tmB, g, ep, stream) : launch2<64>(tmA, tmB, g, ep, stream);
-  const int64_t grid = (int64_t)cdiv(g.M, BM) * g.n_tiles;
-  SG_REQUIRE(grid < (1ll << 31), "sg_igemm(tc): grid too large");
-  if (BN == 128) return launch<128, 3>(tmA, tmB, g, ep, (int)grid, stream);
-  return launch<64, 4>(tmA, tmB, g, ep, (int)grid, stream);
+  ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
+  if (tf32) return BN == 128 ? launch2<128, 1>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream) : launch2<64, 1>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
+  return BN == 128 ? launch2<128, 0>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream) : launch2<64, 0>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
 }
 
 }  // namespace sg

@@ -14,13 +14,24 @@ namespace sg {
 // RAW16: the raw tensor is fp16 (tensor-core modes).  MODE >= 0 fixes the mode at compile time and lets a thread keep
 // the folded per-channel scale / shift of its 8 channels in registers (valid when the grid stride is a multiple of C,
 // which the launcher checks); MODE = -1 is the general runtime-mode path.
+// The fp16 raw tensor a GroupNorm reads is only as good as fp16's range: GroupNorm is scale invariant in the reference,
+// fp16 is not.  The statistics come from the fp32 accumulators, so the mean square of the row is known exactly here:
+// outside [2^-20, 2^20] (rms outside [2^-10, 2^10]: values within a few 10 sigma of saturation at 65504, or so small that
+// the 2^-24 subnormal spacing costs relative precision) the kernel raises *range_flag and the host re-runs the plan with
+// fp32 raw tensors (engine.UNetPlan / Diffusion.sample).  An exactly zero row is fine.
+__device__ __forceinline__ void flag_fp16_range(double mean_sq, int32_t* range_flag) {
+  if (range_flag && (mean_sq > 1048576.0 || (mean_sq > 0.0 && mean_sq < 9.5367431640625e-07) || mean_sq != mean_sq))
+    *range_flag = 1;
+}
+
 template <bool RAW16, int MODE>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ raw_v, const float* __restrict__ partials,
                                                        int P, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int64_t per_row4, int C4,
                                                        int raw_rows, int mode_rt, const float* __restrict__ residual,
                                                        const float* __restrict__ emb, int emb_stride,
-                                                       float* __restrict__ o32, void* __restrict__ o16, int dtype) {
+                                                       float* __restrict__ o32, void* __restrict__ o16, int dtype,
+                                                       int32_t* __restrict__ range_flag) {
   __shared__ double red[2][8];
   __shared__ float stat[2];
   pdl_wait();
@@ -58,6 +69,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
       if (var < 0.0) var = 0.0;
       stat[0] = (float)mean;
       stat[1] = (float)(1.0 / sqrt(var + 1e-5));
+      if (RAW16) flag_fp16_range(tq / cnt, range_flag);
     }
     __syncthreads();
   }
@@ -253,7 +265,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_vcat_kernel(const uint4* __re
                                                             const float* __restrict__ beta, int HW, int W2, int C8,
                                                             int Cs8, const float* __restrict__ x,
                                                             const float* __restrict__ skip, int skip_rows, int h, int w,
-                                                            float sh, float sw, void* __restrict__ o16, int dtype) {
+                                                            float sh, float sw, void* __restrict__ o16, int dtype,
+                                                            int32_t* __restrict__ range_flag) {
   __shared__ double red[2][8];
   __shared__ float stat[2];
   __shared__ __align__(16) float s_sc[VCAT_MAXC], s_sf[VCAT_MAXC];
@@ -291,6 +304,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_vcat_kernel(const uint4* __re
       if (var < 0.0) var = 0.0;
       stat[0] = (float)mean;
       stat[1] = (float)(1.0 / sqrt(var + 1e-5));
+      flag_fp16_range(tq / cnt, range_flag);
     }
     __syncthreads();
   }
@@ -443,7 +457,7 @@ extern "C" {
 
 int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, const float* gamma, const float* beta,
                 int rows, int raw_rows, int HW, int C, int mode, const float* residual, const float* emb, int emb_stride, float* out_f32,
-                void* out_act, int act_dtype, sg_stream_t stream) {
+                void* out_act, int act_dtype, int32_t* range_flag, sg_stream_t stream) {
   SG_REQUIRE(raw_dtype == SG_F32 || raw_dtype == SG_F16, "sg_gn_apply: raw_dtype must be SG_F32 or SG_F16");
   SG_REQUIRE(raw && partials && gamma && beta && (out_f32 || out_act), "sg_gn_apply: null pointer");
   SG_REQUIRE(rows > 0 && HW > 0 && C % 4 == 0 && P > 0, "sg_gn_apply: bad shape rows=%d HW=%d C=%d P=%d", rows, HW, C, P);
@@ -463,7 +477,7 @@ int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, co
   cudaStream_t st = as_stream(stream);
 #define SG_GN_LAUNCH(R16, MD)                                                                                          \
   launch_k(gn_apply_kernel<R16, MD>, grid, dim3(256), 0, st, raw, partials, P, gamma, beta, per_row4, C / 4, raw_rows, mode, \
-           residual, emb, emb_stride, out_f32, out_act, act_dtype)
+           residual, emb, emb_stride, out_f32, out_act, act_dtype, range_flag)
   if (raw_dtype == SG_F16) {
     // fixed-channel fast path: every thread of the grid-stride loop must land on the same 8 channels each pass
     const bool fixed = ((int64_t)chunks * 256 * 8) % C == 0;
@@ -480,7 +494,7 @@ int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, co
 
 int sg_gn_apply_vcat(const void* raw, const float* partials, int P, const float* gamma, const float* beta, int rows,
                      const float* x, const float* skip, int skip_rows, int h, int w, int Cx, int Cs, void* out_act,
-                     int act_dtype, sg_stream_t stream) {
+                     int act_dtype, int32_t* range_flag, sg_stream_t stream) {
   SG_REQUIRE(raw && partials && gamma && beta && x && skip && out_act, "sg_gn_apply_vcat: null pointer");
   SG_REQUIRE(rows > 0 && h >= 1 && w >= 1 && P > 0 && Cx % 8 == 0 && Cs % 8 == 0 && Cx > 0 && Cs > 0,
              "sg_gn_apply_vcat: bad shape rows=%d h=%d w=%d Cx=%d Cs=%d", rows, h, w, Cx, Cs);
@@ -501,7 +515,7 @@ int sg_gn_apply_vcat(const void* raw, const float* partials, int P, const float*
   const float sh = (H2 > 1) ? (float)(h - 1) / (float)(H2 - 1) : 0.f;
   const float sw = (W2 > 1) ? (float)(w - 1) / (float)(W2 - 1) : 0.f;
   launch_k(gn_apply_vcat_kernel, dim3(chunks, rows), dim3(256), 0, as_stream(stream), reinterpret_cast<const uint4*>(raw),
-           partials, P, gamma, beta, H2 * W2, W2, C / 8, Cs / 8, x, skip, skip_rows, h, w, sh, sw, out_act, act_dtype);
+           partials, P, gamma, beta, H2 * W2, W2, C / 8, Cs / 8, x, skip, skip_rows, h, w, sh, sw, out_act, act_dtype, range_flag);
   return launch_status("sg_gn_apply_vcat");
 }
 

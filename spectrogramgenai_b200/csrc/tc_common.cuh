@@ -143,6 +143,16 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with kind::tf32 (fp32 containers in shared memory, K = 8 per instruction): the split-operand fp32 engine
+__device__ __forceinline__ void umma_ss_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                         uint32_t accumulate) {
@@ -216,6 +226,18 @@ __host__ __device__ inline uint32_t make_idesc(int fmt, int M, int N, int a_mn_m
   d |= (uint32_t)b_mn_major << 16;   // b_major
   d |= (uint32_t)(N >> 3) << 17;     // n_dim
   d |= (uint32_t)(M >> 4) << 24;     // m_dim
+  return d;
+}
+
+// kind::tf32 instruction descriptor: fp32 accumulate, A / B = TF32 (format 2), optional MN-major B
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;    // c_format = F32
+  d |= 2u << 7;    // a_format = TF32
+  d |= 2u << 10;   // b_format = TF32
+  d |= (uint32_t)b_mn_major << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
   return d;
 }
 

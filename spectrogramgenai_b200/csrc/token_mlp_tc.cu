@@ -129,6 +129,7 @@ __device__ __forceinline__ void gemm_kc(uint32_t tmem_d, uint32_t a_tile, uint32
   }
 }
 
+constexpr int OUTC_C = 64;  // the fused output conv follows the C = 64 block sa6
 struct TailParams {
   const float* bo;
   const float* ln_g;
@@ -144,33 +145,12 @@ struct TailParams {
   int c_out;      // 1..4
   int log_hw;     // HW is a power of two
   int write_out;  // also write the fp32 token tensor (debug taps)
+  // 1x1 output conv weights [4][OUTC_C] (rows >= c_out zero) followed by the 4 biases, passed BY VALUE: kernel parameters
+  // live in the constant bank, every thread reads the same word at the same time, so they are FFMA constant-bank operands
+  // (no load instructions) -- and, unlike a __constant__ array rewritten per call, belong to this launch alone
+  float outc[4 * 64 + 4];
 };
 
-// 1x1 output conv weights [4][C] (rows >= c_out zero) followed by the 4 biases: every thread reads the same word at the
-// same time, so they are FFMA constant-bank operands (no load instructions); rewritten through the bank's global
-// address by a one-block kernel ahead of each launch (stream order makes it visible)
-constexpr int OUTC_MAXC = 128;
-__constant__ __align__(16) float c_outc[4 * OUTC_MAXC + 4];
-
-__global__ void outc_pack_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ dst,
-                                 int c_out, int C) {
-  pdl_wait();
-  pdl_launch_dependents();
-  for (int i = threadIdx.x; i < 4 * OUTC_MAXC + 4; i += blockDim.x) {
-    float v = 0.f;
-    if (i < 4 * OUTC_MAXC) {
-      const int k = i / OUTC_MAXC, c = i % OUTC_MAXC;
-      if (k < c_out && c < C) v = w[k * C + c];
-    } else if (i - 4 * OUTC_MAXC < c_out) {
-      v = b[i - 4 * OUTC_MAXC];
-    }
-    dst[i] = v;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// sg_attn_tail
-// ------------------------------------------------------------------------------------------------------------------
 template <int C, int DT, bool OUTC>
 __global__ void __launch_bounds__(128, Tok<C>::TAIL_CTAS)
 attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_constant__ CUtensorMap tm_x,
@@ -355,10 +335,10 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
     const bool stage = !DIRECT && (!OUTC || p.write_out);
     float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
     if constexpr (OUTC) {
-      e0 = c_outc[4 * OUTC_MAXC + 0];
-      e1 = c_outc[4 * OUTC_MAXC + 1];
-      e2 = c_outc[4 * OUTC_MAXC + 2];
-      e3 = c_outc[4 * OUTC_MAXC + 3];
+      e0 = p.outc[4 * OUTC_C + 0];
+      e1 = p.outc[4 * OUTC_C + 1];
+      e2 = p.outc[4 * OUTC_C + 2];
+      e3 = p.outc[4 * OUTC_C + 3];
     }
 #pragma unroll
     for (int h = 0; h < C / 32; ++h) {
@@ -378,10 +358,10 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap tm_att, const __grid_consta
           const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            e0 = fmaf(ov[u], c_outc[0 * OUTC_MAXC + ch + u], e0);
-            e1 = fmaf(ov[u], c_outc[1 * OUTC_MAXC + ch + u], e1);
-            e2 = fmaf(ov[u], c_outc[2 * OUTC_MAXC + ch + u], e2);
-            e3 = fmaf(ov[u], c_outc[3 * OUTC_MAXC + ch + u], e3);
+            e0 = fmaf(ov[u], p.outc[0 * OUTC_C + ch + u], e0);
+            e1 = fmaf(ov[u], p.outc[1 * OUTC_C + ch + u], e1);
+            e2 = fmaf(ov[u], p.outc[2 * OUTC_C + ch + u], e2);
+            e3 = fmaf(ov[u], p.outc[3 * OUTC_C + ch + u], e3);
           }
         }
         if (stage) sts128(xrow_chunk_addr(aX, r, h * 8 + c), o);
@@ -653,16 +633,6 @@ static int tmap2d(CUtensorMap* out, int dtype, const void* base, uint64_t inner,
   return make_tmap(out, dtype, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <typename K>
-static int set_smem(K kernel, int bytes, const char* what) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e != cudaSuccess) {
-    set_error("%s: cudaFuncSetAttribute(%d B smem): %s", what, bytes, cudaGetErrorString(e));
-    return SG_ERR_LAUNCH;
-  }
-  return SG_OK;
-}
-
 template <int C, int DT, bool OUTC>
 static int launch_tail(const void* att, const float* x, const void* wo, const void* w1, const void* w2, float* out,
                        TailParams p, int act_dtype, cudaStream_t s) {
@@ -678,15 +648,8 @@ static int launch_tail(const void* att, const float* x, const void* wo, const vo
   p.idesc = make_idesc(act_dtype, 128, C, 0, 0);
   const int per_sm = T::TAIL_CTAS * num_sms();
   const int grid = p.ntiles < per_sm ? p.ntiles : per_sm;
-  static bool cfg = false;
-  if (!cfg) {
-    if ((rc = set_smem(attn_tail_kernel<C, DT, OUTC>, T::TAIL_SMEM, "sg_attn_tail"))) return rc;
-    cfg = true;
-  }
-  if (OUTC)  // fully serialised behind outc_pack_kernel (constant-cache coherence of the bank it rewrites)
-    attn_tail_kernel<C, DT, OUTC><<<grid, 128, T::TAIL_SMEM, s>>>(tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
-  else
-    launch_k(attn_tail_kernel<C, DT, OUTC>, dim3(grid), dim3(128), T::TAIL_SMEM, s, tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
+  if ((rc = set_max_smem<attn_tail_kernel<C, DT, OUTC>>(T::TAIL_SMEM, "sg_attn_tail"))) return rc;
+  launch_k(attn_tail_kernel<C, DT, OUTC>, dim3(grid), dim3(128), T::TAIL_SMEM, s, tm_att, tm_x, tm_out, tm_wo, tm_w1, tm_w2, p);
   return launch_status("sg_attn_tail");
 }
 
@@ -704,11 +667,7 @@ static int launch_inproj(const float* x, const void* w_in, void* qkv, InprojPara
   p.idesc_b = make_idesc(act_dtype, 128, N > NA ? N - NA : NA, 0, 0);
   const int per_sm = T::INPROJ_CTAS * num_sms();
   const int grid = p.ntiles < per_sm ? p.ntiles : per_sm;
-  static bool cfg = false;
-  if (!cfg) {
-    if ((rc = set_smem(ln_inproj_kernel<C, DT>, T::INPROJ_SMEM, "sg_ln_inproj"))) return rc;
-    cfg = true;
-  }
+  if ((rc = set_max_smem<ln_inproj_kernel<C, DT>>(T::INPROJ_SMEM, "sg_ln_inproj"))) return rc;
   launch_k(ln_inproj_kernel<C, DT>, dim3(grid), dim3(128), T::INPROJ_SMEM, s, tm_x, tm_w, tm_w2, tm_qkv, p);
   return launch_status("sg_ln_inproj");
 }
@@ -740,15 +699,11 @@ static int attn_tail_impl(const void* att, const float* x, const void* wo, const
     SG_REQUIRE(outc_w && outc_b && c_out >= 1 && c_out <= 4, "%s: c_out=%d not in 1..4 or null weights", what, c_out);
     SG_REQUIRE(HW > 0 && (HW & (HW - 1)) == 0 && HW >= TM && M % HW == 0, "%s: HW=%d must be a power of two >= %d dividing M", what, HW, TM);
     while ((1 << p.log_hw) < HW) ++p.log_hw;
-    static float* bank = nullptr;  // global address of the constant bank
-    if (!bank) {
-      cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&bank), c_outc);
-      if (e != cudaSuccess) {
-        set_error("%s: cudaGetSymbolAddress: %s", what, cudaGetErrorString(e));
-        return SG_ERR_LAUNCH;
-      }
+    for (int i = 0; i < 4 * OUTC_C + 4; ++i) p.outc[i] = 0.f;
+    for (int k = 0; k < c_out; ++k) {
+      for (int c = 0; c < C; ++c) p.outc[k * OUTC_C + c] = outc_w[k * C + c];  // HOST pointers (see sgb200.h)
+      p.outc[4 * OUTC_C + k] = outc_b[k];
     }
-    launch_k(outc_pack_kernel, dim3(1), dim3(256), 0, s, outc_w, outc_b, bank, c_out, C);
     if (act_dtype == SG_BF16) return launch_tail<64, SG_BF16, true>(att, x, wo, w1, w2, out, p, act_dtype, s);
     return launch_tail<64, SG_F16, true>(att, x, wo, w1, w2, out, p, act_dtype, s);
   }

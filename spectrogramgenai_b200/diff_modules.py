@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, ops
-from .engine import MODES, TIME_DIM, PackedWeights, UNetPlan
+from .engine import MODES, TIME_DIM, PackedWeights, PlanOptions, UNetPlan
 from .vae import VqaeDecoder
 
 __all__ = ["UNet_conditional", "Diffusion", "DiffusionVAE", "EMA", "state_dict_schema"]
@@ -129,10 +129,13 @@ class UNet_conditional(nn.Module):
         self._packed = None
         self._packed_key = None
         self._plans = {}
+        self._weights_gen = 0  # bumped by writers that bypass autograd's version counter (EMA.update_model_average)
+        self._raw16_ok = True  # cleared when a GroupNorm input left fp16's safe range: plans then keep raw tensors in fp32
 
     # ------------------------------------------------------------------ engine plumbing
     def set_compute_dtype(self, mode: str):
-        """'fp32' (CUDA-core engine, <=1e-4 of the reference) or 'bf16' / 'f16' (tcgen05 engine)."""
+        """'fp32' (split-TF32 tensor-core engine, <= 1e-4 of the reference), 'bf16' / 'f16' (tcgen05 16-bit engine) or
+        'fp32_simt' (CUDA-core kernels: the comparator of the parity tests)."""
         if mode not in MODES:
             raise ValueError(f"compute dtype must be one of {sorted(MODES)}")
         self.compute_dtype = mode
@@ -140,7 +143,17 @@ class UNet_conditional(nn.Module):
 
     def _weights_key(self):
         ps = list(self.parameters())
-        return (self.compute_dtype, str(ps[0].device), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+        return (self.compute_dtype, str(ps[0].device), self._weights_gen, tuple(p._version for p in ps),
+                tuple(p.data_ptr() for p in ps))
+
+    def invalidate_packed(self):
+        """Drop the kernel-layout weight copy and every plan / captured graph built on it.  Writers that change parameter
+        storage in place through raw pointers (sg_ema_update) call this: such writes bump neither Parameter._version nor
+        data_ptr, so the cache key alone would not notice them."""
+        self._weights_gen += 1
+        self._packed = None
+        self._packed_key = None
+        self._plans = {}
 
     def packed_weights(self) -> PackedWeights:
         """Kernel-layout weights; rebuilt whenever a parameter was modified (load_state_dict, .to(), ...)."""
@@ -153,12 +166,25 @@ class UNet_conditional(nn.Module):
             self._plans = {}
         return self._packed
 
-    def plan(self, *, n_src, rows, S, use_step=False, debug=False) -> UNetPlan:
+    def plan(self, *, n_src, rows, S, use_step=False, debug=False, options: PlanOptions | None = None) -> UNetPlan:
         w = self.packed_weights()
-        key = (n_src, rows, S, use_step, debug)
+        if options is None:
+            options = PlanOptions(raw16=self._raw16_ok)
+        key = (n_src, rows, S, use_step, debug, options)
         if key not in self._plans:
-            self._plans[key] = UNetPlan(w, n_src=n_src, rows=rows, S=S, use_step=use_step, debug=debug)
+            self._plans[key] = UNetPlan(w, n_src=n_src, rows=rows, S=S, use_step=use_step, debug=debug, options=options)
         return self._plans[key]
+
+    def fp16_range_fallback(self, plan) -> bool:
+        """GroupNorm(1, C) is scale invariant in the reference; the fp16 raw conv outputs of the 16-bit engines are not.
+        After a run: if a GroupNorm input left fp16's safe range (the kernels compare the exact fp32 statistics against
+        [2^-10, 2^10] rms and raise a flag), drop every plan and switch this model to fp32 raw tensors.  Returns True
+        when the caller has to repeat the run."""
+        if not plan.range_overflow():
+            return False
+        self._raw16_ok = False
+        self._plans = {}
+        return True
 
     def release_plans(self):
         self._plans = {}
@@ -172,15 +198,24 @@ class UNet_conditional(nn.Module):
         if y is not None and self.num_classes is None:
             raise AttributeError("'UNet_conditional' object has no attribute 'label_emb'")  # as the reference would
         n, S = x.shape[0], x.shape[2]
-        plan = self.plan(n_src=n, rows=n, S=S)
-        plan.x_in.copy_(x.to(torch.float32))
-        plan.t.copy_(t.reshape(-1).to(torch.float32))
-        if y is None:
-            plan.y.fill_(-1)
-        else:
-            plan.y.copy_(y.reshape(-1).to(torch.int64))
-        plan.run()
-        return plan.eps.clone()
+        if y is not None and n > 0:
+            y = torch.as_tensor(y).reshape(-1)
+            if len(y) != n:
+                raise ValueError(f"y must have one class id per sample ({n}), got {len(y)}")
+            if int(y.min()) < 0 or int(y.max()) >= self.num_classes:
+                raise IndexError("index out of range in self")  # nn.Embedding's error in the reference (:215)
+        while True:
+            plan = self.plan(n_src=n, rows=n, S=S)
+            plan.reset_range_flag()
+            plan.x_in.copy_(x.to(torch.float32))
+            plan.t.copy_(t.reshape(-1).to(torch.float32))
+            if y is None:
+                plan.y.fill_(-1)
+            else:
+                plan.y.copy_(y.reshape(-1).to(torch.int64))
+            plan.run()
+            if not self.fp16_range_fallback(plan):
+                return plan.eps.clone()
 
 
 class EMA:
@@ -193,6 +228,8 @@ class EMA:
     def update_model_average(self, ma_model, current_model):
         for current_params, ma_params in zip(current_model.parameters(), ma_model.parameters()):
             ma_params.data = self.update_average(ma_params.data, current_params.data)
+        if hasattr(ma_model, "invalidate_packed"):
+            ma_model.invalidate_packed()  # the packed copy / plans / graphs of ma_model are stale now
 
     def update_average(self, old, new):
         """old * beta + (1 - beta) * new (:37-40), in place on `old` (the reference rebinds .data to a new tensor)."""
@@ -246,6 +283,7 @@ class Diffusion:
         self.c_in = c_in
         self.num_classes = num_classes
         self.gpu_launches = 0  # kernels launched by the last sample() call
+        self.graph_captures = 0  # CUDA graphs captured so far (a repeated sample() call replays the cached one)
 
     def prepare_noise_schedule(self):
         return torch.linspace(self.beta_start, self.beta_end, self.noise_steps)
@@ -329,6 +367,12 @@ class Diffusion:
             labels = torch.arange(self.num_classes).long().to(self.device)
         labels = torch.as_tensor(labels).reshape(-1)
         samp_is = list(samp_is)
+        if getattr(self, "sav_denoise_path", None):
+            # (:765-769) the trajectory dumps are named by class only, so the label set is sampled ONCE (tiling it would
+            # rewrite every {class}_noise_{i}_*.png len(samp_is) times) and the final images are not saved
+            self.sample(False, labels, **sample_kw)
+            print("not saving image, just noise portions")
+            return []
         sampled_images = self.sample(False, labels.repeat(len(samp_is)), **sample_kw)
         return self.write_images(img_folder, samp_is, labels, sampled_images, colormap=colormap)
 
@@ -402,15 +446,19 @@ class Diffusion:
         if return_trajectory:
             iters = T - 1 if max_steps is None else min(T - 1, max_steps)
             traj = torch.empty((iters + 1, n, c, S, S), dtype=torch.float32, device=self.device)
-        for lo in range(0, n, micro_batch):
-            hi = min(n, lo + micro_batch)
-            nz = None if noise is None else noise[:, lo:hi].contiguous()
-            self._sample_chunk(model, labels[lo:hi], float(cfg_scale), nz, seed, sample_base + lo, out[lo:hi],
-                               use_graph, max_steps, step_hook, None if traj is None else traj[:, lo:hi])
+        with torch.cuda.device(self.device):
+            for lo in range(0, n, micro_batch):
+                hi = min(n, lo + micro_batch)
+                nz = None if noise is None else noise[:, lo:hi].contiguous()
+                args = (model, labels[lo:hi], float(cfg_scale), nz, seed, sample_base + lo, out[lo:hi], use_graph,
+                        max_steps, step_hook, None if traj is None else traj[:, lo:hi])
+                if self._sample_chunk(*args):  # fp16 range guard tripped: the model now plans with fp32 raw tensors
+                    self._sample_chunk(*args)
         return (out, traj) if return_trajectory else out
 
     def _sample_chunk(self, model, labels, cfg, noise, seed, sample_base, out, use_graph, max_steps, step_hook=None,
                       traj=None):
+        """One micro-batch through the captured loop.  Returns True when the run has to be repeated (fp16 range guard)."""
         n = len(labels)
         T = self.noise_steps
         rows = 2 * n if cfg > 0 else n
@@ -432,6 +480,7 @@ class Diffusion:
             torch.cuda.synchronize(self.device)
             plan._warm = True
             self.gpu_launches += launches_per_step
+        plan.reset_range_flag()
         # x_T (:418) and the step counter i = T-1
         if noise is not None:
             x.copy_(noise[0])
@@ -443,11 +492,24 @@ class Diffusion:
         if traj is not None:
             traj[0].copy_(x)
         if use_graph and iters > 0:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                one_step()
-            # capture does not execute: state is still (x_T, T-1)
-            step = g.replay
+            # the captured step bakes in its by-value launch arguments, so the graph is cached with the plan (whose
+            # buffers it references) under exactly those: guidance scale and Philox key.  Injected-noise runs (parity
+            # tests) capture afresh: their graph reads a caller-owned buffer that must not be kept alive here.
+            gkey = (cfg, int(seed), int(sample_base), id(self._coef))
+            graphs = plan.__dict__.setdefault("_graphs", {})
+            entry = graphs.get(gkey) if noise is None else None
+            if entry is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    one_step()
+                # capture does not execute: state is still (x_T, T-1)
+                entry = (g,)
+                if noise is None:
+                    if len(graphs) >= 8:
+                        graphs.pop(next(iter(graphs)))
+                    graphs[gkey] = entry
+                self.graph_captures += 1
+            step = entry[0].replay
         else:
             step = one_step
         for k in range(iters):
@@ -457,11 +519,14 @@ class Diffusion:
             if step_hook is not None:
                 step_hook(T - 1 - k, x, labels)
         self.gpu_launches += iters * launches_per_step
+        if model.fp16_range_fallback(plan):
+            return True
         if out.dtype == torch.uint8:
             ops.to_uint8(x, out)
             self.gpu_launches += 1
         else:
             out.copy_(x)
+        return False
 
 
 class DiffusionVAE(Diffusion):
@@ -516,7 +581,8 @@ class DiffusionVAE(Diffusion):
 
     @torch.no_grad()
     def sample(self, use_ema, labels, cfg_scale=3, *legacy, decode_micro_batch=64, **kw):
-        """sample(use_ema, labels, cfg_scale=3) -> uint8 [n, 1, 4*img_size, 4*img_size] (:630-706)."""
+        """sample(use_ema, labels, cfg_scale=3) -> uint8 [n, 1, 4*img_size, 4*img_size] (:630-706); with
+        return_trajectory=True -> (images, latent trajectory fp32 [K+1, n, 4, img_size, img_size])."""
         if kw.pop("return_float", False):
             raise TypeError("DiffusionVAE.sample returns the decoded uint8 image; use Diffusion.sample for latents")
         self.dump_launches = 0
@@ -529,4 +595,4 @@ class DiffusionVAE(Diffusion):
         launches = self.gpu_launches + self.dump_launches
         out = self.vqae.decode(x, micro_batch=decode_micro_batch)
         self.gpu_launches = launches + self.vqae.gpu_launches
-        return out
+        return (out, traj) if traj is not None else out

@@ -6,8 +6,6 @@ computes on the host and nothing falls back to PyTorch ops.
 """
 from __future__ import annotations
 
-import os
-
 import torch
 
 from . import _cabi
@@ -42,14 +40,24 @@ def conv_in_partials(S: int) -> int:
     return _lib().sg_conv_in_partials(S)
 
 
+def _host_f32(t, name):
+    """Small weights that travel by value as kernel launch parameters: a contiguous fp32 HOST tensor."""
+    if t.dtype != torch.float32 or t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous fp32 HOST tensor (it is passed by value as a launch parameter)")
+    return t
+
+
 def conv_in(x, w, raw, partials):
-    """inc.double_conv.0.  x fp32 NCHW [n_src,c,S,S]; raw fp32 or fp16 [rows,S,S,64]; partials fp32 [rows,P,2]."""
+    """inc.double_conv.0.  x fp32 NCHW [n_src,c,S,S]; w fp32 HOST [64,c,3,3]; raw fp32 or fp16 [rows,S,S,64];
+    partials fp32 [rows,P,2]."""
     n_src, c_in, S, _ = x.shape
     rows = raw.shape[0]
     if raw.dtype not in (torch.float32, torch.float16):
         raise ValueError("conv_in: raw must be fp32 or fp16")
-    check(_lib().sg_conv_in(ptr(_f32(x, "x")), n_src, c_in, S, ptr(_f32(w, "w")), rows, ptr(raw), dtype_code(raw.dtype),
-                            ptr(partials), stream_ptr()), "sg_conv_in")
+    if tuple(w.shape) != (64, c_in, 3, 3):
+        raise ValueError(f"conv_in: w must be [64, {c_in}, 3, 3], got {tuple(w.shape)}")
+    check(_lib().sg_conv_in(ptr(_f32(x, "x")), n_src, c_in, S, ptr(_host_f32(w, "w")), rows, ptr(raw),
+                            dtype_code(raw.dtype), ptr(partials), stream_ptr()), "sg_conv_in")
 
 
 def igemm_partials(engine: int, H: int, W: int, Cout: int) -> int:
@@ -58,7 +66,18 @@ def igemm_partials(engine: int, H: int, W: int, Cout: int) -> int:
 
 def make_igemm_args(a, w, *, rows, H, W, bias=None, residual=None, out_f32=None, out_act=None, partials=None,
                     gelu=False, relu_post=False) -> IgemmArgs:
-    """a: act [rows,H,W,Cin] (any view with that many elements); w: act [taps,Cout,Cin]."""
+    """a: act [rows,H,W,Cin] (any view with that many elements); w: act [taps,Cout,Cin].  The fp32-accurate tensor-core
+    engine takes both as (hi, lo) pairs of fp32 tensors (split_tf32); a single fp32 tensor selects the CUDA-core engine."""
+    a_lo = w_lo = None
+    if isinstance(a, tuple) or isinstance(w, tuple):
+        if not (isinstance(a, tuple) and isinstance(w, tuple)):
+            raise ValueError("igemm: the split-tf32 engine needs (hi, lo) pairs for both the activation and the weight")
+        (a, a_lo), (w, w_lo) = a, w
+        for t in (a, a_lo, w, w_lo):
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("igemm: split operands must be contiguous CUDA fp32 tensors")
+        if a_lo.shape != a.shape or w_lo.shape != w.shape:
+            raise ValueError("igemm: hi / lo shape mismatch")
     taps, Cout, Cin = w.shape
     if a.dtype != w.dtype:
         raise ValueError("activation / weight dtype mismatch")
@@ -76,10 +95,11 @@ def make_igemm_args(a, w, *, rows, H, W, bias=None, residual=None, out_f32=None,
             if a.dtype == torch.float32 or out_act.dtype not in (torch.float16, torch.bfloat16):
                 raise ValueError("igemm: out_act must have the activation dtype (or be a 16-bit tensor in the tensor-core modes)")
             out_dtype = dtype_code(out_act.dtype)
-    args = IgemmArgs(ptr(a), ptr(w), ptr(bias), ptr(residual), ptr(out_f32), ptr(out_act), ptr(partials), rows, H, W,
-                     Cin, Cout, taps, 1 if gelu else (2 if relu_post else 0), _engine_of(a.dtype), dtype_code(a.dtype),
-                     out_dtype)
-    args._keepalive = (a, w, bias, residual, out_f32, out_act, partials)
+    engine = SG_ENGINE_TC if a_lo is not None else _engine_of(a.dtype)
+    args = IgemmArgs(ptr(a), ptr(w), ptr(bias), ptr(residual), ptr(out_f32), ptr(out_act), ptr(partials), ptr(a_lo),
+                     ptr(w_lo), rows, H, W, Cin, Cout, taps, 1 if gelu else (2 if relu_post else 0), engine,
+                     dtype_code(a.dtype), out_dtype)
+    args._keepalive = (a, w, bias, residual, out_f32, out_act, partials, a_lo, w_lo)
     return args
 
 
@@ -92,8 +112,9 @@ def igemm(a, w, **kw):
     igemm_launch(make_igemm_args(a, w, **kw))
 
 
-def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f32=None, out_act=None):
-    """K2.  raw fp32 or fp16 [rows,HW,C] (any shape with rows first, C last); emb: fp32 view [rows, C] (row stride kept)."""
+def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f32=None, out_act=None, range_flag=None):
+    """K2.  raw fp32 or fp16 [rows,HW,C] (any shape with rows first, C last); emb: fp32 view [rows, C] (row stride kept).
+    range_flag: int32[1] set to 1 by the kernel when an fp16 raw row left fp16's safe range (see sgb200.h)."""
     raw_rows, C = raw.shape[0], raw.shape[-1]
     HW = raw.numel() // (raw_rows * C)
     P = partials.shape[1]
@@ -111,10 +132,10 @@ def gn_apply(raw, partials, gamma, beta, *, mode, residual=None, emb=None, out_f
         raise ValueError("gn_apply: raw must be fp32 or fp16")
     check(_lib().sg_gn_apply(ptr(raw), dtype_code(raw.dtype), ptr(partials), P, ptr(gamma), ptr(beta), rows, raw_rows, HW, C, mode,
                              ptr(_f32(residual, "residual")), ptr(emb), emb_stride, ptr(_f32(out_f32, "out_f32")),
-                             ptr(out_act), adt, stream_ptr()), "sg_gn_apply")
+                             ptr(out_act), adt, ptr(range_flag), stream_ptr()), "sg_gn_apply")
 
 
-def gn_apply_vcat(raw, partials, gamma, beta, x, skip, out_act):
+def gn_apply_vcat(raw, partials, gamma, beta, x, skip, out_act, range_flag=None):
     """GELU(GroupNorm(raw) + cat([skip, upsample2x(x)])) -> 16 bit (sg_gn_apply_vcat).  raw fp16 [rows,2h,2w,Cs+Cx];
     x fp32 [rows,h,w,Cx]; skip fp32 [skip_rows,2h,2w,Cs]."""
     rows, h, w, Cx = x.shape
@@ -125,7 +146,7 @@ def gn_apply_vcat(raw, partials, gamma, beta, x, skip, out_act):
         raise ValueError("gn_apply_vcat: skip must be [skip_rows, 2h, 2w, Cs] with rows a multiple of skip_rows")
     check(_lib().sg_gn_apply_vcat(ptr(raw), ptr(partials), partials.shape[1], ptr(gamma), ptr(beta), rows,
                                   ptr(_f32(x, "x")), ptr(_f32(skip, "skip")), skip.shape[0], h, w, Cx, Cs, ptr(out_act),
-                                  dtype_code(out_act.dtype), stream_ptr()), "sg_gn_apply_vcat")
+                                  dtype_code(out_act.dtype), ptr(range_flag), stream_ptr()), "sg_gn_apply_vcat")
 
 
 def maxpool2(x, *, out_f32=None, out_act=None):
@@ -179,7 +200,7 @@ def tconv2_u8(t, w2, b2, *, n, S, out_u8=None, out_f32=None):
                               ptr(out_f32), stream_ptr()), "sg_tconv2_u8")
 
 
-FUSED_TOKEN_C = tuple(int(c) for c in os.environ.get("SGB200_FUSED_C", "64,128").split(",") if c)  # channel counts of the fused SelfAttention head / tail kernels
+FUSED_TOKEN_C = (64, 128)  # channel counts of the fused SelfAttention head / tail kernels
 
 
 def ln_inproj(x, ln_g, ln_b, w_in, b_in, qkv):
@@ -192,8 +213,8 @@ def ln_inproj(x, ln_g, ln_b, w_in, b_in, qkv):
 
 def attn_tail(att, x, wo, bo, ln_g, ln_b, w1, b1, w2, b2, out, *, outc=None):
     """Fused out_proj + residual + LayerNorm + FFN + residual (tcgen05).  att 16-bit [M, C]; x, out fp32 [M, C].
-    outc = (w fp32 [c_out, C], b fp32 [c_out], eps fp32 NCHW [rows, c_out, S, S]) also applies the model's 1x1 output
-    conv to the block output (sg_attn_tail_outc); `out` may then be None."""
+    outc = (w fp32 HOST [c_out, C], b fp32 HOST [c_out], eps fp32 NCHW [rows, c_out, S, S]) also applies the model's 1x1
+    output conv to the block output (sg_attn_tail_outc); `out` may then be None."""
     Cc = x.shape[-1]
     M = x.numel() // Cc
     if outc is not None:
@@ -202,8 +223,8 @@ def attn_tail(att, x, wo, bo, ln_g, ln_b, w1, b1, w2, b2, out, *, outc=None):
         if eps.numel() != (M // HW) * c_out * HW or M % HW:
             raise ValueError("attn_tail: eps does not match the token count")
         check(_lib().sg_attn_tail_outc(ptr(att), ptr(_f32(x, "x")), ptr(wo), ptr(bo), ptr(ln_g), ptr(ln_b), ptr(w1),
-                                       ptr(b1), ptr(w2), ptr(b2), M, Cc, ptr(_f32(out, "out")), ptr(_f32(w, "outc_w")),
-                                       ptr(_f32(b, "outc_b")), c_out, HW, ptr(_f32(eps, "eps")), dtype_code(att.dtype),
+                                       ptr(b1), ptr(w2), ptr(b2), M, Cc, ptr(_f32(out, "out")), ptr(_host_f32(w, "outc_w")),
+                                       ptr(_host_f32(b, "outc_b")), c_out, HW, ptr(_f32(eps, "eps")), dtype_code(att.dtype),
                                        stream_ptr()), "sg_attn_tail_outc")
         return
     check(_lib().sg_attn_tail(ptr(att), ptr(_f32(x, "x")), ptr(wo), ptr(bo), ptr(ln_g), ptr(ln_b), ptr(w1), ptr(b1),
@@ -212,7 +233,15 @@ def attn_tail(att, x, wo, bo, ln_g, ln_b, w1, b1, w2, b2, out, *, outc=None):
 
 
 def attention(qkv, out, *, rows, L, C, engine=None):
-    """K4.  qkv [rows*L, 3C]; out [rows*L, C].  SIMT engine: qkv fp32, out fp32/16-bit.  TC: both 16-bit."""
+    """K4.  qkv [rows*L, 3C]; out [rows*L, C].  SIMT engine: qkv fp32, out fp32/16-bit.  TC: both 16-bit, or -- the
+    fp32-accurate tensor-core engine -- qkv = (hi, lo) pair of fp32 tensors (split_tf32) and out fp32."""
+    if isinstance(qkv, tuple):
+        hi, lo = qkv
+        if hi.numel() != rows * L * 3 * C or lo.shape != hi.shape or out.numel() != rows * L * C or out.dtype != torch.float32:
+            raise ValueError("attention: bad split qkv / out")
+        check(_lib().sg_attention_tf32(ptr(_f32(hi, "qkv_hi")), ptr(_f32(lo, "qkv_lo")), ptr(out), rows, L, C, HEADS,
+                                       stream_ptr()), "sg_attention_tf32")
+        return
     if engine is None:
         engine = _engine_of(qkv.dtype)
     if qkv.numel() != rows * L * 3 * C or out.numel() != rows * L * C:
@@ -258,8 +287,19 @@ def to_uint8(x, out):
 
 
 def set_pdl(mode: int):
-    """Programmatic dependent launch mode of the following launches (0 off, 1 all, 2 small grids); SGB200_PDL wins."""
+    """Programmatic dependent launch mode of this thread's following launches (0 off, 1 all, 2 small grids)."""
     check(_lib().sg_set_pdl(int(mode)), "sg_set_pdl")
+
+
+def split_tf32(x, hi=None, lo=None):
+    """x fp32 -> (hi, lo): hi = tf32(x), lo = tf32(x - hi) -- the operand form of the fp32-accurate tensor-core engine."""
+    x = _f32(x, "x")
+    hi = torch.empty_like(x) if hi is None else hi
+    lo = torch.empty_like(x) if lo is None else lo
+    if hi.numel() != x.numel() or lo.numel() != x.numel():
+        raise ValueError("split_tf32: hi / lo must have x's size")
+    check(_lib().sg_split_tf32(ptr(x), ptr(_f32(hi, "hi")), ptr(_f32(lo, "lo")), x.numel(), stream_ptr()), "sg_split_tf32")
+    return hi, lo
 
 
 def pack_weights(w, dtype):
@@ -279,6 +319,9 @@ def noise_images(x, t, alpha_hat, *, eps=None, seed=0, sample_base=0):
     E = x.numel() // max(n, 1)
     if t.dtype != torch.int64 or not t.is_cuda or t.numel() != n:
         raise ValueError("noise_images: t must be a CUDA int64 tensor with one timestep per sample")
+    T = alpha_hat.numel()
+    if n > 0 and (int(t.min()) < -T or int(t.max()) >= T):
+        raise IndexError(f"index out of range: timesteps must lie in [-{T}, {T})")  # as alpha_hat[t] raises in the reference
     if eps is not None and (eps.shape != x.shape):
         raise ValueError("noise_images: eps must have x's shape")
     x_t = torch.empty_like(x)

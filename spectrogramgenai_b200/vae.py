@@ -16,7 +16,7 @@ import torch
 
 from . import _cabi, ops
 from ._cabi import SG_ENGINE_SIMT, SG_ENGINE_TC
-from .engine import MODES, _pack_conv
+from .engine import MODES, _pack_gemm_weight
 
 HIDDEN, LATENT = 512, 4
 
@@ -33,8 +33,10 @@ class VqaeDecoder:
             self.device = torch.device("cuda", torch.cuda.current_device())
         _cabi.require_b200(self.device)
         self.mode, self.act = mode, MODES[mode]
-        self.tc = mode != "fp32"
-        self.engine = SG_ENGINE_TC if self.tc else SG_ENGINE_SIMT
+        self.tc = mode in ("bf16", "f16")  # 16-bit operand copies
+        self.tf32 = mode == "fp32"         # fp32-accurate tensor-core engine: (hi, lo) split operands
+        self.engine = SG_ENGINE_SIMT if mode == "fp32_simt" else SG_ENGINE_TC
+        wsplit = (lambda t: ops.split_tf32(t)) if self.tf32 else (lambda t: t)
         sd = state_dict
         f32 = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()  # noqa: E731
         for k, shape in (("codebook.embedding", (None, LATENT)), ("decoder.in_proj.weight", (HIDDEN, LATENT, 1, 1)),
@@ -50,13 +52,14 @@ class VqaeDecoder:
         self.codebook = f32("codebook.embedding")
         self.w_in = f32("decoder.in_proj.weight").reshape(HIDDEN, LATENT).contiguous()
         self.b_in = f32("decoder.in_proj.bias")
-        self.w_r1 = f32("decoder.residual_conv_1.weight").reshape(1, HIDDEN, HIDDEN).contiguous().to(self.act)
+        self.w_r1 = wsplit(f32("decoder.residual_conv_1.weight").reshape(1, HIDDEN, HIDDEN).contiguous().to(self.act))
         self.b_r1 = f32("decoder.residual_conv_1.bias")
-        self.w_r2 = _pack_conv(sd["decoder.residual_conv_2.weight"], self.act, self.device)
+        self.w_r2 = _pack_gemm_weight(sd["decoder.residual_conv_2.weight"], self.act, self.device, self.tf32)
         self.b_r2 = f32("decoder.residual_conv_2.bias")
         # ConvTranspose2d weight [ci, co, a, b] -> for each a: Linear [(b, co), ci]
         wt = f32("decoder.strided_t_conv_1.weight")
-        self.w_t1 = [wt[:, :, a, :].permute(2, 1, 0).reshape(1, 2 * HIDDEN, HIDDEN).contiguous().to(self.act) for a in (0, 1)]
+        self.w_t1 = [wsplit(wt[:, :, a, :].permute(2, 1, 0).reshape(1, 2 * HIDDEN, HIDDEN).contiguous().to(self.act))
+                     for a in (0, 1)]
         self.b_t1 = f32("decoder.strided_t_conv_1.bias").repeat(2).contiguous()
         self.w_t2 = f32("decoder.strided_t_conv_2.weight")
         self.b_t2 = f32("decoder.strided_t_conv_2.bias")
@@ -80,6 +83,8 @@ class VqaeDecoder:
             else:
                 b["h0a"], b["h1a"] = b["h0f"], b["h1f"]
                 b["h2a"] = torch.empty((n, S, S, HIDDEN), dtype=f32, device=dev)
+            if self.tf32:
+                b["hi"], b["lo"] = (torch.empty((n, S, S, HIDDEN), dtype=f32, device=dev) for _ in range(2))
             self._bufs = {key: b}  # keep one geometry resident
         return b
 
@@ -104,16 +109,19 @@ class VqaeDecoder:
             tc = self.tc
             ops.dec_in_proj(b["q"], self.w_in, self.b_in, out_f32=b["h0f"], out_act=b["h0a"] if tc else None)
             kw = dict(rows=nb, H=S, W=S)
-            ops.igemm(b["h0a"], self.w_r1, bias=self.b_r1, residual=b["h0f"], relu_post=True, out_f32=b["h1f"],
+            # split-tf32 engine: every GEMM operand goes through one sg_split_tf32 pass into the (hi, lo) scratch pair
+            opnd = (lambda t: ops.split_tf32(t, b["hi"], b["lo"])) if self.tf32 else (lambda t: t)
+            ops.igemm(opnd(b["h0a"]), self.w_r1, bias=self.b_r1, residual=b["h0f"], relu_post=True, out_f32=b["h1f"],
                       out_act=b["h1a"] if tc else None, **kw)
-            ops.igemm(b["h1a"], self.w_r2, bias=self.b_r2, residual=b["h1f"], relu_post=True,
+            ops.igemm(opnd(b["h1a"]), self.w_r2, bias=self.b_r2, residual=b["h1f"], relu_post=True,
                       **({"out_act": b["h2a"]} if tc else {"out_f32": b["h2a"]}), **kw)
+            h2 = opnd(b["h2a"])
             for a in (0, 1):
-                ops.igemm(b["h2a"], self.w_t1[a], bias=self.b_t1, **({"out_act": b["t"][a]} if tc else {"out_f32": b["t"][a]}),
+                ops.igemm(h2, self.w_t1[a], bias=self.b_t1, **({"out_act": b["t"][a]} if tc else {"out_f32": b["t"][a]}),
                           **kw)
             ops.tconv2_u8(b["t"], self.w_t2, self.b_t2, n=nb, S=S, **({"out_f32": out[lo:hi]} if return_float else
                                                                       {"out_u8": out[lo:hi]}))
-            self.gpu_launches += 7
+            self.gpu_launches += 10 if self.tf32 else 7
             if return_indices:
                 g = nb * LATENT * S * S // 4
                 all_idx[lo * LATENT * S * S // 4: lo * LATENT * S * S // 4 + g].copy_(b["idx"][:g])

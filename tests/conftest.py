@@ -17,3 +17,10 @@ def pytest_configure(config):
 def golden():
     """Outputs of the unmodified reference, produced by tests/golden/make_golden.py."""
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_large():
+    """eps at the 256x256-spectrogram geometries (S = 128 from the unmodified reference, S = 256 from the query-chunked
+    oracle), produced by tests/golden/make_golden_large.py."""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_large.npz")))

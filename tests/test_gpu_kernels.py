@@ -225,7 +225,7 @@ def test_conv_in(ops, c_in, S, rows, n_src):
     ref = ref[torch.arange(rows) % n_src]
     raw = torch.empty(rows, S, S, 64, device=DEV)
     part = torch.empty(rows, ops.conv_in_partials(S), 2, device=DEV)
-    ops.conv_in(x.to(DEV), w.to(DEV), raw, part)
+    ops.conv_in(x.to(DEV), w, raw, part)  # w: host tensor (passed by value as a launch parameter)
     assert O.rel_l2(raw.cpu(), ref) < 1e-6
     s = part.cpu().double().sum(1)
     assert torch.allclose(s[:, 0], ref.sum((1, 2, 3)), rtol=1e-4, atol=1e-2)
@@ -233,7 +233,7 @@ def test_conv_in(ops, c_in, S, rows, n_src):
     # fp16 raw output (tensor-core modes): same fp32 statistics, stored value rounded to 11 bits
     raw16 = torch.empty(rows, S, S, 64, device=DEV, dtype=torch.float16)
     part16 = torch.empty_like(part)
-    ops.conv_in(x.to(DEV), w.to(DEV), raw16, part16)
+    ops.conv_in(x.to(DEV), w, raw16, part16)
     assert O.rel_l2(raw16.cpu(), ref) < 4e-4
     assert torch.equal(part16, part)
 
@@ -302,6 +302,60 @@ def test_igemm_conv_tensor_core(ops, rows, H, cin, cout, dtype):
     assert torch.allclose(s[:, 1], (ref ** 2).sum((1, 2, 3)), rtol=1e-5)
 
 
+
+@pytest.mark.parametrize("scale,expect", [(1.0, 0), (3000.0, 1), (2e-4, 1), (30.0, 0), (0.0, 0)])
+def test_gn_apply_fp16_range_flag(ops, scale, expect):
+    """GroupNorm is scale invariant, its fp16 raw input is not: the kernel compares the exact mean square (fp32 statistics)
+    with [2^-20, 2^20] and raises the flag the host uses to fall back to fp32 raw tensors.  All-zero rows are fine."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    rows, H, cin, cout = 2, 16, 64, 64
+    g = gen(45)
+    a = torch.randn(rows, H, H, cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin) * scale).to(torch.bfloat16)
+    raw = torch.empty(rows, H, H, cout, device=DEV, dtype=torch.float16)
+    part = torch.empty(rows, ops.igemm_partials(SG_ENGINE_TC, H, H, cout), 2, device=DEV)
+    ops.igemm(a.to(DEV), pack_conv(w.float(), torch.bfloat16).to(DEV), rows=rows, H=H, W=H, out_act=raw, partials=part)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = torch.empty(rows, H, H, cout, device=DEV, dtype=torch.bfloat16)
+    ones, zeros = torch.ones(cout, device=DEV), torch.zeros(cout, device=DEV)
+    ops.gn_apply(raw, part, ones, zeros, mode=1, out_act=out, range_flag=flag)
+    assert int(flag.item()) == expect
+
+# ---------------------------------------------------------------- fp32-accurate tensor-core engine (split TF32)
+def test_split_tf32(ops):
+    """hi = tf32(x) (10 explicit mantissa bits), lo = tf32(x - hi); hi + lo reproduces x to ~2^-22."""
+    x = torch.randn(4096 * 4, generator=gen(40)) * torch.logspace(-6, 6, 4096 * 4)
+    hi, lo = ops.split_tf32(x.to(DEV))
+    hi, lo = hi.cpu(), lo.cpu()
+    assert (hi.view(torch.int32) & 0x1FFF).eq(0).all() and (lo.view(torch.int32) & 0x1FFF).eq(0).all()
+    assert ((hi - x).abs() <= x.abs() * 2.0 ** -11 + 1e-45).all()
+    assert (((hi.double() + lo.double()) - x.double()).abs() <= x.abs().double() * 2.0 ** -21).all()
+
+
+@pytest.mark.parametrize("rows,H,cin,cout", CONV_CASES + [(2, 64, 64, 64), (1, 64, 128, 128), (2, 16, 96, 64)])
+def test_igemm_conv_split_tf32(ops, rows, H, cin, cout):
+    """3x3 conv on the split-TF32 engine (three kind::tf32 MMAs per product) vs fp64 on the SAME fp32 operands: the bar is
+    the fp32 engine's (2e-6 here; a single TF32 pass gives ~5e-4), and the GroupNorm partials come with it."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    g = gen(41)
+    a = torch.randn(rows, H, H, cin, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)
+    ref = _conv_ref(a, w)
+    raw = torch.full((rows, H, H, cout), float("nan"), device=DEV)
+    part = torch.full((rows, ops.igemm_partials(SG_ENGINE_TC, H, H, cout), 2), float("nan"), device=DEV)
+    ops.igemm(ops.split_tf32(a.to(DEV)), ops.split_tf32(pack_conv(w).to(DEV)), rows=rows, H=H, W=H, out_f32=raw,
+              partials=part)
+    torch.cuda.synchronize()
+    err = O.rel_l2(raw.cpu(), ref)
+    print(f"igemm split-tf32 rows={rows} H={H} {cin}->{cout}: rel-L2 {err:.3e}")
+    assert err < 2e-6
+    s = part.cpu().double().sum(1)
+    assert torch.allclose(s[:, 0], ref.sum((1, 2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (ref ** 2).sum((1, 2, 3)), rtol=1e-5)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("rows,H,cin,cout", [(2, 16, 64, 128), (3, 8, 256, 256), (1, 64, 64, 64)])
 def test_conv_fp16_raw_then_groupnorm(ops, rows, H, cin, cout, dtype):
@@ -363,6 +417,24 @@ def test_igemm_linear_epilogues(ops, rows, H, cin, cout, dtype):
         o16 = torch.empty(M, cout, device=DEV, dtype=dtype)
         ops.igemm(a.to(DEV), wp, rows=rows, H=H, W=H, bias=b.to(DEV), gelu=True, out_act=o16)
         assert O.rel_l2(o16.cpu(), F.gelu(lin)) < 4e-3
+
+
+@pytest.mark.parametrize("rows,H,cin,cout", LIN_CASES)
+def test_igemm_linear_split_tf32(ops, rows, H, cin, cout):
+    g = gen(42)
+    M = rows * H * H
+    a = torch.randn(M, cin, generator=g)
+    w = torch.randn(cout, cin, generator=g) / math.sqrt(cin)
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(M, cout, generator=g)
+    lin = F.linear(a.double(), w.double(), b.double())
+    wp = ops.split_tf32(w.reshape(1, cout, cin).contiguous().to(DEV))
+    ap = ops.split_tf32(a.to(DEV))
+    out = torch.empty(M, cout, device=DEV)
+    ops.igemm(ap, wp, rows=rows, H=H, W=H, bias=b.to(DEV), residual=res.to(DEV), out_f32=out)
+    assert O.rel_l2(out.cpu(), lin + res.double()) < 2e-6
+    ops.igemm(ap, wp, rows=rows, H=H, W=H, bias=b.to(DEV), gelu=True, out_f32=out)
+    assert O.rel_l2(out.cpu(), F.gelu(lin)) < 3e-6
 
 
 def test_conv_out(ops):
@@ -467,9 +539,9 @@ def test_attn_tail_with_fused_output_conv(ops, rows, HW, c_out, dtype):
     ops.attn_tail(*args, plain)
     both = torch.empty(M, C, device=DEV)
     eps1 = torch.full((rows + 1, c_out, HW // 16, 16), float("nan"), device=DEV)
-    ops.attn_tail(*args, both, outc=(d(wc), d(bc), eps1[:rows]))
+    ops.attn_tail(*args, both, outc=(wc, bc, eps1[:rows]))  # outc weights: host tensors (launch parameters)
     eps2 = torch.empty((rows, c_out, HW // 16, 16), device=DEV)
-    ops.attn_tail(*args, None, outc=(d(wc), d(bc), eps2))
+    ops.attn_tail(*args, None, outc=(wc, bc, eps2))
     torch.cuda.synchronize()
     assert torch.equal(plain, both)
     assert torch.equal(eps1[:rows], eps2) and torch.isnan(eps1[rows:]).all()
@@ -479,7 +551,7 @@ def test_attn_tail_with_fused_output_conv(ops, rows, HW, c_out, dtype):
     assert err < 2e-6
     with pytest.raises(Exception):  # C = 128 has no fused output conv
         ops.attn_tail(d(att.reshape(-1, 128)), d(x.reshape(-1, 128)), *args[2:], None,
-                      outc=(d(wc), d(bc), eps2))
+                      outc=(wc, bc, eps2))
 
 
 def _attention_ref(qkv, rows, L, C):
@@ -590,13 +662,59 @@ def test_attention_grid_split_beyond_32768_query_tiles(ops):
     assert torch.isfinite(out.float()).all()
 
 
+
+@pytest.mark.parametrize("rows,L,C", ATT_TC_CASES + [(3, 4096, 64), (2, 128, 256)])
+def test_attention_split_tf32(ops, rows, L, C):
+    """The fp32-accurate attention core (S = Q K^T and O = P V as three kind::tf32 MMAs each on split operands) vs fp64
+    on the same fp32 q / k / v: same bar as the CUDA-core kernel's order of magnitude (1e-5; plain TF32: ~1e-3)."""
+    qkv = torch.randn(rows * L, 3 * C, generator=gen(43)) * 1.5
+    ref = _attention_ref(qkv, rows, L, C)
+    out = torch.full((rows * L, C), float("nan"), device=DEV)
+    ops.attention(ops.split_tf32(qkv.to(DEV)), out, rows=rows, L=L, C=C)
+    torch.cuda.synchronize()
+    err = O.rel_l2(out.cpu(), ref)
+    print(f"attention split-tf32 rows={rows} L={L} C={C}: rel-L2 {err:.3e}")
+    assert err < 1e-5
+
+
+def test_attention_split_tf32_growing_scores(ops):
+    """Scores that grow along the key axis force the lazily tracked softmax reference to be raised tile after tile."""
+    rows, L, C = 2, 1024, 64
+    g = gen(44)
+    qkv = torch.randn(rows * L, 3 * C, generator=g)
+    ramp = torch.linspace(0.2, 6.0, L).repeat(rows)[:, None]
+    qkv[:, C:2 * C] *= ramp  # |k_j| grows with j
+    ref = _attention_ref(qkv, rows, L, C)
+    out = torch.empty(rows * L, C, device=DEV)
+    ops.attention(ops.split_tf32(qkv.to(DEV)), out, rows=rows, L=L, C=C)
+    assert O.rel_l2(out.cpu(), ref) < 1e-5
+
+
+def test_attention_ragged_grid_z(ops):
+    """More than 32768 query tiles that are NOT a multiple of 32768 (e.g. 486 x 2 rows of L = 16384 in the generator at
+    img_size 512): the last grid.z slice is ragged and its surplus CTAs exit.  rows = 1100, L = 4096 -> 35200 tiles."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    rows, L, C = 1100, 4096, 64
+    g = torch.Generator(device=DEV).manual_seed(4)
+    qkv = torch.empty(rows * L, 3 * C, device=DEV, dtype=torch.bfloat16)
+    for r0 in range(0, rows, 100):
+        qkv[r0 * L:(r0 + 100) * L] = torch.randn(100 * L, 3 * C, device=DEV, generator=g).to(torch.bfloat16)
+    out = torch.full((rows * L, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, rows=rows, L=L, C=C, engine=SG_ENGINE_TC)
+    tail = torch.empty(76 * L, C, device=DEV, dtype=torch.bfloat16)  # rows 1024 .. 1099 live in the ragged slice
+    ops.attention(qkv[1024 * L:], tail, rows=76, L=L, C=C, engine=SG_ENGINE_TC)
+    assert torch.equal(tail, out[1024 * L:])
+    assert torch.isfinite(out.float()).all()
+
+
 def test_error_reporting(ops):
     """Bad arguments come back as a status + message (no exception crosses the C ABI, no crash)."""
     from spectrogramgenai_b200._cabi import SgError
 
     x = torch.zeros(2, 4, 24, 24, device=DEV)  # 24 is not a power of two
     with pytest.raises(SgError, match="power of two"):
-        ops.conv_in(x, torch.zeros(64, 4, 3, 3, device=DEV), torch.zeros(2, 24, 24, 64, device=DEV),
+        ops.conv_in(x, torch.zeros(64, 4, 3, 3), torch.zeros(2, 24, 24, 64, device=DEV),
                     torch.zeros(2, 9, 2, device=DEV))
     with pytest.raises(SgError, match="head dim"):
         ops.attention(torch.zeros(4, 3 * 32, device=DEV), torch.zeros(4, 32, device=DEV), rows=1, L=4, C=32)

@@ -47,9 +47,10 @@ def test_igemm_args_struct_matches_header_layout():
 
     from spectrogramgenai_b200._cabi import IgemmArgs
 
-    assert ctypes.sizeof(IgemmArgs) == 7 * 8 + 10 * 4  # 7 pointers, 10 int32 (rows .. taps, act, engine, act_dtype, out_dtype)
-    assert IgemmArgs.rows.offset == 56 and IgemmArgs.act.offset == 56 + 6 * 4
-    assert IgemmArgs.act_dtype.offset == 56 + 8 * 4 and IgemmArgs.out_dtype.offset == 56 + 9 * 4
+    assert ctypes.sizeof(IgemmArgs) == 9 * 8 + 10 * 4  # 9 pointers, 10 int32 (rows .. taps, act, engine, act_dtype, out_dtype)
+    assert IgemmArgs.a_lo.offset == 56 and IgemmArgs.w_lo.offset == 64
+    assert IgemmArgs.rows.offset == 72 and IgemmArgs.act.offset == 72 + 6 * 4
+    assert IgemmArgs.act_dtype.offset == 72 + 8 * 4 and IgemmArgs.out_dtype.offset == 72 + 9 * 4
 
 
 def test_state_dict_schema_matches_reference():
@@ -142,9 +143,11 @@ def _worker(rank, ws, port, n, q):
         idx = torch.arange(base, base + len(lab))
         return (idx[:, None] * 31 + lab[:, None] + torch.arange(4)[None]).to(torch.uint8)
 
-    out = sample_sharded(None, labels, sample_fn=fake_sampler)
+    out = sample_sharded(None, labels, sample_fn=fake_sampler)  # all ranks receive
     want = fake_sampler(labels, 0)
-    q.put((rank, bool(torch.equal(out, want)), tuple(out.shape)))
+    root = sample_sharded(None, labels, sample_fn=fake_sampler, dst=1)  # only rank 1 receives
+    ok_root = (root is None) if rank != 1 else bool(torch.equal(root, want))
+    q.put((rank, bool(torch.equal(out, want)) and ok_root, tuple(out.shape)))
     dist.destroy_process_group()
 
 
