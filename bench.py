@@ -223,21 +223,29 @@ def classify(fn, a, kw):
     from spectrogramgenai_b200 import ops
 
     name = fn.__name__
-    if name == "igemm_launch":
-        g = a[0]
-        M = g.rows * g.H * g.W
-        fl = 2.0 * M * g.Cin * g.Cout * g.taps
-        esz = 4 if g.act_dtype == 0 else 2
-        esz_in = esz * (2 if g.a_lo else 1)  # split-tf32 engine: hi and lo parts are both read
-        by = M * g.Cin * esz_in + g.taps * g.Cin * g.Cout * esz_in + M * g.Cout * (4 if g.out_f32 else 0) \
-            + M * g.Cout * ((2 if g.out_dtype else esz) if g.out_act else 0) + (M * g.Cout * 4 if g.residual else 0)
-        eng = ("tf32x3" if g.a_lo else "tc") if g.engine == 1 else "simt"
-        return (f"igemm_{eng}_conv3x3" if g.taps == 9 else f"igemm_{eng}_linear"), fl, by
+    if name == "igemm":
+        act, w = a[0], a[1]
+        split = isinstance(act, tuple)
+        a0, w0 = (act[0], w[0]) if split else (act, w)
+        taps, Cout, Cin = w0.shape
+        M = kw["rows"] * kw["H"] * kw["W"]
+        fl = 2.0 * M * Cin * Cout * taps
+        esz_in = a0.element_size() * (2 if split else 1)  # split-tf32 engine: hi and lo parts are both read
+        by = M * Cin * esz_in + taps * Cin * Cout * esz_in
+        for k in ("out_f32", "out_act", "residual"):
+            t = kw.get(k)
+            if t is not None:
+                by += t.numel() * t.element_size()
+        eng = "tf32x3" if split else ("simt" if a0.dtype == torch.float32 else "tc")
+        return (f"igemm_{eng}_conv3x3" if taps == 9 else f"igemm_{eng}_linear"), fl, by
     if name == "attention":
         rows, L, C = kw["rows"], kw["L"], kw["C"]
-        q = a[0][0] if isinstance(a[0], tuple) else a[0]
-        qb = q.element_size() * (2 if isinstance(a[0], tuple) else 1)
-        return "attention", 4.0 * rows * L * L * C, rows * L * C * (3 * qb + a[1].element_size())
+        return "attention", 4.0 * rows * L * L * C, rows * L * C * (3 * a[0].element_size() + a[1].element_size())
+    if name == "attention_tf32":
+        rows, L, C = kw["rows"], kw["L"], kw["C"]
+        return "attention", 4.0 * rows * L * L * C, rows * L * C * (3 * 8 + 4)
+    if name == "attn_prep_tf32":
+        return "split_tf32", 0.0, a[0].numel() * 12
     if name == "split_tf32":
         return "split_tf32", 0.0, a[0].numel() * 12
     if name == "gn_apply":

@@ -97,7 +97,8 @@ int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w /* HOS
  * SG_ENGINE_SIMT: fp32 CUDA-core kernel (act_dtype = SG_F32).  SG_ENGINE_TC: tcgen05/TMEM kernel
  * fed by TMA: act_dtype = SG_BF16 or SG_F16 (fp32 accumulate), or act_dtype = SG_F32 = the fp32-accurate engine on
  * split-TF32 operands: a / w hold the hi parts, a_lo / w_lo the lo parts (sg_split_tf32), and the kernel accumulates
- * a_hi w_hi + a_hi w_lo + a_lo w_hi in one fp32 TMEM tile (eps rel-L2 ~1e-6 of the fp32 reference; plain TF32: ~1e-3).
+ * a_lo w_hi + a_hi w_lo + a_hi w_hi in one fp32 TMEM tile (a single TF32 pass: 3e-4 per conv; split: the tensor core's
+ * truncating fp32 accumulation remains, a uniform relative shrink of ~1e-8 K that the GroupNorm behind every conv removes).
  * Requires Cin % 64 == 0 (TC 16-bit) / % 32 (TC fp32) / % 16 (SIMT), Cout % 64 == 0.
  */
 typedef struct {
@@ -207,11 +208,16 @@ int sg_attn_tail_outc(const void* att, const float* x, const void* wo, const flo
  */
 int sg_attention(const void* qkv, void* out, int rows, int L, int C, int heads, int engine, int act_dtype,
                  sg_stream_t stream);
-/* K4 of the fp32-accurate tensor-core engine: the same product with split-TF32 operands.  qkv_hi / qkv_lo fp32
- * [rows*L, 3C] (sg_split_tf32 of the in_proj output), out fp32 [rows*L, C]; S = Q K^T and O = P V are each three
- * kind::tf32 MMAs (hi hi + hi lo + lo hi) into one fp32 TMEM accumulator, the probabilities are split in the kernel. */
-int sg_attention_tf32(const float* qkv_hi, const float* qkv_lo, float* out, int rows, int L, int C, int heads,
-                      sg_stream_t stream);
+/* K4 of the fp32-accurate tensor-core engine: the same product with split-TF32 operands, for L >= 128 (power of two).
+ * sg_attn_prep_tf32: qkv fp32 [rows*L, 3C] (the in_proj output) -> qk_hi / qk_lo fp32 [rows*L, 2C] (split of q | k) and
+ *   vt_hi / vt_lo fp32 [rows*heads*d, L] = the split of V transposed per (batch row, head), so that V^T is a K-major
+ *   B operand (kind::tf32 accepts MN-major operands only in a dedicated swizzle).
+ * sg_attention_tf32: out fp32 [rows*L, C]; S = Q K^T and O = P V are each three kind::tf32 MMAs (lo hi + hi lo + hi hi)
+ *   into one fp32 TMEM accumulator; the probabilities are split in the kernel. */
+int sg_attn_prep_tf32(const float* qkv, float* qk_hi, float* qk_lo, float* vt_hi, float* vt_lo, int rows, int L, int C,
+                      int heads, sg_stream_t stream);
+int sg_attention_tf32(const float* qk_hi, const float* qk_lo, const float* vt_hi, const float* vt_lo, float* out, int rows,
+                      int L, int C, int heads, sg_stream_t stream);
 /* x fp32 [n] -> hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand form of the fp32-accurate tensor-core
  * engine (x - hi is exact in fp32; hi + lo keeps ~21 mantissa bits).  n % 4 == 0, buffers 16-byte aligned. */
 int sg_split_tf32(const float* x, float* hi, float* lo, int64_t n, sg_stream_t stream);

@@ -43,8 +43,9 @@ if what in ("conv", "all"):
         w = (torch.randn(9, cout, cin, device=dev, generator=g) / math.sqrt(9 * cin)).to(dt)
         raw = torch.empty(rows, H, H, cout, device=dev, dtype=torch.float16)  # fp16 raw output, as the engine keeps it
         part = torch.empty(rows, ops.igemm_partials(SG_ENGINE_TC, H, H, cout), 2, device=dev)
-        args = ops.make_igemm_args(a, w, rows=rows, H=H, W=H, out_act=raw, partials=part)
-        timeit(f"conv3x3 H={H} {cin}->{cout} rows={rows}", lambda: ops.igemm_launch(args),
+        args = dict(rows=rows, H=H, W=H, out_act=raw, partials=part)
+        _aw = (a, w)
+        timeit(f"conv3x3 H={H} {cin}->{cout} rows={rows}", lambda: ops.igemm(*_aw, **args),
                flops=2.0 * rows * H * H * cin * cout * 9, nbytes=a.numel() * 2 + raw.numel() * 2)
 if what in ("linear", "all"):
     for (L, cin, cout) in ((4096, 64, 192), (4096, 64, 64), (1024, 128, 384)):
@@ -54,8 +55,9 @@ if what in ("linear", "all"):
         b = torch.randn(cout, device=dev, generator=g)
         res = torch.randn(M, cout, device=dev, generator=g)
         o32 = torch.empty(M, cout, device=dev)
-        args = ops.make_igemm_args(a, w, rows=rows, H=int(math.isqrt(L)), W=int(math.isqrt(L)), bias=b, residual=res, out_f32=o32)
-        timeit(f"linear M={M} {cin}->{cout}", lambda: ops.igemm_launch(args), flops=2.0 * M * cin * cout,
+        args = dict(rows=rows, H=int(math.isqrt(L)), W=int(math.isqrt(L)), bias=b, residual=res, out_f32=o32)
+        _aw = (a, w)
+        timeit(f"linear M={M} {cin}->{cout}", lambda: ops.igemm(*_aw, **args), flops=2.0 * M * cin * cout,
                nbytes=a.numel() * 2 + 2 * o32.numel() * 4)
 if what in ("linear16",):
     for (L, cin, cout) in ((4096, 64, 192), (1024, 128, 384)):
@@ -64,8 +66,9 @@ if what in ("linear16",):
         w = (torch.randn(1, cout, cin, device=dev, generator=g) / math.sqrt(cin)).to(dt)
         b = torch.randn(cout, device=dev, generator=g)
         o16 = torch.empty(M, cout, device=dev, dtype=dt)
-        args = ops.make_igemm_args(a, w, rows=rows, H=int(math.isqrt(L)), W=int(math.isqrt(L)), bias=b, out_act=o16)
-        timeit(f"linear16 M={M} {cin}->{cout}", lambda: ops.igemm_launch(args), flops=2.0 * M * cin * cout,
+        args = dict(rows=rows, H=int(math.isqrt(L)), W=int(math.isqrt(L)), bias=b, out_act=o16)
+        _aw = (a, w)
+        timeit(f"linear16 M={M} {cin}->{cout}", lambda: ops.igemm(*_aw, **args), flops=2.0 * M * cin * cout,
                nbytes=a.numel() * 2 + o16.numel() * 2)
 if what in ("gn", "all"):
     H, C = 64, 128

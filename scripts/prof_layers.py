@@ -38,11 +38,12 @@ print(f"total {tot:.3f} ms over {len(acc)} launches")
 for (fn, a, kw), ms in zip(plan.ops, acc):
     fam, fl, by = bench.classify(fn, a, kw)
     desc = ""
-    if fn.__name__ == "igemm_launch":
-        g = a[0]
-        desc = f"{g.H}x{g.W} {g.Cin}->{g.Cout} taps={g.taps} f32={bool(g.out_f32)} act={bool(g.out_act)} res={bool(g.residual)}"
+    if fn.__name__ == "igemm":
+        w = a[1][0] if isinstance(a[1], tuple) else a[1]
+        desc = (f"{kw['H']}x{kw['W']} {w.shape[2]}->{w.shape[1]} taps={w.shape[0]} f32={kw.get('out_f32') is not None} "
+                f"act={kw.get('out_act') is not None} res={kw.get('residual') is not None}")
     elif fn.__name__ == "gn_apply":
         desc = f"{tuple(a[0].shape[1:])} mode={kw.get('mode')} f32={kw.get('out_f32') is not None} act={kw.get('out_act') is not None} emb={kw.get('emb') is not None}"
-    elif fn.__name__ == "attention":
+    elif fn.__name__ in ("attention", "attention_tf32"):
         desc = f"L={kw['L']} C={kw['C']}"
     print(f"{fam:22s} {desc:60s} {ms:7.3f} ms {fl / ms / 1e9 if ms else 0:8.1f} TF/s {by / ms / 1e6 if ms else 0:8.1f} GB/s")

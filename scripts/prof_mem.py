@@ -64,9 +64,10 @@ for (L, cin, cout, resid, gelu, o32f, o16f) in ((4096, 64, 192, False, False, Fa
     o32 = torch.empty(M, cout, device=dev) if o32f else None
     o16 = torch.empty(M, cout, device=dev, dtype=dt) if o16f else None
     H = int(math.isqrt(L))
-    args = ops.make_igemm_args(a, w, rows=rows, H=H, W=H, bias=b, residual=res, gelu=gelu, out_f32=o32, out_act=o16)
+    args = dict(rows=rows, H=H, W=H, bias=b, residual=res, gelu=gelu, out_f32=o32, out_act=o16)
+    _aw = (a, w)
     nb = a.numel() * 2 + (res.numel() * 4 if resid else 0) + (o32.numel() * 4 if o32f else 0) + (o16.numel() * 2 if o16f else 0)
-    timeit(f"linear M={M} {cin}->{cout} res={resid} gelu={gelu} f32={o32f} bf16={o16f}", lambda: ops.igemm_launch(args), nb)
+    timeit(f"linear M={M} {cin}->{cout} res={resid} gelu={gelu} f32={o32f} bf16={o16f}", lambda: ops.igemm(*_aw, **args), nb)
     del a, res, o32, o16
 x = torch.randn(rows, 32, 32, 64, device=dev, generator=g)
 skip = torch.randn(rows, 64, 64, 64, device=dev, generator=g)

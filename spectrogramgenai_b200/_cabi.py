@@ -54,7 +54,8 @@ PROTOTYPES = {
     "sg_attn_tail_outc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp,
                                _i, _vp]),
     "sg_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "sg_attention_tf32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sg_attn_prep_tf32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sg_attention_tf32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sg_split_tf32": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "sg_conv_out": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "sg_cfg_update": (_i, [_vp, _vp, _i, _i, _f, _vp, _i, _vp, _vp, _u64, _i64, _vp]),

@@ -10,11 +10,16 @@
 // One CTA = 128 consecutive query tokens x one head; key tiles of 64 tokens.  Per key tile:
 //   S   = Q K^T      3 x d/8 tcgen05.mma kind::tf32 (M128 x N64 x K8), K-major operands           -> TMEM cols [0, 64)
 //   P   = exp2(S c - m c)   one query row per thread, fp32; P_hi / P_lo written as swizzled K-major fp32 tiles
-//   O_j = P V        3 x 8 tcgen05.mma (M128 x N=d x K8), V consumed MN-major                     -> TMEM cols [64, 64+d)
+//   O_j = P V        3 x 8 tcgen05.mma (M128 x N=d x K8); B = V^T, K-major                        -> TMEM cols [64, 64+d)
 //   o   = o alpha + O_j     running output / maximum / sum in registers
+// The lo x hi / hi x lo products are issued BEFORE hi x hi: the tensor core's fp32 accumulation truncates, so the small
+// terms are added while the accumulator is still small.
+// V as the B operand of P V would be MN-major, which kind::tf32 only accepts in a dedicated 32-byte-base swizzle; instead
+// sg_attn_prep_tf32 (one pass over the in_proj output) writes, next to the (hi, lo) split of q | k, the split of V
+// TRANSPOSED per (batch row, head): vt [rows * heads * d, L], so that a [d x 64 keys] K-major tile is two TMA boxes.
 // Warp roles (192 threads, as the first 16-bit kernel): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax.
-// L < 128: the query tile holds 128 / L whole batch rows and the two key tiles are the same 128 tokens under a
-// block-diagonal mask.  This engine is the accuracy mode (1 CTA per SM, serial phases): ~5x the CUDA-core kernel, not a
+// Requires L >= 128 (power of two): shorter sequences (a handful of tokens per row, < 1 % of the FLOPs) stay on the CUDA-core
+// kernel.  This engine is the accuracy mode (1 CTA per SM, serial phases): several times the CUDA-core kernel, not a
 // roofline kernel -- the throughput path is attention_tc.cu.
 #include "tc_common.cuh"
 
@@ -29,9 +34,11 @@ struct AttF {
   static constexpr int AE = ROWB / 4;                     // floats per atom row
   static constexpr int Q_ATOM = BM * ROWB, KV_ATOM = BN * ROWB;
   static constexpr int Q_TILE = NATOM * Q_ATOM;           // one of hi / lo
-  static constexpr int KV_TILE = NATOM * KV_ATOM;
+  static constexpr int KV_TILE = NATOM * KV_ATOM;         // K tile [64 keys x d]; the V^T tile [d x 64 keys] = two
+  static constexpr int VT_ATOM = D * 128;                 // [d x 32 keys] SWIZZLE_128B atoms has the same size
+  static_assert(2 * VT_ATOM == KV_TILE, "K and V^T tiles have the same size");
   static constexpr int STAGES = D == 64 ? 1 : 2;
-  static constexpr int KV_STAGE = 4 * KV_TILE;            // K_hi, K_lo, V_hi, V_lo
+  static constexpr int KV_STAGE = 4 * KV_TILE;            // K_hi, K_lo, Vt_hi, Vt_lo
   static constexpr int P_ATOM = BM * 128;                 // [128 queries x 32 keys] fp32, SWIZZLE_128B
   static constexpr int P_TILE = 2 * P_ATOM;               // 64 keys; one of hi / lo
   static constexpr int SMEM = 1024 + 2 * Q_TILE + STAGES * KV_STAGE + 2 * P_TILE + 256;
@@ -40,7 +47,7 @@ struct AttF {
 
 struct AttFGeom {
   int64_t M;  // rows * L tokens
-  int L, logL, C;
+  int L, logL, C, heads;
   int nkv;    // key tiles (64 tokens) per query tile
   float c;    // softmax scale * log2(e)
   uint32_t q_bytes, kv_bytes;  // bytes the TMA boxes of Q (hi + lo) / one K,V stage deliver
@@ -70,6 +77,7 @@ template <int D>
 __global__ void __launch_bounds__(192, 1)
 attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                       const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                      const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
                       const AttFGeom g, float* __restrict__ out) {
   using A = AttF<D>;
   constexpr int ROWB = A::ROWB, NATOM = A::NATOM, AE = A::AE, STAGES = A::STAGES, BN = A::BN, BM = A::BM;
@@ -93,13 +101,17 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
   const int head = blockIdx.x;  // heads fastest: the head slices of a token share cache lines
   const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * BM;
   if (m0 >= g.M) return;
-  const int64_t kv0 = g.L >= BM ? (m0 >> g.logL) << g.logL : m0;  // first key token of this tile's row(s)
+  const int64_t brow = m0 >> g.logL;        // batch row of this query tile (L >= 128: a tile lies inside one row)
+  const int64_t kv0 = brow << g.logL;       // its first key token
+  const int vt_row0 = (int)((brow * g.heads + head) * D);  // first row of this (batch row, head) in vt [rows*heads*d, L]
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQh);
     prefetch_tensormap(&tmQl);
     prefetch_tensormap(&tmKh);
     prefetch_tensormap(&tmKl);
+    prefetch_tensormap(&tmVh);
+    prefetch_tensormap(&tmVl);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -112,12 +124,6 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<128>(tmem_slot);
-  if (g.M < BM) {
-    // tiny problems: the TMA boxes are clamped to M rows, so clear the tiles once (0 x stale NaN would poison the MMAs)
-    for (int i = threadIdx.x; i < (2 * A::Q_TILE + STAGES * A::KV_STAGE) / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    fence_proxy_async();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -145,8 +151,11 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
         for (int a = 0; a < NATOM; ++a) {
           tma_load_2d(st + 0 * A::KV_TILE + a * A::KV_ATOM, &tmKh, &kv_full[s], g.C + head * D + a * AE, tok);
           tma_load_2d(st + 1 * A::KV_TILE + a * A::KV_ATOM, &tmKl, &kv_full[s], g.C + head * D + a * AE, tok);
-          tma_load_2d(st + 2 * A::KV_TILE + a * A::KV_ATOM, &tmKh, &kv_full[s], 2 * g.C + head * D + a * AE, tok);
-          tma_load_2d(st + 3 * A::KV_TILE + a * A::KV_ATOM, &tmKl, &kv_full[s], 2 * g.C + head * D + a * AE, tok);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {  // V^T: [d x 32 keys] boxes at key offset j * 64 + a * 32 of this row's sequence
+          tma_load_2d(st + 2 * A::KV_TILE + a * A::VT_ATOM, &tmVh, &kv_full[s], j * BN + a * 32, vt_row0);
+          tma_load_2d(st + 3 * A::KV_TILE + a * A::VT_ATOM, &tmVl, &kv_full[s], j * BN + a * 32, vt_row0);
         }
       }
     }
@@ -160,12 +169,12 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
         mbar_wait_spin(&kv_full[s], (uint32_t)(j / STAGES) & 1u);
         tc_fence_after();
         const uint32_t st = smem_u32(sKV + s * A::KV_STAGE);
-        // S = Q K^T = Qh Kh + Qh Kl + Ql Kh: K-major A and B, K = d in steps of 8 floats (32 bytes inside the swizzle span).
+        // S = Q K^T = Ql Kh + Qh Kl + Qh Kh: K-major A and B, K = d in steps of 8 floats (32 bytes inside the swizzle span).
         // The S columns are free: p_ready(j-1) was observed before P_{j-1} V was issued.
         uint32_t acc = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint32_t qt = qa + (t == 2 ? A::Q_TILE : 0);
+          const uint32_t qt = qa + (t == 0 ? A::Q_TILE : 0);
           const uint32_t kt = st + (t == 1 ? A::KV_TILE : 0);
 #pragma unroll
           for (int a = 0; a < NATOM; ++a) {
@@ -179,19 +188,19 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
           }
         }
         umma_commit(s_full);
-        // O_j = P V = Ph Vh + Ph Vl + Pl Vh: A = P (K-major, two 32-key SWIZZLE_128B atoms), B = V consumed MN-major
+        // O_j = P V = Pl Vh + Ph Vl + Ph Vh: A = P and B = V^T, both K-major in two 32-key SWIZZLE_128B atoms
         mbar_wait_spin(p_ready, (uint32_t)j & 1u);
         if (j > 0) mbar_wait_spin(o_read, (uint32_t)(j - 1) & 1u);  // O_{j-1} has been added to the running output
         tc_fence_after();
         acc = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint32_t pt = pa + (t == 2 ? A::P_TILE : 0);
+          const uint32_t pt = pa + (t == 0 ? A::P_TILE : 0);
           const uint32_t vt = st + 2 * A::KV_TILE + (t == 1 ? A::KV_TILE : 0);
 #pragma unroll
           for (int k = 0; k < BN / 8; ++k) {
             const uint64_t pd = make_desc_k128(pt + (k >> 2) * A::P_ATOM + (k & 3) * 32);
-            const uint64_t vd = make_desc_f(vt + k * 8 * ROWB, ROWB, NATOM > 1 ? A::KV_ATOM : 0);
+            const uint64_t vd = make_desc_k128(vt + (k >> 2) * A::VT_ATOM + (k & 3) * 32);
             umma_ss_tf32(tmem_o, pd, vd, g.idesc_o, acc);
             acc = 1;
           }
@@ -205,10 +214,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int64_t tok = m0 + r;
-    const bool row_valid = tok < g.M;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool masked = g.L < BM;  // block-diagonal tile (several batch rows) and / or ragged tail
-    const int64_t my_row = tok >> g.logL;
     float o[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) o[i] = 0.f;
@@ -218,7 +224,6 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     for (int j = 0; j < g.nkv; ++j) {
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      const int64_t key0 = kv0 + (int64_t)j * BN;
       // ONE sweep over S: p = exp2(s c - m_ref c) against the maximum known BEFORE this tile, the tile maximum as a
       // by-product.  Exact algebra (o, l are rescaled afterwards); the sweep is repeated only when the tile maximum
       // exceeds the reference by more than 2^60 (always on the first tile, where m_ref = -inf).
@@ -238,17 +243,10 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
             float ph[4], pl[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              float s0 = __uint_as_float(v[i4 * 4 + u]);
-              bool keep = true;
-              if (masked) {
-                const int64_t kt = key0 + cch * 32 + i4 * 4 + u;
-                keep = !(row_valid && (kt >= g.M || (kt >> g.logL) != my_row));
-                if (!keep) s0 = -INFINITY;
-              }
+              const float s0 = __uint_as_float(v[i4 * 4 + u]);
               tmax = fmaxf(tmax, s0);
               float p;
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s0, g.c, -mc)));
-              if (masked && !keep) p = 0.f;
               psum += p;
               ph[u] = tf32_rna(p);
               pl[u] = tf32_rna(p - ph[u]);
@@ -302,7 +300,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
         m_ref = tmax;
       }
     }
-    if (row_valid) {
+    {
       const float inv = 1.0f / l;
       float* dst = out + tok * g.C + head * D;
 #pragma unroll
@@ -318,28 +316,74 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// sg_attn_prep_tf32: in_proj output qkv fp32 [M, 3C] -> split q | k (hi, lo) [M, 2C] and split, per-(row, head) transposed
+// V: vt (hi, lo) [rows * heads * d, L].  One block = 32 tokens of one batch row; 256 threads.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_prep_tf32_kernel(const float* __restrict__ qkv, float* __restrict__ qk_hi,
+                                                             float* __restrict__ qk_lo, float* __restrict__ vt_hi,
+                                                             float* __restrict__ vt_lo, int L, int C) {
+  extern __shared__ float sv[];  // [C][33]: the V slab, transposed
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tiles_per_row = L / 32;
+  const int brow = blockIdx.x / tiles_per_row, t0 = (blockIdx.x % tiles_per_row) * 32;
+  const int64_t tok0 = (int64_t)brow * L + t0;
+  const int C4 = C / 4;
+  // q | k: 32 tokens x 2C floats, float4 per thread, coalesced in and out
+  for (int i = threadIdx.x; i < 32 * 2 * C4; i += blockDim.x) {
+    const int tk = i / (2 * C4), c4 = i % (2 * C4);
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(qkv + (tok0 + tk) * 3 * C) + c4);
+    float4 h, l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+    reinterpret_cast<float4*>(qk_hi + (tok0 + tk) * 2 * C)[c4] = h;
+    reinterpret_cast<float4*>(qk_lo + (tok0 + tk) * 2 * C)[c4] = l;
+  }
+  // v: [32 tokens x C] -> smem [C][33] (conflict-free column writes), then rows of 32 tokens per channel
+  for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) {
+    const int tk = i / C, c = i % C;
+    sv[c * 33 + tk] = __ldcs(qkv + (tok0 + tk) * 3 * C + 2 * C + c);
+  }
+  __syncthreads();
+  // channel c of batch row brow = head c / d, component c % d -> vt row (brow * heads + head) * d + c % d = brow * C + c
+  for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) {
+    const int c = i / 32, tk = i % 32;
+    const float v = sv[c * 33 + tk];
+    const float h = tf32_rna(v);
+    const int64_t o = ((int64_t)brow * C + c) * L + t0 + tk;
+    vt_hi[o] = h;
+    vt_lo[o] = tf32_rna(v - h);
+  }
+}
+
 template <int D>
-static int launch_att_tf32(const float* qkv_hi, const float* qkv_lo, float* out, AttFGeom g, cudaStream_t stream) {
+static int launch_att_tf32(const float* qk_hi, const float* qk_lo, const float* vt_hi, const float* vt_lo, float* out,
+                           AttFGeom g, cudaStream_t stream) {
   using A = AttF<D>;
-  const uint32_t q_rows = (uint32_t)(g.M < A::BM ? g.M : A::BM), kv_rows = (uint32_t)(g.M < A::BN ? g.M : A::BN);
   const CUtensorMapSwizzle sw = A::ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  const uint64_t dims[2] = {(uint64_t)3 * g.C, (uint64_t)g.M};
-  const uint64_t strides[1] = {(uint64_t)3 * g.C * 4};
-  const uint32_t qbox[2] = {(uint32_t)A::AE, q_rows}, kbox[2] = {(uint32_t)A::AE, kv_rows};
-  CUtensorMap tmQh, tmQl, tmKh, tmKl;
+  const uint64_t dims[2] = {(uint64_t)2 * g.C, (uint64_t)g.M};
+  const uint64_t strides[1] = {(uint64_t)2 * g.C * 4};
+  const uint32_t qbox[2] = {(uint32_t)A::AE, (uint32_t)A::BM}, kbox[2] = {(uint32_t)A::AE, (uint32_t)A::BN};
+  const uint64_t vdims[2] = {(uint64_t)g.L, (uint64_t)(g.M / g.L) * g.C};  // [rows * heads * d, L], L contiguous
+  const uint64_t vstrides[1] = {(uint64_t)g.L * 4};
+  const uint32_t vbox[2] = {32u, (uint32_t)D};
+  CUtensorMap tmQh, tmQl, tmKh, tmKl, tmVh, tmVl;
   int rc;
-  if ((rc = make_tmap(&tmQh, SG_F32, 2, qkv_hi, dims, strides, qbox, sw))) return rc;
-  if ((rc = make_tmap(&tmQl, SG_F32, 2, qkv_lo, dims, strides, qbox, sw))) return rc;
-  if ((rc = make_tmap(&tmKh, SG_F32, 2, qkv_hi, dims, strides, kbox, sw))) return rc;
-  if ((rc = make_tmap(&tmKl, SG_F32, 2, qkv_lo, dims, strides, kbox, sw))) return rc;
-  g.q_bytes = 2u * A::NATOM * q_rows * (uint32_t)A::ROWB;
-  g.kv_bytes = 4u * A::NATOM * kv_rows * (uint32_t)A::ROWB;
+  if ((rc = make_tmap(&tmQh, SG_F32, 2, qk_hi, dims, strides, qbox, sw))) return rc;
+  if ((rc = make_tmap(&tmQl, SG_F32, 2, qk_lo, dims, strides, qbox, sw))) return rc;
+  if ((rc = make_tmap(&tmKh, SG_F32, 2, qk_hi, dims, strides, kbox, sw))) return rc;
+  if ((rc = make_tmap(&tmKl, SG_F32, 2, qk_lo, dims, strides, kbox, sw))) return rc;
+  if ((rc = make_tmap(&tmVh, SG_F32, 2, vt_hi, vdims, vstrides, vbox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap(&tmVl, SG_F32, 2, vt_lo, vdims, vstrides, vbox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  g.q_bytes = 2u * A::Q_TILE;
+  g.kv_bytes = (uint32_t)A::KV_STAGE;
   g.idesc_s = make_idesc_tf32(128, A::BN, 0);
-  g.idesc_o = make_idesc_tf32(128, D, 1);  // B = V is MN-major
+  g.idesc_o = make_idesc_tf32(128, D, 0);
   if ((rc = set_max_smem<attention_tf32_kernel<D>>(A::SMEM, "sg_attention_tf32"))) return rc;
-  const int64_t tiles = cdiv(g.M, A::BM);
-  dim3 grid((unsigned)(g.C / D), (unsigned)(tiles < 32768 ? tiles : 32768), (unsigned)cdiv(tiles, 32768));
-  launch_k(attention_tf32_kernel<D>, grid, dim3(192), (size_t)A::SMEM, stream, tmQh, tmQl, tmKh, tmKl, g, out);
+  const int64_t tiles = g.M / A::BM;
+  dim3 grid((unsigned)g.heads, (unsigned)(tiles < 32768 ? tiles : 32768), (unsigned)cdiv(tiles, 32768));
+  launch_k(attention_tf32_kernel<D>, grid, dim3(192), (size_t)A::SMEM, stream, tmQh, tmQl, tmKh, tmKl, tmVh, tmVl, g, out);
   return launch_status("sg_attention_tf32");
 }
 
@@ -349,26 +393,46 @@ static int launch_att_tf32(const float* qkv_hi, const float* qkv_lo, float* out,
 using namespace sg;
 using namespace sg::tc;
 
-extern "C" int sg_attention_tf32(const float* qkv_hi, const float* qkv_lo, float* out, int rows, int L, int C, int heads,
-                                 sg_stream_t stream) {
-  SG_REQUIRE(qkv_hi && qkv_lo && out, "sg_attention_tf32: null pointer");
-  SG_REQUIRE(rows > 0 && L > 0 && (L & (L - 1)) == 0 && heads > 0 && heads <= 65535 && C % heads == 0,
-             "sg_attention_tf32: bad shape rows=%d L=%d C=%d heads=%d (L must be a power of two)", rows, L, C, heads);
-  SG_REQUIRE(((reinterpret_cast<uintptr_t>(qkv_hi) | reinterpret_cast<uintptr_t>(qkv_lo) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+static int att_tf32_check(const char* what, int rows, int L, int C, int heads) {
+  SG_REQUIRE(rows > 0 && L >= 128 && (L & (L - 1)) == 0 && heads > 0 && heads <= 65535 && C % heads == 0,
+             "%s: bad shape rows=%d L=%d C=%d heads=%d (L must be a power of two >= 128)", what, rows, L, C, heads);
+  const int d = C / heads;
+  SG_REQUIRE(d == 16 || d == 32 || d == 64, "%s: head dim %d not in {16,32,64}", what, d);
+  SG_REQUIRE((int64_t)rows * L < (1ll << 31), "%s: too many tokens", what);
+  return SG_OK;
+}
+
+extern "C" int sg_attn_prep_tf32(const float* qkv, float* qk_hi, float* qk_lo, float* vt_hi, float* vt_lo, int rows, int L,
+                                 int C, int heads, sg_stream_t stream) {
+  SG_REQUIRE(qkv && qk_hi && qk_lo && vt_hi && vt_lo, "sg_attn_prep_tf32: null pointer");
+  if (int rc = att_tf32_check("sg_attn_prep_tf32", rows, L, C, heads)) return rc;
+  SG_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(qk_hi) | reinterpret_cast<uintptr_t>(qk_lo)) & 15) == 0,
+             "sg_attn_prep_tf32: buffers must be 16-byte aligned");
+  const size_t smem = (size_t)C * 33 * 4;  // <= 33 KB
+  launch_k(attn_prep_tf32_kernel, dim3((unsigned)(rows * (L / 32))), dim3(256), smem, as_stream(stream), qkv, qk_hi, qk_lo,
+           vt_hi, vt_lo, L, C);
+  return launch_status("sg_attn_prep_tf32");
+}
+
+extern "C" int sg_attention_tf32(const float* qk_hi, const float* qk_lo, const float* vt_hi, const float* vt_lo, float* out,
+                                 int rows, int L, int C, int heads, sg_stream_t stream) {
+  SG_REQUIRE(qk_hi && qk_lo && vt_hi && vt_lo && out, "sg_attention_tf32: null pointer");
+  if (int rc = att_tf32_check("sg_attention_tf32", rows, L, C, heads)) return rc;
+  SG_REQUIRE(((reinterpret_cast<uintptr_t>(qk_hi) | reinterpret_cast<uintptr_t>(qk_lo) | reinterpret_cast<uintptr_t>(vt_hi) |
+               reinterpret_cast<uintptr_t>(vt_lo) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
              "sg_attention_tf32: operands must be 16-byte aligned");
   const int d = C / heads;
-  SG_REQUIRE(d == 16 || d == 32 || d == 64, "sg_attention_tf32: head dim %d not in {16,32,64}", d);
   AttFGeom g;
   g.M = (int64_t)rows * L;
-  SG_REQUIRE(g.M < (1ll << 31), "sg_attention_tf32: too many tokens");
   g.L = L;
   g.logL = 0;
   while ((1 << g.logL) < L) ++g.logL;
   g.C = C;
-  g.nkv = (L >= 128 ? L : 128) / 64;
+  g.heads = heads;
+  g.nkv = L / 64;
   g.c = (1.0f / sqrtf((float)d)) * 1.4426950408889634f;
   cudaStream_t s = as_stream(stream);
-  if (d == 16) return launch_att_tf32<16>(qkv_hi, qkv_lo, out, g, s);
-  if (d == 32) return launch_att_tf32<32>(qkv_hi, qkv_lo, out, g, s);
-  return launch_att_tf32<64>(qkv_hi, qkv_lo, out, g, s);
+  if (d == 16) return launch_att_tf32<16>(qk_hi, qk_lo, vt_hi, vt_lo, out, g, s);
+  if (d == 32) return launch_att_tf32<32>(qk_hi, qk_lo, vt_hi, vt_lo, out, g, s);
+  return launch_att_tf32<64>(qk_hi, qk_lo, vt_hi, vt_lo, out, g, s);
 }

@@ -212,9 +212,8 @@ class UNetPlan:
         P = ops.igemm_partials(self.engine, H, W, cout)
         part = self._alloc((rows, P, 2), torch.float32)
         a_op, tmp = self._gemm_in(a_act)
-        args = ops.make_igemm_args(a_op, w, rows=rows, H=H, W=W, partials=part,
-                                   **({"out_act": raw} if raw16 else {"out_f32": raw}))
-        self._op(ops.igemm_launch, args)
+        self._op(ops.igemm, a_op, w, rows=rows, H=H, W=W, partials=part,
+                 **({"out_act": raw} if raw16 else {"out_f32": raw}))
         self._free(*tmp)
         return raw, part
 
@@ -266,7 +265,7 @@ class UNetPlan:
 
         def linear(a, wname, bname, **kw):
             a_op, tmp = self._gemm_in(a)
-            self._op(ops.igemm_launch, ops.make_igemm_args(a_op, W_[wname], rows=rows, H=H, W=W, bias=W_[bname], **kw))
+            self._op(ops.igemm, a_op, W_[wname], rows=rows, H=H, W=W, bias=W_[bname], **kw)
             self._free(*tmp)
 
         # tcgen05 attention consumes 16-bit q/k/v; the split-tf32 and the CUDA-core cores read fp32
@@ -282,11 +281,15 @@ class UNetPlan:
                    **({"out_act": qkv} if tc_attn else {"out_f32": qkv}))
             self._free(ln1)
         att = self._alloc((M, C), lin_dt)
-        if self.tf32:
-            q_op, tmp = self._gemm_in(qkv)
-            self._op(ops.attention, q_op, att, rows=rows, L=L, C=C)  # sg_attention_tf32
-            self._free(*tmp)
+        if self.tf32 and L >= 128:
+            # split-TF32 core: (hi, lo) of q | k and of V transposed per (row, head), one preparation pass over qkv
+            qk_hi, qk_lo = self._alloc((M, 2 * C), f32), self._alloc((M, 2 * C), f32)
+            vt_hi, vt_lo = self._alloc((rows * C, L), f32), self._alloc((rows * C, L), f32)
+            self._op(ops.attn_prep_tf32, qkv, qk_hi, qk_lo, vt_hi, vt_lo, rows=rows, L=L, C=C)
+            self._op(ops.attention_tf32, qk_hi, qk_lo, vt_hi, vt_lo, att, rows=rows, L=L, C=C)
+            self._free(qk_hi, qk_lo, vt_hi, vt_lo)
         else:
+            # (fp32 engines at L < 128: a handful of tokens per row, the CUDA-core kernel)
             self._op(ops.attention, qkv, att, rows=rows, L=L, C=C, engine=SG_ENGINE_TC if tc_attn else SG_ENGINE_SIMT)
         self._free(qkv)
         if fused and not want_act:

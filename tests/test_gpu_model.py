@@ -338,8 +338,7 @@ def test_eps_matches_oracle_at_batch_64_r64(mode):
 @pytest.mark.parametrize("mode", ["bf16", "f16"])
 @pytest.mark.parametrize("scale", [1e2, 1e4, 1e-3, 1e-5])
 def test_conv_weight_scale_invariance(mode, scale):
-    """Every 3x3 conv weight times `scale` (a power of ten is not exactly representable, so the oracle runs on the scaled
-    weights too): the reference result is unchanged up to rounding because each conv feeds GroupNorm.  The 16-bit
+    """Every 3x3 conv weight times `scale` (the oracle runs on the scaled weights too): the reference result is unchanged up to rounding because each conv feeds GroupNorm.  The 16-bit
     engines keep raw conv outputs in fp16 while they lie in fp16's safe range and otherwise fall back to fp32 raw tensors
     (range flag raised by GroupNorm-apply from the exact fp32 statistics) -- either way eps must stay within the bar."""
     n, s, c = 2, 16, 4
@@ -353,8 +352,9 @@ def test_conv_weight_scale_invariance(mode, scale):
     x, y = golden_inputs(s, c, n)
     t = torch.tensor([700, 30])
     want = O.unet_forward(sd, x, t, y)
-    base = O.unet_forward(make_state_dict(WEIGHT_SEED, c, c, NUM_CLASSES), x, t, y)
-    assert O.rel_l2(want, base) < 1e-4  # the reference itself does not care about the scale
+    if scale > 1:  # (below 1 GroupNorm's eps = 1e-5 is no longer negligible against the variance: the function changes)
+        base = O.unet_forward(make_state_dict(WEIGHT_SEED, c, c, NUM_CLASSES), x, t, y)
+        assert O.rel_l2(want, base) < 1e-4  # the reference itself does not care about the scale
     got = m(x.to(DEV), t.to(DEV), y.to(DEV)).cpu()
     err = O.rel_l2(got, want)
     print(f"scale {scale:g} {mode}: eps rel-L2 {err:.3e}, fp16 raw tensors kept: {m._raw16_ok}")

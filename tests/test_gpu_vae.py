@@ -18,7 +18,9 @@ from tests.golden.make_golden_vae import CASES, VAE_SEED, golden_latents
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 HERE = os.path.dirname(os.path.abspath(__file__))
-TOL = {"fp32": 1e-5, "bf16": 1e-2, "f16": 2e-3}
+# "fp32" on the decoder = split-TF32 tensor cores (no GroupNorm behind its convs to absorb the truncating accumulation: 1e-4
+# bar); "fp32_simt" = CUDA-core kernels, what DiffusionVAE uses for the tail in the fp32 modes (1e-5, identical uint8 image)
+TOL = {"fp32": 1e-4, "fp32_simt": 1e-5, "bf16": 1e-2, "f16": 2e-3}
 
 
 @pytest.fixture(scope="module")
@@ -41,7 +43,7 @@ def _u8_mismatch_is_rounding(u8, want_u8, y_ref):
     return bool(((v - v.round()).abs() < 1e-3).all())
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16", "f16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "bf16", "f16"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_decode_tail_matches_reference(gvae, case, mode):
     tag, S, n, seed = case
@@ -60,7 +62,7 @@ def test_decode_tail_matches_reference(gvae, case, mode):
     assert u8.shape == (n, 1, 4 * S, 4 * S) and u8.dtype == torch.uint8
     assert frac < 1e-3
     assert err < TOL[mode]
-    if mode == "fp32" and frac == 0.0:
+    if mode == "fp32_simt" and frac == 0.0:
         assert same > 0.999 and _u8_mismatch_is_rounding(u8.cpu(), u8_ref, y_ref)
     # the uint8 image is the kernel's own float output pushed through the reference's (un-clamped, wrapping) cast
     assert torch.equal(u8.cpu(), V.image_to_uint8(y.cpu()))
@@ -276,7 +278,7 @@ def test_denoise_trajectory_dumps(tmp_path):
     files = sorted(os.listdir(tmp_path))
     assert files == sorted(f"{names[l]}_noise_{i}_{k}.png" for l in (2, 0) for i in (102, 100, 50, 1)
                            for k in ("latent", "decode"))
-    assert d.dump_launches == 4 * 8 and d.gpu_launches > d.dump_launches
+    assert d.dump_launches == 4 * (d.vqae.gpu_launches + 1) and d.gpu_launches > d.dump_launches
     for i, x in seen.items():
         u8, y, q, _ = V.decode_tail(x.cpu(), vsd, return_all=True)
         lat = V.image_to_uint8(q).numpy()
