@@ -37,12 +37,15 @@ struct AttF {
   static constexpr int KV_TILE = NATOM * KV_ATOM;         // K tile [64 keys x d]; the V^T tile [d x 64 keys] = two
   static constexpr int VT_ATOM = D * 128;                 // [d x 32 keys] SWIZZLE_128B atoms has the same size
   static_assert(2 * VT_ATOM == KV_TILE, "K and V^T tiles have the same size");
-  static constexpr int STAGES = D == 64 ? 1 : 2;
+  // d = 16 (sa5 / sa6: 85 % of the attention FLOPs): one K / V stage keeps the CTA under half of the SM's shared memory,
+  // and two resident CTAs overlap each other's serial chain -- worth more than a prefetched stage; d = 64 has no room for two
+  static constexpr int STAGES = D == 32 ? 2 : 1;
+  static constexpr int CTAS = D == 16 ? 2 : 1;
   static constexpr int KV_STAGE = 4 * KV_TILE;            // K_hi, K_lo, Vt_hi, Vt_lo
   static constexpr int P_ATOM = BM * 128;                 // [128 queries x 32 keys] fp32, SWIZZLE_128B
   static constexpr int P_TILE = 2 * P_ATOM;               // 64 keys; one of hi / lo
   static constexpr int SMEM = 1024 + 2 * Q_TILE + STAGES * KV_STAGE + 2 * P_TILE + 256;
-  static_assert(SMEM <= 227 * 1024, "smem budget");
+  static_assert(CTAS * (SMEM + 1024) <= 228 * 1024, "smem budget");
 };
 
 struct AttFGeom {
@@ -74,7 +77,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, AttF<D>::CTAS)
 attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                       const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                       const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,

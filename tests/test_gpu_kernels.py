@@ -357,7 +357,7 @@ def test_igemm_conv_split_tf32(ops, rows, H, cin, cout):
     err_scaled = O.rel_l2(got / scale, ref)
     print(f"igemm split-tf32 rows={rows} H={H} {cin}->{cout}: rel-L2 {err:.3e}, scale 1{scale - 1:+.2e}, after scale {err_scaled:.3e}")
     assert err < 2e-6 + 1.5e-8 * 9 * cin and abs(scale - 1) < 1.5e-8 * 9 * cin + 1e-6
-    assert err_scaled < 2e-6
+    assert err_scaled < 4e-6
     s = part.cpu().double().sum(1)
     assert torch.allclose(s[:, 0], ref.sum((1, 2, 3)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(s[:, 1], (ref ** 2).sum((1, 2, 3)), rtol=1e-5)
