@@ -28,6 +28,7 @@ SOURCES = [
     "attention_simt.cu",
     "igemm_tc.cu",
     "attention_tc.cu",
+    "attention_tc12.cu",
     "attention_tf32.cu",
     "token_mlp_tc.cu",
     "vae_decode.cu",

@@ -1,0 +1,494 @@
+// K4, v12 (d = 16 heads, L >= 128: sa5 / sa6, 85 % of the attention time): the softmax warps never wait.
+//
+// v8 / v11 run one key tile at a time through a serial chain  S = Q K^T -> sweep -> O_j = P V -> o += O_j  and rely on four
+// resident CTAs to cover the two tensor-core round trips of every tile (ncu: 30 % of the warp samples sit in those waits,
+// XU pipe 61 %).  v12 removes the round trips from the softmax warps' path instead:
+//   * key tiles of 64; S is DOUBLE-BUFFERED in TMEM (columns [0,64) / [64,128)), so S_{i+2} is computed while tile i+1 is
+//     swept; a step of a softmax warp is   wait s_full[i&1] (issued two steps ago) | sweep S_i -> P_i | bar.arrive;
+//   * the output is never read back per tile: the fast pass keeps ONE exponent reference per row (v11's scheme: the maximum
+//     of the row's first 16 scores, no maximum search, no rescale), so O = sum_i P_i V_i simply accumulates in TMEM across
+//     all key tiles (tcgen05.mma accumulate) together with the row sums (v11's ones atom: the PV MMA has N = d + 16);
+//   * P is double-buffered in shared memory, K / V tiles travel through a 6-stage TMA ring;
+//   * a fifth warp sleeps on a named barrier (bar.sync, no polling) and then issues, in order, P_i V_i, S_{i+2} = Q K_{i+2}^T
+//     into the S buffer the sweep has just released, and the TMA load of tile i+4.  tcgen05.commit tracks every MMA issued
+//     before it, so a softmax thread that has observed s_full of step i knows P_{i-2} V_{i-2} is complete: the P buffer and
+//     the K / V stage about to be reused are free without further barriers.
+// 160 TMEM columns (128 + 32) and 62 KB of shared memory per CTA: three CTAs per SM.
+// Overflow (a row whose later scores exceed its first 16 by more than the dynamic range of P) is detected at the end from
+// the tensor-core row sum / the polynomial lanes' exponents; the query tile is then recomputed by the safe pass of v11
+// (classical online softmax, 128-key tiles, warps 0..3, O_j read back per tile) inside the same CTA.
+#include "attention_common.cuh"
+
+#include <type_traits>
+
+namespace sg {
+namespace tc {
+
+struct Att12 {
+  static constexpr int D = 16, ROWB = 32, BN = 64, KVS = 6;
+  static constexpr int Q_TILE = ATT_BM * ROWB;      // 4 KB
+  static constexpr int KV_TILE = BN * ROWB;         // 2 KB (fast pass); the safe pass uses 128-key tiles of 4 KB
+  static constexpr int RING = KVS * 2 * KV_TILE;    // 24 KB >= the safe pass's 2 stages x (K, V) x 4 KB
+  static constexpr int P_TILE = ATT_BM * 128;       // 16 KB: [128 x 64 keys] 16 bit = one SWIZZLE_128B atom column
+  static constexpr int OFF_KV = Q_TILE, OFF_P = OFF_KV + RING, OFF_ONES = OFF_P + 2 * P_TILE, OFF_QLO = OFF_ONES + 1024;
+  static constexpr int OFF_BAR = OFF_QLO + Q_TILE;
+  static constexpr int SMEM = 1024 + OFF_BAR + 256;
+  static_assert(OFF_P % 1024 == 0 && RING >= 4 * ATT_BN * ROWB && 2 * P_TILE == P_BYTES, "layout");
+  static_assert(3 * (SMEM + 1024) <= 228 * 1024 && 4 * (SMEM + 1024) > 228 * 1024, "exactly three CTAs per SM (480 of 512 TMEM columns)");
+};
+
+template <int DT, int POLY>
+__global__ void __launch_bounds__(160, 3)
+attention_tc12_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttGeom g,
+                      uint16_t* __restrict__ out) {
+  using A = Att12;
+  constexpr int D = A::D, ROWB = A::ROWB, BN = A::BN, KVS = A::KVS;
+  constexpr bool NOREF = DT == SG_BF16;  // bf16 P: the exponent needs no per-row reference (see the softmax warps)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + A::OFF_KV;   // fast pass: [KVS] x (K | V) of 64 keys
+  uint8_t* sP = smem + A::OFF_P;     // fast pass: [2] x 16 KB; safe pass: one 32 KB tile of 128 keys
+  uint8_t* sOnes = smem + A::OFF_ONES;  // [16 keys x d] 16-bit ones in V's layout: second N atom of the PV MMA's B operand
+  uint8_t* sQlo = smem + A::OFF_QLO;    // NOREF: low part of the rescaled Q (Q c = hi + lo in 16 bit: no second rounding)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;       // [KVS]
+  uint64_t* s_full = bars + 1 + KVS;  // [2]
+  uint64_t* pv_done = bars + 3 + KVS;
+  uint64_t* fb_kv = bars + 4 + KVS;   // safe pass: [2]
+  uint64_t* fb_s = bars + 6 + KVS;
+  uint64_t* fb_o = bars + 7 + KVS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + KVS);  // [2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x;  // heads fastest: the four 32-byte head slices of a token share one 128-byte line
+  const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
+  if (m0 >= g.M) return;  // ragged last grid.z slice
+  const int64_t kv0 = (m0 >> g.logL) << g.logL;
+  const int nst = g.L / BN;  // >= 2
+
+  if (threadIdx.x == 128) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KVS; ++s) mbar_init(&kv_full[s], 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(pv_done, 1);
+    mbar_init(&fb_kv[0], 1);
+    mbar_init(&fb_kv[1], 1);
+    mbar_init(fb_s, 1);
+    mbar_init(fb_o, 1);
+    fence_barrier_init();
+  }
+  {
+    const uint32_t one2 = DT == SG_BF16 ? 0x3F803F80u : 0x3C003C00u;  // two 1.0 values
+    for (int i = threadIdx.x; i < 16 * ROWB / 4; i += 160) reinterpret_cast<uint32_t*>(sOnes)[i] = one2;
+    fence_proxy_async();
+  }
+  if (warp == 4) {
+    __syncwarp();
+    // two allocations (128 columns: S0 | S1, 32 columns: O | row sums) = 160 columns, three CTAs per SM
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(tmem_slot + 1)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = tmem_slot[0], tmem_o = tmem_slot[1];
+  pdl_wait();  // every activation access (TMA loads included) follows this point
+  pdl_launch_dependents();
+
+  const uint32_t ones_addr = smem_u32(sOnes);
+  const uint64_t q_desc = make_desc_rows(smem_u32(sQ), ROWB), qlo_desc = make_desc_rows(smem_u32(sQlo), ROWB);
+  const uint32_t idesc_s64 = make_idesc(DT, 128, BN, 0, 0);
+  bool bad = false;
+  float l = 0.f;
+  uint64_t o2[D / 2];
+  const int r = (warp & 3) * 32 + lane;
+  const int64_t tok = m0 + r;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t rx = (uint32_t)(r & 7);
+  const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+  const uint64_t c2 = pk2(g.c, g.c);
+
+  if (warp == 4) {
+    // ===================== issuer warp: convergent, one elected lane issues TMA / MMA =====================
+    auto load_tile = [&](int t) {
+      const int s = t % KVS;
+      const int tk = (int)(kv0 + (int64_t)t * BN);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[s], 2u * A::KV_TILE);
+        tma_load_2d(sKV + s * 2 * A::KV_TILE, &tmKV, &kv_full[s], g.C + head * D, tk);
+        tma_load_2d(sKV + s * 2 * A::KV_TILE + A::KV_TILE, &tmKV, &kv_full[s], 2 * g.C + head * D, tk);
+      }
+    };
+    auto issue_s = [&](int t) {  // S_t = Q K_t^T (M128 x N64 x K16) into S buffer t & 1
+      mbar_wait_spin(&kv_full[t % KVS], (uint32_t)(t / KVS) & 1u);
+      tc_fence_after();
+      const uint64_t kd = make_desc_rows(smem_u32(sKV + (t % KVS) * 2 * A::KV_TILE), ROWB);
+      if (elect_one()) {
+        umma_ss(tmem_s + (uint32_t)((t & 1) * BN), q_desc, kd, idesc_s64, 0u);
+        if (NOREF) umma_ss(tmem_s + (uint32_t)((t & 1) * BN), qlo_desc, kd, idesc_s64, 1u);
+        umma_commit(&s_full[t & 1]);
+      }
+    };
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, (uint32_t)A::Q_TILE);
+      tma_load_2d(sQ, &tmQ, q_full, head * D, (int)m0);
+    }
+    for (int t = 0; t < KVS - 2 && t < nst; ++t) load_tile(t);
+    if (NOREF) named_bar_sync<5, 160>();  // the softmax warps have rescaled Q (they waited for q_full themselves)
+    else mbar_wait_spin(q_full, 0);
+    tc_fence_after();
+    issue_s(0);
+    issue_s(1);
+    __syncwarp();
+    for (int i = 0; i < nst; ++i) {
+      const int sb = i & 1;
+      if (sb) named_bar_sync<2, 160>();
+      else named_bar_sync<1, 160>();
+      tc_fence_after();
+      // O += P_i V_i : A = P_i (K-major, one SWIZZLE_128B atom of 64 keys), B = [V slab | ones] consumed MN-major: the
+      // N = d + 16 columns are two swizzle atoms along N and the leading-dimension offset is the distance between them
+      const uint64_t p_desc = make_desc_k128(smem_u32(sP) + (uint32_t)sb * A::P_TILE);
+      const uint32_t v0 = smem_u32(sKV + (i % KVS) * 2 * A::KV_TILE + A::KV_TILE);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          const uint32_t slab = v0 + (uint32_t)(k * 16 * ROWB);
+          const uint64_t bd = (make_desc_rows(slab, ROWB) & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((ones_addr - slab) >> 4) << 16);
+          umma_ss(tmem_o, p_desc + (uint64_t)(2 * k), bd, g.idesc_ol, (uint32_t)((i | k) != 0));
+        }
+        if (i == nst - 1) umma_commit(pv_done);
+      }
+      __syncwarp();
+      if (i + 2 < nst) issue_s(i + 2);  // into the S buffer sweep i has released; its commit also covers P_i V_i
+      if (i + KVS - 2 < nst) load_tile(i + KVS - 2);  // its stage held tile i-2, whose P V the softmax warps have seen complete
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax warps: thread = one query row (TMEM lane quadrant = warp) =====================
+    // Exponent x = (s - m_ref) c.  MUFU lanes: ex2(x).  Polynomial lanes (POLY of every 8 pairs, on the FMA pipe):
+    //   u = sat(x / 252 + 1/2)                 one FFMA.SAT per element: the clamp of x to [-126, 126] is free -- below it
+    //                                          2^x is 0 to P's precision, above it the row sum trips the overflow check
+    //   t = 252 u - 126 + 1.5 2^23             the integer part n of x lands in t's low mantissa bits
+    //   f = 252 u - 126 - n                    |f| <= 1/2
+    //   2^x = p3(f) with n added to the exponent field (Cody-Waite + degree-3 minimax, rel. error 7.5e-5)
+    // i.e. 10 instructions per pair against v11's 12 (two clamps and the running maximum of the exponents are gone).
+    // bf16 P (NOREF): no exponent reference at all.  Q is rescaled once by c = log2(e) / sqrt(d) (each thread its own row
+    // of the Q tile; the product is kept as hi + lo 16-bit parts and S = Q_hi K^T + Q_lo K^T, so the rescaling adds no
+    // second rounding of q), so S is the exponent itself: MUFU lanes take ex2 of the TMEM value directly (no scale FMA).
+    // bf16 / fp32 carry 2^+-126, attention logits are tens at most, and a row sum outside [2^-100, 2^60] sends the tile to
+    // the safe pass.  fp16 P (range 2^-24 .. 2^16) keeps v11's reference: the maximum of the row's first 16 scores.
+    float cu = 1.0f / 252.0f, bu = 0.5f, nmc = 0.f;
+    if constexpr (NOREF) {
+      mbar_wait(q_full, 0);
+      const uint32_t qa = smem_u32(sQ) + (uint32_t)r * ROWB, qb = smem_u32(sQlo) + (uint32_t)r * ROWB;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // the swizzle only permutes 16-byte chunks inside the row: same offsets in both tiles
+        uint32_t w[4], wl[4];
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(qa + h * 16));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack16(w[j], DT);
+          const float a0 = f.x * g.c, a1 = f.y * g.c;
+          w[j] = pack_pair<DT>(a0, a1);
+          const float2 hi = unpack16(w[j], DT);
+          wl[j] = pack_pair<DT>(a0 - hi.x, a1 - hi.y);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(qa + h * 16), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(qb + h * 16), "r"(wl[0]), "r"(wl[1]), "r"(wl[2]), "r"(wl[3]) : "memory");
+      }
+      fence_proxy_async();
+      named_bar_arrive<5, 160>();
+    }
+    const uint64_t k252 = pk2(252.0f, 252.0f), magicp = pk2(12582786.0f, 12582786.0f);  // 1.5 2^23 - 126
+    auto step = [&](int i, auto sb_tag) {
+      constexpr int sb = decltype(sb_tag)::value;
+      const uint32_t t_s = tmem_s + lane_base + (uint32_t)(sb * BN);
+      const uint32_t p_buf = p_row + (uint32_t)sb * A::P_TILE;
+      mbar_wait_spin(&s_full[sb], (uint32_t)(i >> 1) & 1u);  // issued two steps ago: normally complete on the first probe
+      tc_fence_after();
+      uint32_t va[16], vb[16];
+      tmem_ld16(t_s, va);
+      tmem_ld_wait();
+      if (!NOREF && sb == 0 && i == 0) {
+        // the exponent reference: the maximum of the row's first 16 scores; never searched for again in the fast pass
+        float mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(va[e]), __uint_as_float(va[e + 1]));
+        nmc = -mx * g.c;
+        cu = g.c * (1.0f / 252.0f);
+        bu = fmaf(nmc, 1.0f / 252.0f, 0.5f);
+      }
+      const uint64_t nmc2 = pk2(nmc, nmc);
+      auto chunk = [&](const uint32_t(&v)[16], int ch) {  // 16 columns: 8 pairs -> two 16-byte stores of the P row
+        uint32_t pk[8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          float p0, p1;
+          if (pair_is_poly<POLY>(e >> 1)) {
+            float u0, u1;
+            asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u0) : "f"(__uint_as_float(v[e])), "f"(cu), "f"(bu));
+            asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u1) : "f"(__uint_as_float(v[e + 1])), "f"(cu), "f"(bu));
+            const uint64_t u2 = pk2(u0, u1);
+            const uint64_t t2 = fma2(u2, k252, magicp);
+            const uint64_t f2 = fma2(u2, k252, sub2(magicp, t2));  // magicp - t = -(n + 126)
+            uint64_t q = fma2(f2, pk2(0.05517145f, 0.05517145f), pk2(0.24261084f, 0.24261084f));
+            q = fma2(q, f2, pk2(0.69326097f, 0.69326097f));
+            q = fma2(q, f2, pk2(0.99992812f, 0.99992812f));
+            float t0, t1, q0, q1;
+            un2(t2, t0, t1);
+            un2(q, q0, q1);
+            p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+            p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+          } else if constexpr (NOREF) {
+            p0 = ex2(__uint_as_float(v[e]));
+            p1 = ex2(__uint_as_float(v[e + 1]));
+          } else {
+            float x0, x1;
+            un2(fma2(pk2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), c2, nmc2), x0, x1);
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+          }
+          pk[e >> 1] = pack_pair<DT>(p0, p1);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t addr = p_buf + ((((uint32_t)(ch * 2 + u)) ^ rx) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
+                       "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
+                       : "memory");
+        }
+      };
+      tmem_ld16(t_s + 16, vb);  // in flight while chunk 0 is processed
+      chunk(va, 0);
+      tmem_ld_wait();
+      tmem_ld16(t_s + 32, va);
+      chunk(vb, 1);
+      tmem_ld_wait();
+      tmem_ld16(t_s + 48, vb);
+      chunk(va, 2);
+      tmem_ld_wait();
+      chunk(vb, 3);
+      tc_fence_before();    // our tcgen05.ld of S_i precede the MMA that overwrites the buffer
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      if (sb) named_bar_arrive<2, 160>();
+      else named_bar_arrive<1, 160>();
+    };
+    for (int i = 0; i < nst; i += 2) {  // nst = L / 64 is even; the S / P buffer index is a compile-time constant
+      step(i, std::integral_constant<int, 0>{});
+      step(i + 1, std::integral_constant<int, 1>{});
+    }
+    mbar_wait(pv_done, 0);
+    tc_fence_after();
+    uint32_t ov[32];
+    tmem_ld32(tmem_o + lane_base, ov);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < D; e += 2) o2[e >> 1] = pk2(__uint_as_float(ov[e]), __uint_as_float(ov[e + 1]));
+    l = __uint_as_float(ov[D]);
+    // NaN-safe.  An overflowed MUFU lane (+inf) or a polynomial lane clamped at 2^126 makes the tensor-core row sum exceed
+    // l_max (2^60 / 2^24 for fp16 P) or turn into inf / NaN
+    bad = !(l <= g.l_max) || (NOREF && !(l >= 7.8886090522101181e-31f));  // 2^-100
+    tc_fence_before();
+  }
+
+  // every row of the CTA takes the same decision: the MMAs are issued for the whole query tile
+  if (__syncthreads_or(bad)) {
+    // ===================== safe pass (rare): v11's online softmax over 128-key tiles, warps 0..3 =====================
+    if (warp < 4) {
+      constexpr int TILE = ATT_BN * ROWB;  // 4 KB
+      constexpr int W = D + 16;
+      uint8_t* sK = sKV;             // [2 stages]
+      uint8_t* sV = sKV + 2 * TILE;  // [2 stages]
+      const int nkv = g.L / ATT_BN;
+      const uint64_t p_desc = make_desc_k128(smem_u32(sP));
+      const uint32_t t_row = tmem_s + lane_base;
+      const uint32_t p_row2 = p_row;  // same row addressing, atom stride ATT_BM * 128 for keys >= 64
+      auto load_tile = [&](int t) {
+        const int s = t & 1;
+        const int tk = (int)(kv0 + (int64_t)t * ATT_BN);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&fb_kv[s], 2 * g.tile_bytes);
+          tma_load_2d(sK + s * TILE, &tmQ, &fb_kv[s], g.C + head * D, tk);
+          tma_load_2d(sV + s * TILE, &tmQ, &fb_kv[s], 2 * g.C + head * D, tk);
+        }
+      };
+      auto issue_s = [&](int t) {  // S = Q K_t^T (N = 128)
+        mbar_wait_spin(&fb_kv[t & 1], (uint32_t)(t >> 1) & 1u);
+        tc_fence_after();
+        const uint64_t kd = make_desc_rows(smem_u32(sK + (t & 1) * TILE), ROWB);
+        if (elect_one()) {
+          umma_ss(tmem_s, q_desc, kd, g.idesc_s, 0u);
+          if (NOREF) umma_ss(tmem_s, qlo_desc, kd, g.idesc_s, 1u);
+          umma_commit(fb_s);
+        }
+      };
+      auto issue_pv = [&](int t) {
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t v0 = smem_u32(sV + (t & 1) * TILE);
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k) {
+            const uint64_t pd = p_desc + (uint64_t)((k >> 2) * (ATT_BM * 128 / 16) + (k & 3) * 2);
+            const uint32_t slab = v0 + (uint32_t)(k * 16 * ROWB);
+            const uint64_t bd = (make_desc_rows(slab, ROWB) & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((ones_addr - slab) >> 4) << 16);
+            umma_ss(tmem_s, pd, bd, g.idesc_ol, (uint32_t)(k != 0));
+          }
+          umma_commit(fb_o);
+        }
+      };
+      auto tile_max = [&]() {
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t v[16];
+          tmem_ld16(t_row + ch * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        }
+        return mx;
+      };
+      if (warp == 0) {
+        load_tile(0);
+        if (nkv > 1) load_tile(1);
+        issue_s(0);
+        __syncwarp();
+      }
+#pragma unroll
+      for (int i = 0; i < D / 2; ++i) o2[i] = 0ull;
+      l = 0.f;
+      float m_ref = -INFINITY;
+      const float cs = NOREF ? 1.0f : g.c;  // NOREF: the Q tile in shared memory is already scaled by c
+      const uint64_t cs2 = pk2(cs, cs);
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t ph = (uint32_t)j & 1u;
+        mbar_wait(fb_s, ph);
+        tc_fence_after();
+        const float tmax = tile_max();
+        if (tmax > m_ref) {  // exact rescale of the running numerator / denominator (a0 = 0 on the first tile)
+          const float a0 = ex2((m_ref - tmax) * cs);
+          l *= a0;
+          const uint64_t a2 = pk2(a0, a0);
+#pragma unroll
+          for (int i = 0; i < D / 2; ++i) o2[i] = mul2(o2[i], a2);
+          m_ref = tmax;
+        }
+        const float nmc = -m_ref * cs;
+        const uint64_t nmc2 = pk2(nmc, nmc);
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t v[16];
+          tmem_ld16(t_row + ch * 16, v);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const uint64_t x2 = fma2(pk2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), cs2, nmc2);
+            float x0, x1;
+            un2(x2, x0, x1);
+            pk[e >> 1] = pack_pair<DT>(ex2(x0), ex2(x1));  // p <= 1 always
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int jj = ch * 2 + u;
+            const uint32_t addr = p_row2 + (uint32_t)(jj >> 3) * (ATT_BM * 128) + ((((uint32_t)jj & 7u) ^ rx) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
+                         "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
+                         : "memory");
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        if (warp == 0) {
+          named_bar_sync<3, 128>();
+          issue_pv(j);
+          __syncwarp();
+        } else {
+          named_bar_arrive<3, 128>();
+        }
+        mbar_wait(fb_o, ph);
+        tc_fence_after();
+        {
+          uint32_t v[32];
+          tmem_ld32(t_row, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) o2[i >> 1] = add2(o2[i >> 1], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          l += __uint_as_float(v[16]);
+        }
+        tc_fence_before();
+        if (j + 1 < nkv) {
+          if (warp == 0) {
+            named_bar_sync<4, 128>();
+            issue_s(j + 1);
+            if (j + 2 < nkv) load_tile(j + 2);
+            __syncwarp();
+          } else {
+            named_bar_arrive<4, 128>();
+          }
+        }
+      }
+    }
+  }
+  if (warp < 4) {
+    const float inv = 1.0f / l;
+    uint16_t* dst = out + tok * g.C + head * D;
+#pragma unroll
+    for (int i = 0; i < D; i += 8) {
+      float f[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) un2(o2[(i >> 1) + u], f[2 * u], f[2 * u + 1]);
+      uint4 w;
+      w.x = pack_pair<DT>(f[0] * inv, f[1] * inv);
+      w.y = pack_pair<DT>(f[2] * inv, f[3] * inv);
+      w.z = pack_pair<DT>(f[4] * inv, f[5] * inv);
+      w.w = pack_pair<DT>(f[6] * inv, f[7] * inv);
+      *reinterpret_cast<uint4*>(dst + i) = w;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_s) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_o) : "memory");
+  }
+}
+
+template <int DT, int POLY>
+static int launch_att12(const void* qkv, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
+  CUtensorMap tmQ, tmKV;
+  const uint64_t dims[2] = {(uint64_t)3 * g.C, (uint64_t)g.M};
+  const uint64_t strides[1] = {(uint64_t)3 * g.C * 2};
+  const uint32_t qbox[2] = {16u, (uint32_t)ATT_BM}, kbox[2] = {16u, (uint32_t)Att12::BN};
+  int rc;
+  if ((rc = make_tmap(&tmQ, g.act_dtype, 2, qkv, dims, strides, qbox, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_tmap(&tmKV, g.act_dtype, 2, qkv, dims, strides, kbox, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = set_max_smem<attention_tc12_kernel<DT, POLY>>(Att12::SMEM, "sg_attention(tc12)"))) return rc;
+  launch_k(attention_tc12_kernel<DT, POLY>, grid, dim3(160), (size_t)Att12::SMEM, stream, tmQ, tmKV, g, out);
+  return launch_status("sg_attention(tc12)");
+}
+
+}  // namespace tc
+
+// d = 16, L >= 128, M >= 128 (called by attention_tc)
+int attention_tc12(const void* qkv, const tc::AttGeom& g, uint16_t* out, dim3 grid, int poly, cudaStream_t stream) {
+  using namespace tc;
+  if (g.act_dtype == SG_BF16) {
+    if (poly == 2) return launch_att12<SG_BF16, 2>(qkv, g, out, grid, stream);
+    if (poly == 4) return launch_att12<SG_BF16, 4>(qkv, g, out, grid, stream);
+    return launch_att12<SG_BF16, 3>(qkv, g, out, grid, stream);
+  }
+  if (poly == 2) return launch_att12<SG_F16, 2>(qkv, g, out, grid, stream);
+  if (poly == 4) return launch_att12<SG_F16, 4>(qkv, g, out, grid, stream);
+  return launch_att12<SG_F16, 3>(qkv, g, out, grid, stream);
+}
+
+}  // namespace sg
