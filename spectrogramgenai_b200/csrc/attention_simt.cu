@@ -6,7 +6,7 @@
 
 namespace sg {
 
-int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, int variant,
+int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype,
                  cudaStream_t stream);  // attention_tc.cu
 
 template <int D>
@@ -109,9 +109,7 @@ extern "C" int sg_attention(const void* qkv, void* out, int rows, int L, int C, 
              rows, L, C, heads);
   const int d = C / heads;
   SG_REQUIRE(d == 16 || d == 32 || d == 64, "sg_attention: head dim %d not in {16,32,64}", d);
-  // engine >= 8: SG_ENGINE_TC with an explicit kernel generation (attention_tc's `variant`; tests / microbenchmarks)
-  if (engine == SG_ENGINE_TC) return attention_tc(qkv, out, rows, L, C, heads, act_dtype, 0, as_stream(stream));
-  if (engine >= 8) return attention_tc(qkv, out, rows, L, C, heads, act_dtype, engine, as_stream(stream));
+  if (engine == SG_ENGINE_TC) return attention_tc(qkv, out, rows, L, C, heads, act_dtype, as_stream(stream));
   SG_REQUIRE(engine == SG_ENGINE_SIMT, "sg_attention: engine %d", engine);
   SG_REQUIRE(act_dtype == SG_F32 || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_attention: bad out dtype");
   SG_REQUIRE(rows <= 65535 && heads <= 65535, "sg_attention: grid too large");

@@ -16,10 +16,10 @@
 //                 o = o*alpha + O_j   running output, max and sum stay in registers (fp32)
 // TMEM use is 128 columns (O_j aliases the dead S columns), so up to four CTAs share an SM and overlap each
 // other's MMA / MUFU / TMA phases; inside a CTA the phases are serial.
-// Three kernels live here: v8 (L >= 128, d = 32 / 64; four softmax warps, named-barrier hand-offs, packed fp32 body,
-// part of the exponentials on the FMA pipe), v11 (L >= 128, d = 16: v8 with tensor-core row sums) and v1 (the first
-// tcgen05 kernel: 192 threads, warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = softmax; used for L < 128, where
-// a tile holds several batch rows and needs the block-diagonal mask).  The measured history of the other variants
+// Two kernels live here: v8 (L >= 128, d = 32 / 64; four softmax warps, named-barrier hand-offs, packed fp32 body,
+// part of the exponentials on the FMA pipe) and v1 (the first tcgen05 kernel: 192 threads, warp 0 = TMA producer,
+// warp 1 = MMA issuer, warps 2..5 = softmax; used for L < 128, where a tile holds several batch rows and needs the
+// block-diagonal mask).  d = 16 with L >= 128 (sa5 / sa6, 85 % of the attention time) runs v12, attention_tc12.cu.  The measured history of the other variants
 // is in the dispatch comment of attention_tc() below and in profiles/README.md.
 #include <stdlib.h>
 
@@ -570,311 +570,6 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   }
 }
 
-// v11 = v8 with the row sums taken from the tensor core and a two-pass overflow scheme.
-//  * l = sum_j p_ij comes from eight extra M128 x N16 x K16 MMAs per key tile (A = the P tile the PV MMAs read, B = a
-//    512-byte tile of ones), accumulated next to the O partial in the dead S columns: the sweep loses its FADD2 per pair,
-//    which moves the balance point between the MUFU and the FMA pipe from 1/4 to 3/8 polynomial pairs
-//    (scripts/mufu_bench.cu: +9 % on the isolated body; in the kernel 4.11 -> 3.86 ms at sa6, rows = 256).
-//  * pass 0 (fast) never looks for the maximum: the reference is the maximum of the row's first 16 scores and a tile
-//    whose row sum (from the tensor core: +inf / NaN if a p overflowed) or polynomial-lane exponent leaves the safe
-//    range only raises a flag.  If any row of the CTA raised it, the whole query tile is recomputed in pass 1 (safe):
-//    the classical online softmax with a full-tile maximum before every sweep, where p <= 1 always.
-template <int D, int DT, int POLY, int NACC>
-__global__ void __launch_bounds__(128, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
-attention_tc11_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
-  constexpr int ROWB = D * 2;
-  constexpr int TILE = ATT_BN * ROWB;
-  // TMEM columns of accumulator a (NACC independent accumulation chains over the 8 k-steps of a key tile):
-  // O partial [a W, a W + D), row-sum partial [a W + D, a W + D + 16) (16 identical columns), W = D + 16
-  constexpr int W = D + 16;
-  static_assert(NACC * W <= 128 && (ATT_BN / 16) % NACC == 0, "accumulators must fit the dead S columns");
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE;      // [2 stages]
-  uint8_t* sV = sK + 2 * TILE;  // [2 stages]
-  uint8_t* sP = sV + 2 * TILE;
-  uint8_t* sOnes = sP + P_BYTES;  // [16 keys x D] 16-bit ones in V's layout: the second N atom of the PV MMAs' B operand
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ATT11_ONES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;  // [2]
-  uint64_t* s_full = bars + 3;
-  uint64_t* o_full = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // heads are the FASTEST grid dimension: the head slices of a token (d * 2 = 32..128 bytes) share 128-byte lines, so
-  // the heads of one query tile must run together to be served from L2 (with heads slowest, ncu showed 4x the
-  // algorithmic DRAM reads at sa6: every head pass re-fetched all of qkv)
-  const int head = blockIdx.x;
-  const int64_t m0 = ((int64_t)blockIdx.z * 32768 + blockIdx.y) * ATT_BM;
-  if (m0 >= g.M) return;  // ragged last grid.z slice (more than 32768 query tiles, not a multiple of it); nothing was touched yet
-  const int64_t kv0 = (m0 >> g.logL) << g.logL;
-  const int nkv = g.L / ATT_BN;
-  const bool leader = threadIdx.x == 0;
-
-  if (leader) {
-    prefetch_tensormap(&tm);
-    mbar_init(q_full, 1);
-    mbar_init(&kv_full[0], 1);
-    mbar_init(&kv_full[1], 1);
-    mbar_init(s_full, 1);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  {
-    const uint32_t one2 = DT == SG_BF16 ? 0x3F803F80u : 0x3C003C00u;  // two 1.0 values
-    for (int i = threadIdx.x; i < 16 * ROWB / 4; i += 128) reinterpret_cast<uint32_t*>(sOnes)[i] = one2;
-    fence_proxy_async();
-  }
-  if (warp == 0) {
-    __syncwarp();
-    tmem_alloc<128>(tmem_slot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // every activation access (TMA loads included) follows this point; parameters read above are immutable weights
-  pdl_launch_dependents();
-
-  // Issue helpers: called by ALL lanes of warp 0 (convergent); one elected lane executes the TMA / MMA instructions.
-  const uint64_t q_desc = make_desc_rows(smem_u32(sQ), ROWB);
-  const uint64_t p_desc = make_desc_k128(smem_u32(sP));
-  // barrier parities continue across the two passes: pass 1 starts after nkv completions of s_full / o_full and
-  // ceil / floor (nkv / 2) completions of kv_full[0] / kv_full[1]
-  int so_off = 0, kv_off0 = 0, kv_off1 = 0;
-  const uint32_t ones_addr = smem_u32(sOnes);
-  auto load_tile = [&](int t) {
-    const int s = t & 1;
-    const int tok = (int)(kv0 + (int64_t)t * ATT_BN);
-    if (elect_one()) {
-      mbar_arrive_expect_tx(&kv_full[s], 2 * g.tile_bytes);
-      tma_load_2d(sK + s * TILE, &tm, &kv_full[s], g.C + head * D, tok);
-      tma_load_2d(sV + s * TILE, &tm, &kv_full[s], 2 * g.C + head * D, tok);
-    }
-  };
-  auto issue_s = [&](int t) {  // S = Q K_t^T
-    mbar_wait_spin(&kv_full[t & 1], (uint32_t)((t >> 1) + ((t & 1) ? kv_off1 : kv_off0)) & 1u);
-    tc_fence_after();
-    const uint64_t kd = make_desc_rows(smem_u32(sK + (t & 1) * TILE), ROWB);
-    if (elect_one()) {
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) umma_ss(tmem_base, q_desc + 2 * k, kd + 2 * k, g.idesc_s, k != 0);
-      umma_commit(s_full);
-    }
-  };
-  auto issue_pv = [&](int t) {  // O_t = P V_t : A = P (K-major, two SWIZZLE_128B atoms of 64 keys), B = V MN-major
-    tc_fence_after();
-    if (elect_one()) {
-      // B = [V slab | ones slab]: N = D + 16 columns of an MN-major operand are two swizzle atoms along N, and the
-      // descriptor's leading-dimension offset is the distance between them -- the second atom is the tile of ones, so
-      // the same MMA (one read of P) yields the O partial in columns [0, D) and the row sums in [D, D + 16)
-      const uint32_t v0 = smem_u32(sV + (t & 1) * TILE);
-#pragma unroll
-      for (int k = 0; k < ATT_BN / 16; ++k) {
-        const uint64_t pd = p_desc + (uint64_t)((k >> 2) * (ATT_BM * 128 / 16) + (k & 3) * 2);
-        const uint32_t slab = v0 + (uint32_t)(k * 16 * ROWB);
-        const uint64_t bd = (make_desc_rows(slab, ROWB) & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((ones_addr - slab) >> 4) << 16);
-        umma_ss(tmem_base + (uint32_t)((k % NACC) * W), pd, bd, g.idesc_ol, k >= NACC);
-      }
-      umma_commit(o_full);
-    }
-  };
-  const int r = warp * 32 + lane;
-  const int64_t tok = m0 + r;
-  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-  const uint32_t rx = (uint32_t)(r & 7);
-  uint64_t o2[D / 2];
-  float m_ref = 0.f, l = 0.f;
-  const uint64_t c2 = pk2(g.c, g.c);
-  // row maximum of the current S tile (safe pass only)
-  auto tile_max = [&]() {
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int ch = 0; ch < 8; ++ch) {
-      uint32_t v[16];
-      tmem_ld16(t_row + ch * 16, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-    }
-    return mx;
-  };
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, g.tile_bytes);
-      tma_load_2d(sQ, &tm, q_full, head * D, (int)m0);
-    }
-    __syncwarp();
-  }
-  // one pass over the key tiles; `safe` is a compile-time tag so that the fast pass carries none of the safe pass's code
-  auto run_pass = [&](auto safe_tag) -> bool {
-    constexpr bool safe = decltype(safe_tag)::value;
-    if (warp == 0) {
-      load_tile(0);
-      if (nkv > 1) load_tile(1);
-      if (!safe) mbar_wait_spin(q_full, 0);
-      issue_s(0);
-      __syncwarp();
-    }
-#pragma unroll
-    for (int i = 0; i < D / 2; ++i) o2[i] = 0ull;  // two +0.0f
-    l = 0.f;
-    m_ref = -INFINITY;
-    bool bad = false;
-    for (int j = 0; j < nkv; ++j) {
-      const uint32_t ph = (uint32_t)(j + so_off) & 1u;
-      mbar_wait(s_full, ph);
-      tc_fence_after();
-      if constexpr (safe) {
-        const float tmax = tile_max();
-        if (tmax > m_ref) {  // exact rescale of the running numerator / denominator (a0 = 0 on the first tile)
-          const float a0 = ex2((m_ref - tmax) * g.c);
-          l *= a0;
-          const uint64_t a2 = pk2(a0, a0);
-#pragma unroll
-          for (int i = 0; i < D / 2; ++i) o2[i] = mul2(o2[i], a2);
-          m_ref = tmax;
-        }
-      } else if (j == 0) {
-        // fast pass: the reference is the maximum of the row's first 16 scores.  Any reference within the dynamic
-        // range of the 16-bit P / fp32 sums is exact enough, and it is never searched for again.
-        uint32_t v[16];
-        tmem_ld16(t_row, v);
-        tmem_ld_wait();
-        float mx = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-        m_ref = mx;
-      }
-      const float nmc = -m_ref * g.c;
-      const uint64_t nmc2 = pk2(nmc, nmc);
-      float xmax = -INFINITY;  // largest exponent seen by a polynomial lane (its exponent arithmetic wraps, no +inf)
-      {
-        uint32_t va[16], vb[16];
-        tmem_ld16(t_row, va);
-        tmem_ld_wait();
-        auto chunk = [&](const uint32_t(&v)[16], int ch) {  // 16 columns: 8 pairs -> two 16-byte stores of the P row
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const uint64_t x2 = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nmc2);
-            float p0, p1, x0, x1;
-            un2(x2, x0, x1);
-            if (pair_is_poly<POLY>(i >> 1)) {
-              xmax = max3(xmax, x0, x1);
-              ex2_poly2(x2, p0, p1);
-            } else {
-              p0 = ex2(x0);
-              p1 = ex2(x1);
-            }
-            pk[i >> 1] = pack_pair<DT>(p0, p1);
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int jj = ch * 2 + u;
-            const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + ((((uint32_t)jj & 7u) ^ rx) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                         "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                         : "memory");
-          }
-        };
-#pragma unroll
-        for (int ch = 0; ch < 8; ch += 2) {
-          tmem_ld16(t_row + (ch + 1) * 16, vb);  // in flight while chunk ch is processed
-          chunk(va, ch);
-          tmem_ld_wait();
-          if (ch + 2 < 8) tmem_ld16(t_row + (ch + 2) * 16, va);
-          chunk(vb, ch + 1);
-          if (ch + 2 < 8) tmem_ld_wait();
-        }
-      }
-      tc_fence_before();    // our tcgen05.ld of S precede the MMA that overwrites those columns
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      if (warp == 0) {
-        named_bar_sync<1, 128>();
-        issue_pv(j);
-        __syncwarp();
-      } else {
-        named_bar_arrive<1, 128>();
-      }
-      mbar_wait(o_full, ph);
-      tc_fence_after();
-      float l_part = 0.f;
-#pragma unroll
-      for (int acc = 0; acc < NACC; ++acc) {
-        if constexpr (D == 16) {
-          uint32_t v[32];
-          tmem_ld32(t_row + acc * W, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) o2[i >> 1] = add2(o2[i >> 1], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          l_part += __uint_as_float(v[16]);
-        } else {
-#pragma unroll
-          for (int cch = 0; cch < D / 32; ++cch) {
-            uint32_t v[32];
-            tmem_ld32(t_row + acc * W + cch * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2)
-              o2[cch * 16 + (i >> 1)] = add2(o2[cch * 16 + (i >> 1)], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          }
-          uint32_t v[16];
-          tmem_ld16(t_row + acc * W + D, v);
-          tmem_ld_wait();
-          l_part += __uint_as_float(v[0]);
-        }
-      }
-      l += l_part;
-      bad |= !(l_part <= g.l_max) || xmax > g.redo_log2;  // NaN-safe
-      tc_fence_before();
-      if (j + 1 < nkv) {
-        if (warp == 0) {
-          named_bar_sync<2, 128>();
-          // o_full(j) has been observed: every MMA that read K/V stage j&1 is complete -> it can be refilled with tile j+2
-          issue_s(j + 1);
-          if (j + 2 < nkv) load_tile(j + 2);
-          __syncwarp();
-        } else {
-          named_bar_arrive<2, 128>();
-        }
-      }
-    }
-    return bad;
-  };
-  // every row of the CTA takes the same decision: the MMAs are issued for the whole query tile
-  if (__syncthreads_or(run_pass(std::false_type{}))) {
-    so_off = nkv;
-    kv_off0 = (nkv + 1) >> 1;
-    kv_off1 = nkv >> 1;
-    run_pass(std::true_type{});
-  }
-  const float inv = 1.0f / l;
-  uint16_t* dst = out + tok * g.C + head * D;
-#pragma unroll
-  for (int i = 0; i < D; i += 8) {
-    float f[8];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) un2(o2[(i >> 1) + u], f[2 * u], f[2 * u + 1]);
-    uint4 w;
-    w.x = pack_pair<DT>(f[0] * inv, f[1] * inv);
-    w.y = pack_pair<DT>(f[2] * inv, f[3] * inv);
-    w.z = pack_pair<DT>(f[4] * inv, f[5] * inv);
-    w.w = pack_pair<DT>(f[6] * inv, f[7] * inv);
-    *reinterpret_cast<uint4*>(dst + i) = w;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    __syncwarp();
-    tmem_dealloc<128>(tmem_base);
-  }
-}
-
 template <int D, int DT, int POLY, int NACC>
 static int launch_att8(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
   constexpr int smem = att4_smem_bytes<D>();
@@ -883,24 +578,11 @@ static int launch_att8(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, d
   return launch_status("sg_attention(tc8)");
 }
 
-template <int D, int DT, int POLY, int NACC>
-static int launch_att11(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = att4_smem_bytes<D>() + ATT11_ONES;
-  if (int rc = set_max_smem<attention_tc11_kernel<D, DT, POLY, NACC>>(smem, "sg_attention(tc11)")) return rc;
-  launch_k(attention_tc11_kernel<D, DT, POLY, NACC>, grid, dim3(128), smem, stream, tm, g, out);
-  return launch_status("sg_attention(tc11)");
-}
-
-constexpr bool ATT_DEFAULT_V12 = true;
-
 }  // namespace tc
 
-int attention_tc12(const void* qkv, const tc::AttGeom& g, uint16_t* out, dim3 grid, int poly, cudaStream_t stream);  // attention_tc12.cu
+int attention_tc12(const void* qkv, const tc::AttGeom& g, uint16_t* out, dim3 grid, cudaStream_t stream);  // attention_tc12.cu
 
-// variant: 0 = the default kernel for the shape; 11 / 12 (+ 100 * eighths of polynomial exponentials for v12) = that
-// kernel generation for d = 16, L >= 128 (kernel tests and microbenchmarks compare the generations in one process)
-int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, int variant,
-                 cudaStream_t stream) {
+int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, int act_dtype, cudaStream_t stream) {
   using namespace tc;
   SG_REQUIRE(act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_attention(tc): act_dtype must be SG_BF16 or SG_F16");
   SG_REQUIRE(L > 0 && (L & (L - 1)) == 0, "sg_attention(tc): L=%d must be a power of two", L);
@@ -937,21 +619,19 @@ int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, 
   const int64_t tiles = cdiv(g.M, ATT_BM);
   dim3 grid((unsigned)heads, (unsigned)(tiles < 32768 ? tiles : 32768), (unsigned)cdiv(tiles, 32768));
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
-  // Kernel choice (measured on B200, bf16, rows = 128, ms; v2-v7 / v9 / v10 were experiments, see profiles/README.md):
-  //                           v1     v8     v11
-  //   d=16 L=4096 (sa6)       3.07   2.12   2.07      v11 (tensor-core row sums, 3/8 polynomial exp2, one accumulator) for
-  //   d=32 L=1024 (sa1)       0.347  0.188  (slower)  d = 16; v8 (1/4 polynomial exp2, two accumulators) for d = 32 / 64:
-  //   d=16 L=1024 (sa5)       0.226  0.152  0.147     the N = d + 16 PV MMA of v11 is slower than v8's there
+  // Kernel choice (measured on B200, bf16, ms; v2-v7 / v9 / v10 were experiments, see profiles/README.md):
+  //                           v1     v8     v11    v12
+  //   d=16 L=4096 rows=1024   -      -      15.74  14.30   v12 (attention_tc12.cu: double-buffered S, TMEM-resident output,
+  //   d=16 L=1024 rows=1024   -      1.22   1.07   1.01    reference-free exponent) for d = 16; v8 (named-barrier hand-offs,
+  //   d=32 L=1024 rows=128    0.347  0.188  -      -       1/4 polynomial exp2, two accumulators) for d = 32 / 64
   // L < 128: v1, whose tile holds 128 / L batch rows under a block-diagonal mask.
 #define SG_ATT_BY_DTYPE(CALL_BF16, CALL_F16) \
   do {                                       \
     if (act_dtype == SG_BF16) return CALL_BF16; \
     return CALL_F16;                         \
   } while (0)
-  if (L >= ATT_BN && d == 16 && (variant % 100 == 12 || (variant == 0 && ATT_DEFAULT_V12)))
-    return attention_tc12(qkv, g, o, grid, variant / 100, stream);
+  if (L >= ATT_BN && d == 16) return attention_tc12(qkv, g, o, grid, stream);
   if (L >= ATT_BN) {
-    if (d == 16) SG_ATT_BY_DTYPE((launch_att11<16, SG_BF16, 3, 1>(tm, g, o, grid, stream)), (launch_att11<16, SG_F16, 3, 1>(tm, g, o, grid, stream)));
     if (d == 32) SG_ATT_BY_DTYPE((launch_att8<32, SG_BF16, 2, 2>(tm, g, o, grid, stream)), (launch_att8<32, SG_F16, 2, 2>(tm, g, o, grid, stream)));
     SG_ATT_BY_DTYPE((launch_att8<64, SG_BF16, 2, 2>(tm, g, o, grid, stream)), (launch_att8<64, SG_F16, 2, 2>(tm, g, o, grid, stream)));
   }

@@ -9,7 +9,9 @@ writes its own PNG files.
 from __future__ import annotations
 
 import argparse
+import json
 import os
+import time
 from types import SimpleNamespace
 
 import torch
@@ -40,6 +42,10 @@ def parse_args(argv=None):
     p.add_argument("--compute_dtype", type=str, default="bf16", choices=["bf16", "f16", "fp32"])
     p.add_argument("--batch_samples", type=int, default=512,
                    help="spectrograms per sampling call (several samp_i are generated together; images do not depend on it)")
+    p.add_argument("--colormap", type=str, default="viridis", choices=["viridis", "gray"],
+                   help="viridis = matplotlib.cm.viridis as the reference (needs matplotlib); gray = built-in grey ramp "
+                        "(same RGBA PNG format; for boxes without matplotlib)")
+    p.add_argument("--timing_json", type=str, default=None, help="write this rank's timing summary to <path>.<rank>")
     a = p.parse_args(argv)
     for k, v in vars(a).items():
         setattr(c, k, v)
@@ -61,6 +67,13 @@ def main(argv=None):
     diffuser = DiffusionVAE(config.noise_steps, img_size=config.img_size, num_classes=config.num_classes,
                             device=f"cuda:{local}", vqae_path=config.vqae_path, sav_denoise_path=config.sav_denoise_path,
                             class_names=class_names, compute_dtype=config.compute_dtype)
+    if config.colormap == "gray":
+        import numpy as np
+
+        ramp = np.linspace(0.0, 1.0, 256, dtype=np.float32)
+        lut = np.stack([ramp, ramp, ramp, np.ones_like(ramp)], axis=1)
+        diffuser.colormap = lambda a: lut[np.asarray(a, dtype=np.uint8)] if np.asarray(a).dtype == np.uint8 \
+            else lut[(np.clip(np.asarray(a), 0, 1) * 255).astype(np.uint8)]
     diffuser.prepare(config)
     diffuser.load_model(config)
     # each rank takes a contiguous block of samp_i and samples several of them per call so that the batch fills the GPU;
@@ -73,17 +86,47 @@ def main(argv=None):
     labels = torch.arange(config.num_classes).long()
     from concurrent.futures import ThreadPoolExecutor
 
+    stats = {"rank": rank, "world": world, "spectrograms": 0, "sample_s": 0.0, "write_s": 0.0, "write_wait_s": 0.0,
+             "gpu_launches": 0}
+
+    def timed_write(*a):
+        t0 = time.perf_counter()
+        paths = diffuser.write_images(*a)
+        stats["write_s"] += time.perf_counter() - t0
+        return paths
+
+    t_all = time.perf_counter()
+    if config.sav_denoise_path:
+        # (:765-769) trajectory dumps instead of final images; they are named by class only, so one pass over the classes
+        for samp_i in range(config.start_idx + lo, config.start_idx + hi):
+            diffuser.gen_images(config.img_folder, samp_i, labels, seed=config.seed,
+                                sample_base=samp_i * config.num_classes)
+        print("done!")
+        return
     with ThreadPoolExecutor(max_workers=1) as writer:  # colour map + PNG encoding of batch k overlap the sampling of k+1
         pending = None
         for first in range(config.start_idx + lo, config.start_idx + hi, group):
             samp_is = list(range(first, min(first + group, config.start_idx + hi)))
+            t0 = time.perf_counter()
             images = diffuser.sample(False, labels.repeat(len(samp_is)), seed=config.seed,
                                      sample_base=first * config.num_classes)
+            torch.cuda.synchronize()
+            stats["sample_s"] += time.perf_counter() - t0
+            stats["gpu_launches"] += diffuser.gpu_launches
+            stats["spectrograms"] += len(samp_is) * len(labels)
+            t0 = time.perf_counter()
             if pending is not None:
                 pending.result()
-            pending = writer.submit(diffuser.write_images, config.img_folder, samp_is, labels, images)
+            stats["write_wait_s"] += time.perf_counter() - t0
+            pending = writer.submit(timed_write, config.img_folder, samp_is, labels, images)
+        t0 = time.perf_counter()
         if pending is not None:
             pending.result()
+        stats["write_wait_s"] += time.perf_counter() - t0
+    stats["total_s"] = time.perf_counter() - t_all
+    if config.timing_json:
+        with open(f"{config.timing_json}.{rank}", "w") as f:
+            json.dump(stats, f)
     print("done!")
 
 
