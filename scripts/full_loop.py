@@ -12,17 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spectrogramgenai_b200.diff_modules import DiffusionVAE  # noqa: E402
 
 
-def synthetic_vqae(seed=0):
-    """Random VQAE decoder + codebook of the reference's shapes (diff_modules.py:266-270, :326-334)."""
-    g = torch.Generator().manual_seed(seed)
-    u = lambda *shape, fan: (torch.rand(shape, generator=g) * 2 - 1) * (3.0 / fan) ** 0.5  # noqa: E731
-    return {"codebook.embedding": torch.rand(512, 4, generator=g) * 2 - 1,
-            "decoder.in_proj.weight": u(512, 4, 1, 1, fan=4), "decoder.in_proj.bias": u(512, fan=300),
-            "decoder.residual_conv_1.weight": u(512, 512, 1, 1, fan=512), "decoder.residual_conv_1.bias": u(512, fan=300),
-            "decoder.residual_conv_2.weight": u(512, 512, 3, 3, fan=4608), "decoder.residual_conv_2.bias": u(512, fan=300),
-            "decoder.strided_t_conv_1.weight": u(512, 512, 2, 2, fan=512), "decoder.strided_t_conv_1.bias": u(512, fan=300),
-            "decoder.strided_t_conv_2.weight": u(512, 1, 2, 2, fan=512), "decoder.strided_t_conv_2.bias": u(1, fan=300)}
-
+from scripts.synth import synthetic_vqae  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 mode = sys.argv[2] if len(sys.argv) > 2 else "bf16"

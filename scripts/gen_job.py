@@ -29,19 +29,9 @@ def main():
     ap.add_argument("--keep", action="store_true")
     a = ap.parse_args()
     shutil.rmtree(a.work, ignore_errors=True)
-    # synthetic checkpoints are written by a separate process (importing full_loop runs its benchmark otherwise)
-    code = ("import sys, os, torch; sys.path.insert(0, %r);\n"
-            "import importlib.util\n"
-            "src = open(os.path.join(%r, 'scripts', 'full_loop.py')).read().split('n = int(sys.argv[1])')[0]\n"
-            "ns = {}; exec(compile(src, 'full_loop_head', 'exec'), ns)\n"
-            "from spectrogramgenai_b200.diff_modules import UNet_conditional\n"
-            "w = %r\n"
-            "os.makedirs(os.path.join(w, 'models', 'DDPM_conditional_VAE'), exist_ok=True); os.makedirs(os.path.join(w, 'models', 'VQAE'), exist_ok=True)\n"
-            "[os.makedirs(os.path.join(w, 'data', 'train', 'class%%02d' %% k), exist_ok=True) for k in range(27)]\n"
-            "torch.manual_seed(42); m = UNet_conditional(4, 4, num_classes=27)\n"
-            "torch.save(m.state_dict(), os.path.join(w, 'models', 'DDPM_conditional_VAE', 'ckpt.pt')); torch.save({}, os.path.join(w, 'models', 'DDPM_conditional_VAE', 'optim.pt'))\n"
-            "torch.save(ns['synthetic_vqae'](), os.path.join(w, 'models', 'VQAE', 'ckpt.pt'))\n") % (ROOT, ROOT, a.work)
-    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    from scripts.synth import write_generation_inputs
+
+    write_generation_inputs(a.work)
     out_dir = os.path.join(a.work, "diffusion_samples")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
            "--master-port", "29517", "-m", "spectrogramgenai_b200.generate", "--run_name", "DDPM_conditional_VAE",
