@@ -476,7 +476,10 @@ def main():
     # ---- e2e: public API, pinned host labels in, uint8 host images out, the one NCCL gather included ----
     labels_host = labels.clone().pin_memory()
     out_host = torch.empty((world * n, c, S, S), dtype=torch.uint8).pin_memory() if rank == 0 else None
-    d.sample(False, labels_host, 3, seed=seed, sample_base=base, micro_batch=n, max_steps=1)  # warm the API path
+    warm = d.sample(False, labels_host, 3, seed=seed, sample_base=base, micro_batch=n, max_steps=1)  # warm the API path
+    if world > 1:
+        gather_shards(warm, world * n, dst=0)  # ... and NCCL's point-to-point channels (set up lazily on first use)
+    del warm
     sync_all()
     t0 = time.perf_counter()
     u8 = d.sample(False, labels_host, 3, seed=seed, sample_base=base, micro_batch=n, max_steps=K)

@@ -388,12 +388,17 @@ class Diffusion:
         if colormap is None:
             colormap = getattr(self, "colormap", None) or _viridis()
         class_names = getattr(self, "class_names", None) or [str(k) for k in range(self.num_classes or 0)]
-        lab_list = torch.as_tensor(labels).reshape(-1).tolist()
+        lab_list = torch.as_tensor(labels).reshape(-1).tolist() if samp_is is not None else None
         host = sampled_images.cpu().numpy()
         jobs = []
-        for g, samp_i in enumerate(samp_is):
-            for i, lab in enumerate(lab_list):
-                jobs.append((g * len(lab_list) + i, f"{img_folder}/{class_names[lab]}_gen_imgs_{i}_{samp_i}.png"))
+        if samp_is is None:
+            # `labels` = explicit (class id, i, samp_i) triples, one per image: a slice of the flattened (samp_i, class) list
+            for k, (lab, i, samp_i) in enumerate(labels):
+                jobs.append((k, f"{img_folder}/{class_names[lab]}_gen_imgs_{i}_{samp_i}.png"))
+        else:
+            for g, samp_i in enumerate(samp_is):
+                for i, lab in enumerate(lab_list):
+                    jobs.append((g * len(lab_list) + i, f"{img_folder}/{class_names[lab]}_gen_imgs_{i}_{samp_i}.png"))
 
         def one(job):
             k, path = job

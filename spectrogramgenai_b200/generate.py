@@ -1,7 +1,6 @@
 """Generation driver: the B200 counterpart of /root/reference/src/ddpm_conditional_generate.py (same flags, same
-output files).  One process per GPU; with torchrun the sample indices [start_idx, start_idx + num_samples) are split
-across ranks (each index is one `gen_images` call = one spectrogram per class), so no collective is needed: every rank
-writes its own PNG files.
+output files).  One process per GPU; with torchrun the flattened list of (samp_i, class) spectrograms is split across
+ranks in contiguous, balanced slices, so no collective is needed: every rank writes its own PNG files.
 
     python -m spectrogramgenai_b200.generate --run_name DDPM_conditional_VAE --num_samples 50 --img_folder diffusion_samples
     torchrun --nproc-per-node 8 -m spectrogramgenai_b200.generate ...
@@ -76,13 +75,15 @@ def main(argv=None):
             else lut[(np.clip(np.asarray(a), 0, 1) * 255).astype(np.uint8)]
     diffuser.prepare(config)
     diffuser.load_model(config)
-    # each rank takes a contiguous block of samp_i and samples several of them per call so that the batch fills the GPU;
-    # the Philox stream is keyed by (seed, global sample index = samp_i * num_classes + class): every image is the same
-    # on any rank count and for any grouping
+    # The job is the flattened list of (samp_i, class) pairs: global sample index g = (samp_i - start_idx) * num_classes + i,
+    # file {class}_gen_imgs_{i}_{samp_i}.png.  Each rank takes a contiguous slice of it (balanced to one spectrogram) and
+    # samples it in batches of --batch_samples; the Philox stream is keyed by (seed, start_idx * num_classes + g), so every
+    # image is the same on any rank count and for any batching.
     from .sharding import shard_bounds
 
-    lo, hi = shard_bounds(config.num_samples, world, rank)
-    group = max(1, config.batch_samples // config.num_classes)
+    total = config.num_samples * config.num_classes
+    lo, hi = shard_bounds(total, world, rank)
+    group = max(1, config.batch_samples)
     labels = torch.arange(config.num_classes).long()
     from concurrent.futures import ThreadPoolExecutor
 
@@ -98,27 +99,28 @@ def main(argv=None):
     t_all = time.perf_counter()
     if config.sav_denoise_path:
         # (:765-769) trajectory dumps instead of final images; they are named by class only, so one pass over the classes
-        for samp_i in range(config.start_idx + lo, config.start_idx + hi):
+        for samp_i in range(config.start_idx + rank, config.start_idx + config.num_samples, world):
             diffuser.gen_images(config.img_folder, samp_i, labels, seed=config.seed,
                                 sample_base=samp_i * config.num_classes)
         print("done!")
         return
     with ThreadPoolExecutor(max_workers=1) as writer:  # colour map + PNG encoding of batch k overlap the sampling of k+1
         pending = None
-        for first in range(config.start_idx + lo, config.start_idx + hi, group):
-            samp_is = list(range(first, min(first + group, config.start_idx + hi)))
+        for first in range(lo, hi, group):
+            idx = range(first, min(first + group, hi))
+            entries = [(g % config.num_classes, g % config.num_classes, config.start_idx + g // config.num_classes) for g in idx]
             t0 = time.perf_counter()
-            images = diffuser.sample(False, labels.repeat(len(samp_is)), seed=config.seed,
-                                     sample_base=first * config.num_classes)
+            images = diffuser.sample(False, torch.tensor([e[0] for e in entries]), seed=config.seed,
+                                     sample_base=config.start_idx * config.num_classes + first)
             torch.cuda.synchronize()
             stats["sample_s"] += time.perf_counter() - t0
             stats["gpu_launches"] += diffuser.gpu_launches
-            stats["spectrograms"] += len(samp_is) * len(labels)
+            stats["spectrograms"] += len(entries)
             t0 = time.perf_counter()
             if pending is not None:
                 pending.result()
             stats["write_wait_s"] += time.perf_counter() - t0
-            pending = writer.submit(timed_write, config.img_folder, samp_is, labels, images)
+            pending = writer.submit(timed_write, config.img_folder, None, entries, images)
         t0 = time.perf_counter()
         if pending is not None:
             pending.result()
