@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import torch
 from spectrogramgenai_b200 import ops
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-engs = [int(e) for e in sys.argv[2].split(",")] if len(sys.argv) > 2 else [11, 12]
+engs = [1]
 L, C = 4096, 64
 g = torch.Generator(device="cuda").manual_seed(3)
 qkv = torch.randn(rows * L, 3 * C, device="cuda", generator=g).to(torch.bfloat16)

@@ -163,54 +163,61 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      mbar_wait_spin(q_full, 0);
-      const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
-      for (int j = 0; j < g.nkv; ++j) {
-        const int s = j % STAGES;
-        mbar_wait_spin(&kv_full[s], (uint32_t)(j / STAGES) & 1u);
-        tc_fence_after();
-        const uint32_t st = smem_u32(sKV + s * A::KV_STAGE);
-        // S = Q K^T = Ql Kh + Qh Kl + Qh Kh: K-major A and B, K = d in steps of 8 floats (32 bytes inside the swizzle span).
-        // The S columns are free: p_ready(j-1) was observed before P_{j-1} V was issued.
+    // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, descriptors stay in uniform registers, one elected
+    // lane issues -- inside an `if (lane == 0)` region every MMA costs ~15 dependent single-lane instructions, and this
+    // kernel issues 30 small MMAs per key tile =====
+    mbar_wait_spin(q_full, 0);
+    const uint64_t qd0 = make_desc_f(smem_u32(sQ), ROWB, 0);          // + Q_TILE / 16: the lo part; + Q_ATOM / 16: next atom
+    const uint64_t pd0 = make_desc_k128(smem_u32(sP));                // + P_TILE / 16: the lo part
+    for (int j = 0; j < g.nkv; ++j) {
+      const int s = j % STAGES;
+      mbar_wait_spin(&kv_full[s], (uint32_t)(j / STAGES) & 1u);
+      tc_fence_after();
+      const uint32_t st = smem_u32(sKV + s * A::KV_STAGE);
+      const uint64_t kd0 = make_desc_f(st, ROWB, 0);                    // K_hi; + KV_TILE / 16: K_lo
+      const uint64_t vd0 = make_desc_k128(st + 2 * A::KV_TILE);         // Vt_hi; + KV_TILE / 16: Vt_lo
+      // S = Q K^T = Ql Kh + Qh Kl + Qh Kh: K-major A and B, K = d in steps of 8 floats (32 bytes inside the swizzle span).
+      // The S columns are free: p_ready(j-1) was observed before P_{j-1} V was issued.
+      if (elect_one()) {
         uint32_t acc = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint32_t qt = qa + (t == 0 ? A::Q_TILE : 0);
-          const uint32_t kt = st + (t == 1 ? A::KV_TILE : 0);
+          const uint64_t qd = qd0 + (uint64_t)((t == 0 ? A::Q_TILE : 0) >> 4);
+          const uint64_t kd = kd0 + (uint64_t)((t == 1 ? A::KV_TILE : 0) >> 4);
 #pragma unroll
           for (int a = 0; a < NATOM; ++a) {
-            const uint64_t qd = make_desc_f(qt + a * A::Q_ATOM, ROWB, 0);
-            const uint64_t kd = make_desc_f(kt + a * A::KV_ATOM, ROWB, 0);
 #pragma unroll
             for (int k = 0; k < AE / 8; ++k) {
-              umma_ss_tf32(tmem_base, qd + 2 * k, kd + 2 * k, g.idesc_s, acc);
+              umma_ss_tf32(tmem_base, qd + (uint64_t)((a * A::Q_ATOM) >> 4) + 2 * k, kd + (uint64_t)((a * A::KV_ATOM) >> 4) + 2 * k,
+                           g.idesc_s, acc);
               acc = 1;
             }
           }
         }
         umma_commit(s_full);
-        // O_j = P V = Pl Vh + Ph Vl + Ph Vh: A = P and B = V^T, both K-major in two 32-key SWIZZLE_128B atoms
-        mbar_wait_spin(p_ready, (uint32_t)j & 1u);
-        if (j > 0) mbar_wait_spin(o_read, (uint32_t)(j - 1) & 1u);  // O_{j-1} has been added to the running output
-        tc_fence_after();
-        acc = 0;
+      }
+      __syncwarp();
+      // O_j = P V = Pl Vh + Ph Vl + Ph Vh: A = P and B = V^T, both K-major in two 32-key SWIZZLE_128B atoms
+      mbar_wait_spin(p_ready, (uint32_t)j & 1u);
+      if (j > 0) mbar_wait_spin(o_read, (uint32_t)(j - 1) & 1u);  // O_{j-1} has been added to the running output
+      tc_fence_after();
+      if (elect_one()) {
+        uint32_t acc = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint32_t pt = pa + (t == 0 ? A::P_TILE : 0);
-          const uint32_t vt = st + 2 * A::KV_TILE + (t == 1 ? A::KV_TILE : 0);
+          const uint64_t pd = pd0 + (uint64_t)((t == 0 ? A::P_TILE : 0) >> 4);
+          const uint64_t vd = vd0 + (uint64_t)((t == 1 ? A::KV_TILE : 0) >> 4);
 #pragma unroll
           for (int k = 0; k < BN / 8; ++k) {
-            const uint64_t pd = make_desc_k128(pt + (k >> 2) * A::P_ATOM + (k & 3) * 32);
-            const uint64_t vd = make_desc_k128(vt + (k >> 2) * A::VT_ATOM + (k & 3) * 32);
-            umma_ss_tf32(tmem_o, pd, vd, g.idesc_o, acc);
+            umma_ss_tf32(tmem_o, pd + (uint64_t)(((k >> 2) * A::P_ATOM + (k & 3) * 32) >> 4),
+                         vd + (uint64_t)(((k >> 2) * A::VT_ATOM + (k & 3) * 32) >> 4), g.idesc_o, acc);
             acc = 1;
           }
         }
         umma_commit(&kv_empty[s]);
         umma_commit(o_full);
       }
+      __syncwarp();
     }
   } else {
     // ===== softmax + epilogue: thread = one query row (TMEM lane quadrant = warp % 4) =====
@@ -225,7 +232,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
     const uint32_t rx = (uint32_t)(r & 7);
     for (int j = 0; j < g.nkv; ++j) {
-      mbar_wait(s_full, (uint32_t)j & 1u);
+      mbar_wait_spin(s_full, (uint32_t)j & 1u);
       tc_fence_after();
       // ONE sweep over S: p = exp2(s c - m_ref c) against the maximum known BEFORE this tile, the tile maximum as a
       // by-product.  Exact algebra (o, l are rescaled afterwards); the sweep is repeated only when the tile maximum
@@ -251,8 +258,10 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
               float p;
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s0, g.c, -mc)));
               psum += p;
-              ph[u] = tf32_rna(p);
-              pl[u] = tf32_rna(p - ph[u]);
+              // hi = p rounded to TF32 with two integer instructions (p >= 0; cvt.rna.tf32 would put two more conversions
+              // per element on the pipe the exponential already occupies); lo = p - hi is exact, the MMA reads its top 19 bits
+              ph[u] = __uint_as_float((__float_as_uint(p) + 0x1000u) & 0xFFFFE000u);
+              pl[u] = p - ph[u];
             }
             const uint32_t addr = p_row + (uint32_t)cch * A::P_ATOM + ((((uint32_t)i4) ^ rx) << 4);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(ph[0]), "f"(ph[1]), "f"(ph[2]),
@@ -279,7 +288,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
       // ---- O_j and the row sum, both relative to m_ref ----
-      mbar_wait(o_full, (uint32_t)j & 1u);
+      mbar_wait_spin(o_full, (uint32_t)j & 1u);
       tc_fence_after();
 #pragma unroll
       for (int cch = 0; cch < D / 16; ++cch) {
