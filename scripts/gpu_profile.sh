@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-end evidence, ONE ncu command per gpurun call (each follows a plain run of the same command that exited 0):
-#   bash scripts/gpu_profile.sh launches   -> gpurun_out/ncu_launches_r1_final.csv   (launch list of the bench command)
+#   bash scripts/gpu_profile.sh launches   -> gpurun_out/ncu_launches_r2.csv   (launch list of the bench command)
 #   bash scripts/gpu_profile.sh attention  -> gpurun_out/prof_attention_bench.ncu-rep (six attention launches, --set full)
 #   bash scripts/gpu_profile.sh fused      -> gpurun_out/prof_membound.ncu-rep        (fused SelfAttention + Up-block kernels)
 #   bash scripts/gpu_profile.sh conv|gn    -> gpurun_out/prof_{conv,gn}_bench.ncu-rep (scripts/prof_kernels.py shapes)
@@ -10,7 +10,7 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 case "${1:-launches}" in
   launches)
     $CMD > gpurun_out/plain_bench.log 2>&1 &&
-    ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/ncu_launches_r1_final.csv $CMD > gpurun_out/ncu_launches.log 2>&1 ;;
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/ncu_launches_r2.csv $CMD > gpurun_out/ncu_launches.log 2>&1 ;;
   attention)
     $CMD > gpurun_out/plain_bench.log 2>&1 &&
     ncu --set full --clock-control none --import-source on -k regex:attention_tc -c 6 -o gpurun_out/prof_attention_bench -f $CMD > gpurun_out/ncu_attn_bench.log 2>&1 ;;

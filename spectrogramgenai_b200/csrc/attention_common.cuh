@@ -9,7 +9,6 @@ namespace tc {
 constexpr int ATT_BM = 128;   // queries per CTA
 constexpr int ATT_BN = 128;   // keys per tile
 constexpr int P_BYTES = ATT_BM * ATT_BN * 2;  // 32 KB: two SWIZZLE_128B atoms of 64 keys
-constexpr int ATT11_ONES = 2048;               // v11: [16 keys x d] 16-bit tile of ones (d <= 64)
 
 // generic K-/MN-major descriptor for tiles whose rows are one swizzle span of `row_bytes` (32 / 64 / 128)
 __device__ __forceinline__ uint64_t make_desc_rows(uint32_t saddr, int row_bytes) {
@@ -57,10 +56,10 @@ struct AttGeom {
   int nkv;            // key tiles per query tile
   float c;            // softmax scale * log2(e)
   uint32_t tile_bytes;  // bytes of one TMA box (d*2 * min(128, M))
-  uint32_t idesc_s, idesc_o, idesc_1, idesc_ol;  // idesc_ol: v11, N = d + 16 (O partial | row sums)
+  uint32_t idesc_s, idesc_o, idesc_ol;  // idesc_ol: v12, N = d + 16 (O | row sums)
   int act_dtype;
   float redo_log2;  // largest tolerated (tile max - reference max) * c before the tile is recomputed
-  float l_max;      // v11: largest tolerated row sum of one key tile in the fast pass
+  float l_max;      // v12: largest tolerated row sum of the fast pass
 };
 
 

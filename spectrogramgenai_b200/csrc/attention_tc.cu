@@ -603,7 +603,6 @@ int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, 
   g.tile_bytes = box_rows * (uint32_t)d * 2u;
   g.idesc_s = make_idesc(act_dtype, 128, ATT_BN, 0, 0);
   g.idesc_o = make_idesc(act_dtype, 128, d, 0, 1);  // B = V is MN-major
-  g.idesc_1 = make_idesc(act_dtype, 128, 16, 0, 0);
   g.idesc_ol = make_idesc(act_dtype, 128, d + 16, 0, 1);
   g.redo_log2 = act_dtype == SG_BF16 ? 60.0f : 13.0f;  // p <= 2^60 (bf16/fp32 range) / 2^13 (fp16 max 65504)
   g.l_max = act_dtype == SG_BF16 ? 1.152921504606847e18f : 16777216.0f;  // 2^60 / 2^24 (an overflowed fp16 p is +inf)
