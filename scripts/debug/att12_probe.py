@@ -23,24 +23,10 @@ def run(qkv, rows, L, C, eng):
     return out.cpu()
 
 for dt in (torch.bfloat16, torch.float16):
-    for rows, L in [(1, 128), (2, 256), (1, 1024), (2, 4096), (3, 4096)]:
+    for rows, L in [(1, 128), (2, 256), (1, 1024), (2, 4096)]:
         C = 64
         qkv = (torch.randn(rows * L, 3 * C, generator=torch.Generator().manual_seed(12)) * 1.5).to(dt)
-        r = ref(qkv.float(), rows, L, C)
-        e11, e12 = rel(run(qkv, rows, L, C, 11), r), rel(run(qkv, rows, L, C, 12), r)
-        print(f"{dt} rows={rows} L={L}: v11 {e11:.3e}  v12 {e12:.3e}  v12(poly2) {rel(run(qkv, rows, L, C, 212), r):.3e} v12(poly4) {rel(run(qkv, rows, L, C, 412), r):.3e}")
-    # growing scores / overflow of the lazily chosen reference -> safe pass
-    for rows, L in [(2, 1024), (1, 4096), (2, 512)]:
-        C = 64
-        g = torch.Generator().manual_seed(13)
-        qkv = torch.randn(rows * L, 3 * C, generator=g)
-        ramp = torch.linspace(0.2, 9.0, L).repeat(rows)[:, None]
-        qkv[:, C:2 * C] *= ramp
-        qkv[:, :C] *= 3.0
-        qkv = qkv.to(dt)
-        r = ref(qkv.float(), rows, L, C)
-        print(f"{dt} growing rows={rows} L={L}: v11 {rel(run(qkv, rows, L, C, 11), r):.3e}  v12 {rel(run(qkv, rows, L, C, 12), r):.3e}")
-
+        print(f"{dt} rows={rows} L={L}: rel {rel(run(qkv, rows, L, C, 1), ref(qkv.float(), rows, L, C)):.3e}")
 print("=== timing (bf16)")
 def timeit(fn, reps=10):
     for _ in range(3): fn()
@@ -58,6 +44,6 @@ for rows, L in [(128, 4096), (256, 4096), (1024, 4096), (1024, 1024)]:
         qkv[r0 * L:(r0 + 128) * L] = torch.randn(128 * L, 3 * C, device=DEV, generator=g).to(torch.bfloat16)
     out = torch.empty(rows * L, C, device=DEV, dtype=torch.bfloat16)
     res = {}
-    for eng in (11, 12, 212, 412):
-        res[eng] = timeit(lambda: ops.attention(qkv, out, rows=rows, L=L, C=C, engine=eng), reps=5 if rows >= 1024 else 10)
+    for eng in (1,):
+        res[eng] = min(timeit(lambda: ops.attention(qkv, out, rows=rows, L=L, C=C, engine=eng), reps=5 if rows >= 1024 else 10) for _ in range(3))
     print(f"rows={rows} L={L}: " + "  ".join(f"eng{e} {t:.3f} ms" for e, t in res.items()), flush=True)

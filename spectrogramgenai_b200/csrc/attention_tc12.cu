@@ -29,7 +29,7 @@ namespace sg {
 namespace tc {
 
 struct Att12 {
-  static constexpr int D = 16, ROWB = 32, BN = 64, KVS = 6;
+  static constexpr int D = 16, ROWB = 32, BN = 64, KVS = 8;  // KVS: a power of two (stage = tile & 7)
   static constexpr int Q_TILE = ATT_BM * ROWB;      // 4 KB
   static constexpr int KV_TILE = BN * ROWB;         // 2 KB (fast pass); the safe pass uses 128-key tiles of 4 KB
   static constexpr int RING = KVS * 2 * KV_TILE;    // 24 KB >= the safe pass's 2 stages x (K, V) x 4 KB
@@ -151,28 +151,52 @@ attention_tc12_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     issue_s(0);
     issue_s(1);
     __syncwarp();
-    for (int i = 0; i < nst; ++i) {
-      const int sb = i & 1;
+    // The loop below runs once per 64-key tile on the SM sub-partition that also hosts softmax warp 0 of every resident
+    // CTA, so it is written for instruction count: descriptors are 32-bit low words advanced by constants (the high word
+    // never changes), the ring stage is tile & 7, and ONE elected lane does the whole step -- P V MMAs, the mbarrier
+    // wait for K_{i+2}, the S MMAs and the TMA of tile i+6 (only the issuing lane has to observe the barrier).
+    const uint32_t kv_base = smem_u32(sKV);
+    constexpr uint32_t HI_ROWS = (uint32_t)((8 * ROWB) >> 4) | (1u << 14) | (6u << 29);  // SBO, bit 46, SWIZZLE_32B
+    constexpr uint32_t STAGE_K = (uint32_t)(2 * A::KV_TILE) >> 4, STAGE_V = STAGE_K - (STAGE_K << 16);
+    constexpr uint32_t SLAB_V = (uint32_t)(16 * ROWB >> 4) - ((uint32_t)(16 * ROWB >> 4) << 16);
+    const uint32_t k_lo0 = (kv_base >> 4) | (1u << 16);
+    // O += P_i V_i : A = P_i in TMEM (packed 16-bit pairs over the S columns the softmax warps have consumed), B = [V slab |
+    // ones] consumed MN-major: the N = d + 16 columns are two swizzle atoms along N and the leading-dimension offset (bits
+    // 16..29 of the low word) is the distance between them
+    const uint32_t v_lo0 = ((kv_base + A::KV_TILE) >> 4) | (((ones_addr - kv_base - A::KV_TILE) >> 4) << 16);
+    auto issue_step = [&](int i, auto sb_tag) {
+      constexpr int sb = decltype(sb_tag)::value;
       if (sb) named_bar_sync<2, 160>();
       else named_bar_sync<1, 160>();
       tc_fence_after();
-      // O += P_i V_i : A = P_i (K-major, one SWIZZLE_128B atom of 64 keys), B = [V slab | ones] consumed MN-major: the
-      // N = d + 16 columns are two swizzle atoms along N and the leading-dimension offset is the distance between them
-      const uint64_t p_desc = make_desc_k128(smem_u32(sP) + (uint32_t)sb * A::P_TILE);
-      const uint32_t v0 = smem_u32(sKV + (i % KVS) * 2 * A::KV_TILE + A::KV_TILE);
       if (elect_one()) {
+        const uint32_t vlo = v_lo0 + ((uint32_t)i & (KVS - 1)) * STAGE_V;
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k) {
-          const uint32_t slab = v0 + (uint32_t)(k * 16 * ROWB);
-          const uint64_t bd = (make_desc_rows(slab, ROWB) & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)((ones_addr - slab) >> 4) << 16);
-          umma_ss(tmem_o, p_desc + (uint64_t)(2 * k), bd, g.idesc_ol, (uint32_t)((i | k) != 0));
-        }
+        for (int k = 0; k < BN / 16; ++k)
+          umma_ts(tmem_o, tmem_s + (uint32_t)(sb * BN + k * 8), pack64(vlo + (uint32_t)k * SLAB_V, HI_ROWS), g.idesc_ol,
+                  (uint32_t)((i | k) != 0));
         if (i == nst - 1) umma_commit(pv_done);
+        if (i + 2 < nst) {  // S_{i+2} into the buffer sweep i has released (behind P_i V_i in the tensor pipe: in order)
+          const uint32_t t = (uint32_t)i + 2, st = t & (KVS - 1);
+          mbar_wait_spin(&kv_full[st], (t / KVS) & 1u);
+          tc_fence_after();
+          const uint64_t kd = pack64(k_lo0 + st * STAGE_K, HI_ROWS);
+          umma_ss(tmem_s + (uint32_t)(sb * BN), q_desc, kd, idesc_s64, 0u);
+          if (NOREF) umma_ss(tmem_s + (uint32_t)(sb * BN), qlo_desc, kd, idesc_s64, 1u);
+          umma_commit(&s_full[sb]);  // also covers P_i V_i
+        }
+        if (i + KVS - 2 < nst) {  // tile i+6: its stage held tile i-2, whose P V the softmax warps have seen complete
+          const int t = i + KVS - 2, st = t & (KVS - 1);
+          mbar_arrive_expect_tx(&kv_full[st], 2u * A::KV_TILE);
+          tma_load_2d(sKV + st * 2 * A::KV_TILE, &tmKV, &kv_full[st], g.C + head * D, (int)kv0 + t * BN);
+          tma_load_2d(sKV + st * 2 * A::KV_TILE + A::KV_TILE, &tmKV, &kv_full[st], 2 * g.C + head * D, (int)kv0 + t * BN);
+        }
       }
       __syncwarp();
-      if (i + 2 < nst) issue_s(i + 2);  // into the S buffer sweep i has released; its commit also covers P_i V_i
-      if (i + KVS - 2 < nst) load_tile(i + KVS - 2);  // its stage held tile i-2, whose P V the softmax warps have seen complete
-      __syncwarp();
+    };
+    for (int i = 0; i < nst; i += 2) {
+      issue_step(i, std::integral_constant<int, 0>{});
+      issue_step(i + 1, std::integral_constant<int, 1>{});
     }
   } else {
     // ===================== softmax warps: thread = one query row (TMEM lane quadrant = warp) =====================
@@ -214,7 +238,6 @@ attention_tc12_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto step = [&](int i, auto sb_tag) {
       constexpr int sb = decltype(sb_tag)::value;
       const uint32_t t_s = tmem_s + lane_base + (uint32_t)(sb * BN);
-      const uint32_t p_buf = p_row + (uint32_t)sb * A::P_TILE;
       mbar_wait_spin(&s_full[sb], (uint32_t)(i >> 1) & 1u);  // issued two steps ago: normally complete on the first probe
       tc_fence_after();
       uint32_t va[16], vb[16];
@@ -261,13 +284,7 @@ attention_tc12_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
           pk[e >> 1] = pack_pair<DT>(p0, p1);
         }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const uint32_t addr = p_buf + ((((uint32_t)(ch * 2 + u)) ^ rx) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                       "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                       : "memory");
-        }
+        tmem_st8(t_s + (uint32_t)(ch * 8), pk);  // P_i over the S columns this thread has already consumed
       };
       tmem_ld16(t_s + 16, vb);  // in flight while chunk 0 is processed
       chunk(va, 0);
@@ -279,8 +296,8 @@ attention_tc12_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       chunk(va, 2);
       tmem_ld_wait();
       chunk(vb, 3);
-      tc_fence_before();    // our tcgen05.ld of S_i precede the MMA that overwrites the buffer
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tmem_st_wait();
+      tc_fence_before();  // our tcgen05.ld of S_i / tcgen05.st of P_i precede the MMAs that read P_i and overwrite the buffer
       if (sb) named_bar_arrive<2, 160>();
       else named_bar_arrive<1, 160>();
     };
