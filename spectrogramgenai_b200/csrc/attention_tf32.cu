@@ -9,9 +9,12 @@
 //
 // One CTA = 128 consecutive query tokens x one head; key tiles of 64 tokens.  Per key tile:
 //   S   = Q K^T      3 x d/8 tcgen05.mma kind::tf32 (M128 x N64 x K8), K-major operands           -> TMEM cols [0, 64)
-//   P   = exp2(S c - m c)   one query row per thread, fp32; P_hi / P_lo written as swizzled K-major fp32 tiles
-//   O_j = P V        3 x 8 tcgen05.mma (M128 x N=d x K8); B = V^T, K-major                        -> TMEM cols [64, 64+d)
-//   o   = o alpha + O_j     running output / maximum / sum in registers
+//   m   = max(m, max_j S)   one query row per thread; o, l rescaled exactly when the maximum rises
+//   P   = exp2(S c - m c)   fp32; P_hi written over S in place, P_lo into TMEM cols [64, 128) (tcgen05.st)
+//   O_j = P V        3 x 8 tcgen05.mma (M128 x N=d x K8); A = P from TMEM, B = V^T, K-major       -> TMEM cols [128, 128+d)
+//   o   = o + O_j           running output / maximum / sum in registers
+// P never touches shared memory: as swizzled fp32 tiles (round 2's first cut) the probabilities cost 64 KB of stores and
+// 96 KB of tensor-core operand reads per key tile, i.e. the kernel ran at the shared-memory bandwidth.
 // The lo x hi / hi x lo products are issued BEFORE hi x hi: the tensor core's fp32 accumulation truncates, so the small
 // terms are added while the accumulator is still small.
 // V as the B operand of P V would be MN-major, which kind::tf32 only accepts in a dedicated 32-byte-base swizzle; instead
@@ -21,7 +24,7 @@
 // Requires L >= 128 (power of two): shorter sequences (a handful of tokens per row, < 1 % of the FLOPs) stay on the CUDA-core
 // kernel.  This engine is the accuracy mode (1 CTA per SM, serial phases): several times the CUDA-core kernel, not a
 // roofline kernel -- the throughput path is attention_tc.cu.
-#include "tc_common.cuh"
+#include "attention_common.cuh"
 
 namespace sg {
 namespace tc {
@@ -39,13 +42,14 @@ struct AttF {
   static_assert(2 * VT_ATOM == KV_TILE, "K and V^T tiles have the same size");
   // d = 16 (sa5 / sa6: 85 % of the attention FLOPs): one K / V stage keeps the CTA under half of the SM's shared memory,
   // and two resident CTAs overlap each other's serial chain -- worth more than a prefetched stage; d = 64 has no room for two
-  static constexpr int STAGES = D == 32 ? 2 : 1;
-  static constexpr int CTAS = D == 16 ? 2 : 1;
+  // d = 16 (sa5 / sa6: 85 % of the attention FLOPs): 160 TMEM columns and 49 KB of shared memory per CTA, so three
+  // resident CTAs overlap each other's serial chain (S -> sweep -> P V -> O read-back)
+  static constexpr int STAGES = D == 64 ? 1 : 2;
+  static constexpr int CTAS = D == 16 ? 3 : (D == 32 ? 2 : 1);
   static constexpr int KV_STAGE = 4 * KV_TILE;            // K_hi, K_lo, Vt_hi, Vt_lo
-  static constexpr int P_ATOM = BM * 128;                 // [128 queries x 32 keys] fp32, SWIZZLE_128B
-  static constexpr int P_TILE = 2 * P_ATOM;               // 64 keys; one of hi / lo
-  static constexpr int SMEM = 1024 + 2 * Q_TILE + STAGES * KV_STAGE + 2 * P_TILE + 256;
-  static_assert(CTAS * (SMEM + 1024) <= 228 * 1024, "smem budget");
+  static constexpr int O_COLS = D <= 32 ? 32 : 64;        // second TMEM allocation (the first: S / P_hi | P_lo, 128 columns)
+  static constexpr int SMEM = 1024 + 2 * Q_TILE + STAGES * KV_STAGE + 256;
+  static_assert(CTAS * (SMEM + 1024) <= 228 * 1024 && CTAS * (128 + O_COLS) <= 512, "smem / TMEM budget");
 };
 
 struct AttFGeom {
@@ -89,8 +93,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;                             // [hi | lo] x NATOM atoms
   uint8_t* sKV = sQ + 2 * A::Q_TILE;              // [STAGES] x [K_hi | K_lo | V_hi | V_lo]
-  uint8_t* sP = sKV + STAGES * A::KV_STAGE;       // [hi | lo] x 2 atoms of 32 keys
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * A::P_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * A::KV_STAGE);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -126,12 +129,16 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     mbar_init(o_read, 4);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot + 1)), "n"(A::O_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + BN;
+  const uint32_t tmem_base = tmem_slot[0];  // S (P_hi in place) | P_lo
+  const uint32_t tmem_o = tmem_slot[1];
   pdl_wait();  // every activation access (TMA loads included) follows this point
   pdl_launch_dependents();
 
@@ -168,7 +175,6 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     // kernel issues 30 small MMAs per key tile =====
     mbar_wait_spin(q_full, 0);
     const uint64_t qd0 = make_desc_f(smem_u32(sQ), ROWB, 0);          // + Q_TILE / 16: the lo part; + Q_ATOM / 16: next atom
-    const uint64_t pd0 = make_desc_k128(smem_u32(sP));                // + P_TILE / 16: the lo part
     for (int j = 0; j < g.nkv; ++j) {
       const int s = j % STAGES;
       mbar_wait_spin(&kv_full[s], (uint32_t)(j / STAGES) & 1u);
@@ -197,7 +203,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
         umma_commit(s_full);
       }
       __syncwarp();
-      // O_j = P V = Pl Vh + Ph Vl + Ph Vh: A = P and B = V^T, both K-major in two 32-key SWIZZLE_128B atoms
+      // O_j = P V = Pl Vh + Ph Vl + Ph Vh: A = P in TMEM (8 columns per K step), B = V^T K-major in two 32-key SWIZZLE_128B atoms
       mbar_wait_spin(p_ready, (uint32_t)j & 1u);
       if (j > 0) mbar_wait_spin(o_read, (uint32_t)(j - 1) & 1u);  // O_{j-1} has been added to the running output
       tc_fence_after();
@@ -205,12 +211,12 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
         uint32_t acc = 0;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-          const uint64_t pd = pd0 + (uint64_t)((t == 0 ? A::P_TILE : 0) >> 4);
+          const uint32_t pa = tmem_base + (uint32_t)(t == 0 ? BN : 0);
           const uint64_t vd = vd0 + (uint64_t)((t == 1 ? A::KV_TILE : 0) >> 4);
 #pragma unroll
           for (int k = 0; k < BN / 8; ++k) {
-            umma_ss_tf32(tmem_o, pd + (uint64_t)(((k >> 2) * A::P_ATOM + (k & 3) * 32) >> 4),
-                         vd + (uint64_t)(((k >> 2) * A::VT_ATOM + (k & 3) * 32) >> 4), g.idesc_o, acc);
+            umma_ts_tf32(tmem_o, pa + (uint32_t)(k * 8), vd + (uint64_t)(((k >> 2) * A::VT_ATOM + (k & 3) * 32) >> 4),
+                         g.idesc_o, acc);
             acc = 1;
           }
         }
@@ -228,63 +234,52 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     float o[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) o[i] = 0.f;
-    float m_ref = -INFINITY, l = 0.f;  // reference maximum of the exponent; running row sum (relative to m_ref)
-    const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    const uint32_t rx = (uint32_t)(r & 7);
+    float m_ref = -INFINITY, l = 0.f;  // running maximum of the scores; running row sum relative to it
+    const uint32_t t_o = tmem_o + ((uint32_t)(q * 32) << 16);
     for (int j = 0; j < g.nkv; ++j) {
       mbar_wait_spin(s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      // ONE sweep over S: p = exp2(s c - m_ref c) against the maximum known BEFORE this tile, the tile maximum as a
-      // by-product.  Exact algebra (o, l are rescaled afterwards); the sweep is repeated only when the tile maximum
-      // exceeds the reference by more than 2^60 (always on the first tile, where m_ref = -inf).
-      float tmax, psum;
-      bool redo;
-      do {
-        const float mc = m_ref * g.c;
-        tmax = -INFINITY;
-        psum = 0.f;
-#pragma unroll 1
-        for (int cch = 0; cch < BN / 32; ++cch) {
-          uint32_t v[32];
-          tmem_ld32(t_row + cch * 32, v);
-          tmem_ld_wait();
+      // ---- pass 1: the tile maximum; raise the reference first (exact rescale of o, l), so that every p <= 1 ----
+      float tmax = -INFINITY;
 #pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {  // four keys = one 16-byte chunk of the P row
-            float ph[4], pl[4];
+      for (int cch = 0; cch < BN / 16; ++cch) {
+        uint32_t v[16];
+        tmem_ld16(t_row + cch * 16, v);
+        tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float s0 = __uint_as_float(v[i4 * 4 + u]);
-              tmax = fmaxf(tmax, s0);
-              float p;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(s0, g.c, -mc)));
-              psum += p;
-              // hi = p rounded to TF32 with two integer instructions (p >= 0; cvt.rna.tf32 would put two more conversions
-              // per element on the pipe the exponential already occupies); lo = p - hi is exact, the MMA reads its top 19 bits
-              ph[u] = __uint_as_float((__float_as_uint(p) + 0x1000u) & 0xFFFFE000u);
-              pl[u] = p - ph[u];
-            }
-            const uint32_t addr = p_row + (uint32_t)cch * A::P_ATOM + ((((uint32_t)i4) ^ rx) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(ph[0]), "f"(ph[1]), "f"(ph[2]),
-                         "f"(ph[3])
-                         : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + (uint32_t)A::P_TILE), "f"(pl[0]),
-                         "f"(pl[1]), "f"(pl[2]), "f"(pl[3])
-                         : "memory");
-          }
+        for (int i = 0; i < 16; i += 2) tmax = max3(tmax, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      }
+      if (tmax > m_ref) {
+        float a0;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"((m_ref - tmax) * g.c));  // 0 on the first tile
+        l *= a0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] *= a0;
+        m_ref = tmax;
+      }
+      // ---- pass 2: p = exp2(s c - m c); P_hi over S in place, P_lo next to it ----
+      const float mc = m_ref * g.c;
+      float psum = 0.f;
+#pragma unroll
+      for (int cch = 0; cch < BN / 16; ++cch) {
+        uint32_t v[16], pl[16];
+        tmem_ld16(t_row + cch * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          float p;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(__uint_as_float(v[u]), g.c, -mc)));
+          psum += p;
+          // hi = p rounded to TF32 with two integer instructions (p >= 0; cvt.rna.tf32 would put two more conversions
+          // per element on the pipe the exponential already occupies); lo = p - hi is exact, the MMA reads its top 19 bits
+          v[u] = (__float_as_uint(p) + 0x1000u) & 0xFFFFE000u;
+          pl[u] = __float_as_uint(p - __uint_as_float(v[u]));
         }
-        const bool over = (tmax - m_ref) * g.c > 60.0f;  // also true while m_ref == -inf
-        redo = __any_sync(0xffffffffu, over);
-        if (over) {
-          float a0;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"((m_ref - tmax) * g.c));  // 0 on the first tile
-          l *= a0;
-#pragma unroll
-          for (int i = 0; i < D; ++i) o[i] *= a0;
-          m_ref = tmax;
-        }
-      } while (redo);
-      tc_fence_before();    // our tcgen05.ld of S precede the next S MMA
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tmem_st16(t_row + cch * 16, v);
+        tmem_st16(t_row + BN + cch * 16, pl);
+      }
+      tmem_st_wait();
+      tc_fence_before();  // our tcgen05.ld of S / tcgen05.st of P precede the MMAs that read P and overwrite S
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
       // ---- O_j and the row sum, both relative to m_ref ----
@@ -293,7 +288,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
 #pragma unroll
       for (int cch = 0; cch < D / 16; ++cch) {
         uint32_t v[16];
-        tmem_ld16(t_row + BN + cch * 16, v);
+        tmem_ld16(t_o + cch * 16, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[cch * 16 + i] += __uint_as_float(v[i]);
@@ -302,15 +297,6 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_read);
-      // ---- raise the reference to the new running maximum (exact rescale of o, l) ----
-      if (tmax > m_ref) {
-        float a1;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"((m_ref - tmax) * g.c));
-        l *= a1;
-#pragma unroll
-        for (int i = 0; i < D; ++i) o[i] *= a1;
-        m_ref = tmax;
-      }
     }
     {
       const float inv = 1.0f / l;
@@ -325,6 +311,7 @@ attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<A::O_COLS>(tmem_o);
   }
 }
 
