@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 14
+#define SG_ABI_VERSION 15
 
 typedef enum { SG_F32 = 0, SG_BF16 = 1, SG_F16 = 2 } sg_dtype;
 typedef enum { SG_ENGINE_SIMT = 0, SG_ENGINE_TC = 1 } sg_engine;
@@ -96,7 +96,7 @@ int sg_conv_in(const float* x, int n_src, int c_in, int S, const float* w /* HOS
  * + bias[co]; GELU(erf) if gelu; + residual[m, co].  M = rows*H*W.
  * SG_ENGINE_SIMT: fp32 CUDA-core kernel (act_dtype = SG_F32).  SG_ENGINE_TC: tcgen05/TMEM kernel
  * fed by TMA: act_dtype = SG_BF16 or SG_F16 (fp32 accumulate), or act_dtype = SG_F32 = the fp32-accurate engine on
- * split-TF32 operands: a / w hold the hi parts, a_lo / w_lo the lo parts (sg_split_tf32), and the kernel accumulates
+ * split-TF32 operands: a / w hold the hi parts (a: the fp32 activation itself), a_lo / w_lo the lo parts (sg_split_tf32), and the kernel accumulates
  * a_lo w_hi + a_hi w_lo + a_hi w_hi in one fp32 TMEM tile (a single TF32 pass: 3e-4 per conv; split: the tensor core's
  * truncating fp32 accumulation remains, a uniform relative shrink of ~1e-8 K that the GroupNorm behind every conv removes).
  * Requires Cin % 64 == 0 (TC 16-bit) / % 32 (TC fp32) / % 16 (SIMT), Cout % 64 == 0.
@@ -218,8 +218,14 @@ int sg_attn_prep_tf32(const float* qkv, float* qk_hi, float* qk_lo, float* vt_hi
                       int heads, sg_stream_t stream);
 int sg_attention_tf32(const float* qk_hi, const float* qk_lo, const float* vt_hi, const float* vt_lo, float* out, int rows,
                       int L, int C, int heads, sg_stream_t stream);
-/* x fp32 [n] -> hi = tf32(x) (round to nearest), lo = tf32(x - hi): the operand form of the fp32-accurate tensor-core
- * engine (x - hi is exact in fp32; hi + lo keeps ~21 mantissa bits).  n % 4 == 0, buffers 16-byte aligned. */
+/* Operands of the fp32-accurate tensor-core engine.  kind::tf32 multiplies the top 19 bits of every fp32 container, so
+ * an fp32 tensor x is used as two operands whose sum keeps ~22 mantissa bits:
+ *   hi != NULL (weights, packed once):  hi = tf32(x) (round to nearest), lo = tf32(x - hi);
+ *   hi == NULL (activations):           x ITSELF is the high operand (the tensor core reads trunc19(x)) and only
+ *                                       lo = tf32(x - trunc19(x)) is written.
+ * The activation form needs no pass of its own when the kernel that produces x writes lo next to it: sg_gn_apply (fp32 raw),
+ * sg_maxpool2 and sg_upsample_cat do so when called with act_dtype = SG_F32 and out_act = the lo tensor.
+ * n % 4 == 0, buffers 16-byte aligned. */
 int sg_split_tf32(const float* x, float* hi, float* lo, int64_t n, sg_stream_t stream);
 
 /* ---- outc: 1x1 conv 64 -> c_out with bias, NHWC fp32 in, NCHW fp32 out (:166,:195) ---- */

@@ -14,7 +14,7 @@ from . import build as _build
 
 SG_F32, SG_BF16, SG_F16 = 0, 1, 2
 SG_ENGINE_SIMT, SG_ENGINE_TC = 0, 1
-ABI_VERSION = 14
+ABI_VERSION = 15
 SG_ACT_NONE, SG_ACT_GELU, SG_ACT_RELU_POST = 0, 1, 2
 
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float

@@ -74,12 +74,6 @@ __device__ __forceinline__ uint64_t make_desc_f(uint32_t saddr, int row_bytes, u
   return d;
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
 template <int D>
 __global__ void __launch_bounds__(192, AttF<D>::CTAS)
 attention_tf32_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,

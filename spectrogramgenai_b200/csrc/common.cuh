@@ -143,11 +143,32 @@ __device__ __forceinline__ float2 unpack16(uint32_t w, int dtype) {
   if (dtype == SG_BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
   return __half22float2(*reinterpret_cast<__half2*>(&w));
 }
-// store 4 consecutive values to an fp32 and/or 16-bit destination at element offset `off`
+// ---- operands of the split-TF32 (fp32-accurate tensor-core) engine ----
+// tcgen05 kind::tf32 reads the top 19 bits of each fp32 container, i.e. it multiplies trunc19(x).  Two operand forms:
+//   weights (packed once):   hi = rna_tf32(w), lo = rna_tf32(w - hi)                      (sg_split_tf32 with hi != NULL)
+//   activations:             hi = the fp32 tensor ITSELF, lo = rna_tf32(x - trunc19(x))   (tf32_lo below)
+// x - trunc19(x) is exact (13 significant bits); rounding it to TF32 leaves |x - (trunc19(x) + lo)| <= 2^-22 |x|, unbiased.
+// The activation form costs one extra 4-byte store in the kernel that produces x and no separate pass over it.
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_lo(float x) {
+  return tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+__device__ __forceinline__ float4 tf32_lo4(float a, float b, float c, float d) {
+  return make_float4(tf32_lo(a), tf32_lo(b), tf32_lo(c), tf32_lo(d));
+}
+
+// store 4 consecutive values to an fp32 and/or a second destination at element offset `off`: 16-bit copies (dtype
+// SG_BF16 / SG_F16) or, dtype == SG_F32, the TF32 low parts of the values
 __device__ __forceinline__ void store4_dual(float* o32, void* o16, int dtype, int64_t off, float a, float b, float c,
                                             float d) {
   if (o32) *reinterpret_cast<float4*>(o32 + off) = make_float4(a, b, c, d);
-  if (o16) {
+  if (o16 && dtype == SG_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(o16) + off) = tf32_lo4(a, b, c, d);
+  } else if (o16) {
     uint2 v;
     v.x = pack16(a, b, dtype);
     v.y = pack16(c, d, dtype);

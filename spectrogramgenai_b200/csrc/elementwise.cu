@@ -187,7 +187,10 @@ __global__ void __launch_bounds__(256) upsample_cat_kernel(const float* __restri
         __stcs(reinterpret_cast<float4*>(o32 + off), v[0]);
         __stcs(reinterpret_cast<float4*>(o32 + off + 4), v[1]);
       }
-      if (o16) {
+      if (o16 && dtype == SG_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(o16) + off) = tf32_lo4(v[0].x, v[0].y, v[0].z, v[0].w);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(o16) + off + 4) = tf32_lo4(v[1].x, v[1].y, v[1].z, v[1].w);
+      } else if (o16) {
         uint4 wv;
         wv.x = pack16(v[0].x, v[0].y, dtype);
         wv.y = pack16(v[0].z, v[0].w, dtype);
@@ -243,7 +246,13 @@ __global__ void __launch_bounds__(256) upsample_cat_paired_kernel(const float* _
       __stcs(reinterpret_cast<float4*>(o32 + off_x), v[0]);
       __stcs(reinterpret_cast<float4*>(o32 + off_x + 4), v[1]);
     }
-    if (o16) {
+    if (o16 && dtype == SG_F32) {
+      float* ol = reinterpret_cast<float*>(o16);
+      *reinterpret_cast<float4*>(ol + off_s) = tf32_lo4(s0.x, s0.y, s0.z, s0.w);
+      *reinterpret_cast<float4*>(ol + off_s + 4) = tf32_lo4(s1.x, s1.y, s1.z, s1.w);
+      *reinterpret_cast<float4*>(ol + off_x) = tf32_lo4(v[0].x, v[0].y, v[0].z, v[0].w);
+      *reinterpret_cast<float4*>(ol + off_x + 4) = tf32_lo4(v[1].x, v[1].y, v[1].z, v[1].w);
+    } else if (o16) {
       uint4 ws, wx;
       ws.x = pack16(s0.x, s0.y, dtype); ws.y = pack16(s0.z, s0.w, dtype);
       ws.z = pack16(s1.x, s1.y, dtype); ws.w = pack16(s1.z, s1.w, dtype);
@@ -349,11 +358,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 
 // fp32 -> (hi, lo) with hi = tf32(x) (round to nearest, ties away) and lo = tf32(x - hi): x - hi is exact in fp32, so
 // hi + lo carries 21-22 of x's 24 mantissa bits and both parts are exactly representable TF32 operands.
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// hi == NULL: the activation form (common.cuh) -- x itself is the high operand and only lo = tf32_lo(x) is written.
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
                                                          float4* __restrict__ lo, int64_t n4) {
   pdl_wait();
@@ -361,6 +366,10 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restric
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = __ldcs(x + i);
+  if (hi == nullptr) {
+    lo[i] = tf32_lo4(v.x, v.y, v.z, v.w);
+    return;
+  }
   float4 h, l;
   h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
   l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
@@ -449,7 +458,7 @@ int sg_pack_weights(const float* w, int Cout, int Cin, int taps, void* out, int 
 }
 
 int sg_split_tf32(const float* x, float* hi, float* lo, int64_t n, sg_stream_t stream) {
-  SG_REQUIRE(x && hi && lo && n > 0 && n % 4 == 0, "sg_split_tf32: null pointer or n=%lld not a positive multiple of 4", (long long)n);
+  SG_REQUIRE(x && lo && n > 0 && n % 4 == 0, "sg_split_tf32: null pointer or n=%lld not a positive multiple of 4", (long long)n);
   SG_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
              "sg_split_tf32: buffers must be 16-byte aligned");
   const int64_t n4 = n / 4;
@@ -468,7 +477,7 @@ int sg_maxpool2(const float* in, int rows, int H, int W, int C, float* out_f32, 
                 sg_stream_t stream) {
   SG_REQUIRE(in && (out_f32 || out_act), "sg_maxpool2: null pointer");
   SG_REQUIRE(rows > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "sg_maxpool2: bad shape");
-  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_maxpool2: out_act needs a 16-bit dtype");
+  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16 || act_dtype == SG_F32, "sg_maxpool2: bad act_dtype");
   const int64_t total4 = (int64_t)rows * (H / 2) * (W / 2) * (C / 4);
   launch_k(maxpool2_kernel, dim3(cdiv(total4, 256)), dim3(256), 0, as_stream(stream), in, total4, H / 2, W / 2, C / 4, out_f32,
            out_act, act_dtype);
@@ -480,7 +489,7 @@ int sg_upsample_cat(const float* x, const float* skip, int rows, int skip_rows, 
   SG_REQUIRE(skip_rows > 0 && rows % skip_rows == 0, "sg_upsample_cat: rows=%d must be a multiple of skip_rows=%d", rows, skip_rows);
   SG_REQUIRE(x && skip && (out_f32 || out_act), "sg_upsample_cat: null pointer");
   SG_REQUIRE(rows > 0 && h >= 1 && w >= 1 && Cx % 4 == 0 && Cs % 4 == 0, "sg_upsample_cat: bad shape");
-  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_upsample_cat: out_act needs a 16-bit dtype");
+  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16 || act_dtype == SG_F32, "sg_upsample_cat: bad act_dtype");
   const int64_t row4 = (int64_t)(2 * h) * (2 * w) * ((Cx + Cs) / 4);  // float4's per row
   SG_REQUIRE(row4 < (1ll << 31) && rows <= 65535, "sg_upsample_cat: row too large / too many rows");
   // torch: scale = (in - 1) / (out - 1) in fp32 (area_pixel_compute_scale, align_corners=True)

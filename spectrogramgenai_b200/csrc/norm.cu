@@ -466,7 +466,8 @@ int sg_gn_apply(const void* raw, int raw_dtype, const float* partials, int P, co
   SG_REQUIRE(mode >= 0 && mode <= 2, "sg_gn_apply: mode %d", mode);
   SG_REQUIRE(mode != 2 || residual, "sg_gn_apply: mode 2 needs a residual");
   SG_REQUIRE(!emb || emb_stride % 4 == 0, "sg_gn_apply: emb stride must be a multiple of 4");
-  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16, "sg_gn_apply: out_act needs a 16-bit dtype");
+  SG_REQUIRE(!out_act || act_dtype == SG_BF16 || act_dtype == SG_F16 || (act_dtype == SG_F32 && raw_dtype == SG_F32),
+             "sg_gn_apply: out_act is 16 bit, or (fp32 raw only) the fp32 TF32-low-part tensor");
   const int64_t per_row4 = (int64_t)HW * (C / 4);
   // enough blocks to fill 148 SMs x 8 resident blocks, at most one float4 per thread per pass
   int chunks = cdiv(per_row4, 256 * 4);

@@ -134,6 +134,7 @@ class UNetPlan:
         self.rows_p = n_src if (rows == 2 * n_src and options.shared_prefix) else rows
         self.debug = debug  # keep every buffer alive and expose per-block outputs in self.taps
         self._pool = {}
+        self._lo = {}  # split-tf32 engine: data_ptr of an fp32 activation -> its lo part, until the consuming GEMM
         self.nbytes = 0
         self.ops = []
         self.n_launches = 0
@@ -178,13 +179,25 @@ class UNetPlan:
         self.n_launches += 1  # every entry point used by the plan is exactly one kernel launch
 
     def _gemm_in(self, t):
-        """GEMM operand form of an activation buffer: the buffer itself, or -- split-tf32 engine -- a fresh (hi, lo) pair
-        written by one sg_split_tf32 pass.  Returns (operand, buffers to free after the consuming launch)."""
+        """GEMM operand form of an activation buffer: the buffer itself, or -- split-tf32 engine -- the pair (t, lo): the
+        fp32 tensor is its own high part and lo = tf32(t - trunc19(t)) was written next to it by the producing kernel
+        (_lo_out) or, failing that, by one sg_split_tf32 pass.  Returns (operand, buffers to free after the consumer)."""
         if not self.tf32:
             return t, ()
-        hi, lo = self._alloc(t.shape, torch.float32), self._alloc(t.shape, torch.float32)
-        self._op(ops.split_tf32, t, hi, lo)
-        return (hi, lo), (hi, lo)
+        lo = self._lo.pop(t.data_ptr(), None)
+        if lo is None:
+            lo = self._alloc(t.shape, torch.float32)
+            self._op(ops.split_tf32_lo, t, lo)
+        return (t, lo), (lo,)
+
+    def _lo_out(self, t):
+        """split-tf32 engine: a lo buffer for the producer of fp32 tensor `t` to fill (as its fp32 `out_act`); the GEMM
+        that consumes t picks it up in _gemm_in.  None in the other engines."""
+        if not self.tf32:
+            return None
+        lo = self._alloc(t.shape, torch.float32)
+        self._lo[t.data_ptr()] = lo
+        return lo
 
     def _pair(self, shape, want_f32=True, want_act=True):
         """(fp32 buffer, GEMM-operand buffer) for one logical tensor; in fp32 mode they are the same buffer."""
@@ -230,7 +243,8 @@ class UNetPlan:
             raw1, part1 = self._conv(x[1], f"{p}.double_conv.0.weight", rows, H, W)
         mid = self._pair(raw1.shape, want_f32=False, want_act=True)
         self._op(ops.gn_apply, raw1, part1, W_[f"{p}.double_conv.1.weight"], W_[f"{p}.double_conv.1.bias"], mode=1,
-                 out_f32=None if self.tc else mid[0], out_act=mid[1] if self.tc else None, range_flag=self.range_flag)
+                 out_f32=None if self.tc else mid[0], out_act=mid[1] if self.tc else self._lo_out(mid[0]),
+                 range_flag=self.range_flag)
         self._free(raw1, part1)
         raw2, part2 = self._conv(mid[1], f"{p}.double_conv.3.weight", rows, H, W)
         self._free_pair(mid)
@@ -243,7 +257,8 @@ class UNetPlan:
         else:
             self._op(ops.gn_apply, raw2, part2, W_[f"{p}.double_conv.4.weight"], W_[f"{p}.double_conv.4.bias"],
                      mode=2 if residual else 0, residual=x[0] if residual else None, emb=emb,
-                     out_f32=out[0], out_act=out[1] if self.tc else None, range_flag=self.range_flag)
+                     out_f32=out[0], out_act=out[1] if self.tc else (self._lo_out(out[0]) if want_act else None),
+                     range_flag=self.range_flag)
         self._free(raw2, part2)
         return out
 
@@ -324,7 +339,7 @@ class UNetPlan:
     def _down(self, p, x, rows, H, W, C, *, out_rows=None):
         h, w = H // 2, W // 2
         pooled = self._pair((rows, h, w, C))
-        self._op(ops.maxpool2, x[0], out_f32=pooled[0], out_act=pooled[1] if self.tc else None)
+        self._op(ops.maxpool2, x[0], out_f32=pooled[0], out_act=pooled[1] if self.tc else self._lo_out(pooled[0]))
         d1 = self._double_conv(f"{p}.maxpool_conv.1", pooled, rows, h, w, residual=True, want_f32=False)
         self._free_pair(pooled)
         d2 = self._double_conv(f"{p}.maxpool_conv.2", d1, rows, h, w, emb=self._emb_slice(p), want_act=False,
@@ -339,7 +354,7 @@ class UNetPlan:
         # the residual DoubleConv recomputes its fp32 residual from (x, skip) (sg_gn_apply_vcat)
         vcat = self.raw16 and x[0].shape[-1] == skip[0].shape[-1] and self.opt.vcat
         cat = self._pair((rows, H, W, ct), want_f32=not vcat)
-        self._op(ops.upsample_cat, x[0], skip[0], out_f32=cat[0], out_act=cat[1] if self.tc else None)
+        self._op(ops.upsample_cat, x[0], skip[0], out_f32=cat[0], out_act=cat[1] if self.tc else self._lo_out(cat[0]))
         u1 = self._double_conv(f"{p}.conv.0", cat, rows, H, W, residual=("vcat", x[0], skip[0]) if vcat else True,
                                want_f32=False)
         self._free_pair(cat)
@@ -412,6 +427,7 @@ class UNetPlan:
             keep["sa6"] = a[0]
             self._op(ops.conv_out, a[0].view(rows, S * S, 64), W_["outc.weight"], W_["outc.bias"], self.eps)
             self._free_pair(a)
+        assert not self._lo, "a lo operand was produced for a tensor no GEMM consumed"
         self._pool.clear()
 
     def run(self):

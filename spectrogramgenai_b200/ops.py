@@ -473,6 +473,22 @@ def _split_tf32(x, hi, lo):
           "sg_split_tf32")
 
 
+@_torch_op("(Tensor x, Tensor(a!) lo) -> ()")
+def _split_tf32_lo(x, lo):
+    if lo.numel() != x.numel():
+        raise ValueError("split_tf32_lo: lo must have x's size")
+    check(_lib().sg_split_tf32(ptr(_f32(x, "x")), None, ptr(_f32(lo, "lo")), x.numel(), stream_ptr()), "sg_split_tf32")
+
+
+def split_tf32_lo(x, lo=None):
+    """Activation operand form of the fp32-accurate tensor-core engine: x itself is the high part (the tensor core reads
+    its top 19 bits), returns lo = tf32(x - trunc19(x)).  gn_apply / maxpool2 / upsample_cat write the same lo tensor
+    themselves when given an fp32 `out_act`."""
+    lo = torch.empty_like(x) if lo is None else lo
+    _split_tf32_lo(x, lo)
+    return lo
+
+
 def split_tf32(x, hi=None, lo=None):
     """x fp32 -> (hi, lo): hi = tf32(x), lo = tf32(x - hi) -- the operand form of the fp32-accurate tensor-core engine."""
     hi = torch.empty_like(x) if hi is None else hi

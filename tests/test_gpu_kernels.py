@@ -333,6 +333,67 @@ def test_split_tf32(ops):
     assert (((hi.double() + lo.double()) - x.double()).abs() <= x.abs().double() * 2.0 ** -21).all()
 
 
+def _trunc19(x):
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def test_split_tf32_lo_and_producers(ops):
+    """Activation operand form: the fp32 tensor is its own high part (kind::tf32 reads its top 19 bits) and
+    lo = tf32(x - trunc19(x)).  sg_split_tf32(hi = NULL) and the producers that write lo next to their fp32 output
+    (GroupNorm-apply on fp32 raw, maxpool, upsample + concat) agree bit for bit."""
+    g = gen(45)
+    x = torch.randn(4096 * 4, generator=g) * torch.logspace(-6, 6, 4096 * 4)
+    lo = ops.split_tf32_lo(x.to(DEV)).cpu()
+    assert (lo.view(torch.int32) & 0x1FFF).eq(0).all()
+    assert (((_trunc19(x).double() + lo.double()) - x.double()).abs() <= x.abs().double() * 2.0 ** -21).all()
+    # GroupNorm-apply (fp32 raw), all three modes
+    rows, H, C = 3, 8, 64
+    raw = torch.randn(rows, H, H, C, generator=g).to(DEV)
+    part = torch.stack([raw.sum((1, 2, 3)), (raw * raw).sum((1, 2, 3))], -1).reshape(rows, 1, 2).contiguous()
+    gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
+    res = torch.randn(rows, H, H, C, generator=g).to(DEV)
+    for mode in (0, 1, 2):
+        o32, ol = torch.empty_like(raw), torch.empty_like(raw)
+        ops.gn_apply(raw, part, gamma, beta, mode=mode, residual=res if mode == 2 else None, out_f32=o32, out_act=ol)
+        assert torch.equal(ol, ops.split_tf32_lo(o32))
+        only = torch.empty_like(raw)
+        ops.gn_apply(raw, part, gamma, beta, mode=mode, residual=res if mode == 2 else None, out_f32=only)
+        assert torch.equal(only, o32)
+    x4 = torch.randn(2, 16, 16, 64, generator=g).to(DEV)
+    p32, pl = torch.empty(2, 8, 8, 64, device=DEV), torch.empty(2, 8, 8, 64, device=DEV)
+    ops.maxpool2(x4, out_f32=p32, out_act=pl)
+    assert torch.equal(pl, ops.split_tf32_lo(p32))
+    for cx, cs in ((64, 64), (32, 64), (4, 12)):  # paired / 8-wide / generic kernels
+        xs, sk = torch.randn(2, 8, 8, cx, generator=g).to(DEV), torch.randn(2, 16, 16, cs, generator=g).to(DEV)
+        c32, cl = torch.empty(2, 16, 16, cx + cs, device=DEV), torch.empty(2, 16, 16, cx + cs, device=DEV)
+        ops.upsample_cat(xs, sk, out_f32=c32, out_act=cl)
+        assert torch.equal(cl, ops.split_tf32_lo(c32))
+
+
+@pytest.mark.parametrize("rows,H,cin,cout", [(2, 16, 64, 128), (1, 64, 128, 128), (2, 8, 512, 512)])
+def test_igemm_conv_split_tf32_activation_form(ops, rows, H, cin, cout):
+    """The same conv with the activation given as (x, tf32_lo(x)) -- the form the engine uses -- is as accurate as with the
+    rounded (hi, lo) pair."""
+    from spectrogramgenai_b200._cabi import SG_ENGINE_TC
+
+    g = gen(46)
+    a = torch.randn(rows, H, H, cin, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)
+    ref = _conv_ref(a, w)
+    ad = a.to(DEV)
+    wp = ops.split_tf32(pack_conv(w).to(DEV))
+    outs = []
+    for a_op in ((ad, ops.split_tf32_lo(ad)), ops.split_tf32(ad)):
+        raw = torch.full((rows, H, H, cout), float("nan"), device=DEV)
+        part = torch.full((rows, ops.igemm_partials(SG_ENGINE_TC, H, H, cout), 2), float("nan"), device=DEV)
+        ops.igemm(a_op, wp, rows=rows, H=H, W=H, out_f32=raw, partials=part)
+        got = raw.cpu().double()
+        scale = float((got * ref).sum() / (ref * ref).sum())
+        outs.append(O.rel_l2(got / scale, ref))
+    print(f"igemm split-tf32 {cin}->{cout} H={H}: activation form {outs[0]:.3e}, rounded pair {outs[1]:.3e}")
+    assert outs[0] < 8e-6 and outs[0] < 1.2 * outs[1] + 5e-7  # (the K = 4608 case sits at 5e-6 in both forms: accumulation)
+
+
 @pytest.mark.parametrize("rows,H,cin,cout", CONV_CASES + [(2, 64, 64, 64), (1, 64, 128, 128), (2, 16, 96, 64)])
 def test_igemm_conv_split_tf32(ops, rows, H, cin, cout):
     """3x3 conv on the split-TF32 engine (three kind::tf32 MMAs per product) vs fp64 on the SAME fp32 operands: the bar is
