@@ -51,13 +51,52 @@ def load_peaks():
 # clocks
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, board power and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md's clocks line).
+    NVML is polled from a thread every 10 ms (initialised before the region starts, so even a 0.3 s region gets tens of
+    samples; `nvidia-smi -lms` needs 0.1 - 0.4 s before its first line); nvidia-smi is the fallback when pynvml is absent."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,enforced.power.limit")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.handle, self.samples, self._stop, self.thread = None, None, [], threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:  # CUDA_VISIBLE_DEVICES may renumber the devices: go through the UUID
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), pw, {k for k, b in bits.items() if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                           str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -70,12 +109,26 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+            nv, h = self.nvml, self.handle
+            sm = sorted(s[0] for s in self.samples)
+            pw = sorted(s[1] for s in self.samples)
+            reasons = set().union(*[s[2] for s in self.samples]) if self.samples else set()
+            try:
+                mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+                plim = nv.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            except Exception:
+                mx, plim = None, None
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                    "reasons": sorted(reasons), "power_w": round(pw[len(pw) // 2], 2) if pw else None, "power_limit_w": plim,
+                    "source": "NVML polled every 10 ms during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons, pw, plim = [], None, set(), [], None
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [s.strip() for s in ln.split(",")]
             if len(f) < 7:
@@ -85,7 +138,7 @@ class ClockSampler:
                 mx = float(f[1])
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
             try:  # board power during the timed region next to the enforced limit: the sustained loop is power-bound
@@ -96,7 +149,8 @@ class ClockSampler:
         sm.sort()
         pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons), "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": plim}
+                "reasons": sorted(reasons), "power_w": pw[len(pw) // 2] if pw else None, "power_limit_w": plim,
+                "source": "nvidia-smi -lms 100 during the timed region"}
 
 
 # ----------------------------------------------------------------------------------------------------
