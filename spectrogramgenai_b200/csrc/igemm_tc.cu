@@ -291,11 +291,18 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
 // One CTA per SM (<= 215 KB smem, up to 512 TMEM columns).  Warp roles (320 threads): 0 = TMA producer,
 // 1 = TMEM allocator + MMA issuer, 2..5 = epilogue of rows [0,128), 6..9 = epilogue of rows [128,256).
 // =====================================================================================================
-template <int BN>
+// SLAB (Cout = 64 3x3 layers on 64- / 32-pixel-wide images, 16-bit operands): those layers are bound by L2 -> smem operand
+// traffic (tensor pipe 36 %: a 256 x 64 tile re-reads its A tile for each of the nine taps and only 64 output channels
+// amortise it).  A stage is then (64-channel slice, column shift dx): ONE TMA box of the tile's image rows plus a halo
+// row above and below, shifted by dx -- {64, W, 256/W + 2, 1} -- serves the three taps (dy = -1, 0, +1) as views that
+// start dy image rows further down (row pitch W x 128 B = 8 / 4 KB: a multiple of the 1024-byte swizzle atom, so the
+// views are ordinary descriptors), with the three taps' weight tiles behind it: 72 KB per 24 MMAs instead of 120 KB.
+constexpr int SLAB_A_BYTES = 48 * 1024;  // (256 / W + 2) rows x W pixels x 128 B: 48 KB (W = 64) / 40 KB (W = 32)
+template <int BN, bool SLAB = false>
 struct V2 {
-  static constexpr int STAGES = BN == 128 ? 3 : 4;  // 48 KB / 40 KB per stage
+  static constexpr int STAGES = SLAB ? 2 : (BN == 128 ? 3 : 4);  // 72 KB / 48 KB / 40 KB per stage
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE = 2 * A_BYTES + B_BYTES;
+  static constexpr int STAGE = SLAB ? SLAB_A_BYTES + 3 * B_BYTES : 2 * A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 4 * BN;  // 2 buffers x 2 accumulators: 512 (BN=128) / 256 (BN=64)
   static constexpr int THREADS = 320;
   static_assert(1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES <= 227 * 1024, "smem budget");
@@ -321,13 +328,13 @@ __device__ __forceinline__ void tile_coords(const IgemmGeom& g, int mt, int& cn,
 // fp32 TMEM tile, so the product carries ~21 mantissa bits (the dropped lo x lo term is 2^-22 relative) at 1/6 of the
 // 16-bit rate.  A k-block is the same 128-byte swizzle span either way (64 x 16 bit or 32 x fp32) and one MMA consumes
 // 32 bytes of it (K = 16 or K = 8), so tiles, descriptors and the pipeline are identical.
-template <int BN, int KIND>
+template <int BN, int KIND, bool SLAB>
 __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmA_lo,
                                                            const __grid_constant__ CUtensorMap tmB_lo, const IgemmGeom g,
                                                            const IgemmEpi ep, const int num_tiles) {
-  using K = V2<BN>;
+  using K = V2<BN, SLAB>;
   constexpr int STAGES = K::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk1 = g.taps * g.cblocks;  // k-blocks of one pass
-  const int nk = nk1 * g.passes;
+  const int nk = SLAB ? 3 * g.cblocks : nk1 * g.passes;  // SLAB: stages = (channel slice, column shift)
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -382,6 +389,19 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait_spin(&empty[s], ((it / STAGES) & 1u) ^ 1u);
+        if constexpr (SLAB) {
+          const int c0 = (kb / 3) * BK, dxi = kb % 3;  // dx = dxi - 1; the slab starts one image row above the tile
+          uint8_t* st = smem + s * K::STAGE;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[s], g.tx_bytes);
+            tma_load_4d(st, &tmA, &full[s], c0, dxi - 1, ch0 - 1, cn0);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi)
+              tma_load_2d(st + SLAB_A_BYTES + dyi * K::B_BYTES, &tmB, &full[s], c0, (dyi * 3 + dxi) * g.Cout + n0);
+          }
+          __syncwarp();
+          continue;
+        }
         const int pass = KIND == 1 ? kb / nk1 : 0, kk = kb - pass * nk1;
         const int tap = kk / g.cblocks, c0 = (kk % g.cblocks) * g.bke;
         int dy = 0, dx = 0;
@@ -417,6 +437,24 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
         mbar_wait_spin(&full[s], (it / STAGES) & 1u);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * K::STAGE);
+        if constexpr (SLAB) {
+          const uint32_t pitch = (uint32_t)g.W * 128u;  // bytes of one image row of the slab
+          if (elect_one()) {
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const uint64_t a0 = make_desc_k128(sa + dyi * pitch), a1 = make_desc_k128(sa + dyi * pitch + A_BYTES);
+              const uint64_t bd = make_desc_k128(sa + SLAB_A_BYTES + dyi * K::B_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_ss(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, (kb | dyi | k) != 0);
+                umma_ss(acc1, a1 + 2 * k, bd + 2 * k, g.idesc, (kb | dyi | k) != 0);
+              }
+            }
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
+          continue;
+        }
         const uint64_t a0 = make_desc_k128(sa), a1 = make_desc_k128(sa + A_BYTES);
         const uint64_t bd = make_desc_k128(sa + 2 * A_BYTES);
         if (elect_one()) {
@@ -464,11 +502,11 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   }
 }
 
-template <int BN, int KIND>
+template <int BN, int KIND, bool SLAB = false>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_lo,
                    const IgemmGeom& g, const IgemmEpi& ep, cudaStream_t stream) {
-  constexpr int smem = V2<BN>::SMEM;
-  if (int rc = set_max_smem<igemm_tc2_kernel<BN, KIND>>(smem, "sg_igemm(tc2)")) return rc;
+  constexpr int smem = V2<BN, SLAB>::SMEM;
+  if (int rc = set_max_smem<igemm_tc2_kernel<BN, KIND, SLAB>>(smem, "sg_igemm(tc2)")) return rc;
   const int64_t mt2 = cdiv(g.M, 2 * BM);
   const int64_t tiles = mt2 * g.n_tiles;
   if (tiles >= (1ll << 31)) {
@@ -476,8 +514,8 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     return SG_ERR_ARG;
   }
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  launch_k(igemm_tc2_kernel<BN, KIND>, dim3(grid), dim3(V2<BN>::THREADS), smem, stream, tmA, tmB, tmA_lo, tmB_lo, g, ep,
-           (int)tiles);
+  launch_k(igemm_tc2_kernel<BN, KIND, SLAB>, dim3(grid), dim3(V2<BN, SLAB>::THREADS), smem, stream, tmA, tmB, tmA_lo, tmB_lo,
+           g, ep, (int)tiles);
   return launch_status("sg_igemm(tc2)");
 }
 
@@ -486,9 +524,17 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 // A operand maps of one activation tensor (hi or lo part): NHWC rank-4 {C, W, H, rows} for the 3x3 convs, {Cin, M, 1, 1}
 // for Linear layers; box = one 128-byte channel span x 128 pixels.
 static int make_a_map(CUtensorMap* tm, const sg_igemm_args* a, const void* base, int dtype, int esz, int bke, int64_t M,
-                      uint32_t* box_rows) {
+                      uint32_t* box_rows, bool slab = false) {
   using tc::make_tmap;
   const uint64_t cb = (uint64_t)a->Cin * esz;
+  if (slab) {  // the 256-pixel tile's image rows + one halo row above and below, full width (shifted by dx at load time)
+    const uint32_t th = 256u / (uint32_t)a->W + 2u;
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->rows};
+    const uint64_t strides[3] = {cb, cb * a->W, cb * a->W * a->H};
+    const uint32_t box[4] = {(uint32_t)bke, (uint32_t)a->W, th, 1};
+    *box_rows = (uint32_t)a->W * th;
+    return make_tmap(tm, dtype, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
   if (a->taps == 1) {
     const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)M, 1, 1};
     const uint64_t strides[3] = {cb, cb * M, cb * M};
@@ -541,7 +587,10 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
   CUtensorMap tmA, tmB, tmA_lo, tmB_lo;
   uint32_t box_rows = 0;
   int rc;
-  if ((rc = make_a_map(&tmA, a, a->a, a->act_dtype, esz, bke, g.M, &box_rows))) return rc;
+  // Cout = 64 3x3 layers on 64- / 32-pixel-wide images: the slab pipeline (see V2)
+  const bool slab = !tf32 && BN == 64 && a->taps == 9 && (a->W == 64 || a->W == 32) && a->H % (256 / a->W) == 0 &&
+                    HW % 256 == 0;
+  if ((rc = make_a_map(&tmA, a, a->a, a->act_dtype, esz, bke, g.M, &box_rows, slab))) return rc;
   const uint64_t wdims[2] = {(uint64_t)a->Cin, (uint64_t)a->taps * a->Cout};
   const uint64_t wstrides[1] = {(uint64_t)a->Cin * esz};
   const uint32_t wbox[2] = {(uint32_t)bke, (uint32_t)BN};
@@ -553,7 +602,7 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
     tmA_lo = tmA;
     tmB_lo = tmB;
   }
-  g.tx_bytes = 2u * box_rows * 128u + (uint32_t)BN * 128u;
+  g.tx_bytes = slab ? box_rows * 128u + 3u * (uint32_t)BN * 128u : 2u * box_rows * 128u + (uint32_t)BN * 128u;
 
   IgemmEpi ep;
   ep.bias = a->bias; ep.residual = a->residual; ep.out_f32 = a->out_f32; ep.out_act = a->out_act;
@@ -564,6 +613,7 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
   }
   ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
   if (tf32) return BN == 128 ? launch2<128, 1>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream) : launch2<64, 1>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
+  if (slab) return launch2<64, 0, true>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
   return BN == 128 ? launch2<128, 0>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream) : launch2<64, 0>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
 }
 
