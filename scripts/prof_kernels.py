@@ -47,6 +47,16 @@ if what in ("conv", "all"):
         _aw = (a, w)
         timeit(f"conv3x3 H={H} {cin}->{cout} rows={rows}", lambda: ops.igemm(*_aw, **args),
                flops=2.0 * rows * H * H * cin * cout * 9, nbytes=a.numel() * 2 + raw.numel() * 2)
+if what in ("conv64",):  # the Cout = 64 layers (slab pipeline)
+    for (H, cin, cout) in ((64, 128, 64), (64, 64, 64), (32, 128, 64)):
+        a = torch.randn(rows, H, H, cin, device=dev, generator=g).to(dt)
+        w = (torch.randn(9, cout, cin, device=dev, generator=g) / math.sqrt(9 * cin)).to(dt)
+        raw = torch.empty(rows, H, H, cout, device=dev, dtype=torch.float16)
+        part = torch.empty(rows, ops.igemm_partials(SG_ENGINE_TC, H, H, cout), 2, device=dev)
+        args = dict(rows=rows, H=H, W=H, out_act=raw, partials=part)
+        _aw = (a, w)
+        timeit(f"conv3x3 H={H} {cin}->{cout} rows={rows}", lambda: ops.igemm(*_aw, **args),
+               flops=2.0 * rows * H * H * cin * cout * 9, nbytes=a.numel() * 2 + raw.numel() * 2)
 if what in ("linear", "all"):
     for (L, cin, cout) in ((4096, 64, 192), (4096, 64, 64), (1024, 128, 384)):
         M = rows * L
