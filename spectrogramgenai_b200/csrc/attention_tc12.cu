@@ -8,13 +8,18 @@
 //   * the output is never read back per tile: the fast pass keeps ONE exponent reference per row (v11's scheme: the maximum
 //     of the row's first 16 scores, no maximum search, no rescale), so O = sum_i P_i V_i simply accumulates in TMEM across
 //     all key tiles (tcgen05.mma accumulate) together with the row sums (v11's ones atom: the PV MMA has N = d + 16);
-//   * P is double-buffered in shared memory, K / V tiles travel through a 6-stage TMA ring;
+//   * P never touches shared memory: a thread writes its packed 16-bit probabilities with tcgen05.st over the S columns it
+//     has just consumed (P_i aliases the first 32 of S_i's 64 columns) and P_i V_i takes its A operand from TMEM.  As
+//     swizzled smem tiles P cost 16 KB of STS + 16 KB of tensor-core operand reads per tile, which with the Q / K / V
+//     reads kept the 128 B/clk shared-memory port ~85 % busy (the stall showed up as mio_throttle on the MUFU
+//     instructions: they share the MIO queue with the stores).  K / V tiles travel through an 8-stage TMA ring;
 //   * a fifth warp sleeps on a named barrier (bar.sync, no polling) and then issues, in order, P_i V_i, S_{i+2} = Q K_{i+2}^T
-//     into the S buffer the sweep has just released, and the TMA load of tile i+4.  tcgen05.commit tracks every MMA issued
-//     before it, so a softmax thread that has observed s_full of step i knows P_{i-2} V_{i-2} is complete: the P buffer and
-//     the K / V stage about to be reused are free without further barriers.
-// 160 TMEM columns (128 + 32) and 62 KB of shared memory per CTA: three CTAs per SM.
-// Instruction diet (the kernel is bound by issue slots and the MUFU pipe together, ncu: 4.8 instructions per exponential
+//     into the S buffer the sweep has just released (the tensor pipe executes a thread's MMAs in order, so P_i is read
+//     before S_{i+2} overwrites it), and the TMA load of tile i+6.  tcgen05.commit tracks every MMA issued before it, so a
+//     softmax thread that has observed s_full of step i knows P_{i-2} V_{i-2} is complete: the K / V stage about to be
+//     reused is free without further barriers.
+// 160 TMEM columns (128 + 32) and 76 KB of shared memory per CTA (32 KB of it the safe pass's P tile): three CTAs per SM.
+// Instruction diet (the kernel is bound by issue slots and the MUFU pipe together, ncu: 3.9 instructions per exponential
 // after the first version's 5.5): bf16 P needs no exponent reference at all -- Q is rescaled by c once (kept as hi + lo, so no
 // second rounding) and S is the exponent itself; the polynomial lanes clamp with one FFMA.SAT instead of two FMNMX and
 // need no running maximum.
@@ -32,7 +37,7 @@ struct Att12 {
   static constexpr int D = 16, ROWB = 32, BN = 64, KVS = 8;  // KVS: a power of two (stage = tile & 7)
   static constexpr int Q_TILE = ATT_BM * ROWB;      // 4 KB
   static constexpr int KV_TILE = BN * ROWB;         // 2 KB (fast pass); the safe pass uses 128-key tiles of 4 KB
-  static constexpr int RING = KVS * 2 * KV_TILE;    // 24 KB >= the safe pass's 2 stages x (K, V) x 4 KB
+  static constexpr int RING = KVS * 2 * KV_TILE;    // 32 KB >= the safe pass's 2 stages x (K, V) x 4 KB
   static constexpr int P_TILE = ATT_BM * 128;       // 16 KB: [128 x 64 keys] 16 bit = one SWIZZLE_128B atom column
   static constexpr int OFF_KV = Q_TILE, OFF_P = OFF_KV + RING, OFF_ONES = OFF_P + 2 * P_TILE, OFF_QLO = OFF_ONES + 1024;
   static constexpr int OFF_BAR = OFF_QLO + Q_TILE;
@@ -53,7 +58,7 @@ attention_tc12_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + A::OFF_KV;   // fast pass: [KVS] x (K | V) of 64 keys
-  uint8_t* sP = smem + A::OFF_P;     // fast pass: [2] x 16 KB; safe pass: one 32 KB tile of 128 keys
+  uint8_t* sP = smem + A::OFF_P;     // safe pass only: one 32 KB tile of 128 keys (the fast pass keeps P in TMEM)
   uint8_t* sOnes = smem + A::OFF_ONES;  // [16 keys x d] 16-bit ones in V's layout: second N atom of the PV MMA's B operand
   uint8_t* sQlo = smem + A::OFF_QLO;    // NOREF: low part of the rescaled Q (Q c = hi + lo in 16 bit: no second rounding)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A::OFF_BAR);
@@ -324,7 +329,6 @@ attention_tc12_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     // ===================== safe pass (rare): v11's online softmax over 128-key tiles, warps 0..3 =====================
     if (warp < 4) {
       constexpr int TILE = ATT_BN * ROWB;  // 4 KB
-      constexpr int W = D + 16;
       uint8_t* sK = sKV;             // [2 stages]
       uint8_t* sV = sKV + 2 * TILE;  // [2 stages]
       const int nkv = g.L / ATT_BN;
