@@ -8,13 +8,12 @@
 //   buffer, no halo logic and no predication anywhere.  The box lands as 128 rows x 128 B (SWIZZLE_128B),
 //   which is exactly the canonical K-major UMMA operand tile.
 // * B operand: weights pre-packed [tap][Cout][Cin] (16-bit), rank-2 map, box {64, BN}.
-// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block into a TMEM accumulator;
-//   tcgen05.commit releases the smem stage back to the producer and finally signals the epilogue.
+// * One elected lane of the MMA warp issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block into each of the tile's two
+//   TMEM accumulators; tcgen05.commit releases the smem stage back to the producer and finally signals the epilogue.
 // * Epilogue warps read TMEM (tcgen05.ld 32x32b: one accumulator row per thread), apply bias / GELU /
 //   residual, write fp32 and/or 16-bit outputs, and emit deterministic GroupNorm(1,C) partial sums.
-// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
-// Two CTAs are resident per SM (<= 101 KB smem, <= 128 TMEM columns each), so one CTA's epilogue overlaps
-// the other's main loop.
+// Persistent CTAs, one per SM, 256-pixel work tiles, double-buffered TMEM accumulators: see igemm_tc2_kernel below (warp
+// roles, the split-TF32 passes of the fp32 engine and the slab pipeline of the Cout = 64 layers).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
