@@ -281,7 +281,10 @@ def test_igemm_conv_simt_with_groupnorm(ops, rows, H, cin, cout):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("rows,H,cin,cout", CONV_CASES + [(2, 64, 64, 64), (1, 64, 128, 128)])
+# (.., 64) at H = 64 / 32: the slab pipeline of the Cout = 64 layers (one TMA box per column shift serves three taps); the
+# 16-row case has more 256-pixel tiles (256) than SMs, the 3- and 5-row cases an uneven last wave
+@pytest.mark.parametrize("rows,H,cin,cout", CONV_CASES + [(2, 64, 64, 64), (1, 64, 128, 128), (3, 64, 128, 64), (5, 32, 64, 64),
+                                                          (16, 64, 64, 64), (2, 32, 192, 64)])
 def test_igemm_conv_tensor_core(ops, rows, H, cin, cout, dtype):
     from spectrogramgenai_b200._cabi import SG_ENGINE_TC
 
