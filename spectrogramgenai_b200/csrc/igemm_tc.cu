@@ -296,16 +296,23 @@ __device__ __forceinline__ void epilogue_coalesced(uint32_t tmem_acc, int64_t m0
 // row above and below, shifted by dx -- {64, W, 256/W + 2, 1} -- serves the three taps (dy = -1, 0, +1) as views that
 // start dy image rows further down (row pitch W x 128 B = 8 / 4 KB: a multiple of the 1024-byte swizzle atom, so the
 // views are ordinary descriptors), with the three taps' weight tiles behind it: 72 KB per 24 MMAs instead of 120 KB.
+// SLAB = 2 (Cin = 64 as well: the 64 -> 64 layers): the nine 8 KB weight tiles are loaded ONCE per CTA and stay resident, a
+// stage is the A slab alone -- a third of the L2 reads of SLAB = 1 were weight tiles every CTA re-fetched for every tile.
+// What is left (ncu: tensor pipe 47-50 %, smem->tensor 56 %): an M128 x N64 x K16 MMA is 32 clocks of math but reads 4 KB
+// of A + 2 KB of B through the shared-memory port the TMA fills share -- N = 64 gives the A bytes too little reuse; an L2
+// prefetch of the next tile's slab measured 6 % slower (the layer is not latency-bound).
 constexpr int SLAB_A_BYTES = 48 * 1024;  // (256 / W + 2) rows x W pixels x 128 B: 48 KB (W = 64) / 40 KB (W = 32)
-template <int BN, bool SLAB = false>
+template <int BN, int SLAB = 0>
 struct V2 {
-  static constexpr int STAGES = SLAB ? 2 : (BN == 128 ? 3 : 4);  // 72 KB / 48 KB / 40 KB per stage
+  static constexpr int STAGES = SLAB ? 2 : (BN == 128 ? 3 : 4);  // 72 KB (48 KB) / 48 KB / 40 KB per stage
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE = SLAB ? SLAB_A_BYTES + 3 * B_BYTES : 2 * A_BYTES + B_BYTES;
+  static constexpr int STAGE = SLAB == 2 ? SLAB_A_BYTES : (SLAB == 1 ? SLAB_A_BYTES + 3 * B_BYTES : 2 * A_BYTES + B_BYTES);
+  static constexpr int RES_B = SLAB == 2 ? 9 * B_BYTES : 0;  // resident weight tiles, behind the stage ring
   static constexpr int TMEM_COLS = 4 * BN;  // 2 buffers x 2 accumulators: 512 (BN=128) / 256 (BN=64)
   static constexpr int THREADS = 320;
-  static_assert(1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES <= 227 * 1024, "smem budget");
-  static constexpr int SMEM = 1024 + STAGES * STAGE + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES;
+  static constexpr int RING = STAGES * STAGE + RES_B;  // bytes in front of the barriers
+  static_assert(1024 + RING + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES <= 227 * 1024, "smem budget");
+  static constexpr int SMEM = 1024 + RING + 256 + 2 * BM * 2 * 4 + 8 * EPI_SCRATCH + BIAS_BYTES;
 };
 
 __device__ __forceinline__ void tile_coords(const IgemmGeom& g, int mt, int& cn, int& ch, int& cw) {
@@ -327,7 +334,7 @@ __device__ __forceinline__ void tile_coords(const IgemmGeom& g, int mt, int& cn,
 // fp32 TMEM tile, so the product carries ~21 mantissa bits (the dropped lo x lo term is 2^-22 relative) at 1/6 of the
 // 16-bit rate.  A k-block is the same 128-byte swizzle span either way (64 x 16 bit or 32 x fp32) and one MMA consumes
 // 32 bytes of it (K = 16 or K = 8), so tiles, descriptors and the pipeline are identical.
-template <int BN, int KIND, bool SLAB>
+template <int BN, int KIND, int SLAB>
 __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmA_lo,
@@ -338,13 +345,15 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * K::STAGE);
+  uint8_t* res_b = smem + STAGES * K::STAGE;  // SLAB == 2: the nine resident weight tiles
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + K::RING);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + STAGES * K::STAGE + 256);           // [2 groups][128][2]
-  float* scratch_all = reinterpret_cast<float*>(smem + STAGES * K::STAGE + 256 + 2 * BM * 2 * 4);  // [8 warps]
+  uint64_t* b_full = tmem_empty + 2;      // SLAB == 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  float(*rowstat)[2] = reinterpret_cast<float(*)[2]>(smem + K::RING + 256);           // [2 groups][128][2]
+  float* scratch_all = reinterpret_cast<float*>(smem + K::RING + 256 + 2 * BM * 2 * 4);  // [8 warps]
   float* s_bias = scratch_all + 8 * (EPI_SCRATCH / 4);
   for (int i = threadIdx.x; i < g.Cout; i += blockDim.x) s_bias[i] = ep.bias ? __ldg(ep.bias + i) : 0.f;
 
@@ -367,6 +376,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 256);
     }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<K::TMEM_COLS>(tmem_slot);
@@ -380,6 +390,14 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   if (warp == 0) {
     // ===== TMA producer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
     uint32_t it = 0;  // running k-block counter across tiles
+    if constexpr (SLAB == 2) {  // weights are immutable: loaded once, resident for every tile of this CTA
+      if (elect_one()) {
+        mbar_arrive_expect_tx(b_full, (uint32_t)K::RES_B);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) tma_load_2d(res_b + t * K::B_BYTES, &tmB, b_full, 0, t * g.Cout);
+      }
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt2 = tile / g.n_tiles, n0 = (tile % g.n_tiles) * BN;
       int cn0, ch0, cw0, cn1, ch1, cw1;
@@ -394,9 +412,11 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
           if (elect_one()) {
             mbar_arrive_expect_tx(&full[s], g.tx_bytes);
             tma_load_4d(st, &tmA, &full[s], c0, dxi - 1, ch0 - 1, cn0);
+            if constexpr (SLAB == 1) {
 #pragma unroll
-            for (int dyi = 0; dyi < 3; ++dyi)
-              tma_load_2d(st + SLAB_A_BYTES + dyi * K::B_BYTES, &tmB, &full[s], c0, (dyi * 3 + dxi) * g.Cout + n0);
+              for (int dyi = 0; dyi < 3; ++dyi)
+                tma_load_2d(st + SLAB_A_BYTES + dyi * K::B_BYTES, &tmB, &full[s], c0, (dyi * 3 + dxi) * g.Cout + n0);
+            }
           }
           __syncwarp();
           continue;
@@ -426,6 +446,10 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer: warp-uniform loop, descriptors in uniform registers, one elected lane issues =====
     uint32_t it = 0, lt = 0;
+    if constexpr (SLAB == 2) {
+      mbar_wait_spin(b_full, 0);
+      tc_fence_after();
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const uint32_t buf = lt & 1u;
       mbar_wait_spin(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator pair
@@ -442,7 +466,9 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
 #pragma unroll
             for (int dyi = 0; dyi < 3; ++dyi) {
               const uint64_t a0 = make_desc_k128(sa + dyi * pitch), a1 = make_desc_k128(sa + dyi * pitch + A_BYTES);
-              const uint64_t bd = make_desc_k128(sa + SLAB_A_BYTES + dyi * K::B_BYTES);
+              // SLAB == 2: one channel slice, so kb IS the column shift; tap = dy * 3 + dx
+              const uint64_t bd = make_desc_k128(SLAB == 2 ? smem_u32(res_b) + (uint32_t)((dyi * 3 + kb) * K::B_BYTES)
+                                                           : sa + SLAB_A_BYTES + dyi * K::B_BYTES);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 umma_ss(acc0, a0 + 2 * k, bd + 2 * k, g.idesc, (kb | dyi | k) != 0);
@@ -501,7 +527,7 @@ __global__ void __launch_bounds__(320, 1) igemm_tc2_kernel(const __grid_constant
   }
 }
 
-template <int BN, int KIND, bool SLAB = false>
+template <int BN, int KIND, int SLAB = 0>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_lo,
                    const IgemmGeom& g, const IgemmEpi& ep, cudaStream_t stream) {
   constexpr int smem = V2<BN, SLAB>::SMEM;
@@ -601,7 +627,8 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
     tmA_lo = tmA;
     tmB_lo = tmB;
   }
-  g.tx_bytes = slab ? box_rows * 128u + 3u * (uint32_t)BN * 128u : 2u * box_rows * 128u + (uint32_t)BN * 128u;
+  const bool resident = slab && a->Cin == tc::BK;  // the 64 -> 64 layers: nine 8 KB weight tiles stay in shared memory
+  g.tx_bytes = slab ? box_rows * 128u + (resident ? 0u : 3u * (uint32_t)BN * 128u) : 2u * box_rows * 128u + (uint32_t)BN * 128u;
 
   IgemmEpi ep;
   ep.bias = a->bias; ep.residual = a->residual; ep.out_f32 = a->out_f32; ep.out_act = a->out_act;
@@ -612,7 +639,8 @@ int igemm_tc(const sg_igemm_args* a, cudaStream_t stream) {
   }
   ep.P = sg_igemm_partials(SG_ENGINE_TC, a->H, a->W, a->Cout);
   if (tf32) return BN == 128 ? launch2<128, 1>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream) : launch2<64, 1>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
-  if (slab) return launch2<64, 0, true>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
+  if (resident) return launch2<64, 0, 2>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
+  if (slab) return launch2<64, 0, 1>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
   return BN == 128 ? launch2<128, 0>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream) : launch2<64, 0>(tmA, tmB, tmA_lo, tmB_lo, g, ep, stream);
 }
 
