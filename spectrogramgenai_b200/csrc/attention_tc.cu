@@ -286,7 +286,7 @@ static int launch_att(const CUtensorMap& tm, const AttGeom& g, uint16_t* out, di
 
 template <int D>
 constexpr int att4_smem_bytes() {
-  return 1024 + ATT_BM * D * 2 /*Q*/ + 2 * 2 * ATT_BN * D * 2 /*K,V x 2 stages*/ + P_BYTES + 256;
+  return 1024 + ATT_BM * D * 2 /*Q*/ + 2 * 2 * ATT_BN * D * 2 /*K,V x 2 stages*/ + 256;  // P lives in TMEM
 }
 
 // =====================================================================================================
@@ -295,23 +295,29 @@ constexpr int att4_smem_bytes() {
 // Here the CTA is just the four softmax warps (128 threads, four CTAs per SM, up to 128 registers); the hand-offs
 // are named barriers: warps 1..3 bar.arrive and go on to wait for the product, warp 0 bar.sync's and its lane 0
 // issues the tcgen05.mma's (and the next TMA loads) in line.  Nothing spins while the others compute.
-//   per key tile:  sweep S_j -> P_j | bar 1 | [P_j V_j] | wait o_full | o += O_j | bar 2 | [TMA j+2, S_{j+1}] | wait s_full
+//   per key tile:  max S_j | sweep S_j -> P_j | bar 1 | [P_j V_j] | wait o_full | o += O_j | bar 2 | [TMA j+2, S_{j+1}] | wait s_full
 // Inner body as v5 (FFMA2 / FADD2 / FMNMX3, 16-column double-buffered TMEM reads, POLY/8 pairs on the FMA pipe).
+// P never touches shared memory (round 2): the packed probabilities go back into TMEM with tcgen05.st -- columns
+// [64, 128) of the 128 S columns, swept from the last chunk to the first so that chunk ch's eight P columns 64 + 8 ch ..
+// lie inside the already consumed range [16 ch, 128) -- and P_j V_j takes its A operand from TMEM, its NACC accumulators
+// from columns [0, 64).  Without the 32 KB P tile the CTA needs 41 KB (d = 32) / 81 KB (d = 64) of shared memory: four /
+// two CTAs per SM instead of three / one (sa1 1.38 -> 1.21 ms, sa2 0.33 -> 0.19 ms).  S does not survive the sweep, so
+// the exponent reference is raised to the tile maximum FIRST (one extra pass of TMEM loads and 3-input maxima, exact
+// rescale of o, l): every p <= 1, no overflow guard, no second sweep.
 // =====================================================================================================
 template <int D, int DT, int POLY, int NACC>
-__global__ void __launch_bounds__(128, (D == 64 ? 2 : (D == 32 ? 3 : 4)))
+__global__ void __launch_bounds__(128, (D == 64 ? 2 : 4))
 attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, uint16_t* __restrict__ out) {
   constexpr int ROWB = D * 2;
   constexpr int TILE = ATT_BN * ROWB;
-  static_assert(NACC * D <= 128 && (ATT_BN / 16) % NACC == 0, "accumulators must fit the dead S columns");
+  static_assert(NACC * D <= 64 && (ATT_BN / 16) % NACC == 0, "accumulators live in S columns [0, 64), P in [64, 128)");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE;      // [2 stages]
   uint8_t* sV = sK + 2 * TILE;  // [2 stages]
-  uint8_t* sP = sV + 2 * TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * TILE);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;  // [2]
   uint64_t* s_full = bars + 3;
@@ -351,7 +357,6 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
 
   // Issue helpers: called by ALL lanes of warp 0 (convergent); one elected lane executes the TMA / MMA instructions.
   const uint64_t q_desc = make_desc_rows(smem_u32(sQ), ROWB);
-  const uint64_t p_desc = make_desc_k128(smem_u32(sP));
   auto load_tile = [&](int t) {
     const int s = t & 1;
     const int tok = (int)(kv0 + (int64_t)t * ATT_BN);
@@ -371,14 +376,14 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
       umma_commit(s_full);
     }
   };
-  auto issue_pv = [&](int t) {  // O_t = P V_t : A = P (K-major, two SWIZZLE_128B atoms of 64 keys), B = V MN-major
+  auto issue_pv = [&](int t) {  // O_t = P V_t : A = P in TMEM (columns [64, 128), eight per 16-key slab), B = V MN-major
     tc_fence_after();
     const uint64_t vd = make_desc_rows(smem_u32(sV + (t & 1) * TILE), ROWB);
     if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < ATT_BN / 16; ++k)
-        umma_ss(tmem_base + (uint32_t)((k % NACC) * D), p_desc + (uint64_t)((k >> 2) * (ATT_BM * 128 / 16) + (k & 3) * 2),
-                vd + (uint64_t)(k * 16 * ROWB / 16), g.idesc_o, k >= NACC);
+        umma_ts(tmem_base + (uint32_t)((k % NACC) * D), tmem_base + 64u + (uint32_t)(k * 8), vd + (uint64_t)(k * 16 * ROWB / 16),
+                g.idesc_o, k >= NACC);
       umma_commit(o_full);
     }
   };
@@ -397,15 +402,12 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
   const int r = warp * 32 + lane;
   const int64_t tok = m0 + r;
   const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t p_row = smem_u32(sP) + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-  const uint32_t rx = (uint32_t)(r & 7);
   uint64_t o2[D / 2];
 #pragma unroll
   for (int i = 0; i < D / 2; ++i) o2[i] = 0ull;  // two +0.0f
   float m_ref = 0.f, l = 0.f;
   const uint64_t c2 = pk2(g.c, g.c);
-  const float psum_max = exp2f(g.redo_log2);
-  // row maximum of the current S tile (first tile, and the rare tiles that overflow the reference)
+  // row maximum of the current S tile
   auto tile_max = [&]() {
     float mx = -INFINITY;
 #pragma unroll 1
@@ -422,42 +424,30 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
     const uint32_t ph = (uint32_t)j & 1u;
     mbar_wait(s_full, ph);
     tc_fence_after();
-    if (j == 0) {
-      // initial reference: the maximum of the row's first 16 scores only (1/8 of the full-tile pre-pass).  Any reference
-      // within 2^redo_log2 of the true maximum is exact enough -- P keeps its relative precision in bf16 / fp16 and the
-      // row sum is fp32 -- and one that is too low is caught by the overflow guard below like on any later tile.
-      uint32_t v[16];
-      tmem_ld16(t_row, v);
-      tmem_ld_wait();
-      float mx = -INFINITY;
+    // raise the reference to the tile maximum first (exact rescale of o, l; a0 = 0 on the first tile, where o = l = 0)
+    const float tmax = tile_max();
+    if (tmax > m_ref || j == 0) {
+      const float a0 = j == 0 ? 0.f : ex2((m_ref - tmax) * g.c);
+      l *= a0;
+      const uint64_t a2 = pk2(a0, a0);
 #pragma unroll
-      for (int e = 0; e < 16; e += 2) mx = max3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-      m_ref = mx;
+      for (int i = 0; i < D / 2; ++i) o2[i] = mul2(o2[i], a2);
+      m_ref = tmax;
     }
-    // The reference m_ref is NOT tracked per tile (that costs an FMNMX per pair): p = exp2((s - m_ref) c) may exceed 1.
-    // Overflow guard: the tile's row sum (MUFU lanes saturate to +inf) and the maximum over the polynomial lanes only
-    // (their exponent arithmetic wraps instead of saturating).  If either exceeds 2^redo_log2 the reference is raised
-    // to the tile maximum (exact rescale of o, l) and the tile is swept again.
-    uint64_t psum2;
-    bool redo;
-    do {
-      const float nmc = -m_ref * g.c;
-      const uint64_t nmc2 = pk2(nmc, nmc);
-      float xmax = -INFINITY;  // largest exponent seen by a polynomial lane
-      psum2 = 0ull;
+    const float nmc = -m_ref * g.c;
+    const uint64_t nmc2 = pk2(nmc, nmc);
+    uint64_t psum2 = 0ull;
+    {
       uint32_t va[16], vb[16];
-      tmem_ld16(t_row, va);
+      tmem_ld16(t_row + 7 * 16, va);
       tmem_ld_wait();
-      auto chunk = [&](const uint32_t(&v)[16], int ch) {  // 16 columns: 8 pairs -> two 16-byte stores of the P row
+      auto chunk = [&](const uint32_t(&v)[16], int ch) {  // 16 columns: 8 pairs -> eight packed P columns
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const uint64_t x2 = fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nmc2);
           float p0, p1;
           if (pair_is_poly<POLY>(i >> 1)) {
-            float x0, x1;
-            un2(x2, x0, x1);
-            xmax = max3(xmax, x0, x1);
             ex2_poly2(x2, p0, p1);
           } else {
             float x0, x1;
@@ -468,42 +458,20 @@ attention_tc8_kernel(const __grid_constant__ CUtensorMap tm, const AttGeom g, ui
           pk[i >> 1] = pack_pair<DT>(p0, p1);
           psum2 = add2(psum2, pk2(p0, p1));
         }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int jj = ch * 2 + u;
-          const uint32_t addr = p_row + (uint32_t)(jj >> 3) * (ATT_BM * 128) + ((((uint32_t)jj & 7u) ^ rx) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[u * 4]), "r"(pk[u * 4 + 1]),
-                       "r"(pk[u * 4 + 2]), "r"(pk[u * 4 + 3])
-                       : "memory");
-        }
+        tmem_st8(t_row + 64u + (uint32_t)(ch * 8), pk);
       };
 #pragma unroll
-      for (int ch = 0; ch < 8; ch += 2) {
-        tmem_ld16(t_row + (ch + 1) * 16, vb);  // in flight while chunk ch is processed
+      for (int ch = 7; ch > 0; ch -= 2) {  // last chunk first: P only overwrites S columns that have been read
+        tmem_ld16(t_row + (ch - 1) * 16, vb);  // in flight while chunk ch is processed
         chunk(va, ch);
         tmem_ld_wait();
-        if (ch + 2 < 8) tmem_ld16(t_row + (ch + 2) * 16, va);
-        chunk(vb, ch + 1);
-        if (ch + 2 < 8) tmem_ld_wait();
+        if (ch - 2 >= 0) tmem_ld16(t_row + (ch - 2) * 16, va);
+        chunk(vb, ch - 1);
+        if (ch - 2 >= 0) tmem_ld_wait();
       }
-      float ps0, ps1;
-      un2(psum2, ps0, ps1);
-      const bool over = !(ps0 + ps1 <= psum_max) || xmax > g.redo_log2;  // NaN-safe
-      redo = __any_sync(0xffffffffu, over);
-      if (redo) {
-        const float tmax = tile_max();
-        if (over && tmax > m_ref) {
-          const float a0 = ex2((m_ref - tmax) * g.c);
-          l *= a0;
-          const uint64_t a2 = pk2(a0, a0);
-#pragma unroll
-          for (int i = 0; i < D / 2; ++i) o2[i] = mul2(o2[i], a2);
-          m_ref = tmax;
-        }
-      }
-    } while (redo);
-    tc_fence_before();    // our tcgen05.ld of S precede the MMA that overwrites those columns
-    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tmem_st_wait();
+    }
+    tc_fence_before();  // our tcgen05.ld of S and tcgen05.st of P precede the MMAs that read P and overwrite those columns
     if (warp == 0) {
       named_bar_sync<1, 128>();
       issue_pv(j);
@@ -618,11 +586,12 @@ int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, 
   const int64_t tiles = cdiv(g.M, ATT_BM);
   dim3 grid((unsigned)heads, (unsigned)(tiles < 32768 ? tiles : 32768), (unsigned)cdiv(tiles, 32768));
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
-  // Kernel choice (measured on B200, bf16, ms; v2-v7 / v9 / v10 were experiments, see profiles/README.md):
-  //                           v1     v8     v11    v12
-  //   d=16 L=4096 rows=1024   -      -      15.74  14.30   v12 (attention_tc12.cu: double-buffered S, TMEM-resident output,
-  //   d=16 L=1024 rows=1024   -      1.22   1.07   1.01    reference-free exponent) for d = 16; v8 (named-barrier hand-offs,
-  //   d=32 L=1024 rows=128    0.347  0.188  -      -       1/4 polynomial exp2, two accumulators) for d = 32 / 64
+  // Kernel choice (measured on B200, bf16, ms; v2-v7 / v9 - v11 were experiments, see profiles/README.md):
+  //                           v1     v8 (P in smem)  v8 (P in TMEM)  v12
+  //   d=16 L=4096 rows=1024   -      -               -               12.9    v12 (attention_tc12.cu: double-buffered S, output and P
+  //   d=16 L=1024 rows=1024   -      1.22            -               0.90    resident in TMEM, reference-free exponent) for d = 16;
+  //   d=32 L=1024 rows=1024   -      1.38            1.21            -       v8 (named-barrier hand-offs, 1/4 polynomial exp2, P in
+  //   d=64 L=256  rows=1024   -      0.33            0.19            -       TMEM, two / one accumulators) for d = 32 / 64
   // L < 128: v1, whose tile holds 128 / L batch rows under a block-diagonal mask.
 #define SG_ATT_BY_DTYPE(CALL_BF16, CALL_F16) \
   do {                                       \
@@ -632,7 +601,7 @@ int attention_tc(const void* qkv, void* out, int rows, int L, int C, int heads, 
   if (L >= ATT_BN && d == 16) return attention_tc12(qkv, g, o, grid, stream);
   if (L >= ATT_BN) {
     if (d == 32) SG_ATT_BY_DTYPE((launch_att8<32, SG_BF16, 2, 2>(tm, g, o, grid, stream)), (launch_att8<32, SG_F16, 2, 2>(tm, g, o, grid, stream)));
-    SG_ATT_BY_DTYPE((launch_att8<64, SG_BF16, 2, 2>(tm, g, o, grid, stream)), (launch_att8<64, SG_F16, 2, 2>(tm, g, o, grid, stream)));
+    SG_ATT_BY_DTYPE((launch_att8<64, SG_BF16, 2, 1>(tm, g, o, grid, stream)), (launch_att8<64, SG_F16, 2, 1>(tm, g, o, grid, stream)));
   }
   if (d == 16) SG_ATT_BY_DTYPE((launch_att<16, SG_BF16, 0>(tm, g, o, grid, stream)), (launch_att<16, SG_F16, 0>(tm, g, o, grid, stream)));
   if (d == 32) SG_ATT_BY_DTYPE((launch_att<32, SG_BF16, 0>(tm, g, o, grid, stream)), (launch_att<32, SG_F16, 0>(tm, g, o, grid, stream)));
