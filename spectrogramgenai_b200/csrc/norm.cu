@@ -373,9 +373,20 @@ __global__ void __launch_bounds__(256, 4) gn_apply_vcat_kernel(const uint4* __re
   };
   unsigned p = first / (unsigned)Cs8;
   const unsigned dp = stride / (unsigned)Cs8;
+  // software pipeline (as gn_apply_kernel's GELU mode): the raw loads of the next pixel are issued before this one is
+  // normalised
+  uint4 n_s = make_uint4(0, 0, 0, 0), n_x = n_s;
+  if (first < nu) {
+    n_s = __ldcs(rrow + (size_t)p * C8 + k);
+    n_x = __ldcs(rrow + (size_t)p * C8 + k + Cs8);
+  }
   for (unsigned i = first; i < nu; i += stride, p += dp) {
     const size_t e_s = (size_t)p * C8 + k, e_x = e_s + Cs8;  // units of 8 channels inside the row
-    const uint4 h_s = __ldcs(rrow + e_s), h_x = __ldcs(rrow + e_x);
+    const uint4 h_s = n_s, h_x = n_x;
+    if (i + stride < nu) {
+      n_s = __ldcs(rrow + (size_t)(p + dp) * C8 + k);
+      n_x = __ldcs(rrow + (size_t)(p + dp) * C8 + k + Cs8);
+    }
     const unsigned ho = p / (unsigned)W2, wo = p - ho * (unsigned)W2;
     const float fy = sh * (float)ho, fx = sw * (float)wo;
     const int y0 = (int)fy, x0 = (int)fx;
