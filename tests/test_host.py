@@ -110,6 +110,27 @@ def test_schedule_matches_golden(golden):
     assert (torch.cumprod(1.0 - beta, 0).numpy() == golden["sched_alpha_hat"]).all()
 
 
+def test_gelu_logistic_coefficients_reproduce_erf_gelu():
+    """The 16-bit engines' GroupNorm-apply evaluates GELU as x / (1 + 2^(x p(x^2))) (csrc/common.cuh gelu_logistic2,
+    coefficients from scripts/fit_gelu.py).  Evaluated here in fp32 with the constants read from the source: within 4e-6
+    absolute of the exact erf GELU (nn.GELU(), /root/reference/src/diff_modules.py:84,91) for |x| <= 14, p > 0 so that
+    large |x| saturate to x and -0 without a clamp."""
+    src = open(os.path.join(ROOT, "spectrogramgenai_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("void gelu_logistic2("):]
+    body = body[:body.index("\n}\n")]
+    c = [float(m) for m in re.findall(r"pk2\((-?[0-9.]+(?:e-?[0-9]+)?)f,", body)]
+    assert len(c) == 6 and c[5] == 1.0, c  # c4, c3, c2, c1, c0 (Horner order), then the 1.0 of 1 + e
+    x = torch.linspace(-14.0, 14.0, 1_400_001, dtype=torch.float32)
+    t = x * x
+    p = torch.full_like(x, c[0])
+    for k in c[1:5]:
+        p = p * t + k
+    y = x * (1.0 / (1.0 + torch.exp2(x * p)))
+    err = (y.double() - torch.nn.functional.gelu(x.double())).abs().max().item()
+    assert err < 4e-6, err
+    assert (p < 0).all()  # p carries the factor -log2(e): the logit x * (-p / log2 e) keeps the sign of x everywhere
+
+
 def test_shard_bounds_partition():
     from spectrogramgenai_b200.sharding import shard_bounds
 
